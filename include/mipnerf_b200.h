@@ -1,0 +1,162 @@
+/* mipnerf_b200.h — C ABI of libmipnerf_b200.so: the B200 (sm_100a) Mip-NeRF per-ray hot path.
+ *
+ * The reference (hjxwhy/mipnerf_pl) has no FFI layer: its boundary for this path is the Python
+ * call surface `MipNerf.forward` (models/mip_nerf.py:172-248) and the free functions it reaches in
+ * models/mip.py.  Each entry point below names the reference function it replaces.  The host-side
+ * mirror that binds these symbols (ctypes) is mipnerf_pl_b200/_cabi.py; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to row-major fp32 unless stated otherwise; the library never
+ *     allocates or frees device memory and keeps no state besides the thread-local error string;
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it (no sync inside);
+ *   - return value: 0 on success, negative MIPNERF_B200_E* on failure (`mipnerf_b200_last_error()`
+ *     gives the text).  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef MIPNERF_B200_H_
+#define MIPNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIPNERF_B200_ABI_VERSION 1
+
+#define MIPNERF_B200_OK 0
+#define MIPNERF_B200_EINVAL (-1)       /* bad argument (NULL pointer, negative size, ...)            */
+#define MIPNERF_B200_EUNSUPPORTED (-2) /* config outside what the kernels implement                  */
+#define MIPNERF_B200_ECUDA (-3)        /* a CUDA runtime call or launch failed                       */
+#define MIPNERF_B200_EWORKSPACE (-4)   /* workspace smaller than mipnerf_b200_workspace_bytes()      */
+
+/* Arithmetic the MLP contraction runs in (everything else on the path is always fp32). */
+#define MIPNERF_B200_FP32 0 /* CUDA-core FFMA, fp32 operands: the 1e-4 parity mode                   */
+#define MIPNERF_B200_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM             */
+#define MIPNERF_B200_FP16 2 /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM             */
+
+/* One torch.nn.Linear: weight [out_features, in_features] row-major, bias [out_features]. */
+typedef struct mipnerf_b200_linear {
+  const float* weight;
+  const float* bias;
+  int32_t in_features;
+  int32_t out_features;
+} mipnerf_b200_linear;
+
+/* Constructor arguments of MipNerf that change the arithmetic (models/mip_nerf.py:117-141). */
+typedef struct mipnerf_b200_config {
+  int32_t num_samples; /* per level; CUDA path needs num_samples % 32 == 0 and <= 256               */
+  int32_t num_levels;
+  int32_t min_deg_point, max_deg_point, deg_view;
+  int32_t use_viewdirs, disparity, disable_integration;
+  float resample_padding, density_bias, rgb_padding;
+  int32_t net_depth, net_width, net_depth_condition, net_width_condition, skip_index;
+  int32_t num_rgb_channels, num_density_channels; /* must be 3 and 1                                */
+} mipnerf_b200_config;
+
+/* MLP parameters in state_dict order (models/mip_nerf.py:19-73):
+ * layers.0 .. layers.{net_depth-1}, density_layer, extra_layer, view_layers.0 .. , color_layer.
+ * `packed` is the optional tensor-core operand image written by mipnerf_b200_pack_weights. */
+typedef struct mipnerf_b200_weights {
+  const mipnerf_b200_linear* linears;
+  int32_t num_linears;
+  int32_t packed_precision; /* MIPNERF_B200_BF16/FP16 the image was packed for, or -1              */
+  const void* packed;
+  size_t packed_bytes;
+} mipnerf_b200_weights;
+
+/* Rays namedtuple fields used by forward (datasets/datasets.py:13-16; lossmult is not read). */
+typedef struct mipnerf_b200_rays {
+  const float* origins;    /* [B,3] */
+  const float* directions; /* [B,3] not normalised */
+  const float* viewdirs;   /* [B,3] */
+  const float* radii;      /* [B,1] */
+  const float* near;       /* [B,1] */
+  const float* far;        /* [B,1] */
+  int64_t num_rays;
+} mipnerf_b200_rays;
+
+/* One element of the list MipNerf.forward returns (models/mip_nerf.py:246). */
+typedef struct mipnerf_b200_level_out {
+  float* comp_rgb;  /* [B,3]            */
+  float* distance;  /* [B]              */
+  float* acc;       /* [B]              */
+  float* weights;   /* [B,N]   nullable */
+  float* t_samples; /* [B,N+1] nullable */
+  int64_t* inds;    /* [B,N+1] nullable; searchsorted indices of the resampler (levels >= 1)       */
+} mipnerf_b200_level_out;
+
+const char* mipnerf_b200_last_error(void);
+int mipnerf_b200_abi_version(void);
+
+/* Bytes of scratch `mipnerf_b200_forward` / `mipnerf_b200_mlp_forward` need for `num_rays` rays. */
+size_t mipnerf_b200_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays, int precision);
+
+/* Size of / builder for the tensor-core operand image of the MLP weights (device -> device). */
+size_t mipnerf_b200_packed_weights_bytes(const mipnerf_b200_config* cfg, int precision);
+int mipnerf_b200_pack_weights(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                              int precision, void* packed_out, size_t packed_bytes, void* stream);
+
+/* MipNerf.forward (models/mip_nerf.py:172-248).  `t_rand` [B,N+1] in [0,1) and `u_jitter`
+ * [B,N+1] in [0, 1/(N+1)-eps) replace torch.rand / uniform_ (models/mip.py:159, :201-202) when
+ * `randomized` != 0 (both required then).  `outs` has cfg->num_levels entries. */
+int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                         const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                         const float* u_jitter, int white_bkgd, int precision,
+                         mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- per-stage entry points (unit parity against the functions of models/mip.py) ---- */
+
+/* sample_along_rays (models/mip.py:127-165): t_samples [B,N+1], means/covs [B,N,3] (nullable). */
+int mipnerf_b200_sample_along_rays(const mipnerf_b200_rays* rays, int num_samples, int randomized,
+                                   int disparity, const float* t_rand, float* t_samples,
+                                   float* means, float* covs, void* stream);
+
+/* cast_rays, cone + diagonal (models/mip.py:81-103): t_samples [B,N+1] -> means, covs [B,N,3]. */
+int mipnerf_b200_cast_rays(const mipnerf_b200_rays* rays, const float* t_samples, int num_samples,
+                           float* means, float* covs, void* stream);
+
+/* integrated_pos_enc, diagonal (models/mip.py:322-350): means, covs [M,3] -> out [M, 6*(max-min)]. */
+int mipnerf_b200_integrated_pos_enc(const float* means, const float* covs, int64_t num_points,
+                                    int min_deg, int max_deg, float* out, void* stream);
+
+/* pos_enc (models/mip.py:353-363): x [B,3] -> out [B, 6*(max-min) (+3)]. */
+int mipnerf_b200_pos_enc(const float* x, int64_t num_points, int min_deg, int max_deg,
+                         int append_identity, float* out, void* stream);
+
+/* MLP.forward (models/mip_nerf.py:75-111): x [B*N, xyz_dim], view_enc [B, view_dim] or NULL ->
+ * raw_rgb [B*N,3], raw_density [B*N,1]. */
+int mipnerf_b200_mlp_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                             const float* x, const float* view_enc, int64_t num_rays,
+                             int samples_per_ray, int precision, float* raw_rgb, float* raw_density,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+size_t mipnerf_b200_mlp_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays,
+                                        int samples_per_ray, int precision);
+
+/* volumetric_rendering (models/mip.py:366-401): rgb [B,N,3], density [B,N,1] already activated. */
+int mipnerf_b200_volumetric_rendering(const float* rgb, const float* density,
+                                      const float* t_samples, const float* dirs, int64_t num_rays,
+                                      int num_samples, int white_bkgd, float* comp_rgb,
+                                      float* distance, float* acc, float* weights, void* stream);
+
+/* sorted_piecewise_constant_pdf (models/mip.py:168-229): bins [B,nb+1], weights [B,nb] (NOT
+ * modified) -> samples [B,num_samples]; inds (nullable) are the searchsorted(right=True) results. */
+int mipnerf_b200_sorted_piecewise_constant_pdf(const float* bins, const float* weights,
+                                               int64_t num_rays, int num_bins, int num_samples,
+                                               int randomized, const float* u_jitter,
+                                               float* samples, int64_t* inds, void* stream);
+
+/* resample_along_rays (models/mip.py:232-280): blur-pool + padding + inverse CDF + cast_rays. */
+int mipnerf_b200_resample_along_rays(const mipnerf_b200_rays* rays, const float* t_samples,
+                                     const float* weights, int num_samples, int randomized,
+                                     const float* u_jitter, float resample_padding,
+                                     float* new_t_samples, float* means, float* covs, int64_t* inds,
+                                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIPNERF_B200_H_ */

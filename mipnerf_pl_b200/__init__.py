@@ -1,0 +1,20 @@
+"""mipnerf_pl_b200 — B200-native (sm_100a) Mip-NeRF per-ray hot path behind the
+reference's Python surface (hjxwhy/mipnerf_pl: models/mip_nerf.py, models/mip.py).
+
+Importing the package never touches CUDA; the first op call loads
+libmipnerf_b200.so and raises if it is missing (no CPU fallback).
+"""
+from .rays import (Rays, Rays_keys, namedtuple_map, rearrange_render_image, blender_rays, spheric_pose,
+                   random_ray_batch, rays_to_torch)
+from .mip_nerf import MLP, MipNerf
+from .nerf_system import MipNeRFSystem, default_hparams, calc_psnr
+from .ops import (sample_along_rays, resample_along_rays, cast_rays, integrated_pos_enc, pos_enc,
+                  sorted_piecewise_constant_pdf, volumetric_rendering)
+from .weights import make_state_dict
+
+__all__ = [
+    "Rays", "Rays_keys", "namedtuple_map", "rearrange_render_image", "blender_rays", "spheric_pose",
+    "random_ray_batch", "rays_to_torch", "MLP", "MipNerf", "MipNeRFSystem", "default_hparams", "calc_psnr",
+    "sample_along_rays", "resample_along_rays", "cast_rays", "integrated_pos_enc", "pos_enc",
+    "sorted_piecewise_constant_pdf", "volumetric_rendering", "make_state_dict",
+]

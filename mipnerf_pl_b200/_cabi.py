@@ -1,0 +1,118 @@
+"""ctypes binding of libmipnerf_b200.so (include/mipnerf_b200.h).
+
+The library is the product; this file only marshals pointers.  If the shared
+object is missing the import of the ops fails loudly — there is no CPU or
+PyTorch fallback behind it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libmipnerf_b200.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+
+OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
+FP32, BF16, FP16 = 0, 1, 2
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
+
+_f32p = C.POINTER(C.c_float)
+_i64p = C.POINTER(C.c_int64)
+
+
+class Linear(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p),
+                ("in_features", C.c_int32), ("out_features", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [("num_samples", C.c_int32), ("num_levels", C.c_int32),
+                ("min_deg_point", C.c_int32), ("max_deg_point", C.c_int32), ("deg_view", C.c_int32),
+                ("use_viewdirs", C.c_int32), ("disparity", C.c_int32), ("disable_integration", C.c_int32),
+                ("resample_padding", C.c_float), ("density_bias", C.c_float), ("rgb_padding", C.c_float),
+                ("net_depth", C.c_int32), ("net_width", C.c_int32), ("net_depth_condition", C.c_int32),
+                ("net_width_condition", C.c_int32), ("skip_index", C.c_int32),
+                ("num_rgb_channels", C.c_int32), ("num_density_channels", C.c_int32)]
+
+
+class Weights(C.Structure):
+    _fields_ = [("linears", C.POINTER(Linear)), ("num_linears", C.c_int32),
+                ("packed_precision", C.c_int32), ("packed", C.c_void_p), ("packed_bytes", C.c_size_t)]
+
+
+class RaysStruct(C.Structure):
+    _fields_ = [("origins", C.c_void_p), ("directions", C.c_void_p), ("viewdirs", C.c_void_p),
+                ("radii", C.c_void_p), ("near", C.c_void_p), ("far", C.c_void_p), ("num_rays", C.c_int64)]
+
+
+class LevelOut(C.Structure):
+    _fields_ = [("comp_rgb", C.c_void_p), ("distance", C.c_void_p), ("acc", C.c_void_p),
+                ("weights", C.c_void_p), ("t_samples", C.c_void_p), ("inds", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/mipnerf_b200.h declares.
+_V = C.c_void_p
+_SIGNATURES = {
+    "mipnerf_b200_last_error": (C.c_char_p, []),
+    "mipnerf_b200_abi_version": (C.c_int, []),
+    "mipnerf_b200_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int64, C.c_int]),
+    "mipnerf_b200_packed_weights_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int]),
+    "mipnerf_b200_pack_weights": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.c_int, _V, C.c_size_t, _V]),
+    "mipnerf_b200_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.c_int,
+                                       _V, _V, C.c_int, C.c_int, C.POINTER(LevelOut), _V, C.c_size_t, _V]),
+    "mipnerf_b200_sample_along_rays": (C.c_int, [C.POINTER(RaysStruct), C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V]),
+    "mipnerf_b200_cast_rays": (C.c_int, [C.POINTER(RaysStruct), _V, C.c_int, _V, _V, _V]),
+    "mipnerf_b200_integrated_pos_enc": (C.c_int, [_V, _V, C.c_int64, C.c_int, C.c_int, _V, _V]),
+    "mipnerf_b200_pos_enc": (C.c_int, [_V, C.c_int64, C.c_int, C.c_int, C.c_int, _V, _V]),
+    "mipnerf_b200_mlp_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), _V, _V, C.c_int64, C.c_int,
+                                           C.c_int, _V, _V, _V, C.c_size_t, _V]),
+    "mipnerf_b200_mlp_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int64, C.c_int, C.c_int]),
+    "mipnerf_b200_volumetric_rendering": (C.c_int, [_V, _V, _V, _V, C.c_int64, C.c_int, C.c_int, _V, _V, _V, _V, _V]),
+    "mipnerf_b200_sorted_piecewise_constant_pdf": (C.c_int, [_V, _V, C.c_int64, C.c_int, C.c_int, C.c_int, _V, _V, _V, _V]),
+    "mipnerf_b200_resample_along_rays": (C.c_int, [C.POINTER(RaysStruct), _V, _V, C.c_int, C.c_int, _V, C.c_float,
+                                                   _V, _V, _V, _V, _V]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib: Optional[C.CDLL] = None
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"(or `python -m mipnerf_pl_b200.build`). There is no CPU fallback for this path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if handle.mipnerf_b200_abi_version() != 1:
+            raise ImportError("libmipnerf_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().mipnerf_b200_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    """Turn a C-ABI status into the exception the reference would raise."""
+    if rc == OK:
+        return
+    msg = f"{what}: {last_error()}"
+    if rc == EUNSUPPORTED:
+        raise NotImplementedError(msg)  # reference raises NotImplementedError for unsupported modes
+    if rc == EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(msg)

@@ -1,0 +1,470 @@
+// api.cu — the extern "C" surface declared in include/mipnerf_b200.h and the level loop of
+// MipNerf.forward (models/mip_nerf.py:172-248) expressed as kernel launches on one stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/mipnerf_b200.h"
+#include "kernels.h"
+#include "mlp_tc.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return fail(MIPNERF_B200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                  __FILE__, __LINE__);                                                           \
+  } while (0)
+
+constexpr int64_t kChunkRaysFp32 = 4096;  // bounds the fp32 path's activation scratch (~1.8 GB)
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Dims {
+  int xyz_dim, view_dim, n_lin;
+};
+
+int check_config(const mipnerf_b200_config* c, Dims* d) {
+  if (!c) return fail(MIPNERF_B200_EINVAL, "config is NULL");
+  if (c->num_samples <= 0 || c->num_samples % 32 != 0 || c->num_samples > 256 ||
+      (c->num_samples / 32 == 5) || (c->num_samples / 32 == 7))
+    return fail(MIPNERF_B200_EUNSUPPORTED, "num_samples=%d: need a multiple of 32 in {32,64,96,128,192,256}",
+                c->num_samples);
+  if (c->num_levels < 1) return fail(MIPNERF_B200_EINVAL, "num_levels=%d", c->num_levels);
+  if (c->max_deg_point <= c->min_deg_point || c->min_deg_point < -60 || c->max_deg_point > 60)
+    return fail(MIPNERF_B200_EINVAL, "bad point degrees [%d,%d)", c->min_deg_point, c->max_deg_point);
+  if (c->deg_view < 0 || c->deg_view > 60) return fail(MIPNERF_B200_EINVAL, "deg_view=%d", c->deg_view);
+  if (c->net_depth < 1 || c->net_width < 1 || c->skip_index < 1 || c->net_depth_condition < 0 ||
+      c->net_width_condition < 1)
+    return fail(MIPNERF_B200_EINVAL, "bad MLP shape");
+  if (c->num_rgb_channels != 3 || c->num_density_channels != 1)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "only 3 rgb / 1 density channels (volumetric_rendering assumes it)");
+  const int last = c->net_depth - 1;
+  if (last > 0 && last % c->skip_index == 0)
+    return fail(MIPNERF_B200_EUNSUPPORTED,
+                "skip connection after the last trunk layer: the reference's density_layer cannot take it");
+  if (!c->use_viewdirs && c->net_width != c->net_width_condition)
+    return fail(MIPNERF_B200_EUNSUPPORTED,
+                "use_viewdirs=False needs net_width == net_width_condition (reference color_layer shape)");
+  d->xyz_dim = (c->max_deg_point - c->min_deg_point) * 6;
+  d->view_dim = c->deg_view * 6 + 3;
+  d->n_lin = c->net_depth + 2 + c->net_depth_condition + 1;
+  return MIPNERF_B200_OK;
+}
+
+int check_weights(const mipnerf_b200_config* c, const Dims& d, const mipnerf_b200_weights* w) {
+  if (!w || !w->linears) return fail(MIPNERF_B200_EINVAL, "weights are NULL");
+  if (w->num_linears != d.n_lin)
+    return fail(MIPNERF_B200_EINVAL, "expected %d linears (state_dict order), got %d", d.n_lin, w->num_linears);
+  auto expect = [&](int idx, int in, int out, const char* name) {
+    const mipnerf_b200_linear& l = w->linears[idx];
+    if (!l.weight || !l.bias) return fail(MIPNERF_B200_EINVAL, "%s has a NULL tensor", name);
+    if (l.in_features != in || l.out_features != out)
+      return fail(MIPNERF_B200_EINVAL, "%s is [%d,%d], expected [%d,%d]", name, l.out_features, l.in_features,
+                  out, in);
+    return MIPNERF_B200_OK;
+  };
+  int rc;
+  for (int i = 0; i < c->net_depth; ++i) {
+    int in = i == 0 ? d.xyz_dim : c->net_width;
+    if (i > 1 && (i - 1) % c->skip_index == 0) in = c->net_width + d.xyz_dim;  // models/mip_nerf.py:40-42
+    if ((rc = expect(i, in, c->net_width, "layers[i]"))) return rc;
+  }
+  if ((rc = expect(c->net_depth, c->net_width, 1, "density_layer"))) return rc;
+  if ((rc = expect(c->net_depth + 1, c->net_width, c->net_width, "extra_layer"))) return rc;
+  for (int i = 0; i < c->net_depth_condition; ++i) {
+    const int in = i == 0 ? c->net_width + d.view_dim : c->net_width_condition;
+    if ((rc = expect(c->net_depth + 2 + i, in, c->net_width_condition, "view_layers[i]"))) return rc;
+  }
+  return expect(d.n_lin - 1, c->net_width_condition, 3, "color_layer");
+}
+
+int check_rays(const mipnerf_b200_rays* r) {
+  if (!r) return fail(MIPNERF_B200_EINVAL, "rays is NULL");
+  if (r->num_rays < 0) return fail(MIPNERF_B200_EINVAL, "num_rays=%lld", (long long)r->num_rays);
+  if (r->num_rays > 0 && (!r->origins || !r->directions || !r->radii || !r->near || !r->far))
+    return fail(MIPNERF_B200_EINVAL, "a ray field is NULL");
+  return MIPNERF_B200_OK;
+}
+
+mipnerf_b200_rays offset_rays(const mipnerf_b200_rays& r, int64_t off, int64_t count) {
+  mipnerf_b200_rays o = r;
+  o.origins = r.origins + off * 3;
+  o.directions = r.directions + off * 3;
+  o.viewdirs = r.viewdirs ? r.viewdirs + off * 3 : nullptr;
+  o.radii = r.radii + off;
+  o.near = r.near + off;
+  o.far = r.far + off;
+  o.num_rays = count;
+  return o;
+}
+
+// Scratch layout for one chunk of R rays on the fp32 path.
+struct Fp32Scratch {
+  float *enc, *h0, *h1, *venc, *c0, *c1, *raw_rgb, *raw_density, *t[2], *w[2];
+  size_t bytes;
+};
+
+Fp32Scratch carve_fp32(const mipnerf_b200_config* c, const Dims& d, int64_t rays, void* base,
+                       bool mlp_only = false) {
+  Fp32Scratch s{};
+  const size_t m = (size_t)rays * c->num_samples;
+  size_t off = 0;
+  auto take = [&](size_t elems) {
+    float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+    off += align_up(elems * sizeof(float));
+    return p;
+  };
+  s.h0 = take(m * c->net_width);
+  s.h1 = take(m * c->net_width);
+  s.c0 = take(m * c->net_width_condition);
+  s.c1 = take(m * c->net_width_condition);
+  if (mlp_only) {
+    s.bytes = off;
+    return s;
+  }
+  s.enc = take(m * d.xyz_dim);
+  s.venc = take((size_t)rays * d.view_dim);
+  s.raw_rgb = take(m * 3);
+  s.raw_density = take(m);
+  for (int i = 0; i < 2; ++i) {
+    s.t[i] = take((size_t)rays * (c->num_samples + 1));
+    s.w[i] = take(m);
+  }
+  s.bytes = off;
+  return s;
+}
+
+// MLP.forward on the fp32 path (models/mip_nerf.py:75-111).
+int mlp_forward_fp32(const mipnerf_b200_config* c, const Dims& d, const mipnerf_b200_weights* w,
+                     const float* x, const float* venc, int64_t rays, int n, const Fp32Scratch& s,
+                     float* raw_rgb, float* raw_density, cudaStream_t st) {
+  const int64_t m = rays * n;
+  const float* cur = x;
+  int cur_k = d.xyz_dim;
+  bool concat = false;
+  for (int i = 0; i < c->net_depth; ++i) {
+    const mipnerf_b200_linear& l = w->linears[i];
+    float* out = (i & 1) ? s.h1 : s.h0;
+    CUDA_TRY(mipnerf::launch_linear_f32(cur, cur_k, cur_k, concat ? x : nullptr, d.xyz_dim,
+                                        concat ? d.xyz_dim : 0, 1, l.weight, l.bias, out, c->net_width, m,
+                                        c->net_width, 1, st));
+    cur = out;
+    cur_k = c->net_width;
+    concat = (i % c->skip_index == 0 && i > 0);  // models/mip_nerf.py:96-97
+  }
+  const mipnerf_b200_linear& dl = w->linears[c->net_depth];
+  CUDA_TRY(mipnerf::launch_linear_f32(cur, cur_k, cur_k, nullptr, 0, 0, 1, dl.weight, dl.bias, raw_density,
+                                      1, m, 1, 0, st));
+  const float* feat = cur;
+  int feat_k = cur_k;
+  if (c->use_viewdirs) {
+    const mipnerf_b200_linear& el = w->linears[c->net_depth + 1];
+    float* bott = (cur == s.h0) ? s.h1 : s.h0;
+    CUDA_TRY(mipnerf::launch_linear_f32(cur, cur_k, cur_k, nullptr, 0, 0, 1, el.weight, el.bias, bott,
+                                        c->net_width, m, c->net_width, 0, st));
+    feat = bott;
+    feat_k = c->net_width;
+    for (int j = 0; j < c->net_depth_condition; ++j) {
+      const mipnerf_b200_linear& vl = w->linears[c->net_depth + 2 + j];
+      float* out = (j & 1) ? s.c1 : s.c0;
+      CUDA_TRY(mipnerf::launch_linear_f32(feat, feat_k, feat_k, j == 0 ? venc : nullptr, d.view_dim,
+                                          j == 0 ? d.view_dim : 0, n, vl.weight, vl.bias, out,
+                                          c->net_width_condition, m, c->net_width_condition, 1, st));
+      feat = out;
+      feat_k = c->net_width_condition;
+    }
+    if (c->net_depth_condition == 0) {
+      // view_layers is an empty Sequential: the colour head would see width+view_dim inputs, which
+      // the reference's color_layer (net_width_condition inputs) cannot take.
+      return fail(MIPNERF_B200_EUNSUPPORTED, "net_depth_condition=0 with use_viewdirs");
+    }
+  }
+  const mipnerf_b200_linear& cl = w->linears[d.n_lin - 1];
+  CUDA_TRY(mipnerf::launch_linear_f32(feat, feat_k, feat_k, nullptr, 0, 0, 1, cl.weight, cl.bias, raw_rgb, 3,
+                                      m, 3, 0, st));
+  return MIPNERF_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mipnerf_b200_last_error(void) { return g_last_error.c_str(); }
+int mipnerf_b200_abi_version(void) { return MIPNERF_B200_ABI_VERSION; }
+
+size_t mipnerf_b200_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays, int precision) {
+  Dims d;
+  if (check_config(cfg, &d) != MIPNERF_B200_OK || num_rays < 0) return 0;
+  if (precision == MIPNERF_B200_FP32) {
+    const int64_t r = num_rays < kChunkRaysFp32 ? num_rays : kChunkRaysFp32;
+    return carve_fp32(cfg, d, r > 0 ? r : 1, nullptr).bytes;
+  }
+  return mipnerf::tc_workspace_bytes(cfg, num_rays, precision);
+}
+
+size_t mipnerf_b200_packed_weights_bytes(const mipnerf_b200_config* cfg, int precision) {
+  Dims d;
+  if (check_config(cfg, &d) != MIPNERF_B200_OK) return 0;
+  return mipnerf::tc_packed_bytes(cfg, precision);
+}
+
+int mipnerf_b200_pack_weights(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w, int precision,
+                              void* packed_out, size_t packed_bytes, void* stream) {
+  Dims d;
+  int rc;
+  if ((rc = check_config(cfg, &d))) return rc;
+  if ((rc = check_weights(cfg, d, w))) return rc;
+  if (!packed_out) return fail(MIPNERF_B200_EINVAL, "packed_out is NULL");
+  const size_t need = mipnerf::tc_packed_bytes(cfg, precision);
+  if (need == 0)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "no tensor-core kernel for this MLP shape / precision %d", precision);
+  if (packed_bytes < need)
+    return fail(MIPNERF_B200_EWORKSPACE, "packed buffer %zu < %zu bytes", packed_bytes, need);
+  cudaError_t e = mipnerf::tc_pack_weights(cfg, w, precision, packed_out, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(MIPNERF_B200_ECUDA, "pack_weights: %s", cudaGetErrorString(e));
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                         const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                         const float* u_jitter, int white_bkgd, int precision, mipnerf_b200_level_out* outs,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  Dims d;
+  int rc;
+  if ((rc = check_config(cfg, &d))) return rc;
+  if ((rc = check_weights(cfg, d, w))) return rc;
+  if ((rc = check_rays(rays))) return rc;
+  if (!outs) return fail(MIPNERF_B200_EINVAL, "outs is NULL");
+  if (cfg->use_viewdirs && rays->num_rays > 0 && !rays->viewdirs)
+    return fail(MIPNERF_B200_EINVAL, "use_viewdirs but rays.viewdirs is NULL");
+  if (randomized && (!t_rand || (cfg->num_levels > 1 && !u_jitter)))
+    return fail(MIPNERF_B200_EINVAL, "randomized=1 needs t_rand and u_jitter (the ABI takes the noise as input)");
+  for (int l = 0; l < cfg->num_levels; ++l)
+    if (rays->num_rays > 0 && (!outs[l].comp_rgb || !outs[l].distance || !outs[l].acc))
+      return fail(MIPNERF_B200_EINVAL, "outs[%d] misses comp_rgb/distance/acc", l);
+  const size_t need = mipnerf_b200_workspace_bytes(cfg, rays->num_rays, precision);
+  if (rays->num_rays > 0 && (!workspace || workspace_bytes < need))
+    return fail(MIPNERF_B200_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = cfg->num_samples;
+  const float rgb_scale = (float)(1.0 + 2.0 * (double)cfg->rgb_padding);
+
+  if (precision != MIPNERF_B200_FP32) {
+    if (!mipnerf::tc_supported(cfg, precision))
+      return fail(MIPNERF_B200_EUNSUPPORTED,
+                  "tensor-core path supports only the default 8x256 / N=128 / deg 0..16 / deg_view 4 model "
+                  "with precision bf16|fp16; use MIPNERF_B200_FP32 for other shapes");
+    if (!w->packed || w->packed_precision != precision ||
+        w->packed_bytes < mipnerf::tc_packed_bytes(cfg, precision))
+      return fail(MIPNERF_B200_EINVAL, "weights->packed missing or packed for another precision");
+    cudaError_t e = mipnerf::tc_forward(cfg, w, rays, randomized, t_rand, u_jitter, white_bkgd, precision,
+                                        outs, workspace, workspace_bytes, st);
+    if (e != cudaSuccess) return fail(MIPNERF_B200_ECUDA, "tc_forward: %s", cudaGetErrorString(e));
+    return MIPNERF_B200_OK;
+  }
+
+  for (int64_t off = 0; off < rays->num_rays; off += kChunkRaysFp32) {
+    const int64_t cnt = (rays->num_rays - off) < kChunkRaysFp32 ? (rays->num_rays - off) : kChunkRaysFp32;
+    const mipnerf_b200_rays rc_ = offset_rays(*rays, off, cnt);
+    const Fp32Scratch s = carve_fp32(cfg, d, cnt, workspace);
+    if (cfg->use_viewdirs)
+      CUDA_TRY(mipnerf::launch_pos_enc(rc_.viewdirs, s.venc, cnt, 0, cfg->deg_view, 1, st));
+    const float *t_prev = nullptr, *w_prev = nullptr;
+    for (int l = 0; l < cfg->num_levels; ++l) {
+      float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (n + 1) : s.t[l & 1];
+      float* w_cur = outs[l].weights ? outs[l].weights + off * n : s.w[l & 1];
+      if (l == 0) {
+        CUDA_TRY(mipnerf::launch_coarse_t(rc_.near, rc_.far, t_rand ? t_rand + off * (n + 1) : nullptr, t_cur,
+                                          cnt, n, randomized, cfg->disparity, st));
+      } else {
+        CUDA_TRY(mipnerf::launch_resample(t_prev, w_prev, u_jitter ? u_jitter + off * (n + 1) : nullptr, t_cur,
+                                          outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr, cnt, n, n + 1,
+                                          randomized, 1, cfg->resample_padding, st));
+      }
+      CUDA_TRY(mipnerf::launch_ipe_from_t(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc, cnt, n,
+                                          cfg->min_deg_point, cfg->max_deg_point, cfg->disable_integration,
+                                          st));
+      if ((rc = mlp_forward_fp32(cfg, d, w, s.enc, cfg->use_viewdirs ? s.venc : nullptr, cnt, n, s, s.raw_rgb,
+                                 s.raw_density, st)))
+        return rc;
+      CUDA_TRY(mipnerf::launch_composite(s.raw_rgb, s.raw_density, t_cur, rc_.directions,
+                                         outs[l].comp_rgb + off * 3, outs[l].distance + off, outs[l].acc + off,
+                                         w_cur, cnt, n, white_bkgd, 1, cfg->density_bias, rgb_scale,
+                                         cfg->rgb_padding, st));
+      t_prev = t_cur;
+      w_prev = w_cur;
+    }
+  }
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_sample_along_rays(const mipnerf_b200_rays* rays, int num_samples, int randomized,
+                                   int disparity, const float* t_rand, float* t_samples, float* means,
+                                   float* covs, void* stream) {
+  int rc;
+  if ((rc = check_rays(rays))) return rc;
+  if (num_samples < 1 || !t_samples) return fail(MIPNERF_B200_EINVAL, "bad num_samples / t_samples");
+  if (randomized && !t_rand) return fail(MIPNERF_B200_EINVAL, "randomized=1 needs t_rand");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(mipnerf::launch_coarse_t(rays->near, rays->far, t_rand, t_samples, rays->num_rays, num_samples,
+                                    randomized, disparity, st));
+  if (means && covs)
+    CUDA_TRY(mipnerf::launch_cast_rays(rays->origins, rays->directions, rays->radii, t_samples, means, covs,
+                                       rays->num_rays, num_samples, st));
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_cast_rays(const mipnerf_b200_rays* rays, const float* t_samples, int num_samples,
+                           float* means, float* covs, void* stream) {
+  int rc;
+  if ((rc = check_rays(rays))) return rc;
+  if (num_samples < 1 || !t_samples || !means || !covs) return fail(MIPNERF_B200_EINVAL, "NULL argument");
+  CUDA_TRY(mipnerf::launch_cast_rays(rays->origins, rays->directions, rays->radii, t_samples, means, covs,
+                                     rays->num_rays, num_samples, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_integrated_pos_enc(const float* means, const float* covs, int64_t num_points, int min_deg,
+                                    int max_deg, float* out, void* stream) {
+  if (num_points < 0 || (num_points > 0 && (!means || !covs || !out)) || max_deg <= min_deg ||
+      min_deg < -60 || max_deg > 60)
+    return fail(MIPNERF_B200_EINVAL, "bad argument");
+  CUDA_TRY(mipnerf::launch_ipe(means, covs, out, num_points, min_deg, max_deg, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_pos_enc(const float* x, int64_t num_points, int min_deg, int max_deg, int append_identity,
+                         float* out, void* stream) {
+  if (num_points < 0 || (num_points > 0 && (!x || !out)) || max_deg < min_deg || min_deg < -60 || max_deg > 60)
+    return fail(MIPNERF_B200_EINVAL, "bad argument");
+  CUDA_TRY(mipnerf::launch_pos_enc(x, out, num_points, min_deg, max_deg, append_identity, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_mlp_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w, const float* x,
+                             const float* view_enc, int64_t num_rays, int samples_per_ray, int precision,
+                             float* raw_rgb, float* raw_density, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  Dims d;
+  int rc;
+  mipnerf_b200_config c2;
+  if (!cfg) return fail(MIPNERF_B200_EINVAL, "config is NULL");
+  c2 = *cfg;
+  c2.num_samples = 32;  // the MLP itself does not care; validate the rest
+  if ((rc = check_config(&c2, &d))) return rc;
+  if ((rc = check_weights(cfg, d, w))) return rc;
+  if (num_rays < 0 || samples_per_ray < 1) return fail(MIPNERF_B200_EINVAL, "bad sizes");
+  if (num_rays == 0) return MIPNERF_B200_OK;
+  if (!x || !raw_rgb || !raw_density || (cfg->use_viewdirs && !view_enc))
+    return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision != MIPNERF_B200_FP32) {
+    if (!mipnerf::tc_mlp_supported(cfg, samples_per_ray, precision))
+      return fail(MIPNERF_B200_EUNSUPPORTED, "tensor-core MLP: default 8x256 model, 128 samples/ray only");
+    if (!w->packed || w->packed_precision != precision)
+      return fail(MIPNERF_B200_EINVAL, "weights->packed missing or packed for another precision");
+    cudaError_t e = mipnerf::tc_mlp_forward(cfg, w, x, view_enc, num_rays, precision, raw_rgb, raw_density, st);
+    if (e != cudaSuccess) return fail(MIPNERF_B200_ECUDA, "tc_mlp_forward: %s", cudaGetErrorString(e));
+    return MIPNERF_B200_OK;
+  }
+  c2.num_samples = samples_per_ray;
+  const int64_t max_rows = kChunkRaysFp32 * 128;
+  int64_t per = max_rows / samples_per_ray;
+  if (per < 1) per = 1;
+  const size_t need = mipnerf_b200_mlp_workspace_bytes(cfg, num_rays, samples_per_ray, precision);
+  if (!workspace || workspace_bytes < need)
+    return fail(MIPNERF_B200_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
+  for (int64_t off = 0; off < num_rays; off += per) {
+    const int64_t cnt = (num_rays - off) < per ? (num_rays - off) : per;
+    const Fp32Scratch s = carve_fp32(&c2, d, cnt, workspace, /*mlp_only=*/true);
+    const int64_t row = off * samples_per_ray;
+    if ((rc = mlp_forward_fp32(cfg, d, w, x + row * d.xyz_dim, view_enc ? view_enc + off * d.view_dim : nullptr,
+                               cnt, samples_per_ray, s, raw_rgb + row * 3, raw_density + row, st)))
+      return rc;
+  }
+  return MIPNERF_B200_OK;
+}
+
+size_t mipnerf_b200_mlp_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays, int samples_per_ray,
+                                        int precision) {
+  Dims d;
+  if (!cfg || num_rays < 0 || samples_per_ray < 1) return 0;
+  mipnerf_b200_config c2 = *cfg;
+  c2.num_samples = 32;
+  if (check_config(&c2, &d) != MIPNERF_B200_OK) return 0;
+  if (precision != MIPNERF_B200_FP32) return 256;
+  c2.num_samples = samples_per_ray;
+  int64_t per = (kChunkRaysFp32 * 128) / samples_per_ray;
+  if (per < 1) per = 1;
+  if (per > num_rays) per = num_rays > 0 ? num_rays : 1;
+  return carve_fp32(&c2, d, per, nullptr, true).bytes;
+}
+
+int mipnerf_b200_volumetric_rendering(const float* rgb, const float* density, const float* t_samples,
+                                      const float* dirs, int64_t num_rays, int num_samples, int white_bkgd,
+                                      float* comp_rgb, float* distance, float* acc, float* weights,
+                                      void* stream) {
+  if (num_rays < 0 || num_samples < 1) return fail(MIPNERF_B200_EINVAL, "bad sizes");
+  if (num_rays == 0) return MIPNERF_B200_OK;
+  if (!rgb || !density || !t_samples || !dirs || !comp_rgb || !distance || !acc)
+    return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  cudaError_t e = mipnerf::launch_composite(rgb, density, t_samples, dirs, comp_rgb, distance, acc, weights,
+                                            num_rays, num_samples, white_bkgd, 0, 0.f, 1.f, 0.f,
+                                            (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "num_samples=%d: need a multiple of 32 in {32..256}", num_samples);
+  CUDA_TRY(e);
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_sorted_piecewise_constant_pdf(const float* bins, const float* weights, int64_t num_rays,
+                                               int num_bins, int num_samples, int randomized,
+                                               const float* u_jitter, float* samples, int64_t* inds,
+                                               void* stream) {
+  if (num_rays < 0 || num_bins < 1 || num_samples < 2) return fail(MIPNERF_B200_EINVAL, "bad sizes");
+  if (num_bins % 32 != 0 || num_bins > 1024)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "num_bins=%d: need a multiple of 32, <= 1024", num_bins);
+  if (num_rays == 0) return MIPNERF_B200_OK;
+  if (!bins || !weights || !samples || (randomized && !u_jitter)) return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  CUDA_TRY(mipnerf::launch_resample(bins, weights, u_jitter, samples, inds, num_rays, num_bins, num_samples,
+                                    randomized, 0, 0.f, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_resample_along_rays(const mipnerf_b200_rays* rays, const float* t_samples, const float* weights,
+                                     int num_samples, int randomized, const float* u_jitter,
+                                     float resample_padding, float* new_t_samples, float* means, float* covs,
+                                     int64_t* inds, void* stream) {
+  int rc;
+  if ((rc = check_rays(rays))) return rc;
+  if (num_samples < 32 || num_samples % 32 != 0 || num_samples > 1024)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "num_samples=%d: need a multiple of 32, <= 1024", num_samples);
+  if (rays->num_rays == 0) return MIPNERF_B200_OK;
+  if (!t_samples || !weights || !new_t_samples || (randomized && !u_jitter))
+    return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(mipnerf::launch_resample(t_samples, weights, u_jitter, new_t_samples, inds, rays->num_rays,
+                                    num_samples, num_samples + 1, randomized, 1, resample_padding, st));
+  if (means && covs)
+    CUDA_TRY(mipnerf::launch_cast_rays(rays->origins, rays->directions, rays->radii, new_t_samples, means,
+                                       covs, rays->num_rays, num_samples, st));
+  return MIPNERF_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// mlp_tc.h — internal interface of the tcgen05 (tensor-core) path, implemented in mlp_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mipnerf_b200.h"
+
+namespace mipnerf {
+
+// true iff (cfg, precision) is the shape the fused tensor-core kernels are specialised for.
+bool tc_supported(const mipnerf_b200_config* cfg, int precision);
+bool tc_mlp_supported(const mipnerf_b200_config* cfg, int samples_per_ray, int precision);
+size_t tc_packed_bytes(const mipnerf_b200_config* cfg, int precision);
+size_t tc_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays, int precision);
+cudaError_t tc_pack_weights(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w, int precision,
+                            void* packed_out, cudaStream_t st);
+cudaError_t tc_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                       const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                       const float* u_jitter, int white_bkgd, int precision, mipnerf_b200_level_out* outs,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st);
+cudaError_t tc_mlp_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w, const float* x,
+                           const float* view_enc, int64_t num_rays, int precision, float* raw_rgb,
+                           float* raw_density, cudaStream_t st);
+
+}  // namespace mipnerf

@@ -1,0 +1,445 @@
+// ray_kernels.cu — the non-MLP stages of the path as stand-alone sm_100a kernels.
+//
+// These are the building blocks of the fp32 parity path and of the per-stage C-ABI entry points:
+//   coarse fenceposts            models/mip.py:145-163
+//   cast_rays (cone, diagonal)   models/mip.py:81-103  (+ :50-78, :22-36)
+//   integrated_pos_enc / pos_enc models/mip.py:322-363
+//   volumetric_rendering         models/mip.py:366-401 (+ activations models/mip_nerf.py:236-238)
+//   resample_along_rays          models/mip.py:232-280 (+ sorted_piecewise_constant_pdf :168-229)
+// Compositing and resampling are warp-per-ray: one ray's N samples live in one warp's registers /
+// shared-memory slice, reductions are shuffles, no cross-warp traffic.
+#include "kernels.h"
+#include "ray_math.cuh"
+
+namespace mipnerf {
+
+// ---------------------------------------------------------------------------------------------
+// coarse fenceposts: one thread per (ray, j)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float coarse_t(float near, float far, float s, int disparity) {
+  if (disparity) {
+    // 1 / (1/near*(1-s) + 1/far*s)        (models/mip.py:150)
+    const float a = __fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, s));
+    const float b = __fmul_rn(__fdiv_rn(1.0f, far), s);
+    return __fdiv_rn(1.0f, __fadd_rn(a, b));
+  }
+  return __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), s));  // near + (far-near)*s   (:153)
+}
+
+__global__ void coarse_t_kernel(const float* __restrict__ near, const float* __restrict__ far,
+                                const float* __restrict__ t_rand, float* __restrict__ t_out,
+                                int64_t num_rays, int n, int randomized, int disparity) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = num_rays * (n + 1);
+  if (idx >= total) return;
+  const int64_t ray = idx / (n + 1);
+  const int j = (int)(idx % (n + 1));
+  const float nr = __ldg(near + ray), fr = __ldg(far + ray);
+  const float inv_n = 1.0f / (float)n;  // linspace(0,1,n+1)[j] == fl32(j/n) for the n we accept
+  auto tj = [&](int k) { return coarse_t(nr, fr, __fmul_rn((float)k, inv_n), disparity); };
+  float t = tj(j);
+  if (randomized) {
+    // mids / upper / lower (models/mip.py:156-160)
+    const float lower = j == 0 ? t : __fmul_rn(0.5f, __fadd_rn(t, tj(j - 1)));
+    const float upper = j == n ? t : __fmul_rn(0.5f, __fadd_rn(tj(j + 1), t));
+    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(t_rand + idx)));
+  }
+  t_out[idx] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cast_rays: one thread per (ray, sample) -> means, covs [B,N,3]
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_rays_kernel(const float* __restrict__ origins,
+                                 const float* __restrict__ directions,
+                                 const float* __restrict__ radii, const float* __restrict__ t,
+                                 float* __restrict__ means, float* __restrict__ covs,
+                                 int64_t num_rays, int n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * n) return;
+  const int64_t ray = idx / n;
+  const int j = (int)(idx % n);
+  const RayGeom g = load_ray_geom(origins, directions, radii, ray);
+  const float t0 = __ldg(t + ray * (n + 1) + j), t1 = __ldg(t + ray * (n + 1) + j + 1);
+  float tm, tv, rv, mean[3], cov[3];
+  frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
+  lift_gaussian(g, tm, tv, rv, mean, cov);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    means[idx * 3 + c] = mean[c];
+    covs[idx * 3 + c] = cov[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// IPE from explicit (means, covs): one thread per (point, degree*3+coord); coalesced stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void ipe_kernel(const float* __restrict__ means, const float* __restrict__ covs,
+                           float* __restrict__ out, int64_t num_points, int min_deg, int num_deg) {
+  const int half = num_deg * 3;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_points * half) return;
+  const int64_t p = idx / half;
+  const int f = (int)(idx % half);
+  const int l = min_deg + f / 3, c = f % 3;
+  float fs, fc;
+  ipe_pair<false>(__ldg(means + p * 3 + c), __ldg(covs + p * 3 + c), l, fs, fc);
+  out[p * 2 * half + f] = fs;
+  out[p * 2 * half + half + f] = fc;
+}
+
+// IPE straight from fenceposts (cast_rays fused in): what forward() uses, no means/covs in HBM.
+__global__ void ipe_from_t_kernel(const float* __restrict__ origins,
+                                  const float* __restrict__ directions,
+                                  const float* __restrict__ radii, const float* __restrict__ t,
+                                  float* __restrict__ out, int64_t num_rays, int n, int min_deg,
+                                  int num_deg, int disable_integration) {
+  const int half = num_deg * 3;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * n * half) return;
+  const int64_t p = idx / half;
+  const int f = (int)(idx % half);
+  const int64_t ray = p / n;
+  const int j = (int)(p % n);
+  const int l = min_deg + f / 3, c = f % 3;
+  const RayGeom g = load_ray_geom(origins, directions, radii, ray);
+  const float t0 = __ldg(t + ray * (n + 1) + j), t1 = __ldg(t + ray * (n + 1) + j + 1);
+  float tm, tv, rv, mean[3], cov[3];
+  frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
+  lift_gaussian(g, tm, tv, rv, mean, cov);
+  float fs, fc;
+  ipe_pair<false>(mean[c], disable_integration ? 0.0f : cov[c], l, fs, fc);
+  out[p * 2 * half + f] = fs;
+  out[p * 2 * half + half + f] = fc;
+}
+
+// pos_enc: one thread per (point, output feature)
+__global__ void pos_enc_kernel(const float* __restrict__ x, float* __restrict__ out,
+                               int64_t num_points, int min_deg, int num_deg, int append_identity) {
+  const int half = num_deg * 3;
+  const int width = 2 * half + (append_identity ? 3 : 0);
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_points * width) return;
+  const int64_t p = idx / width;
+  int f = (int)(idx % width);
+  if (append_identity) {
+    if (f < 3) {
+      out[idx] = __ldg(x + p * 3 + f);
+      return;
+    }
+    f -= 3;
+  }
+  const int is_cos = f >= half;
+  if (is_cos) f -= half;
+  const int l = min_deg + f / 3, c = f % 3;
+  const float y = __fmul_rn(__ldg(x + p * 3 + c), __int_as_float((127 + l) << 23));
+  out[idx] = sinf(is_cos ? __fadd_rn(y, MIPNERF_HALF_PI_F32) : y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// volumetric_rendering: warp per ray, lane owns P = N/32 consecutive samples.
+// ---------------------------------------------------------------------------------------------
+template <int P, bool kActivate>
+__global__ void composite_kernel(const float* __restrict__ rgb_in, const float* __restrict__ dens_in,
+                                 const float* __restrict__ t, const float* __restrict__ dirs,
+                                 float* __restrict__ comp_rgb, float* __restrict__ distance,
+                                 float* __restrict__ acc_out, float* __restrict__ weights_out,
+                                 int64_t num_rays, int white_bkgd, float density_bias,
+                                 float rgb_scale, float rgb_padding) {
+  constexpr int N = P * 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= num_rays) return;
+  const float dx = __ldg(dirs + ray * 3), dy = __ldg(dirs + ray * 3 + 1), dz = __ldg(dirs + ray * 3 + 2);
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.linalg.norm      (:386)
+  const float* tr = t + ray * (N + 1);
+  float tt[P + 1];
+#pragma unroll
+  for (int p = 0; p <= P; ++p) tt[p] = __ldg(tr + lane * P + p);
+  float dd[P];
+  double run = 0.0;
+  double incl[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    float dens = __ldg(dens_in + ray * N + lane * P + p);
+    if (kActivate) dens = density_activation(dens, density_bias);
+    const float delta = __fmul_rn(__fsub_rn(tt[p + 1], tt[p]), dnorm);
+    dd[p] = __fmul_rn(dens, delta);
+    run += (double)dd[p];
+    incl[p] = run;
+  }
+  double total;
+  const double before = warp_excl_scan_f64(run, lane, total);
+  float wsum = 0.f, dsum = 0.f, r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    // exclusive cumsum, fp64 running sum rounded per prefix like torch.cumsum(float32)   (:389-392)
+    const double excl = before + (p == 0 ? 0.0 : incl[p - 1]);
+    const float cum = (lane == 0 && p == 0) ? 0.0f : (float)excl;
+    const float alpha = __fsub_rn(1.0f, expf(-dd[p]));
+    const float w = __fmul_rn(alpha, expf(-cum));
+    const int64_t s = ray * N + lane * P + p;
+    if (weights_out) weights_out[s] = w;
+    float cr = __ldg(rgb_in + s * 3), cg = __ldg(rgb_in + s * 3 + 1), cb = __ldg(rgb_in + s * 3 + 2);
+    if (kActivate) {
+      cr = rgb_activation(cr, rgb_scale, rgb_padding);
+      cg = rgb_activation(cg, rgb_scale, rgb_padding);
+      cb = rgb_activation(cb, rgb_scale, rgb_padding);
+    }
+    r += w * cr;
+    g += w * cg;
+    b += w * cb;
+    wsum += w;
+    dsum += w * __fmul_rn(0.5f, __fadd_rn(tt[p], tt[p + 1]));
+  }
+  r = warp_sum(r), g = warp_sum(g), b = warp_sum(b), wsum = warp_sum(wsum), dsum = warp_sum(dsum);
+  if (lane == 0) {
+    // nan_to_num then clamp to [t_0, t_N]                                             (:398)
+    const float t_first = __ldg(tr), t_last = __ldg(tr + N);
+    float d = dsum;
+    if (isnan(d)) d = 0.f;
+    else if (isinf(d)) d = d > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    d = fminf(fmaxf(d, t_first), t_last);
+    const float bg = white_bkgd ? __fsub_rn(1.0f, wsum) : 0.0f;
+    comp_rgb[ray * 3 + 0] = r + bg;
+    comp_rgb[ray * 3 + 1] = g + bg;
+    comp_rgb[ray * 3 + 2] = b + bg;
+    distance[ray] = d;
+    acc_out[ray] = wsum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inverse-CDF resampling: warp per ray.
+// Shared memory per warp: s_w[nb] (weights -> pdf), s_cdf[nb+1], s_bins[nb+1].
+// Bit-exactness notes: the row sum uses torch's 32-strided-accumulator order, the
+// CDF is a float64 running sum rounded per prefix; every other op is element-wise IEEE.
+// ---------------------------------------------------------------------------------------------
+template <bool kBlur>
+__device__ __forceinline__ void resample_warp(const float* __restrict__ bins_g,
+                                              const float* __restrict__ w_g, int nb, int ns,
+                                              int randomized, const float* __restrict__ jitter_g,
+                                              float padding, float* s_w, float* s_cdf,
+                                              float* s_bins, float* __restrict__ out_g,
+                                              int64_t* __restrict__ inds_g, int lane) {
+  const int chunks = nb >> 5;
+  for (int i = lane; i <= nb; i += 32) s_bins[i] = __ldg(bins_g + i);
+  for (int i = lane; i < nb; i += 32) s_cdf[i] = __ldg(w_g + i);  // raw weights staged in s_cdf
+  __syncwarp();
+  // blur-pool + padding (models/mip.py:252-257), 32-strided ownership: lane owns 32*i + lane
+  float acc = 0.f;
+  for (int i = 0; i < chunks; ++i) {
+    const int k = 32 * i + lane;
+    float w;
+    if (kBlur) {
+      const float wl = s_cdf[k > 0 ? k - 1 : 0], wc = s_cdf[k], wr = s_cdf[k < nb - 1 ? k + 1 : nb - 1];
+      const float m0 = fmaxf(wl, wc), m1 = fmaxf(wc, wr);
+      w = __fadd_rn(__fmul_rn(0.5f, __fadd_rn(m0, m1)), padding);
+    } else {
+      w = s_cdf[k];
+    }
+    s_w[k] = w;
+    acc = i == 0 ? w : __fadd_rn(acc, w);
+  }
+  // torch.sum order: 4 ILP partials per 8-lane vector, then the 8 lanes in order (:182)
+  const int l8 = lane & 7;
+  float part = __shfl_sync(0xffffffffu, acc, l8);
+  part = __fadd_rn(part, __shfl_sync(0xffffffffu, acc, l8 + 8));
+  part = __fadd_rn(part, __shfl_sync(0xffffffffu, acc, l8 + 16));
+  part = __fadd_rn(part, __shfl_sync(0xffffffffu, acc, l8 + 24));
+  float wsum = __shfl_sync(0xffffffffu, part, 0);
+#pragma unroll
+  for (int j = 1; j < 8; ++j) wsum = __fadd_rn(wsum, __shfl_sync(0xffffffffu, part, j));
+  // eps padding (:183-185)
+  const float pad = fmaxf(0.0f, __fsub_rn(1e-5f, wsum));
+  const float pad_each = __fdiv_rn(pad, (float)nb);
+  wsum = __fadd_rn(wsum, pad);
+  bool tiny = false;
+  for (int i = 0; i < chunks; ++i) {
+    const int k = 32 * i + lane;
+    const float pdf = __fdiv_rn(__fadd_rn(s_w[k], pad_each), wsum);  // (:189)
+    s_w[k] = pdf;
+    tiny |= (pdf != 0.0f && pdf < 1.862645149230957e-09f && k < nb - 1);  // 2^-29
+  }
+  __syncwarp();
+  // cdf = [0, min(1, cumsum(pdf[:-1])), 1]   (:190-195).  With every non-zero pdf >= 2^-29 all
+  // float64 partial sums are exact, so the parallel scan equals torch's sequential one bit for
+  // bit; otherwise fall back to the sequential order on lane 0.
+  if (__any_sync(0xffffffffu, tiny)) {
+    if (lane == 0) {
+      double run = 0.0;
+      s_cdf[0] = 0.0f;
+      for (int k = 0; k < nb - 1; ++k) {
+        run += (double)s_w[k];
+        s_cdf[k + 1] = fminf(1.0f, (float)run);
+      }
+      s_cdf[nb] = 1.0f;
+    }
+  } else {
+    double run = 0.0;
+    for (int p = 0; p < chunks; ++p) {
+      const int k = lane * chunks + p;
+      if (k < nb - 1) run += (double)s_w[k];
+    }
+    double total;
+    double before = warp_excl_scan_f64(run, lane, total);
+    for (int p = 0; p < chunks; ++p) {
+      const int k = lane * chunks + p;
+      if (k < nb - 1) {
+        before += (double)s_w[k];
+        s_cdf[k + 1] = fminf(1.0f, (float)before);
+      }
+    }
+    if (lane == 0) {
+      s_cdf[0] = 0.0f;
+      s_cdf[nb] = 1.0f;
+    }
+  }
+  __syncwarp();
+  // u (:198-208), searchsorted(right=True) (:211), interpolation (:219-228)
+  const float one_m_eps = 1.0f - MIPNERF_F32_EPS;
+  const float step = randomized ? (float)(1.0 / (double)ns) : __fdiv_rn(one_m_eps, (float)(ns - 1));
+  for (int j = lane; j < ns; j += 32) {
+    float u = __fmul_rn((float)j, step);
+    if (randomized) u = fminf(__fadd_rn(u, __ldg(jitter_g + j)), one_m_eps);
+    int lo = 0, hi = nb + 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_cdf[mid] <= u) lo = mid + 1;
+      else hi = mid;
+    }
+    const int below = lo - 1 > 0 ? lo - 1 : 0;
+    const int above = lo < nb ? lo : nb;
+    const float cb = s_cdf[below], ca = s_cdf[above];
+    const float bb = s_bins[below], ba = s_bins[above];
+    float denom = __fsub_rn(ca, cb);
+    if (denom < 1e-5f) denom = 1.0f;
+    const float tt = __fdiv_rn(__fsub_rn(u, cb), denom);
+    out_g[j] = __fadd_rn(bb, __fmul_rn(tt, __fsub_rn(ba, bb)));
+    if (inds_g) inds_g[j] = (int64_t)lo;
+  }
+}
+
+template <bool kBlur>
+__global__ void resample_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                const float* __restrict__ jitter, float* __restrict__ out,
+                                int64_t* __restrict__ inds, int64_t num_rays, int nb, int ns,
+                                int randomized, float padding) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (ray >= num_rays) return;
+  float* s_w = smem + (size_t)warp * (3 * nb + 2);
+  float* s_cdf = s_w + nb;
+  float* s_bins = s_cdf + nb + 1;
+  resample_warp<kBlur>(bins + ray * (nb + 1), weights + ray * nb, nb, ns, randomized,
+                       jitter ? jitter + ray * ns : nullptr, padding, s_w, s_cdf, s_bins,
+                       out + ray * ns, inds ? inds + ray * ns : nullptr, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+cudaError_t launch_coarse_t(const float* near, const float* far, const float* t_rand, float* t_out,
+                            int64_t num_rays, int n, int randomized, int disparity, cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  coarse_t_kernel<<<blocks_for(num_rays * (n + 1), 256), 256, 0, st>>>(near, far, t_rand, t_out, num_rays,
+                                                                     n, randomized, disparity);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast_rays(const float* origins, const float* directions, const float* radii,
+                             const float* t, float* means, float* covs, int64_t num_rays, int n,
+                             cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  cast_rays_kernel<<<blocks_for(num_rays * n, 256), 256, 0, st>>>(origins, directions, radii, t, means,
+                                                                 covs, num_rays, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ipe(const float* means, const float* covs, float* out, int64_t num_points,
+                       int min_deg, int max_deg, cudaStream_t st) {
+  const int nd = max_deg - min_deg;
+  if (num_points == 0 || nd <= 0) return cudaSuccess;
+  ipe_kernel<<<blocks_for(num_points * nd * 3, 256), 256, 0, st>>>(means, covs, out, num_points, min_deg, nd);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ipe_from_t(const float* origins, const float* directions, const float* radii,
+                              const float* t, float* out, int64_t num_rays, int n, int min_deg,
+                              int max_deg, int disable_integration, cudaStream_t st) {
+  const int nd = max_deg - min_deg;
+  if (num_rays == 0 || nd <= 0) return cudaSuccess;
+  ipe_from_t_kernel<<<blocks_for(num_rays * n * nd * 3, 256), 256, 0, st>>>(
+      origins, directions, radii, t, out, num_rays, n, min_deg, nd, disable_integration);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pos_enc(const float* x, float* out, int64_t num_points, int min_deg, int max_deg,
+                           int append_identity, cudaStream_t st) {
+  const int nd = max_deg - min_deg;
+  const int width = 6 * nd + (append_identity ? 3 : 0);
+  if (num_points == 0 || width == 0) return cudaSuccess;
+  pos_enc_kernel<<<blocks_for(num_points * width, 256), 256, 0, st>>>(x, out, num_points, min_deg, nd,
+                                                                     append_identity);
+  return cudaGetLastError();
+}
+
+template <bool kActivate>
+static cudaError_t launch_composite_t(const float* rgb, const float* dens, const float* t,
+                                      const float* dirs, float* comp_rgb, float* distance, float* acc,
+                                      float* weights, int64_t num_rays, int n, int white_bkgd,
+                                      float density_bias, float rgb_scale, float rgb_padding,
+                                      cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  const unsigned grid = blocks_for(num_rays, 4);
+#define MIPNERF_COMPOSITE_CASE(PP)                                                                   \
+  case PP:                                                                                           \
+    composite_kernel<PP, kActivate><<<grid, 128, 0, st>>>(rgb, dens, t, dirs, comp_rgb, distance,    \
+                                                          acc, weights, num_rays, white_bkgd,        \
+                                                          density_bias, rgb_scale, rgb_padding);     \
+    break;
+  switch (n / 32) {
+    MIPNERF_COMPOSITE_CASE(1)
+    MIPNERF_COMPOSITE_CASE(2)
+    MIPNERF_COMPOSITE_CASE(3)
+    MIPNERF_COMPOSITE_CASE(4)
+    MIPNERF_COMPOSITE_CASE(6)
+    MIPNERF_COMPOSITE_CASE(8)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef MIPNERF_COMPOSITE_CASE
+  return cudaGetLastError();
+}
+
+cudaError_t launch_composite(const float* rgb, const float* dens, const float* t, const float* dirs,
+                             float* comp_rgb, float* distance, float* acc, float* weights,
+                             int64_t num_rays, int n, int white_bkgd, int activate,
+                             float density_bias, float rgb_scale, float rgb_padding, cudaStream_t st) {
+  if (activate)
+    return launch_composite_t<true>(rgb, dens, t, dirs, comp_rgb, distance, acc, weights, num_rays, n,
+                                    white_bkgd, density_bias, rgb_scale, rgb_padding, st);
+  return launch_composite_t<false>(rgb, dens, t, dirs, comp_rgb, distance, acc, weights, num_rays, n,
+                                   white_bkgd, density_bias, rgb_scale, rgb_padding, st);
+}
+
+cudaError_t launch_resample(const float* bins, const float* weights, const float* jitter, float* out,
+                            int64_t* inds, int64_t num_rays, int nb, int ns, int randomized, int blur,
+                            float padding, cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  const int warps = 4;
+  const size_t smem = (size_t)warps * (3 * nb + 2) * sizeof(float);
+  const unsigned grid = blocks_for(num_rays, warps);
+  if (blur)
+    resample_kernel<true><<<grid, warps * 32, smem, st>>>(bins, weights, jitter, out, inds, num_rays, nb,
+                                                         ns, randomized, padding);
+  else
+    resample_kernel<false><<<grid, warps * 32, smem, st>>>(bins, weights, jitter, out, inds, num_rays, nb,
+                                                          ns, randomized, padding);
+  return cudaGetLastError();
+}
+
+}  // namespace mipnerf

@@ -1,0 +1,151 @@
+// ray_math.cuh — per-ray device math shared by every kernel on the path.
+//
+// Each function restates one piece of the reference's models/mip.py with the SAME fp32 operation
+// order; the pieces that decide downstream bit patterns (fenceposts, Gaussian means, the
+// resampler) use __f*_rn intrinsics so nvcc cannot contract them into FMAs (torch-CPU rounds every
+// op).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace mipnerf {
+
+#define MIPNERF_HALF_PI_F32 1.57079637050628662109375f  // fl32(0.5*pi) = 0x3FC90FDB (models/mip.py:350)
+#define MIPNERF_F32_EPS 1.1920928955078125e-07f          // torch.finfo(float32).eps
+
+struct RayGeom {
+  float o[3];     // origin
+  float d[3];     // direction (not normalised)
+  float d_sq[3];  // d*d                     (models/mip.py:29)
+  float null[3];  // 1 - d*d/(sum d*d+1e-10) (models/mip.py:30)
+  float radius_sq;
+};
+
+__device__ __forceinline__ RayGeom load_ray_geom(const float* __restrict__ origins,
+                                                 const float* __restrict__ directions,
+                                                 const float* __restrict__ radii, int64_t ray) {
+  RayGeom g;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    g.o[c] = __ldg(origins + ray * 3 + c);
+    g.d[c] = __ldg(directions + ray * 3 + c);
+    g.d_sq[c] = __fmul_rn(g.d[c], g.d[c]);
+  }
+  // torch.sum over 3 contiguous elements is sequential; + float32(1e-10)  (models/mip.py:25)
+  float dn = __fadd_rn(__fadd_rn(__fadd_rn(g.d_sq[0], g.d_sq[1]), g.d_sq[2]), 1e-10f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) g.null[c] = __fsub_rn(1.0f, __fdiv_rn(g.d_sq[c], dn));
+  float r = __ldg(radii + ray);
+  g.radius_sq = __fmul_rn(r, r);
+  return g;
+}
+
+// conical_frustum_to_gaussian, stable branch (models/mip.py:65-72).
+__device__ __forceinline__ void frustum_moments(float t0, float t1, float radius_sq, float& t_mean,
+                                                float& t_var, float& r_var) {
+  const float mu = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+  const float hw = __fmul_rn(__fsub_rn(t1, t0), 0.5f);
+  const float mu2 = __fmul_rn(mu, mu);
+  const float hw2 = __fmul_rn(hw, hw);
+  const float hw4 = __fmul_rn(hw2, hw2);  // reference: pow(hw,4) (<=1 ulp away; feeds variances only)
+  const float denom = __fadd_rn(__fmul_rn(3.0f, mu2), hw2);
+  t_mean = __fadd_rn(mu, __fdiv_rn(__fmul_rn(__fmul_rn(2.0f, mu), hw2), denom));
+  const float c415 = 0.26666666666666666f;  // float32(4/15)
+  const float num = __fmul_rn(hw4, __fsub_rn(__fmul_rn(12.0f, mu2), hw2));
+  t_var = __fsub_rn(__fdiv_rn(hw2, 3.0f),
+                    __fmul_rn(c415, __fdiv_rn(num, __fmul_rn(denom, denom))));
+  const float c512 = 0.4166666666666667f;  // float32(5/12)
+  const float a = __fadd_rn(__fdiv_rn(mu2, 4.0f), __fmul_rn(c512, hw2));
+  const float b = __fdiv_rn(__fmul_rn(c415, hw4), denom);
+  r_var = __fmul_rn(radius_sq, __fsub_rn(a, b));
+}
+
+// lift_gaussian diagonal branch + origin shift (models/mip.py:24-36, :102).
+__device__ __forceinline__ void lift_gaussian(const RayGeom& g, float t_mean, float t_var,
+                                              float r_var, float mean[3], float cov[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    mean[c] = __fadd_rn(__fmul_rn(g.d[c], t_mean), g.o[c]);
+    cov[c] = __fadd_rn(__fmul_rn(t_var, g.d_sq[c]), __fmul_rn(r_var, g.null[c]));
+  }
+}
+
+// One IPE feature pair for coordinate value `m`, variance `v`, degree l (scale 2^l):
+//   sin-half  exp(-0.5*v*4^l) * sin(m*2^l)
+//   cos-half  exp(-0.5*v*4^l) * sin(fl32(m*2^l + fl32(pi/2)))        (models/mip.py:335-350,:286)
+// When the damping factor underflows to exactly 0 the feature is +-0 whatever sin returns, so the
+// sine (and its slow large-argument path) is skipped — bit-identical up to the sign of zero.
+template <bool kFast>
+__device__ __forceinline__ void ipe_pair(float m, float v, int l, float& f_sin, float& f_cos);
+
+__device__ __forceinline__ float sin_reduced_fast(float x) {
+  // 2-term Cody-Waite reduction to [-pi, pi] (exact under FMA for |x| < 2^18) + MUFU.SIN.
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(k, -6.283185482025146484375f, x);      // fl32(2*pi)
+  r = fmaf(k, 1.7484555e-07f, r);                       // 2*pi - fl32(2*pi) = -1.7484555e-07
+  return __sinf(r);
+}
+
+template <>
+__device__ __forceinline__ void ipe_pair<false>(float m, float v, int l, float& f_sin, float& f_cos) {
+  const float scale = __int_as_float((127 + l) << 23);       // 2^l
+  const float scale_sq = __int_as_float((127 + 2 * l) << 23);  // 4^l
+  const float e_arg = __fmul_rn(-0.5f, __fmul_rn(v, scale_sq));
+  if (e_arg < -104.0f) {  // expf(x) == 0 for x < -103.98
+    f_sin = 0.0f;
+    f_cos = 0.0f;
+    return;
+  }
+  const float e = expf(e_arg);
+  const float y = __fmul_rn(m, scale);
+  f_sin = __fmul_rn(e, sinf(y));
+  f_cos = __fmul_rn(e, sinf(__fadd_rn(y, MIPNERF_HALF_PI_F32)));
+}
+
+template <>
+__device__ __forceinline__ void ipe_pair<true>(float m, float v, int l, float& f_sin, float& f_cos) {
+  const float scale = __int_as_float((127 + l) << 23);
+  const float scale_sq = __int_as_float((127 + 2 * l) << 23);
+  const float e_arg = -0.5f * v * scale_sq;
+  if (e_arg < -104.0f) {
+    f_sin = 0.0f;
+    f_cos = 0.0f;
+    return;
+  }
+  const float e = __expf(e_arg);
+  const float y = m * scale;
+  f_sin = e * sin_reduced_fast(y);
+  f_cos = e * sin_reduced_fast(__fadd_rn(y, MIPNERF_HALF_PI_F32));
+}
+
+// rgb = sigmoid(raw)*(1+2*pad) - pad ; density = softplus(raw + bias)   (models/mip_nerf.py:236-238)
+// rgb_scale = float32(1 + 2*pad) is formed on the host in double like Python does.
+__device__ __forceinline__ float rgb_activation(float raw, float rgb_scale, float rgb_padding) {
+  const float s = 1.0f / (1.0f + expf(-raw));
+  return __fsub_rn(__fmul_rn(s, rgb_scale), rgb_padding);
+}
+__device__ __forceinline__ float density_activation(float raw, float density_bias) {
+  const float x = __fadd_rn(raw, density_bias);
+  return x > 20.0f ? x : log1pf(expf(x));  // torch.nn.Softplus(beta=1, threshold=20)
+}
+
+// ---- warp helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_excl_scan_f64(double v, int lane, double& total) {
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  total = __shfl_sync(0xffffffffu, inc, 31);
+  double excl = __shfl_up_sync(0xffffffffu, inc, 1);
+  return lane == 0 ? 0.0 : excl;
+}
+
+}  // namespace mipnerf

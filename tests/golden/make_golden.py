@@ -1,0 +1,214 @@
+"""Generate the golden fixtures in this directory FROM THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified hjxwhy/mipnerf_pl `models.mip` / `models.mip_nerf`, runs them on CPU
+(fp32) on deterministic inputs, and stores inputs + outputs as small .npz files.  The tests pin
+`oracle/mipnerf_oracle.py` and the CUDA kernels against these files.  Nothing from the reference's
+source is copied; only its numerical outputs are recorded.
+
+The resampler's `inds` are not returned by the reference, so they are captured by wrapping
+`torch.searchsorted` while the reference's own `sorted_piecewise_constant_pdf` runs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
+REF = os.environ.get("MIPNERF_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
+
+from models import mip as ref_mip  # noqa: E402  (reference)
+from models.mip_nerf import MipNerf as RefMipNerf  # noqa: E402  (reference)
+from datasets.datasets import Rays as RefRays  # noqa: E402  (reference)
+
+from mipnerf_pl_b200.rays import random_ray_batch  # noqa: E402  (ours: input generator only)
+from mipnerf_pl_b200.weights import make_state_dict  # noqa: E402
+
+torch.set_num_threads(8)
+F32_EPS = float(torch.finfo(torch.float32).eps)
+
+
+class CaptureSearchsorted:
+    """Record what torch.searchsorted returns inside the reference call."""
+
+    def __enter__(self):
+        self.calls = []
+        self._orig = torch.searchsorted
+
+        def wrapped(*a, **k):
+            out = self._orig(*a, **k)
+            self.calls.append(out.clone())
+            return out
+        torch.searchsorted = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        torch.searchsorted = self._orig
+
+
+def to_ref_rays(r):
+    return RefRays(*[getattr(r, k) for k in RefRays._fields])
+
+
+def rays_dict(r):
+    return {f"rays_{k}": getattr(r, k).numpy() for k in r._fields}
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def forward_case(name, num_rays, seed, weights_kind, randomized, white_bkgd, multiscale=False, **model_kw):
+    rays = random_ray_batch(num_rays, seed=seed, multiscale=multiscale)
+    shape_kw = {}
+    if "max_deg_point" in model_kw or "min_deg_point" in model_kw:
+        shape_kw["xyz_dim"] = 6 * (model_kw.get("max_deg_point", 16) - model_kw.get("min_deg_point", 0))
+    sd = make_state_dict(seed=seed, kind=weights_kind, **shape_kw)
+    model = RefMipNerf(**model_kw)
+    model.load_state_dict(sd)
+    model.eval()
+    n = model.num_samples
+    extra = {}
+    if randomized:
+        # replay the reference's draws: torch.rand(B,N+1) at level 0 (mip.py:159), then
+        # empty(B,N+1).uniform_(to=s-eps) at level 1 (mip.py:201-202), from a seeded CPU generator.
+        torch.manual_seed(1234 + seed)
+        extra["t_rand"] = torch.rand(num_rays, n + 1).numpy()
+        if model.num_levels > 1:
+            s = 1 / (n + 1)
+            extra["u_jitter"] = torch.empty(num_rays, n + 1).uniform_(to=(s - F32_EPS)).numpy()
+        torch.manual_seed(1234 + seed)
+    with torch.no_grad(), CaptureSearchsorted() as cap:
+        ret = model(to_ref_rays(rays), randomized, white_bkgd)
+    out = dict(rays_dict(rays))
+    out.update(extra)
+    for lvl, (rgb, dist, acc, w, t) in enumerate(ret):
+        out[f"l{lvl}_comp_rgb"], out[f"l{lvl}_distance"], out[f"l{lvl}_acc"] = rgb.numpy(), dist.numpy(), acc.numpy()
+        out[f"l{lvl}_weights"], out[f"l{lvl}_t_samples"] = w.numpy(), t.numpy()
+    for i, inds in enumerate(cap.calls):
+        out[f"l{i + 1}_inds"] = inds.numpy()
+    out["meta"] = np.array([seed, int(randomized), int(white_bkgd)], dtype=np.int64)
+    save(name, **out)
+
+
+def resampler_case():
+    g = torch.Generator().manual_seed(7)
+    b, n = 24, 128
+    dists = {
+        "random4": torch.rand(b, n, generator=g) ** 4,
+        "near_uniform": 0.01 + 1e-6 * torch.rand(b, n, generator=g),
+        "uniform": torch.full((b, n), 0.01),
+        "tiny": 1e-9 * torch.rand(b, n, generator=g),           # exercises the eps padding branch
+        "spiky": torch.zeros(b, n).scatter_(1, torch.randint(0, n, (b, 3), generator=g), 1.0),
+        "zeros": torch.zeros(b, n),
+    }
+    out = {}
+    base = torch.linspace(2.0, 6.0, n + 1)[None].repeat(b, 1)
+    bins = base + 0.02 * torch.rand(b, n + 1, generator=g)
+    bins = torch.sort(bins, dim=-1).values
+    out["bins"] = bins.numpy()
+    s = 1 / (n + 1)
+    torch.manual_seed(99)
+    jitter = torch.empty(b, n + 1).uniform_(to=(s - F32_EPS))
+    out["u_jitter"] = jitter.numpy()
+    for name, w in dists.items():
+        out[f"{name}_weights"] = w.numpy()
+        for rand in (False, True):
+            tag = f"{name}_{'rand' if rand else 'det'}"
+            torch.manual_seed(99)  # reference draws the same jitter again
+            with CaptureSearchsorted() as cap:
+                samples = ref_mip.sorted_piecewise_constant_pdf(bins.clone(), w.clone(), n + 1, rand)
+            out[f"{tag}_samples"] = samples.numpy()
+            out[f"{tag}_inds"] = cap.calls[0].numpy()
+    # full resample_along_rays (blur + padding) on compositing-like weights
+    w = torch.rand(b, n, generator=g) ** 6
+    w = w / w.sum(-1, keepdim=True) * torch.rand(b, 1, generator=g)
+    rays = random_ray_batch(b, seed=3)
+    with CaptureSearchsorted() as cap:
+        new_t, (means, covs) = ref_mip.resample_along_rays(rays.origins, rays.directions, rays.radii, bins.clone(),
+                                                           w.clone(), False, "cone", True, 0.01)
+    out.update({"rs_weights": w.numpy(), "rs_new_t": new_t.numpy(), "rs_means": means.numpy(),
+                "rs_covs": covs.numpy(), "rs_inds": cap.calls[0].numpy()})
+    out.update({f"rs_{k}": v for k, v in rays_dict(rays).items()})
+    # a 64-bin histogram (config-0 sized)
+    w64 = torch.rand(b, 64, generator=g) ** 3
+    bins64 = torch.sort(2 + 4 * torch.rand(b, 65, generator=g), dim=-1).values
+    with CaptureSearchsorted() as cap:
+        s64 = ref_mip.sorted_piecewise_constant_pdf(bins64.clone(), w64.clone(), 65, False)
+    out.update({"n64_weights": w64.numpy(), "n64_bins": bins64.numpy(), "n64_samples": s64.numpy(),
+                "n64_inds": cap.calls[0].numpy()})
+    save("resampler.npz", **out)
+
+
+def stages_case():
+    g = torch.Generator().manual_seed(11)
+    b, n = 12, 128
+    rays = random_ray_batch(b, seed=5, multiscale=True)
+    out = dict(rays_dict(rays))
+    # sample_along_rays: deterministic, disparity, randomized (seeded)
+    t, (m, c) = ref_mip.sample_along_rays(rays.origins, rays.directions, rays.radii, n, rays.near, rays.far,
+                                          False, False, "cone")
+    out.update(sa_t=t.numpy(), sa_means=m.numpy(), sa_covs=c.numpy())
+    t, (m, c) = ref_mip.sample_along_rays(rays.origins, rays.directions, rays.radii, n, rays.near, rays.far,
+                                          False, True, "cone")
+    out.update(sa_disp_t=t.numpy(), sa_disp_means=m.numpy(), sa_disp_covs=c.numpy())
+    torch.manual_seed(21)
+    t_rand = torch.rand(b, n + 1)
+    torch.manual_seed(21)
+    t, (m, c) = ref_mip.sample_along_rays(rays.origins, rays.directions, rays.radii, n, rays.near, rays.far,
+                                          True, False, "cone")
+    out.update(sa_rand_t_rand=t_rand.numpy(), sa_rand_t=t.numpy(), sa_rand_means=m.numpy(), sa_rand_covs=c.numpy())
+    # IPE on the randomized Gaussians (+ a stress set with tiny/huge covariances) and view PE
+    enc = ref_mip.integrated_pos_enc((m, c), 0, 16)
+    out["ipe_enc"] = enc.numpy()
+    m2 = 6 * (torch.rand(4, 16, 3, generator=g) - 0.5)   # reference IPE wants [B,N,3]
+    c2 = 10 ** (-9 + 9 * torch.rand(4, 16, 3, generator=g))
+    out.update(ipe2_means=m2.numpy(), ipe2_covs=c2.numpy(),
+               ipe2_enc=ref_mip.integrated_pos_enc((m2, c2), 0, 16).numpy(),
+               ipe2_enc_deg2_9=ref_mip.integrated_pos_enc((m2, c2), 2, 9).numpy())
+    out["pe_view"] = ref_mip.pos_enc(rays.viewdirs, 0, 4, True).numpy()
+    out["pe_view_noid"] = ref_mip.pos_enc(rays.viewdirs, 0, 4, False).numpy()
+    # volumetric_rendering on random activations with a hard surface in some rays
+    rgb = torch.rand(b, n, 3, generator=g)
+    dens = 30 * torch.rand(b, n, 1, generator=g) ** 8
+    dens[::3, 40:44] = 500.0
+    for wb in (True, False):
+        comp, dist, acc, w = ref_mip.volumetric_rendering(rgb, dens, t, rays.directions, wb)
+        tag = "vr_white" if wb else "vr_black"
+        out.update({f"{tag}_comp": comp.numpy(), f"{tag}_dist": dist.numpy(), f"{tag}_acc": acc.numpy(),
+                    f"{tag}_weights": w.numpy()})
+    out.update(vr_rgb=rgb.numpy(), vr_density=dens.numpy(), vr_t=t.numpy())
+    # MLP.forward
+    model = RefMipNerf()
+    model.load_state_dict(make_state_dict(seed=2))
+    x = enc[:4]
+    venc = ref_mip.pos_enc(rays.viewdirs[:4], 0, 4, True)
+    with torch.no_grad():
+        raw_rgb, raw_density = model.mlp(x, venc)
+    out.update(mlp_x=x.numpy(), mlp_venc=venc.numpy(), mlp_raw_rgb=raw_rgb.numpy(),
+               mlp_raw_density=raw_density.numpy())
+    save("stages.npz", **out)
+
+
+if __name__ == "__main__":
+    forward_case("forward_xavier.npz", 40, seed=0, weights_kind="xavier", randomized=False, white_bkgd=True)
+    forward_case("forward_trained_like.npz", 40, seed=1, weights_kind="trained_like", randomized=False,
+                 white_bkgd=False, multiscale=True)
+    forward_case("forward_randomized.npz", 24, seed=2, weights_kind="trained_like", randomized=True,
+                 white_bkgd=True)
+    forward_case("forward_config0.npz", 256, seed=3, weights_kind="xavier", randomized=False, white_bkgd=True,
+                 num_samples=64, num_levels=1)
+    resampler_case()
+    stages_case()
+    with open(os.path.join(HERE, "VERSIONS.txt"), "w") as f:
+        f.write(f"torch {torch.__version__}\nnumpy {np.__version__}\nreference {REF} (hjxwhy/mipnerf_pl @ 6c07452)\n"
+                f"cpu_capability {torch.backends.cpu.get_cpu_capability()}\n")

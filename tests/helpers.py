@@ -1,0 +1,70 @@
+"""Shared test helpers: golden loading, oracle access, comparison with the stated tolerances."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.abspath(os.path.join(HERE, ".."))
+GOLDEN = os.path.join(HERE, "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import mipnerf_oracle as oracle  # noqa: E402  (tests are allowed to import the oracle)
+from mipnerf_pl_b200.rays import Rays  # noqa: E402
+from mipnerf_pl_b200.weights import make_state_dict  # noqa: E402
+
+# Tolerance policy (BASELINE.json north_star / SURVEY.md §8c): 1e-4 relative with an absolute floor.
+RTOL = 1e-4
+FLOORS = {"comp_rgb": 1e-3, "acc": 1e-3, "distance": 1e-2, "weights": 1e-3, "t_samples": 1e-2}
+
+
+def golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def golden_rays(g, prefix="rays_", device="cpu"):
+    return Rays(*[torch.from_numpy(g[prefix + k]).to(device) for k in Rays._fields])
+
+
+def oracle_rays(r):
+    return oracle.Rays(*[getattr(r, k).cpu() for k in Rays._fields])
+
+
+def rel_err(a, b, floor):
+    """max |a-b| / max(|b|, floor)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+def assert_close(a, b, floor, rtol=RTOL, what=""):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    if isinstance(b, torch.Tensor):
+        b = b.detach().cpu().numpy()
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    e = rel_err(a, b, floor)
+    assert e <= rtol, f"{what}: max rel err {e:.3e} > {rtol:.1e} (floor {floor})"
+    return e
+
+
+def assert_level_close(got, want, rtol=RTOL, what=""):
+    """got/want: (comp_rgb, distance, acc, weights, t_samples)."""
+    errs = {}
+    for name, g, w in zip(("comp_rgb", "distance", "acc", "weights", "t_samples"), got, want):
+        errs[name] = assert_close(g, w, FLOORS[name], rtol, f"{what}{name}")
+    return errs
+
+
+def golden_levels(g):
+    out = []
+    lvl = 0
+    while f"l{lvl}_comp_rgb" in g:
+        out.append(tuple(g[f"l{lvl}_{k}"] for k in ("comp_rgb", "distance", "acc", "weights", "t_samples")))
+        lvl += 1
+    return out
+
+
+def prefixed(sd, prefix=""):
+    return {prefix + k: v for k, v in sd.items()}
