@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — rays/sec of the Mip-NeRF per-ray hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp16|fp32] [--impl reference]
+
+One "step" = one MipNerf.forward-equivalent (both levels, full 5-tuple written) over one batch of
+4096 synthetic Blender-shape rays at 128+128 samples (BASELINE configs[1]) on every rank; weights are
+the deterministic random-init set of the reference architecture (no checkpoint is reachable).
+
+  value    rays/s with the batch already resident in HBM, CUDA-event timed on the launch stream,
+           L2 flushed (untimed) between steps, max over ranks, whole-job aggregate (weak scaling:
+           every rank renders its own 4096-ray batch and the fine RGB is all-gathered over NCCL).
+  e2e      same metric through the public API with HOST (pinned) ray buffers: H2D of the batch and
+           D2H of the rendered pixels inside the timed region.
+  roofline MLP-FLOP roofline of the dominant kernel: algorithmic FLOPs per launch / live launch
+           duration (library-side CUDA events) against MEASURED_PEAKS.json bf16 peak.
+  cpu_baseline  the CPU oracle (port of the reference's torch path) on this box's host cores, on a
+           bounded sample of the same workload.
+
+`--impl reference` times that CPU arm alone (rank 0 only) and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE = 2 * 610304
+SAMPLES_PER_RAY = 256                   # 128 coarse + 128 fine
+FLOP_PER_RAY = FLOP_PER_SAMPLE * SAMPLES_PER_RAY
+BATCH = 4096
+H2D_BYTES_PER_RAY = 13 * 4              # the 7 Rays fields
+D2H_BYTES_PER_RAY = (3 + 3 + 1) * 4     # coarse rgb, fine rgb, distance (render_image's outputs)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        p["_source"] = "measured"
+        return p
+    except Exception:  # noqa: BLE001
+        p = dict(FALLBACK_PEAKS)
+        p["_source"] = "fallback"
+        return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except Exception:  # noqa: BLE001
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(num_rays, steps, warmup):
+    """The reference's CPU torch path (oracle port) on all host threads; returns rays/s."""
+    import torch
+    import mipnerf_pl_b200 as mp
+    from oracle import mipnerf_oracle as oracle  # allowed here: this IS the CPU arm
+    torch.set_num_threads(os.cpu_count() or 1)
+    rays = oracle.Rays(*mp.random_ray_batch(num_rays, seed=0))
+    sd = mp.make_state_dict(seed=0, kind="xavier")
+    for _ in range(warmup):
+        oracle.forward(sd, oracle.Rays(*[f[:256] for f in rays]), False, True)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle.forward(sd, rays, False, True)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return num_rays / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 1024
+    rps, dt, cores = cpu_arm(sample, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "rays/sec (4096-ray batch, 128+128 samples)", "value": rps,
+        "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "lego single-scale 800x800, 4096-ray batch, 128+128 samples (configs[1])",
+                   "step": f"CPU oracle forward on a {sample}-ray sample of the batch"},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {BATCH} rays per step, fp32 torch-CPU oracle (port of "
+                                   "models/mip_nerf.py:172-248), randomized=False"},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16", "fp16"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import mipnerf_pl_b200 as mp
+    from mipnerf_pl_b200 import _cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+
+    model = mp.MipNerf()
+    precision = args.precision
+    if precision is None:
+        cfg = model._config()
+        precision = "bf16" if lib.mipnerf_b200_packed_weights_bytes(C.byref(cfg), _cabi.BF16) > 0 else "fp32"
+    model.precision = precision
+    model.load_state_dict(mp.make_state_dict(seed=0, kind="xavier"))
+    model = model.to(dev).eval()
+
+    B = args.batch
+    host_rays = mp.random_ray_batch(B, seed=rank)                       # pinned host copy (e2e arm)
+    host_rays = mp.namedtuple_map(lambda t: t.pin_memory(), host_rays)
+    rays = mp.namedtuple_map(lambda t: t.to(dev), host_rays)            # resident copy (value arm)
+    gathered = torch.empty(world * B, 3, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step():
+        ret = model(rays, False, True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, ret[-1][0])
+        return ret
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- value: device-timed steps, L2 flushed between them -------------------------------------
+    _cabi.profile_snapshot(reset=True)
+    lib.mipnerf_b200_profile_enable(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        step()
+        stops[i].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    lib.mipnerf_b200_profile_enable(0)
+    prof = _cabi.profile_snapshot(reset=True)
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region -------------------------
+    out_host = torch.empty(B, 7, pin_memory=True)
+
+    def e2e_step():
+        r = mp.namedtuple_map(lambda t: t.to(dev, non_blocking=True), host_rays)
+        ret = model(r, False, True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, ret[-1][0])
+        out_host[:, 0:3].copy_(ret[0][0], non_blocking=True)
+        out_host[:, 3:6].copy_(ret[-1][0], non_blocking=True)
+        out_host[:, 6].copy_(ret[-1][1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the pixels every step
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peaks = load_peaks()
+    timed = {k: v for k, v in prof.items() if v[2] > 0}
+    dominant = max(timed, key=lambda k: timed[k][1]) if timed else None
+    launches_total = sum(v[0] for v in prof.values())
+    roofline = None
+    if dominant:
+        n_l, ms_l, tn_l = prof[dominant]
+        per_launch_ms = ms_l / tn_l
+        # FLOPs one launch of the dominant kernel performs: the step's MLP FLOPs split over its launches
+        mlp_kernels = ("mlp_level_tc", "mlp_tc", "linear_f32")
+        flops_step = B * FLOP_PER_RAY
+        launches_per_step = n_l / args.steps
+        flops_per_launch = flops_step / launches_per_step if dominant in mlp_kernels else 0.0
+        achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops"]
+        roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "peak_source": f"{peaks['_source']} MEASURED_PEAKS.json bf16_tflops (burst)",
+                    "launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
+                    "share_of_step": ms_l / max(total_ms, 1e-9),
+                    "step_frac_of_roofline": (value / world) * FLOP_PER_RAY / 1e12 / peak}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        sample = 1024
+        rps, dt, cores = cpu_arm(sample, 2, 1)
+        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+               "sample": f"{sample} of {B} rays (same rays/weights), 2 timed runs of the fp32 torch-CPU oracle"}
+
+    line = {
+        "metric": "rays/sec (4096-ray batch, 128+128 samples)", "value": value, "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision], "data": "synthetic",
+        "config": {"workload": "lego single-scale 800x800 Blender-shape rays, 4096-ray batch, 128 coarse + 128 "
+                               "fine samples (BASELINE configs[1])",
+                   "global_batch_rays": world * B, "rays_per_gpu": B, "mlp_operands": precision,
+                   "weights": "random-init xavier (seed 0) of the reference 8x256 architecture",
+                   "l2": "flushed between steps (256 MiB memset, untimed)",
+                   "parallelism": f"ray-sharded x{world}, all_gather of fine RGB" if world > 1 else "single GPU",
+                   "wall_s_timed_region_incl_flush": wall},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": B * H2D_BYTES_PER_RAY,
+                "d2h_bytes_per_step": B * D2H_BYTES_PER_RAY},
+        "gpu_launches": launches_total,
+        "kernel_launches": {k: v[0] for k, v in prof.items() if v[0]},
+        "kernel_ms": {k: round(v[1], 4) for k, v in prof.items() if v[2]},
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -156,6 +156,21 @@ int mipnerf_b200_resample_along_rays(const mipnerf_b200_rays* rays, const float*
                                      float* new_t_samples, float* means, float* covs, int64_t* inds,
                                      void* stream);
 
+/* Hardware self-test of the tcgen05 building blocks (descriptor / swizzle / TMEM conventions):
+ * d[128,n] = a[128,k] . b[n,k]^T, 16-bit operands (precision BF16|FP16), fp32 accumulate in TMEM.
+ * variant bit 0: B through a pre-swizzled image + cp.async.bulk (needs `scratch`); bit 1: A in TMEM. */
+int mipnerf_b200_selftest_umma(const float* a, const float* b, float* d, int n, int k, int precision,
+                               int variant, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- launch accounting (bench.py: `gpu_launches`, live launch duration of the dominant kernel) ----
+ * Every kernel launch of the library is counted per kernel id; with timing enabled each launch is
+ * also bracketed by CUDA events on its stream.  profile_read synchronises the pending events. */
+int mipnerf_b200_profile_enable(int timing_on);
+int mipnerf_b200_profile_num_kernels(void);
+const char* mipnerf_b200_profile_kernel_name(int kernel_id);
+int mipnerf_b200_profile_read(int kernel_id, int64_t* launches, double* timed_ms,
+                              int64_t* timed_launches, int reset);
+
 #ifdef __cplusplus
 }
 #endif

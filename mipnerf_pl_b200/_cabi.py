@@ -73,6 +73,11 @@ _SIGNATURES = {
     "mipnerf_b200_sorted_piecewise_constant_pdf": (C.c_int, [_V, _V, C.c_int64, C.c_int, C.c_int, C.c_int, _V, _V, _V, _V]),
     "mipnerf_b200_resample_along_rays": (C.c_int, [C.POINTER(RaysStruct), _V, _V, C.c_int, C.c_int, _V, C.c_float,
                                                    _V, _V, _V, _V, _V]),
+    "mipnerf_b200_selftest_umma": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_int, _V, C.c_size_t, _V]),
+    "mipnerf_b200_profile_enable": (C.c_int, [C.c_int]),
+    "mipnerf_b200_profile_num_kernels": (C.c_int, []),
+    "mipnerf_b200_profile_kernel_name": (C.c_char_p, [C.c_int]),
+    "mipnerf_b200_profile_read": (C.c_int, [C.c_int, _i64p, C.POINTER(C.c_double), _i64p, C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -116,3 +121,14 @@ def check(rc: int, what: str) -> None:
     if rc == EINVAL:
         raise ValueError(msg)
     raise RuntimeError(msg)
+
+
+def profile_snapshot(reset: bool = False) -> dict:
+    """{kernel name: (launches, timed_ms, timed_launches)} from the library's launch accounting."""
+    l = lib()
+    out = {}
+    for k in range(l.mipnerf_b200_profile_num_kernels()):
+        n, ms, tn = C.c_int64(0), C.c_double(0.0), C.c_int64(0)
+        l.mipnerf_b200_profile_read(k, C.byref(n), C.byref(ms), C.byref(tn), int(reset))
+        out[l.mipnerf_b200_profile_kernel_name(k).decode()] = (n.value, ms.value, tn.value)
+    return out

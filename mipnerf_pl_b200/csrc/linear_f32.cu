@@ -8,6 +8,7 @@
 // fp32 round-off of torch's sgemm; this path exists to demonstrate the 1e-4 parity bar, the
 // tensor-core path (mlp_tc.cu) is the fast one.
 #include "kernels.h"
+#include "profile.h"
 
 namespace mipnerf {
 
@@ -123,6 +124,7 @@ cudaError_t launch_linear_f32(const float* x1, int ld1, int k1, const float* x2,
     ld2 = ld1;
   }
   if (x2_row_div < 1) x2_row_div = 1;
+  LaunchScope scope(kKernLinearF32, st);
   if (n <= 8) {
     const int warps = 8;
     linear_f32_small_n_kernel<<<(unsigned)((m + warps - 1) / warps), warps * 32, 0, st>>>(

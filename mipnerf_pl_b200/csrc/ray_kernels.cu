@@ -9,6 +9,7 @@
 // Compositing and resampling are warp-per-ray: one ray's N samples live in one warp's registers /
 // shared-memory slice, reductions are shuffles, no cross-warp traffic.
 #include "kernels.h"
+#include "profile.h"
 #include "ray_math.cuh"
 
 namespace mipnerf {
@@ -345,6 +346,7 @@ static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)(
 cudaError_t launch_coarse_t(const float* near, const float* far, const float* t_rand, float* t_out,
                             int64_t num_rays, int n, int randomized, int disparity, cudaStream_t st) {
   if (num_rays == 0) return cudaSuccess;
+  LaunchScope scope(kKernCoarseT, st);
   coarse_t_kernel<<<blocks_for(num_rays * (n + 1), 256), 256, 0, st>>>(near, far, t_rand, t_out, num_rays,
                                                                      n, randomized, disparity);
   return cudaGetLastError();
@@ -354,6 +356,7 @@ cudaError_t launch_cast_rays(const float* origins, const float* directions, cons
                              const float* t, float* means, float* covs, int64_t num_rays, int n,
                              cudaStream_t st) {
   if (num_rays == 0) return cudaSuccess;
+  LaunchScope scope(kKernCastRays, st);
   cast_rays_kernel<<<blocks_for(num_rays * n, 256), 256, 0, st>>>(origins, directions, radii, t, means,
                                                                  covs, num_rays, n);
   return cudaGetLastError();
@@ -363,6 +366,7 @@ cudaError_t launch_ipe(const float* means, const float* covs, float* out, int64_
                        int min_deg, int max_deg, cudaStream_t st) {
   const int nd = max_deg - min_deg;
   if (num_points == 0 || nd <= 0) return cudaSuccess;
+  LaunchScope scope(kKernIpe, st);
   ipe_kernel<<<blocks_for(num_points * nd * 3, 256), 256, 0, st>>>(means, covs, out, num_points, min_deg, nd);
   return cudaGetLastError();
 }
@@ -372,6 +376,7 @@ cudaError_t launch_ipe_from_t(const float* origins, const float* directions, con
                               int max_deg, int disable_integration, cudaStream_t st) {
   const int nd = max_deg - min_deg;
   if (num_rays == 0 || nd <= 0) return cudaSuccess;
+  LaunchScope scope(kKernIpe, st);
   ipe_from_t_kernel<<<blocks_for(num_rays * n * nd * 3, 256), 256, 0, st>>>(
       origins, directions, radii, t, out, num_rays, n, min_deg, nd, disable_integration);
   return cudaGetLastError();
@@ -382,6 +387,7 @@ cudaError_t launch_pos_enc(const float* x, float* out, int64_t num_points, int m
   const int nd = max_deg - min_deg;
   const int width = 6 * nd + (append_identity ? 3 : 0);
   if (num_points == 0 || width == 0) return cudaSuccess;
+  LaunchScope scope(kKernPosEnc, st);
   pos_enc_kernel<<<blocks_for(num_points * width, 256), 256, 0, st>>>(x, out, num_points, min_deg, nd,
                                                                      append_identity);
   return cudaGetLastError();
@@ -394,6 +400,7 @@ static cudaError_t launch_composite_t(const float* rgb, const float* dens, const
                                       float density_bias, float rgb_scale, float rgb_padding,
                                       cudaStream_t st) {
   if (num_rays == 0) return cudaSuccess;
+  LaunchScope scope(kKernComposite, st);
   const unsigned grid = blocks_for(num_rays, 4);
 #define MIPNERF_COMPOSITE_CASE(PP)                                                                   \
   case PP:                                                                                           \
@@ -430,6 +437,7 @@ cudaError_t launch_resample(const float* bins, const float* weights, const float
                             int64_t* inds, int64_t num_rays, int nb, int ns, int randomized, int blur,
                             float padding, cudaStream_t st) {
   if (num_rays == 0) return cudaSuccess;
+  LaunchScope scope(kKernResample, st);
   const int warps = 4;
   const size_t smem = (size_t)warps * (3 * nb + 2) * sizeof(float);
   const unsigned grid = blocks_for(num_rays, warps);

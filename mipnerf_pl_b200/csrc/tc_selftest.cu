@@ -1,0 +1,174 @@
+// tc_selftest.cu — hardware self-test of the tcgen05 building blocks in tc_common.cuh.
+//
+// D[128,N] = A[128,K] . B[N,K]^T with 16-bit operands and fp32 accumulation in TMEM, through exactly
+// the operand layout, descriptors, barriers and TMEM load path the fused kernels use:
+//   variant bit 0: B arrives as a pre-swizzled global image via cp.async.bulk + mbarrier tx bytes
+//                  (otherwise threads write it with st.shared like the A operand);
+//   variant bit 1: A is staged in TMEM with tcgen05.st and the MMA is the TS form.
+// tests/test_gpu_tc.py compares D with a torch matmul of the rounded operands.
+#include "../../include/mipnerf_b200.h"
+#include "profile.h"
+#include "tc_common.cuh"
+
+namespace mipnerf {
+namespace {
+
+using namespace tc;
+
+template <int kFmt>
+__global__ void pack_b_image_kernel(const float* __restrict__ b, uint8_t* __restrict__ image, int n, int k) {
+  // image: slabs of [n rows x 128 B], element (row, kk) at sw128_offset(row, kk % 64) in slab kk / 64
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slabs = (k + 63) / 64;
+  if (idx >= n * slabs * 64) return;
+  const int row = idx / (slabs * 64);
+  const int kk = idx % (slabs * 64);
+  const float v = kk < k ? b[(size_t)row * k + kk] : 0.f;
+  uint16_t* dst = reinterpret_cast<uint16_t*>(image + (size_t)(kk / 64) * n * 128 + sw128_offset(row, kk % 64));
+  *dst = to16<kFmt>(v);
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ b_image,
+                     float* __restrict__ d, int n, int k, int variant) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);  // SW128 atoms need 1024-B alignment
+  const int slabs = (k + 63) / 64;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)slabs * 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)slabs * n * 128);
+  uint64_t* bar_b = bars;
+  uint64_t* bar_mma = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool b_bulk = variant & 1, a_tmem = variant & 2;
+
+  if (tid == 0) {
+    mbar_init(bar_b, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+
+  // A operand (row = tid) into SW128 slabs, zero padded to the slab width
+  for (int s = 0; s < slabs; ++s)
+    for (int c = 0; c < 8; ++c) {
+      uint32_t w[4];
+      for (int q = 0; q < 4; ++q) {
+        const int k0 = s * 64 + c * 8 + q * 2;
+        const float lo = k0 < k ? a[(size_t)tid * k + k0] : 0.f;
+        const float hi = k0 + 1 < k ? a[(size_t)tid * k + k0 + 1] : 0.f;
+        w[q] = pack2<kFmt>(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(sA + (size_t)s * 16384 + sw128_offset(tid, c * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  if (!b_bulk) {
+    for (int row = tid; row < n; row += 128)
+      for (int s = 0; s < slabs; ++s)
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[4];
+          for (int q = 0; q < 4; ++q) {
+            const int k0 = s * 64 + c * 8 + q * 2;
+            const float lo = k0 < k ? b[(size_t)row * k + k0] : 0.f;
+            const float hi = k0 + 1 < k ? b[(size_t)row * k + k0 + 1] : 0.f;
+            w[q] = pack2<kFmt>(lo, hi);
+          }
+          *reinterpret_cast<uint4*>(sB + (size_t)s * n * 128 + sw128_offset(row, c * 8)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
+        }
+  }
+  fence_proxy_async_smem();  // st.shared operands -> async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (b_bulk && tid == 0) {
+    mbar_arrive_expect_tx(bar_b, (uint32_t)(slabs * n * 128));
+    for (int s = 0; s < slabs; ++s)
+      bulk_g2s(sB + (size_t)s * n * 128, b_image + (size_t)s * n * 128, (uint32_t)(n * 128), bar_b);
+  }
+  if (a_tmem) {
+    // row tid -> TMEM lane tid, columns 256 + kk/2 (two 16-bit elements per 32-bit column)
+    for (int c0 = 0; c0 < k / 2; c0 += 16) {
+      uint32_t v[16];
+      for (int q = 0; q < 16; ++q) {
+        const int k0 = (c0 + q) * 2;
+        v[q] = pack2<kFmt>(a[(size_t)tid * k + k0], a[(size_t)tid * k + k0 + 1]);
+      }
+      tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+
+  if (tid == 0) {
+    if (b_bulk) mbar_wait(bar_b, 0);
+    const uint32_t idesc = make_idesc_f16(128, n, kFmt);
+    uint32_t acc = 0;
+    for (int s = 0; s < slabs; ++s) {
+      const int steps = ((k - s * 64) < 64 ? (k - s * 64) : 64) / 16;
+      for (int j = 0; j < steps; ++j) {
+        const uint64_t bdesc = make_sw128_desc(smem_u32(sB + (size_t)s * n * 128) + j * 32);
+        if (a_tmem) {
+          umma_ts(tmem_base, tmem_base + 256 + (s * 64 + j * 16) / 2, bdesc, idesc, acc);
+        } else {
+          const uint64_t adesc = make_sw128_desc(smem_u32(sA + (size_t)s * 16384) + j * 32);
+          umma_ss(tmem_base, adesc, bdesc, idesc, acc);
+        }
+        acc = 1;
+      }
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  for (int c = 0; c < n; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int q = 0; q < 32; ++q) d[(size_t)tid * n + c + q] = __uint_as_float(v[q]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+}  // namespace mipnerf
+
+extern "C" int mipnerf_b200_selftest_umma(const float* a, const float* b, float* d, int n, int k, int precision,
+                                          int variant, void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace mipnerf;
+  if (!a || !b || !d || n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || k > 384) return MIPNERF_B200_EINVAL;
+  if ((variant & 2) && (k % 32)) return MIPNERF_B200_EINVAL;
+  if (precision != MIPNERF_B200_BF16 && precision != MIPNERF_B200_FP16) return MIPNERF_B200_EINVAL;
+  const int slabs = (k + 63) / 64;
+  const size_t image = (size_t)slabs * n * 128;
+  if ((variant & 1) && (!scratch || scratch_bytes < image)) return MIPNERF_B200_EWORKSPACE;
+  const size_t smem = 1024 + (size_t)slabs * 16384 + image + 64;
+  if (smem > 227 * 1024) return MIPNERF_B200_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool bf = precision == MIPNERF_B200_BF16;
+  cudaError_t e;
+  if (variant & 1) {
+    const int total = n * slabs * 64;
+    if (bf) pack_b_image_kernel<1><<<(total + 255) / 256, 256, 0, st>>>(b, (uint8_t*)scratch, n, k);
+    else pack_b_image_kernel<0><<<(total + 255) / 256, 256, 0, st>>>(b, (uint8_t*)scratch, n, k);
+  }
+  if (bf) {
+    e = cudaFuncSetAttribute(umma_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return MIPNERF_B200_ECUDA;
+    umma_selftest_kernel<1><<<1, 128, smem, st>>>(a, b, (const uint8_t*)scratch, d, n, k, variant);
+  } else {
+    e = cudaFuncSetAttribute(umma_selftest_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return MIPNERF_B200_ECUDA;
+    umma_selftest_kernel<0><<<1, 128, smem, st>>>(a, b, (const uint8_t*)scratch, d, n, k, variant);
+  }
+  return cudaGetLastError() == cudaSuccess ? MIPNERF_B200_OK : MIPNERF_B200_ECUDA;
+}

@@ -1,0 +1,131 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, the host mirror keeps
+the reference's API/state_dict layout, helpers behave, and errors surface without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, make_state_dict, oracle
+
+import mipnerf_pl_b200 as mp
+from mipnerf_pl_b200 import _cabi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    return _cabi.lib()
+
+
+def test_header_symbols_all_exported(lib):
+    header = open(os.path.join(ROOT, "include", "mipnerf_b200.h")).read()
+    declared = set(re.findall(r"\b(mipnerf_b200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes parsed"
+    assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mipnerf_b200_abi_version() == 1
+
+
+def test_ctypes_structs_match_header_layout():
+    assert C.sizeof(_cabi.Linear) == 24
+    assert C.sizeof(_cabi.Config) == 18 * 4
+    assert C.sizeof(_cabi.RaysStruct) == 7 * 8
+    assert C.sizeof(_cabi.LevelOut) == 6 * 8
+    assert C.sizeof(_cabi.Weights) == 8 + 4 + 4 + 8 + 8
+
+
+def test_argument_validation_without_gpu(lib):
+    cfg = mp.MipNerf()._config()
+    assert lib.mipnerf_b200_workspace_bytes(C.byref(cfg), 4096, _cabi.FP32) > 1 << 30
+    assert lib.mipnerf_b200_workspace_bytes(C.byref(cfg), 10 ** 9, _cabi.FP32) == \
+        lib.mipnerf_b200_workspace_bytes(C.byref(cfg), 4096, _cabi.FP32), "scratch is bounded by the chunk size"
+    bad = mp.MipNerf(num_samples=100)._config()
+    assert lib.mipnerf_b200_workspace_bytes(C.byref(bad), 16, _cabi.FP32) == 0
+    rc = lib.mipnerf_b200_forward(C.byref(bad), None, None, 0, None, None, 1, 0, None, None, 0, None)
+    assert rc == _cabi.EUNSUPPORTED and b"num_samples" in lib.mipnerf_b200_last_error()
+    rc = lib.mipnerf_b200_forward(C.byref(cfg), None, None, 0, None, None, 1, 0, None, None, 0, None)
+    assert rc == _cabi.EINVAL
+    with pytest.raises(NotImplementedError):
+        _cabi.check(_cabi.EUNSUPPORTED, "x")
+    with pytest.raises(ValueError):
+        _cabi.check(_cabi.EINVAL, "x")
+
+
+def test_cpu_tensors_are_rejected_no_fallback():
+    model = mp.MipNerf()
+    rays = mp.random_ray_batch(8, seed=0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(rays, False, True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mp.pos_enc(rays.viewdirs, 0, 4)
+
+
+def test_state_dict_layout_matches_reference_keys():
+    model = mp.MipNerf()
+    keys = list(model.state_dict().keys())
+    want = list(make_state_dict(0).keys())
+    assert keys == want
+    assert sum(p.numel() for p in model.parameters()) == 612740
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert shapes["mlp.layers.5.0.weight"] == (256, 352) and shapes["mlp.view_layers.0.0.weight"] == (128, 283)
+    system = mp.MipNeRFSystem(mp.default_hparams())
+    assert all(k.startswith("mip_nerf.mlp.") for k in system.state_dict())
+    assert len(system.state_dict()) == 24
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    system = mp.MipNeRFSystem(mp.default_hparams())
+    sd = {"mip_nerf." + k: v for k, v in make_state_dict(3).items()}
+    ckpt = {"state_dict": sd, "hyper_parameters": mp.default_hparams(), "epoch": 27, "global_step": 329999}
+    path = tmp_path / "epoch=27-step=329999.ckpt"
+    torch.save(ckpt, path)
+    loaded = mp.MipNeRFSystem.load_from_checkpoint(str(path))
+    for k, v in loaded.state_dict().items():
+        assert torch.equal(v, sd[k])
+    assert loaded.val_chunk_size == 8192
+
+
+def test_unsupported_modes_raise_like_reference():
+    with pytest.raises(NotImplementedError):
+        mp.MipNerf(rgb_activation="tanh")
+    with pytest.raises(NotImplementedError):
+        mp.MipNerf(density_activation="relu")
+    with pytest.raises(NotImplementedError):
+        mp.MipNerf(mlp_net_activation="gelu")
+    system = mp.MipNeRFSystem(mp.default_hparams())
+    with pytest.raises(NotImplementedError):
+        system.training_step(None, 0)
+
+
+def test_rearrange_render_image_chunks():
+    h, w = 5, 7
+    full = mp.blender_rays(mp.spheric_pose(0.3), height=800, width=800)
+    sub = mp.Rays(*[f[:h, :w][None] for f in full])
+    rays = mp.rays_to_torch(sub, flatten=False)
+    chunks, mask = mp.rearrange_render_image(rays, 8)
+    assert [c.origins.shape[0] for c in chunks] == [8, 8, 8, 8, 3]
+    assert mask.shape == (1, h, w, 1)
+    assert torch.equal(torch.cat([c.directions for c in chunks]), rays.directions.reshape(-1, 3))
+
+
+def test_synthetic_blender_rays_shape():
+    r = mp.blender_rays(mp.spheric_pose(1.0))
+    assert r.origins.shape == (800, 800, 3) and r.radii.dtype == np.float32
+    assert abs(float(np.linalg.norm(r.origins[0, 0])) - 4.0) < 1e-5
+    assert abs(float(r.radii.mean()) - 5.196e-4) < 2e-6
+    n = np.linalg.norm(r.directions, axis=-1)
+    assert n.min() >= 1.0 - 1e-6 and n.max() < 1.13
+    ms = mp.random_ray_batch(64, seed=1, multiscale=True)
+    assert sorted(set(ms.lossmult.flatten().tolist())) == [1.0, 4.0, 16.0, 64.0]
+
+
+def test_weights_generator_is_deterministic():
+    a, b = make_state_dict(5), make_state_dict(5)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    x = make_state_dict(0)["mlp.layers.0.0.weight"]
+    assert abs(float(x.abs().max()) - (6 / (96 + 256)) ** 0.5) < 1e-3
