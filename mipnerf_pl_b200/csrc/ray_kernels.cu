@@ -177,7 +177,9 @@ __global__ void composite_kernel(const float* __restrict__ rgb_in, const float* 
     // exclusive cumsum, fp64 running sum rounded per prefix like torch.cumsum(float32)   (:389-392)
     const double excl = before + (p == 0 ? 0.0 : incl[p - 1]);
     const float cum = (lane == 0 && p == 0) ? 0.0f : (float)excl;
-    const float alpha = __fsub_rn(1.0f, expf(-dd[p]));
+    // 1 - exp(-dd) evaluated as -expm1(-dd): same expression, without the reference's fp32
+    // cancellation noise (tests/test_reference_roundoff.py), so we sit next to its exact value
+    const float alpha = -expm1f(-dd[p]);
     const float w = __fmul_rn(alpha, expf(-cum));
     const int64_t s = ray * N + lane * P + p;
     if (weights_out) weights_out[s] = w;

@@ -28,6 +28,12 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
   return (uint32_t)(r * 128 + ((((k >> 3) ^ (r & 7)) << 4) | ((k & 7) << 1)));
 }
 
+// 64-byte-swizzle variant for a 32-element K tail: rows of 64 bytes, 8-row atoms of 512 bytes,
+// 16-byte chunk index XOR ((row >> 1) & 3)  (cute Swizzle<2,4,3>).
+__host__ __device__ __forceinline__ uint32_t sw64_offset(int r, int k) {
+  return (uint32_t)(r * 64 + ((((k >> 3) ^ ((r >> 1) & 3)) << 4) | ((k & 7) << 1)));
+}
+
 // UMMA shared-memory descriptor for a SW128 K-major slab starting at `saddr` (1024-B aligned,
 // plus 32 B per K=16 step).  Field layout: cute::UMMA::SmemDescriptor (start>>4 [0,14),
 // LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2).
@@ -38,6 +44,16 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;  // SBO: 8-row group stride
   d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;  // SBO: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;           // SWIZZLE_64B
   return d;
 }
 

@@ -14,9 +14,15 @@ from oracle import mipnerf_oracle as oracle  # noqa: E402  (tests are allowed to
 from mipnerf_pl_b200.rays import Rays  # noqa: E402
 from mipnerf_pl_b200.weights import make_state_dict  # noqa: E402
 
-# Tolerance policy (BASELINE.json north_star / SURVEY.md §8c): 1e-4 relative with an absolute floor.
+# Tolerance policy (BASELINE.json north_star / SURVEY.md §8c): |a-b| <= 1e-4 * max(|b|, floor).
+# The floors are set by the reference's OWN fp32 noise: alpha = 1 - exp(-sigma*delta) cancels
+# catastrophically for thin media (1 ulp of exp() near 1.0 is 6e-8, i.e. 6e-4 of an alpha of 1e-4), and
+# torch-CPU's exp is MKL's vsExp, which cannot be reproduced bit for bit.  test_reference_roundoff.py
+# measures that noise (reference fp32 vs the same formulas in float64) on the golden inputs:
+# ~6e-7 abs on comp_rgb/acc, ~3e-8 on individual weights; the floors grant 3-4x that.
+# (The kernels evaluate alpha as -expm1(-x), i.e. they sit next to the exact value.)
 RTOL = 1e-4
-FLOORS = {"comp_rgb": 1e-3, "acc": 1e-3, "distance": 1e-2, "weights": 1e-3, "t_samples": 1e-2}
+FLOORS = {"comp_rgb": 0.02, "acc": 0.02, "distance": 0.2, "weights": 1e-3, "t_samples": 1e-2}
 
 
 def golden(name):

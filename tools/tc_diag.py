@@ -11,8 +11,8 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..",
 from test_gpu_tc import run_selftest  # noqa: E402
 
 for precision in ("bf16", "fp16"):
-    for variant in (0, 1, 2, 3):
-        for n, k in ((256, 256), (256, 96), (128, 64), (16, 32)):
+    for variant in (4,):
+        for n, k in ((128, 32), (256, 32)):
             try:
                 d, ref = run_selftest(n, k, precision, variant)
                 err = (d.double() - ref).abs()
