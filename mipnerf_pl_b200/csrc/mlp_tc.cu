@@ -1,11 +1,586 @@
-// placeholder until the tcgen05 kernels land: reports "unsupported" for every shape.
+// mlp_tc.cu — the tensor-core path: one fused kernel per sampling level that does, per ray,
+//   fenceposts -> conical-frustum Gaussians -> IPE features        (models/mip.py:81-103, 322-350)
+//   -> 8x256 trunk + density / bottleneck / view / colour heads    (models/mip_nerf.py:75-111)
+//   -> activations + front-to-back alpha compositing               (models/mip_nerf.py:236-238, mip.py:366-401)
+// without any intermediate tensor touching HBM.  Per level the kernel reads 52 B of ray data and the
+// [B,129] fenceposts and writes comp_rgb/distance/acc/weights; the weights stream from L2.
+//
+// Mapping (sm_100a, 1 persistent CTA per SM, 320 threads):
+//   * tile = one ray = 128 samples = UMMA M.  Each CTA keeps TWO rays in flight ("slots") so that
+//     while slot 0's epilogue warps turn an accumulator into the next layer's A operand, the tensor
+//     core runs slot 1's layer.  TMEM: 2 x 256 fp32 columns (the whole 512).
+//   * warp 0    : weight producer — cp.async.bulk of pre-swizzled [128 x 64] operand stages
+//   * warp 1    : MMA issuer     — tcgen05.mma kind::f16, M=128, N=128 (two N halves per layer)
+//   * warps 2-5 : slot 0 workers, warps 6-9: slot 1 workers — thread = sample row = TMEM lane:
+//                 IPE -> st.shared (SW128 A operand), epilogues (tcgen05.ld, +bias, ReLU, 16-bit
+//                 pack), density/colour heads on CUDA cores, 128-thread compositing scan.
+//   * layer-5 skip connection = extra K slabs read from the feature tile (no concat), the
+//     per-ray view-direction term of the view layer is a per-ray bias vector (pre-kernel).
+// A operand: 4 SW128 slabs (64 KB) per slot, overwritten in place layer after layer; features:
+// SW128 slab (K 0..63) + SW64 slab (K 64..95) per slot; weight ring: 3 x 16 KB.
 #include "mlp_tc.h"
+
+#include "kernels.h"
+#include "profile.h"
+#include "ray_math.cuh"
+#include "tc_common.cuh"
+
 namespace mipnerf {
-bool tc_supported(const mipnerf_b200_config*, int) { return false; }
-bool tc_mlp_supported(const mipnerf_b200_config*, int, int) { return false; }
-size_t tc_packed_bytes(const mipnerf_b200_config*, int) { return 0; }
-size_t tc_workspace_bytes(const mipnerf_b200_config*, int64_t, int) { return 0; }
-cudaError_t tc_pack_weights(const mipnerf_b200_config*, const mipnerf_b200_weights*, int, void*, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t tc_forward(const mipnerf_b200_config*, const mipnerf_b200_weights*, const mipnerf_b200_rays*, int, const float*, const float*, int, int, mipnerf_b200_level_out*, void*, size_t, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t tc_mlp_forward(const mipnerf_b200_config*, const mipnerf_b200_weights*, const float*, const float*, int64_t, int, float*, float*, cudaStream_t) { return cudaErrorNotSupported; }
+namespace {
+
+using namespace tc;
+
+constexpr int kN = 128;         // samples per ray (UMMA M)
+constexpr int kWidth = 256;     // trunk width
+constexpr int kCond = 128;      // view layer width
+constexpr int kFeat = 96;       // IPE width
+constexpr int kViewDim = 27;
+constexpr int kNumLayers = 10;  // 8 trunk + extra_layer + view layer
+constexpr int kThreads = 320;
+constexpr int kStages = 3;
+constexpr uint32_t kStageBytes = 16384;  // [128 x 64] 16-bit, SW128
+constexpr uint32_t kTailBytes = 8192;    // [128 x 32] 16-bit, SW64
+constexpr uint32_t kABytes = 65536;      // 4 slabs
+constexpr uint32_t kFBytes = kStageBytes + kTailBytes;
+constexpr uint32_t kSmemA = 0;
+constexpr uint32_t kSmemF = kSmemA + 2 * kABytes;
+constexpr uint32_t kSmemW = kSmemF + 2 * kFBytes;
+constexpr uint32_t kSmemMisc = kSmemW + kStages * kStageBytes;
+constexpr uint32_t kMiscBytes = 128 + 16 + 2 * 128 * 4 + 8 * 4 + 2 * 4 * 8 * 4;
+constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // + slack for 1024-B alignment
+static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+// Biases and the two CUDA-core heads, broadcast-read by every thread: constant bank.
+struct SmallParams {
+  float bias[9][kWidth];      // layers.0..7, extra_layer
+  float w_density[kWidth];    // density_layer.weight
+  float w_color[3][kCond];    // color_layer.weight
+  float b_density;
+  float b_color[3];
+};
+__constant__ SmallParams c_small;
+
+// byte offsets of each layer's stage sequence inside the packed image
+__host__ __device__ constexpr uint32_t layer_bytes(int l) {
+  return l == 0 ? 2u * (kStageBytes + kTailBytes)
+         : l == 5 ? 2u * (4u * kStageBytes + kStageBytes + kTailBytes)
+         : l == 9 ? 4u * kStageBytes
+                  : 8u * kStageBytes;
 }
+__host__ __device__ constexpr uint32_t layer_offset(int l) {
+  uint32_t o = 0;
+  for (int i = 0; i < l; ++i) o += layer_bytes(i);
+  return o;
+}
+constexpr uint32_t kImageStageBytes = layer_offset(kNumLayers);
+constexpr size_t kImageBytes = ((size_t)kImageStageBytes + 255) / 256 * 256 + ((sizeof(SmallParams) + 255) / 256 * 256);
+constexpr size_t kSmallOffset = ((size_t)kImageStageBytes + 255) / 256 * 256;
+
+__host__ __device__ constexpr int num_slabs(int l) { return l == 0 ? 2 : (l == 5 ? 6 : 4); }
+__host__ __device__ constexpr int num_halves(int l) { return l == 9 ? 1 : 2; }
+// slab s of layer l: is it the 32-wide SW64 tail?
+__host__ __device__ constexpr bool slab_is_tail(int l, int s) { return (l == 0 && s == 1) || (l == 5 && s == 5); }
+
+struct LevelParams {
+  const uint8_t* wimage;
+  const float* origins;
+  const float* directions;
+  const float* radii;
+  const float* t;          // [B,129] fenceposts of this level
+  const float* view_bias;  // [B,128]  b_view + W_view[:,256:] . pos_enc(viewdir)
+  float* comp_rgb;
+  float* distance;
+  float* acc;
+  float* weights;  // [B,128]
+  int64_t num_rays;
+  int rounds;
+  int white_bkgd;
+  int disable_integration;
+  float density_bias, rgb_scale, rgb_padding;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+template <int kFmt>
+__device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<kFmt>(x[0], x[1]), pack2<kFmt>(x[2], x[3]),
+                                              pack2<kFmt>(x[4], x[5]), pack2<kFmt>(x[6], x[7]));
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem + kSmemA;
+  uint8_t* sF = smem + kSmemF;
+  uint8_t* sW = smem + kSmemW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemMisc);
+  uint64_t* w_full = bars;         // [kStages]  producer -> MMA   (tx bytes)
+  uint64_t* w_empty = bars + 3;    // [kStages]  MMA -> producer   (tcgen05.commit)
+  uint64_t* a_ready = bars + 6;    // [2]        workers -> MMA    (128 arrivals)
+  uint64_t* acc_full = bars + 8;   // [2]        MMA -> workers    (tcgen05.commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 128);
+  float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 144);  // [2][128]
+  float* cs = vb_s + 256;                                          // [2][4]   scan carries
+  float* ps = cs + 8;                                              // [2][4][8] partial sums
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_ready[s], 128);
+      mbar_init(&acc_full[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int rounds = p.rounds;
+
+  if (warp == 0) {
+    // ============================ weight producer ============================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int round = 0; round < rounds; ++round)
+        for (int l = 0; l < kNumLayers; ++l) {
+          const uint8_t* lbase = p.wimage + layer_offset(l);
+          const int nh = num_halves(l), ns = num_slabs(l);
+          for (int slot = 0; slot < 2; ++slot) {
+            const uint8_t* src = lbase;
+            for (int h = 0; h < nh; ++h)
+              for (int s = 0; s < ns; ++s) {
+                const uint32_t bytes = slab_is_tail(l, s) ? kTailBytes : kStageBytes;
+                mbar_wait(&w_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&w_full[st], bytes);
+                bulk_g2s(sW + st * kStageBytes, src, bytes, &w_full[st]);
+                src += bytes;
+                if (++st == kStages) {
+                  st = 0;
+                  ph ^= 1;
+                }
+              }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    const uint32_t idesc = make_idesc_f16(128, 128, kFmt);
+    int st = 0;
+    uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
+    for (int round = 0; round < rounds; ++round)
+      for (int l = 0; l < kNumLayers; ++l) {
+        const int nh = num_halves(l), ns = num_slabs(l);
+        for (int slot = 0; slot < 2; ++slot) {
+          if (slot == 0) {
+            mbar_wait(&a_ready[0], ph_ready0);
+            ph_ready0 ^= 1;
+          } else {
+            mbar_wait(&a_ready[1], ph_ready1);
+            ph_ready1 ^= 1;
+          }
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + slot * kABytes);
+          const uint32_t f_base = smem_u32(sF + slot * kFBytes);
+          for (int h = 0; h < nh; ++h) {
+            const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
+            for (int s = 0; s < ns; ++s) {
+              mbar_wait(&w_full[st], wph);
+              tc_fence_after();
+              const bool tail = slab_is_tail(l, s);
+              const bool from_feat = (l == 0) || (l == 5 && s >= 4);
+              const int fs = (l == 0) ? s : s - 4;
+              const uint32_t a_addr = from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
+              const uint32_t b_addr = smem_u32(sW + st * kStageBytes);
+              if (lane == 0) {
+                if (tail) {
+#pragma unroll
+                  for (int j = 0; j < 2; ++j)
+                    umma_ss(d_tmem, make_sw64_desc(a_addr + j * 32), make_sw64_desc(b_addr + j * 32), idesc,
+                            (s > 0 || j > 0) ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    umma_ss(d_tmem, make_sw128_desc(a_addr + j * 32), make_sw128_desc(b_addr + j * 32), idesc,
+                            (s > 0 || j > 0) ? 1u : 0u);
+                }
+                umma_commit(&w_empty[st]);  // stage reusable once these MMAs have read it
+              }
+              __syncwarp();
+              if (++st == kStages) {
+                st = 0;
+                wph ^= 1;
+              }
+            }
+          }
+          if (lane == 0) umma_commit(&acc_full[slot]);  // accumulator of (l, slot) complete
+          __syncwarp();
+        }
+      }
+  } else {
+    // ============================ slot workers ============================
+    const int slot = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access == sample quarter
+    const int row = q * 32 + lane;
+    uint8_t* myA = sA + slot * kABytes;
+    uint8_t* myF = sF + slot * kFBytes;
+    const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
+    uint32_t ph_acc = 0;
+    for (int round = 0; round < rounds; ++round) {
+      const int64_t tile = ((int64_t)round * gridDim.x + blockIdx.x) * 2 + slot;
+      const bool valid = tile < p.num_rays;
+      const int64_t ray = valid ? tile : p.num_rays - 1;
+      // ---- conical-frustum Gaussian of sample `row` and its 96 IPE features -> feature tile
+      const RayGeom g = load_ray_geom(p.origins, p.directions, p.radii, ray);
+      const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+      float mean[3], cov[3];
+      {
+        float tm, tv, rv;
+        frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
+        lift_gaussian(g, tm, tv, rv, mean, cov);
+        if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
+      }
+      vb_s[slot * 128 + row] = __ldg(p.view_bias + ray * kCond + row);
+#pragma unroll
+      for (int gi = 0; gi < 6; ++gi) {
+        float fsin[8], fcos[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
+          ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
+        }
+        store8<kFmt>(myF + sw128_offset(row, gi * 8), fsin);  // K = f
+        if (gi < 2)
+          store8<kFmt>(myF + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
+        else
+          store8<kFmt>(myF + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();  // previous tile's TMEM reads are done before its accumulator is reused
+      mbar_arrive(&a_ready[slot]);
+
+      float dens = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+      for (int l = 0; l < kNumLayers; ++l) {
+        mbar_wait(&acc_full[slot], ph_acc);
+        ph_acc ^= 1;
+        tc_fence_after();
+        if (l < 9) {
+          // trunk / bottleneck epilogue: +bias, ReLU (trunk only), 16-bit pack -> next A operand
+#pragma unroll 1
+          for (int c0 = 0; c0 < kWidth; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + c0, v);
+            tmem_ld_wait();
+            uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = c0 + j * 8 + e;
+                float y = __uint_as_float(v[j * 8 + e]) + c_small.bias[l][c];
+                if (l < 8) y = fmaxf(y, 0.f);
+                if (l == 7) dens = fmaf(y, c_small.w_density[c], dens);  // density_layer on fp32 h7
+                x[e] = y;
+              }
+              store8<kFmt>(slab + sw128_offset(row, (c0 & 63) + j * 8), x);
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&a_ready[slot]);
+        } else {
+          // view layer epilogue + colour head (models/mip_nerf.py:108-110)
+#pragma unroll 1
+          for (int c0 = 0; c0 < kCond; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int c = c0 + e;
+              const float y = fmaxf(__uint_as_float(v[e]) + vb_s[slot * 128 + c], 0.f);
+              rgb0 = fmaf(y, c_small.w_color[0][c], rgb0);
+              rgb1 = fmaf(y, c_small.w_color[1][c], rgb1);
+              rgb2 = fmaf(y, c_small.w_color[2][c], rgb2);
+            }
+          }
+        }
+      }
+      // ---- activations + compositing over the ray's 128 samples (4 warps of this slot)
+      const float density = density_activation(dens + c_small.b_density, p.density_bias);
+      const float cr = rgb_activation(rgb0 + c_small.b_color[0], p.rgb_scale, p.rgb_padding);
+      const float cg = rgb_activation(rgb1 + c_small.b_color[1], p.rgb_scale, p.rgb_padding);
+      const float cb = rgb_activation(rgb2 + c_small.b_color[2], p.rgb_scale, p.rgb_padding);
+      const float dnorm = sqrtf(g.d[0] * g.d[0] + g.d[1] * g.d[1] + g.d[2] * g.d[2]);
+      const float dd = density * ((t1 - t0) * dnorm);
+      float incl = dd;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0.f;
+      if (lane == 31) cs[slot * 4 + q] = incl;
+      named_bar_sync(1 + slot, 128);
+      float before = 0.f;
+      for (int qq = 0; qq < q; ++qq) before += cs[slot * 4 + qq];
+      const float w = -expm1f(-dd) * expf(-(before + excl));
+      if (valid) p.weights[ray * kN + row] = w;
+      float pr = warp_sum(w * cr), pg = warp_sum(w * cg), pb = warp_sum(w * cb), pw = warp_sum(w),
+            pd = warp_sum(w * (0.5f * (t0 + t1)));
+      if (lane == 0) {
+        float* dst = ps + (slot * 4 + q) * 8;
+        dst[0] = pr, dst[1] = pg, dst[2] = pb, dst[3] = pw, dst[4] = pd;
+      }
+      named_bar_sync(1 + slot, 128);
+      if (row == 0 && valid) {
+        float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int qq = 0; qq < 4; ++qq)
+          for (int k = 0; k < 5; ++k) s[k] += ps[(slot * 4 + qq) * 8 + k];
+        const float t_first = __ldg(p.t + ray * (kN + 1)), t_last = __ldg(p.t + ray * (kN + 1) + kN);
+        float d = s[4];
+        if (isnan(d)) d = 0.f;
+        else if (isinf(d)) d = d > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        d = fminf(fmaxf(d, t_first), t_last);
+        const float bg = p.white_bkgd ? 1.0f - s[3] : 0.f;
+        p.comp_rgb[ray * 3 + 0] = s[0] + bg;
+        p.comp_rgb[ray * 3 + 1] = s[1] + bg;
+        p.comp_rgb[ray * 3 + 2] = s[2] + bg;
+        p.distance[ray] = d;
+        p.acc[ray] = s[3];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// view-direction term of the view layer as a per-ray bias: vb[r][n] = b[n] + W[n][256:283] . venc[r]
+__global__ void view_bias_kernel(const float* __restrict__ venc, const float* __restrict__ w,
+                                 const float* __restrict__ b, float* __restrict__ out, int64_t num_rays) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * kCond) return;
+  const int64_t ray = idx / kCond;
+  const int n = (int)(idx % kCond);
+  float acc = __ldg(b + n);
+  const float* wr = w + (size_t)n * (kWidth + kViewDim) + kWidth;
+  const float* v = venc + ray * kViewDim;
+#pragma unroll
+  for (int k = 0; k < kViewDim; ++k) acc = fmaf(__ldg(wr + k), __ldg(v + k), acc);
+  out[idx] = acc;
+}
+
+// ---- weight packing ---------------------------------------------------------------------------
+template <int kFmt>
+__global__ void pack_stage_kernel(const float* __restrict__ w, int in_features, int row0, int kbase, int kcount,
+                                  uint8_t* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * kcount) return;
+  const int i = idx / kcount, j = idx % kcount;
+  const float v = w[(size_t)(row0 + i) * in_features + kbase + j];
+  const uint32_t off = kcount == 64 ? sw128_offset(i, j) : sw64_offset(i, j);
+  *reinterpret_cast<uint16_t*>(dst + off) = to16<kFmt>(v);
+}
+
+struct SmallSrc {
+  const float* bias[9];
+  const float* w_density;
+  const float* b_density;
+  const float* w_color;
+  const float* b_color;
+};
+__global__ void pack_small_params_kernel(const SmallSrc src, SmallParams* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 9 * kWidth) out->bias[i / kWidth][i % kWidth] = src.bias[i / kWidth][i % kWidth];
+  if (i < kWidth) out->w_density[i] = src.w_density[i];
+  if (i < 3 * kCond) out->w_color[i / kCond][i % kCond] = src.w_color[i];
+  if (i == 0) out->b_density = src.b_density[0];
+  if (i < 3) out->b_color[i] = src.b_color[i];
+}
+
+struct TcScratch {
+  float *venc, *vbias, *t[2], *w[2];
+  size_t bytes;
+};
+constexpr int64_t kChunkRaysTc = 65536;
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+TcScratch carve_tc(int64_t rays, void* base) {
+  TcScratch s{};
+  size_t off = 0;
+  auto take = [&](size_t elems) {
+    float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+    off += align_up(elems * sizeof(float));
+    return p;
+  };
+  s.venc = take((size_t)rays * kViewDim);
+  s.vbias = take((size_t)rays * kCond);
+  for (int i = 0; i < 2; ++i) {
+    s.t[i] = take((size_t)rays * (kN + 1));
+    s.w[i] = take((size_t)rays * kN);
+  }
+  s.bytes = off;
+  return s;
+}
+
+int g_num_sms = 0;
+bool g_attr_set[2] = {false, false};
+
+template <int kFmt>
+cudaError_t launch_level(const LevelParams& p, cudaStream_t st) {
+  if (!g_attr_set[kFmt]) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_level_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemTotal);
+    if (e != cudaSuccess) return e;
+    g_attr_set[kFmt] = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  LevelParams q = p;
+  const int64_t pairs = (p.num_rays + 1) / 2;
+  const int grid = (int)(pairs < g_num_sms ? pairs : g_num_sms);
+  q.rounds = (int)((p.num_rays + 2 * (int64_t)grid - 1) / (2 * (int64_t)grid));
+  LaunchScope scope(kKernMlpLevelTc, st);
+  mlp_level_kernel<kFmt><<<grid, kThreads, kSmemTotal, st>>>(q);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tc_supported(const mipnerf_b200_config* c, int precision) {
+  return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16) && c->num_samples == kN &&
+         c->min_deg_point == 0 && c->max_deg_point == 16 && c->deg_view == 4 && c->use_viewdirs &&
+         c->net_depth == 8 && c->net_width == kWidth && c->net_depth_condition == 1 &&
+         c->net_width_condition == kCond && c->skip_index == 4 && c->num_rgb_channels == 3 &&
+         c->num_density_channels == 1;
+}
+bool tc_mlp_supported(const mipnerf_b200_config*, int, int) { return false; }
+
+size_t tc_packed_bytes(const mipnerf_b200_config* c, int precision) {
+  return tc_supported(c, precision) ? kImageBytes : 0;
+}
+
+size_t tc_workspace_bytes(const mipnerf_b200_config* c, int64_t num_rays, int precision) {
+  if (!tc_supported(c, precision)) return 0;
+  const int64_t r = num_rays < kChunkRaysTc ? num_rays : kChunkRaysTc;
+  return carve_tc(r > 0 ? r : 1, nullptr).bytes;
+}
+
+cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_weights* w, int precision,
+                            void* packed_out, cudaStream_t st) {
+  if (!tc_supported(c, precision)) return cudaErrorNotSupported;
+  uint8_t* img = static_cast<uint8_t*>(packed_out);
+  cudaError_t e = cudaMemsetAsync(img, 0, kImageBytes, st);
+  if (e != cudaSuccess) return e;
+  LaunchScope scope(kKernPackWeights, st);
+  for (int l = 0; l < kNumLayers; ++l) {
+    const int li = l < 8 ? l : (l == 8 ? 9 : 10);  // layers.l | extra_layer | view_layers.0
+    const mipnerf_b200_linear& lin = w->linears[li];
+    uint8_t* dst = img + layer_offset(l);
+    for (int h = 0; h < num_halves(l); ++h)
+      for (int s = 0; s < num_slabs(l); ++s) {
+        const bool tail = slab_is_tail(l, s);
+        const int kcount = tail ? 32 : 64;
+        int kbase = s * 64;
+        if (l == 5 && s >= 4) kbase = kWidth + (s - 4) * 64;  // [h | x] concat order (mip_nerf.py:96-97)
+        const int threads = 128 * kcount;
+        if (precision == MIPNERF_B200_BF16)
+          pack_stage_kernel<1><<<(threads + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, kbase,
+                                                                    kcount, dst);
+        else
+          pack_stage_kernel<0><<<(threads + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, kbase,
+                                                                    kcount, dst);
+        dst += tail ? kTailBytes : kStageBytes;
+      }
+  }
+  SmallSrc src;
+  for (int l = 0; l < 8; ++l) src.bias[l] = w->linears[l].bias;
+  src.bias[8] = w->linears[9].bias;  // extra_layer
+  src.w_density = w->linears[8].weight;
+  src.b_density = w->linears[8].bias;
+  src.w_color = w->linears[11].weight;
+  src.b_color = w->linears[11].bias;
+  pack_small_params_kernel<<<(9 * kWidth + 255) / 256, 256, 0, st>>>(src,
+                                                                      reinterpret_cast<SmallParams*>(img + kSmallOffset));
+  return cudaGetLastError();
+}
+
+cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights* w, const mipnerf_b200_rays* rays,
+                       int randomized, const float* t_rand, const float* u_jitter, int white_bkgd, int precision,
+                       mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const uint8_t* img = static_cast<const uint8_t*>(w->packed);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_small, img + kSmallOffset, sizeof(SmallParams), 0,
+                                          cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return e;
+  const mipnerf_b200_linear& view = w->linears[10];
+  const float rgb_scale = (float)(1.0 + 2.0 * (double)c->rgb_padding);
+  for (int64_t off = 0; off < rays->num_rays; off += kChunkRaysTc) {
+    const int64_t cnt = (rays->num_rays - off) < kChunkRaysTc ? (rays->num_rays - off) : kChunkRaysTc;
+    const TcScratch s = carve_tc(cnt, workspace);
+    if (s.bytes > workspace_bytes) return cudaErrorInvalidValue;
+    const float* origins = rays->origins + off * 3;
+    const float* directions = rays->directions + off * 3;
+    const float* radii = rays->radii + off;
+    if ((e = launch_pos_enc(rays->viewdirs + off * 3, s.venc, cnt, 0, c->deg_view, 1, st)) != cudaSuccess) return e;
+    {
+      LaunchScope scope(kKernPosEnc, st);
+      view_bias_kernel<<<(unsigned)((cnt * kCond + 255) / 256), 256, 0, st>>>(s.venc, view.weight, view.bias, s.vbias,
+                                                                              cnt);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    const float *t_prev = nullptr, *w_prev = nullptr;
+    for (int l = 0; l < c->num_levels; ++l) {
+      float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (kN + 1) : s.t[l & 1];
+      float* w_cur = outs[l].weights ? outs[l].weights + off * kN : s.w[l & 1];
+      if (l == 0)
+        e = launch_coarse_t(rays->near + off, rays->far + off, t_rand ? t_rand + off * (kN + 1) : nullptr, t_cur, cnt,
+                            kN, randomized, c->disparity, st);
+      else
+        e = launch_resample(t_prev, w_prev, u_jitter ? u_jitter + off * (kN + 1) : nullptr, t_cur,
+                            outs[l].inds ? outs[l].inds + off * (kN + 1) : nullptr, cnt, kN, kN + 1, randomized, 1,
+                            c->resample_padding, st);
+      if (e != cudaSuccess) return e;
+      LevelParams p{};
+      p.wimage = img;
+      p.origins = origins, p.directions = directions, p.radii = radii;
+      p.t = t_cur;
+      p.view_bias = s.vbias;
+      p.comp_rgb = outs[l].comp_rgb + off * 3;
+      p.distance = outs[l].distance + off;
+      p.acc = outs[l].acc + off;
+      p.weights = w_cur;
+      p.num_rays = cnt;
+      p.white_bkgd = white_bkgd;
+      p.disable_integration = c->disable_integration;
+      p.density_bias = c->density_bias, p.rgb_scale = rgb_scale, p.rgb_padding = c->rgb_padding;
+      e = precision == MIPNERF_B200_BF16 ? launch_level<1>(p, st) : launch_level<0>(p, st);
+      if (e != cudaSuccess) return e;
+      t_prev = t_cur;
+      w_prev = w_cur;
+    }
+  }
+  return cudaSuccess;
+}
+
+cudaError_t tc_mlp_forward(const mipnerf_b200_config*, const mipnerf_b200_weights*, const float*, const float*, int64_t,
+                           int, float*, float*, cudaStream_t) {
+  return cudaErrorNotSupported;
+}
+
+}  // namespace mipnerf

@@ -253,10 +253,34 @@ DEFAULT_CONFIG = dict(
     mlp_num_density_channels=1)
 
 
+def _mlp_forward_16bit(params, x, view_enc, net_depth, skip_index, prefix, dt):
+    """MLP.forward with the operand rounding of the tensor-core kernels emulated (fp32 accumulate):
+    trunk / bottleneck / view-layer GEMM operands (activations AND weights) rounded to `dt`;
+    density head, view-direction term and colour head stay fp32 — exactly the split documented in
+    mipnerf_pl_b200/csrc/mlp_tc.cu.  Test infrastructure for the bf16/fp16 modes only."""
+    def r(t):
+        return t.to(dt).to(torch.float32)
+    inputs = x
+    for i in range(net_depth):
+        x = F.relu(F.linear(r(x), r(params[f"{prefix}layers.{i}.0.weight"]), params[f"{prefix}layers.{i}.0.bias"]))
+        if i % skip_index == 0 and i > 0:
+            x = torch.cat([x, inputs], dim=-1)
+    raw_density = F.linear(x, params[f"{prefix}density_layer.weight"], params[f"{prefix}density_layer.bias"])
+    bott = F.linear(r(x), r(params[f"{prefix}extra_layer.weight"]), params[f"{prefix}extra_layer.bias"])
+    wv, bv = params[f"{prefix}view_layers.0.0.weight"], params[f"{prefix}view_layers.0.0.bias"]
+    k = bott.shape[-1]
+    v = F.relu(F.linear(r(bott), r(wv[:, :k])) + (F.linear(view_enc, wv[:, k:]) + bv)[:, None, :])
+    raw_rgb = F.linear(v, params[f"{prefix}color_layer.weight"], params[f"{prefix}color_layer.bias"])
+    return raw_rgb, raw_density
+
+
 def mlp_forward(params: Dict[str, torch.Tensor], x, view_enc, net_depth=8, skip_index=4,
-                net_depth_condition=1, prefix="mlp."):
+                net_depth_condition=1, prefix="mlp.", operand_dtype=None):
     """MLP.forward (models/mip_nerf.py:75-111) over a state_dict-style mapping
     with the reference's key names (``mlp.layers.{i}.0.weight`` ...)."""
+    if operand_dtype is not None:
+        assert view_enc is not None and net_depth_condition == 1
+        return _mlp_forward_16bit(params, x, view_enc, net_depth, skip_index, prefix, operand_dtype)
     inputs = x
     for i in range(net_depth):
         x = F.relu(F.linear(x, params[f"{prefix}layers.{i}.0.weight"], params[f"{prefix}layers.{i}.0.bias"]))
@@ -276,7 +300,7 @@ def mlp_forward(params: Dict[str, torch.Tensor], x, view_enc, net_depth=8, skip_
 
 def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white_bkgd: bool,
             config: Optional[dict] = None, t_rand=None, u_jitter=None,
-            return_debug=False) -> List[Tuple[torch.Tensor, ...]]:
+            return_debug=False, operand_dtype=None) -> List[Tuple[torch.Tensor, ...]]:
     """MipNerf.forward (models/mip_nerf.py:172-248): list over levels of
     (comp_rgb [B,3], distance [B], acc [B], weights [B,N], t_samples [B,N+1])."""
     cfg = dict(DEFAULT_CONFIG)
@@ -300,7 +324,8 @@ def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white
             enc = integrated_pos_enc(means, covs, cfg["min_deg_point"], cfg["max_deg_point"])
             view_enc = pos_enc(rays.viewdirs, 0, cfg["deg_view"], True) if cfg["use_viewdirs"] else None
             raw_rgb, raw_density = mlp_forward(params, enc, view_enc, cfg["mlp_net_depth"],
-                                               cfg["mlp_skip_index"], cfg["mlp_net_depth_condition"])
+                                               cfg["mlp_skip_index"], cfg["mlp_net_depth_condition"],
+                                               operand_dtype=operand_dtype)
             rgb = torch.sigmoid(raw_rgb) * (1 + 2 * cfg["rgb_padding"]) - cfg["rgb_padding"]
             density = F.softplus(raw_density + cfg["density_bias"])
             comp_rgb, distance, acc, weights = volumetric_rendering(rgb, density, t, rays.directions, white_bkgd)

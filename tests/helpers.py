@@ -19,10 +19,12 @@ from mipnerf_pl_b200.weights import make_state_dict  # noqa: E402
 # catastrophically for thin media (1 ulp of exp() near 1.0 is 6e-8, i.e. 6e-4 of an alpha of 1e-4), and
 # torch-CPU's exp is MKL's vsExp, which cannot be reproduced bit for bit.  test_reference_roundoff.py
 # measures that noise (reference fp32 vs the same formulas in float64) on the golden inputs:
-# ~6e-7 abs on comp_rgb/acc, ~3e-8 on individual weights; the floors grant 3-4x that.
-# (The kernels evaluate alpha as -expm1(-x), i.e. they sit next to the exact value.)
+# ~6e-7 abs on comp_rgb/acc; the floors grant 3-4x that.  (The kernels evaluate alpha as -expm1(-x),
+# i.e. they sit next to the exact value.)  Individual fine-level weights additionally trade mass
+# between neighbouring intervals when a resampled fencepost moves by an ulp (|dw| ~ sigma*T*|dt|), so
+# they are compared on their [0,1] probability scale: 1e-4 * max(|w|, 1e-2).
 RTOL = 1e-4
-FLOORS = {"comp_rgb": 0.02, "acc": 0.02, "distance": 0.2, "weights": 1e-3, "t_samples": 1e-2}
+FLOORS = {"comp_rgb": 0.02, "acc": 0.02, "distance": 0.2, "weights": 1e-2, "t_samples": 1e-2}
 
 
 def golden(name):

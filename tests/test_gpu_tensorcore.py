@@ -1,0 +1,98 @@
+"""The fused tcgen05 path (bf16 / fp16 operands, fp32 accumulate) on real hardware.
+
+Two oracles:
+  * the fp32 oracle (== the reference): measures what 16-bit operands cost; asserted against the
+    bounds SURVEY.md §7.3 predicts (bf16 ~4e-4 relative on RGB with xavier weights, fp16 ~8x better);
+  * the same oracle with the kernel's operand rounding emulated on the CPU: isolates kernel bugs
+    (layout, barriers, heads, compositing) from rounding — must agree ~10x tighter.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import FLOORS, assert_close, make_state_dict, oracle, oracle_rays, rel_err
+
+pytestmark = pytest.mark.gpu
+
+import mipnerf_pl_b200 as mp  # noqa: E402
+
+DEV = "cuda:0"
+DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def run(precision, kind, rays, seed=4, white=True):
+    model = mp.MipNerf(precision=precision)
+    model.load_state_dict(make_state_dict(seed=seed, kind=kind))
+    model = model.to(DEV).eval()
+    out = model(mp.namedtuple_map(lambda t: t.to(DEV), rays), False, white)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_tc_forward_vs_emulated_oracle(precision):
+    rays = mp.random_ray_batch(300, seed=21, multiscale=True)       # 300: ragged vs 2 rays/CTA
+    params = make_state_dict(seed=4, kind="xavier")
+    want = oracle.forward(params, oracle_rays(rays), False, True, operand_dtype=DT[precision])
+    got = run(precision, "xavier", rays)
+    tol = 2e-3 if precision == "bf16" else 4e-4
+    for lvl in range(2):
+        for k, name in enumerate(("comp_rgb", "distance", "acc", "weights", "t_samples")):
+            e = rel_err(got[lvl][k].cpu().numpy(), want[lvl][k].numpy(), FLOORS[name] * 10)
+            print(f"{precision} level {lvl} {name}: rel err vs emulated oracle {e:.3e}")
+            assert e <= tol, (precision, lvl, name, e)
+
+
+@pytest.mark.parametrize("precision,bound", [("bf16", 1e-3), ("fp16", 1e-4)])
+def test_tc_forward_vs_fp32_reference(precision, bound):
+    rays = mp.random_ray_batch(512, seed=22)
+    params = make_state_dict(seed=0, kind="xavier")
+    want = oracle.forward(params, oracle_rays(rays), False, True)
+    got = run(precision, "xavier", rays, seed=0)
+    for lvl in range(2):
+        err = float((got[lvl][0].cpu() - want[lvl][0]).abs().max())
+        rel = float(((got[lvl][0].cpu() - want[lvl][0]).abs() / want[lvl][0].abs().clamp_min(1e-2)).max())
+        print(f"{precision} level {lvl}: comp_rgb max abs err {err:.3e}, max rel err {rel:.3e} vs fp32 reference")
+        assert rel <= bound, (precision, lvl, rel)
+
+
+def test_tc_trained_like_and_black_background():
+    rays = mp.random_ray_batch(256, seed=23)
+    params = make_state_dict(seed=5, kind="trained_like")
+    want = oracle.forward(params, oracle_rays(rays), False, False, operand_dtype=torch.bfloat16)
+    got = run("bf16", "trained_like", rays, seed=5, white=False)
+    for lvl in range(2):
+        e = rel_err(got[lvl][0].cpu().numpy(), want[lvl][0].numpy(), 0.2)
+        print(f"trained_like level {lvl}: comp_rgb rel err vs emulated oracle {e:.3e}")
+        assert e <= 2e-2
+        assert torch.all(got[lvl][3] >= 0) and torch.all(got[lvl][2] <= 1 + 1e-4)
+
+
+def test_tc_batch_split_invariance_and_sizes():
+    model = mp.MipNerf(precision="bf16")
+    model.load_state_dict(make_state_dict(seed=1))
+    model = model.to(DEV).eval()
+    rays = mp.namedtuple_map(lambda t: t.to(DEV), mp.random_ray_batch(1000, seed=3))
+    full = model(rays, False, True)
+    a = model(mp.Rays(*[f[:333] for f in rays]), False, True)
+    b = model(mp.Rays(*[f[333:] for f in rays]), False, True)
+    for lvl in range(2):
+        for k in range(5):
+            assert torch.equal(torch.cat([a[lvl][k], b[lvl][k]]), full[lvl][k]), (lvl, k)
+    one = model(mp.Rays(*[f[:1] for f in rays]), False, True)
+    assert torch.equal(one[1][0], full[1][0][:1])
+    assert model(mp.Rays(*[f[:0] for f in rays]), False, True)[1][0].shape == (0, 3)
+
+
+def test_tc_full_batch_properties():
+    model = mp.MipNerf(precision="bf16")
+    model.load_state_dict(make_state_dict(seed=9, kind="trained_like"))
+    model = model.to(DEV).eval()
+    rays = mp.namedtuple_map(lambda t: t.to(DEV), mp.random_ray_batch(4096, seed=0))
+    white, black = model(rays, False, True), model(rays, False, False)
+    for lvl in range(2):
+        rgb_w, dist, acc, w, t = white[lvl]
+        assert torch.isfinite(rgb_w).all() and torch.all(w >= 0) and torch.all(acc <= 1 + 1e-4)
+        assert torch.all(t[:, 1:] >= t[:, :-1])
+        assert torch.allclose(rgb_w, black[lvl][0] + (1 - acc)[:, None], atol=1e-5)
+        assert torch.allclose(w.sum(-1), acc, atol=1e-4)
