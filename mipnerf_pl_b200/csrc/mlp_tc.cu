@@ -16,9 +16,17 @@
 //                 pack), density/colour heads on CUDA cores, 128-thread compositing scan.
 //   * layer-5 skip connection = extra K slabs read from the feature tile (no concat), the
 //     per-ray view-direction term of the view layer is a per-ray bias vector (pre-kernel).
+// CTA-pair mode (kPair, default): the grid is launched as 2-CTA clusters and the MMA is
+// tcgen05.mma.cta_group::2 (M=256: rays of both CTAs, N=256): each CTA stages only ITS half of every
+// weight tile (N rows rank*128..), so L2->SMEM weight traffic and SMEM operand reads per SM halve.
+// The leader CTA's warp 1 issues for the pair; the other CTA's warp 1 relays "my half has landed";
+// epilogue warps of both CTAs arrive on the leader's a_ready barrier (remote mbarrier arrive);
+// tcgen05.commit multicasts stage-free / accumulator-full to both CTAs.
 // A operand: 4 SW128 slabs (64 KB) per slot, overwritten in place layer after layer; features:
 // SW128 slab (K 0..63) + SW64 slab (K 64..95) per slot; weight ring: 3 x 16 KB.
 #include "mlp_tc.h"
+
+#include <cstdlib>
 
 #include "kernels.h"
 #include "profile.h"
@@ -73,8 +81,11 @@ __host__ __device__ constexpr uint32_t layer_offset(int l) {
   return o;
 }
 constexpr uint32_t kImageStageBytes = layer_offset(kNumLayers);
-constexpr size_t kImageBytes = ((size_t)kImageStageBytes + 255) / 256 * 256 + ((sizeof(SmallParams) + 255) / 256 * 256);
-constexpr size_t kSmallOffset = ((size_t)kImageStageBytes + 255) / 256 * 256;
+// pair mode splits the 128-wide view layer into two 64-row halves: 2 x 4 stages of [64 x 64] (8 KB)
+constexpr uint32_t kViewPairOffset = kImageStageBytes;
+constexpr uint32_t kViewPairStage = 8192;
+constexpr size_t kSmallOffset = ((size_t)kViewPairOffset + 2 * 4 * kViewPairStage + 255) / 256 * 256;
+constexpr size_t kImageBytes = kSmallOffset + ((sizeof(SmallParams) + 255) / 256 * 256);
 
 __host__ __device__ constexpr int num_slabs(int l) { return l == 0 ? 2 : (l == 5 ? 6 : 4); }
 __host__ __device__ constexpr int num_halves(int l) { return l == 9 ? 1 : 2; }
@@ -109,7 +120,7 @@ __device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
                                               pack2<kFmt>(x[4], x[5]), pack2<kFmt>(x[6], x[7]));
 }
 
-template <int kFmt>
+template <int kFmt, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -122,26 +133,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   uint64_t* w_empty = bars + 3;    // [kStages]  MMA -> producer   (tcgen05.commit)
   uint64_t* a_ready = bars + 6;    // [2]        workers -> MMA    (128 arrivals)
   uint64_t* acc_full = bars + 8;   // [2]        MMA -> workers    (tcgen05.commit)
+  uint64_t* w_peer = bars + 10;    // [kStages]  pair mode, leader: the peer CTA's half of the stage landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 128);
   float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 144);  // [2][128]
   float* cs = vb_s + 256;                                          // [2][4]   scan carries
   float* ps = cs + 8;                                              // [2][4][8] partial sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
+      mbar_init(&w_peer[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&a_ready[s], 128);
+      mbar_init(&a_ready[s], kPair ? 8 : 4);  // one arrive per worker warp (of both CTAs in pair mode)
       mbar_init(&acc_full[s], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) {
+    if (kPair) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int rounds = p.rounds;
@@ -153,13 +171,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       uint32_t ph = 0;
       for (int round = 0; round < rounds; ++round)
         for (int l = 0; l < kNumLayers; ++l) {
-          const uint8_t* lbase = p.wimage + layer_offset(l);
-          const int nh = num_halves(l), ns = num_slabs(l);
+          // pair mode: this CTA streams only half `rank` of the layer (64 rows for the view layer)
+          const uint8_t* lbase =
+              !kPair ? p.wimage + layer_offset(l)
+                     : (l == 9 ? p.wimage + kViewPairOffset + rank * 4 * kViewPairStage
+                               : p.wimage + layer_offset(l) + rank * (layer_bytes(l) / 2));
+          const int nh = kPair ? 1 : num_halves(l), ns = num_slabs(l);
           for (int slot = 0; slot < 2; ++slot) {
             const uint8_t* src = lbase;
             for (int h = 0; h < nh; ++h)
               for (int s = 0; s < ns; ++s) {
-                const uint32_t bytes = slab_is_tail(l, s) ? kTailBytes : kStageBytes;
+                const uint32_t bytes =
+                    (kPair && l == 9) ? kViewPairStage : (slab_is_tail(l, s) ? kTailBytes : kStageBytes);
                 mbar_wait(&w_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&w_full[st], bytes);
                 bulk_g2s(sW + st * kStageBytes, src, bytes, &w_full[st]);
@@ -174,27 +197,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    const uint32_t idesc = make_idesc_f16(128, 128, kFmt);
-    int st = 0;
-    uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
-    for (int round = 0; round < rounds; ++round)
-      for (int l = 0; l < kNumLayers; ++l) {
-        const int nh = num_halves(l), ns = num_slabs(l);
-        for (int slot = 0; slot < 2; ++slot) {
-          if (slot == 0) {
-            mbar_wait(&a_ready[0], ph_ready0);
-            ph_ready0 ^= 1;
-          } else {
-            mbar_wait(&a_ready[1], ph_ready1);
-            ph_ready1 ^= 1;
-          }
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + slot * kABytes);
-          const uint32_t f_base = smem_u32(sF + slot * kFBytes);
-          for (int h = 0; h < nh; ++h) {
-            const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
+    if (kPair && rank == 0) {
+      // leader of the CTA pair: one cta_group::2 MMA covers both CTAs' rays (M=256) and both N halves
+      const uint32_t idesc = make_idesc_f16(256, 256, kFmt);
+      const uint32_t idesc_view = make_idesc_f16(256, 128, kFmt);
+      int st = 0;
+      uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
+      for (int round = 0; round < rounds; ++round)
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int ns = num_slabs(l);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (slot == 0) {
+              mbar_wait_cluster(&a_ready[0], ph_ready0);
+              ph_ready0 ^= 1;
+            } else {
+              mbar_wait_cluster(&a_ready[1], ph_ready1);
+              ph_ready1 ^= 1;
+            }
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + slot * kABytes);
+            const uint32_t f_base = smem_u32(sF + slot * kFBytes);
+            const uint32_t d_tmem = tmem_base + slot * 256;
             for (int s = 0; s < ns; ++s) {
               mbar_wait(&w_full[st], wph);
+              mbar_wait_cluster(&w_peer[st], wph);
               tc_fence_after();
               const bool tail = slab_is_tail(l, s);
               const bool from_feat = (l == 0) || (l == 5 && s >= 4);
@@ -202,18 +228,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
               const uint32_t a_addr = from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
               const uint32_t b_addr = smem_u32(sW + st * kStageBytes);
               if (lane == 0) {
+                const uint32_t id = l == 9 ? idesc_view : idesc;
                 if (tail) {
 #pragma unroll
                   for (int j = 0; j < 2; ++j)
-                    umma_ss(d_tmem, make_sw64_desc(a_addr + j * 32), make_sw64_desc(b_addr + j * 32), idesc,
-                            (s > 0 || j > 0) ? 1u : 0u);
+                    umma_ss_pair(d_tmem, make_sw64_desc(a_addr + j * 32), make_sw64_desc(b_addr + j * 32), id,
+                                 (s > 0 || j > 0) ? 1u : 0u);
                 } else {
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
-                    umma_ss(d_tmem, make_sw128_desc(a_addr + j * 32), make_sw128_desc(b_addr + j * 32), idesc,
-                            (s > 0 || j > 0) ? 1u : 0u);
+                    umma_ss_pair(d_tmem, make_sw128_desc(a_addr + j * 32), make_sw128_desc(b_addr + j * 32), id,
+                                 (s > 0 || j > 0) ? 1u : 0u);
                 }
-                umma_commit(&w_empty[st]);  // stage reusable once these MMAs have read it
+                umma_commit_pair(&w_empty[st]);  // frees this stage in BOTH CTAs
               }
               __syncwarp();
               if (++st == kStages) {
@@ -221,11 +248,83 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                 wph ^= 1;
               }
             }
+            if (lane == 0) umma_commit_pair(&acc_full[slot]);
+            __syncwarp();
           }
-          if (lane == 0) umma_commit(&acc_full[slot]);  // accumulator of (l, slot) complete
-          __syncwarp();
         }
+    } else if (kPair) {
+      // non-leader CTA: relay "my half of stage st has landed" to the leader's w_peer barrier
+      if (lane == 0) {
+        int st = 0;
+        uint32_t wph = 0;
+        for (int round = 0; round < rounds; ++round)
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int ns = num_slabs(l);
+            for (int slot = 0; slot < 2; ++slot)
+              for (int s = 0; s < ns; ++s) {
+                mbar_wait(&w_full[st], wph);
+                mbar_arrive_cluster(mapa_u32(smem_u32(&w_peer[st]), 0));
+                if (++st == kStages) {
+                  st = 0;
+                  wph ^= 1;
+                }
+              }
+          }
       }
+    } else {
+      const uint32_t idesc = make_idesc_f16(128, 128, kFmt);
+      int st = 0;
+      uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
+      for (int round = 0; round < rounds; ++round)
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int nh = num_halves(l), ns = num_slabs(l);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (slot == 0) {
+              mbar_wait(&a_ready[0], ph_ready0);
+              ph_ready0 ^= 1;
+            } else {
+              mbar_wait(&a_ready[1], ph_ready1);
+              ph_ready1 ^= 1;
+            }
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + slot * kABytes);
+            const uint32_t f_base = smem_u32(sF + slot * kFBytes);
+            for (int h = 0; h < nh; ++h) {
+              const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
+              for (int s = 0; s < ns; ++s) {
+                mbar_wait(&w_full[st], wph);
+                tc_fence_after();
+                const bool tail = slab_is_tail(l, s);
+                const bool from_feat = (l == 0) || (l == 5 && s >= 4);
+                const int fs = (l == 0) ? s : s - 4;
+                const uint32_t a_addr = from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
+                const uint32_t b_addr = smem_u32(sW + st * kStageBytes);
+                if (lane == 0) {
+                  if (tail) {
+  #pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                      umma_ss(d_tmem, make_sw64_desc(a_addr + j * 32), make_sw64_desc(b_addr + j * 32), idesc,
+                              (s > 0 || j > 0) ? 1u : 0u);
+                  } else {
+  #pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      umma_ss(d_tmem, make_sw128_desc(a_addr + j * 32), make_sw128_desc(b_addr + j * 32), idesc,
+                              (s > 0 || j > 0) ? 1u : 0u);
+                  }
+                  umma_commit(&w_empty[st]);  // stage reusable once these MMAs have read it
+                }
+                __syncwarp();
+                if (++st == kStages) {
+                  st = 0;
+                  wph ^= 1;
+                }
+              }
+            }
+            if (lane == 0) umma_commit(&acc_full[slot]);  // accumulator of (l, slot) complete
+            __syncwarp();
+          }
+        }
+    }
   } else {
     // ============================ slot workers ============================
     const int slot = (warp - 2) >> 2;
@@ -235,8 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     uint8_t* myF = sF + slot * kFBytes;
     const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
     uint32_t ph_acc = 0;
+    const uint32_t a_ready_leader = kPair ? mapa_u32(smem_u32(&a_ready[slot]), 0) : 0u;
     for (int round = 0; round < rounds; ++round) {
-      const int64_t tile = ((int64_t)round * gridDim.x + blockIdx.x) * 2 + slot;
+      const int64_t tile = kPair ? ((((int64_t)round * (gridDim.x >> 1) + (blockIdx.x >> 1)) * 2 + slot) * 2 + rank)
+                                 : (((int64_t)round * gridDim.x + blockIdx.x) * 2 + slot);
       const bool valid = tile < p.num_rays;
       const int64_t ray = valid ? tile : p.num_rays - 1;
       // ---- conical-frustum Gaussian of sample `row` and its 96 IPE features -> feature tile
@@ -266,7 +367,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
       fence_proxy_async_smem();
       tc_fence_before();  // previous tile's TMEM reads are done before its accumulator is reused
-      mbar_arrive(&a_ready[slot]);
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(a_ready_leader);
+        else mbar_arrive(&a_ready[slot]);
+      }
 
       float dens = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
       for (int l = 0; l < kNumLayers; ++l) {
@@ -297,7 +402,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           }
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(&a_ready[slot]);
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair) mbar_arrive_cluster(a_ready_leader);
+            else mbar_arrive(&a_ready[slot]);
+          }
         } else {
           // view layer epilogue + colour head (models/mip_nerf.py:108-110)
 #pragma unroll 1
@@ -364,7 +473,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (kPair) cluster_sync_all();  // no CTA exits while its peer may still signal it
+  if (warp == 0) {
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // view-direction term of the view layer as a per-ray bias: vb[r][n] = b[n] + W[n][256:283] . venc[r]
@@ -385,9 +498,9 @@ __global__ void view_bias_kernel(const float* __restrict__ venc, const float* __
 // ---- weight packing ---------------------------------------------------------------------------
 template <int kFmt>
 __global__ void pack_stage_kernel(const float* __restrict__ w, int in_features, int row0, int kbase, int kcount,
-                                  uint8_t* __restrict__ dst) {
+                                  uint8_t* __restrict__ dst, int nrows) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 128 * kcount) return;
+  if (idx >= nrows * kcount) return;
   const int i = idx / kcount, j = idx % kcount;
   const float v = w[(size_t)(row0 + i) * in_features + kbase + j];
   const uint32_t off = kcount == 64 ? sw128_offset(i, j) : sw64_offset(i, j);
@@ -437,15 +550,15 @@ TcScratch carve_tc(int64_t rays, void* base) {
 }
 
 int g_num_sms = 0;
-bool g_attr_set[2] = {false, false};
+bool g_attr_set[2][2] = {{false, false}, {false, false}};
 
-template <int kFmt>
-cudaError_t launch_level(const LevelParams& p, cudaStream_t st) {
-  if (!g_attr_set[kFmt]) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_level_kernel<kFmt>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemTotal);
+template <int kFmt, bool kPair>
+cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
+  auto kern = mlp_level_kernel<kFmt, kPair>;
+  if (!g_attr_set[kFmt][kPair]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
     if (e != cudaSuccess) return e;
-    g_attr_set[kFmt] = true;
+    g_attr_set[kFmt][kPair] = true;
   }
   if (g_num_sms == 0) {
     int dev = 0;
@@ -453,12 +566,43 @@ cudaError_t launch_level(const LevelParams& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   LevelParams q = p;
+  LaunchScope scope(kKernMlpLevelTc, st);
+  if (kPair) {
+    const int64_t quads = (p.num_rays + 3) / 4;  // a CTA pair holds 4 rays (2 slots x 2 CTAs)
+    const int pairs = (int)(quads < g_num_sms / 2 ? quads : g_num_sms / 2);
+    q.rounds = (int)((p.num_rays + 4 * (int64_t)pairs - 1) / (4 * (int64_t)pairs));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, q);
+  }
   const int64_t pairs = (p.num_rays + 1) / 2;
   const int grid = (int)(pairs < g_num_sms ? pairs : g_num_sms);
   q.rounds = (int)((p.num_rays + 2 * (int64_t)grid - 1) / (2 * (int64_t)grid));
-  LaunchScope scope(kKernMlpLevelTc, st);
-  mlp_level_kernel<kFmt><<<grid, kThreads, kSmemTotal, st>>>(q);
+  kern<<<grid, kThreads, kSmemTotal, st>>>(q);
   return cudaGetLastError();
+}
+
+// MIPNERF_B200_TC_VARIANT=single selects the 1-CTA kernel (cta_group::1); default is the CTA pair.
+bool use_pair_variant() {
+  const char* v = getenv("MIPNERF_B200_TC_VARIANT");
+  return !(v && v[0] == 's');
+}
+
+cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
+  const bool pair = use_pair_variant();
+  if (precision == MIPNERF_B200_BF16)
+    return pair ? launch_level_t<1, true>(p, st) : launch_level_t<1, false>(p, st);
+  return pair ? launch_level_t<0, true>(p, st) : launch_level_t<0, false>(p, st);
 }
 
 }  // namespace
@@ -502,11 +646,25 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
         const int threads = 128 * kcount;
         if (precision == MIPNERF_B200_BF16)
           pack_stage_kernel<1><<<(threads + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, kbase,
-                                                                    kcount, dst);
+                                                                    kcount, dst, 128);
         else
           pack_stage_kernel<0><<<(threads + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, kbase,
-                                                                    kcount, dst);
+                                                                    kcount, dst, 128);
         dst += tail ? kTailBytes : kStageBytes;
+      }
+  }
+  {  // pair-mode view layer: two 64-row halves
+    const mipnerf_b200_linear& lin = w->linears[10];
+    uint8_t* dst = img + kViewPairOffset;
+    for (int r = 0; r < 2; ++r)
+      for (int s = 0; s < 4; ++s) {
+        if (precision == MIPNERF_B200_BF16)
+          pack_stage_kernel<1><<<(64 * 64 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 64, 64,
+                                                                     dst, 64);
+        else
+          pack_stage_kernel<0><<<(64 * 64 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 64, 64,
+                                                                     dst, 64);
+        dst += kViewPairStage;
       }
   }
   SmallSrc src;
@@ -569,7 +727,7 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
       p.white_bkgd = white_bkgd;
       p.disable_integration = c->disable_integration;
       p.density_bias = c->density_bias, p.rgb_scale = rgb_scale, p.rgb_padding = c->rgb_padding;
-      e = precision == MIPNERF_B200_BF16 ? launch_level<1>(p, st) : launch_level<0>(p, st);
+      e = launch_level(p, precision, st);
       if (e != cudaSuccess) return e;
       t_prev = t_cur;
       w_prev = w_cur;

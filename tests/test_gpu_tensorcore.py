@@ -20,6 +20,13 @@ DEV = "cuda:0"
 DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
 
+@pytest.fixture(autouse=True, params=["pair", "single"])
+def tc_variant(request, monkeypatch):
+    """Both kernel variants: the CTA-pair kernel (cta_group::2, default) and the 1-CTA kernel."""
+    monkeypatch.setenv("MIPNERF_B200_TC_VARIANT", request.param)
+    return request.param
+
+
 def run(precision, kind, rays, seed=4, white=True):
     model = mp.MipNerf(precision=precision)
     model.load_state_dict(make_state_dict(seed=seed, kind=kind))
