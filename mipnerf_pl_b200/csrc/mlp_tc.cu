@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&w_full[i], 1);
+      mbar_init(&w_full[i], (kPair && rank == 0) ? 2 : 1);  // leader: own producer + the peer's relay
       mbar_init(&w_empty[i], 1);
       mbar_init(&w_peer[i], 1);
     }
@@ -197,134 +197,96 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (kPair && rank == 0) {
-      // leader of the CTA pair: one cta_group::2 MMA covers both CTAs' rays (M=256) and both N halves
-      const uint32_t idesc = make_idesc_f16(256, 256, kFmt);
-      const uint32_t idesc_view = make_idesc_f16(256, 128, kFmt);
-      int st = 0;
-      uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
-      for (int round = 0; round < rounds; ++round)
-        for (int l = 0; l < kNumLayers; ++l) {
-          const int ns = num_slabs(l);
-          for (int slot = 0; slot < 2; ++slot) {
-            if (slot == 0) {
-              mbar_wait_cluster(&a_ready[0], ph_ready0);
-              ph_ready0 ^= 1;
-            } else {
-              mbar_wait_cluster(&a_ready[1], ph_ready1);
-              ph_ready1 ^= 1;
-            }
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + slot * kABytes);
-            const uint32_t f_base = smem_u32(sF + slot * kFBytes);
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            for (int s = 0; s < ns; ++s) {
-              mbar_wait(&w_full[st], wph);
-              mbar_wait_cluster(&w_peer[st], wph);
-              tc_fence_after();
-              const bool tail = slab_is_tail(l, s);
-              const bool from_feat = (l == 0) || (l == 5 && s >= 4);
-              const int fs = (l == 0) ? s : s - 4;
-              const uint32_t a_addr = from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
-              const uint32_t b_addr = smem_u32(sW + st * kStageBytes);
-              if (lane == 0) {
-                const uint32_t id = l == 9 ? idesc_view : idesc;
-                if (tail) {
-#pragma unroll
-                  for (int j = 0; j < 2; ++j)
-                    umma_ss_pair(d_tmem, make_sw64_desc(a_addr + j * 32), make_sw64_desc(b_addr + j * 32), id,
-                                 (s > 0 || j > 0) ? 1u : 0u);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    umma_ss_pair(d_tmem, make_sw128_desc(a_addr + j * 32), make_sw128_desc(b_addr + j * 32), id,
-                                 (s > 0 || j > 0) ? 1u : 0u);
-                }
-                umma_commit_pair(&w_empty[st]);  // frees this stage in BOTH CTAs
+    // One elected lane runs the whole role; every operand is derived from warp-uniform values
+    // (shuffled bases, loop counters) so the tcgen05 operands stay in uniform registers.
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA), 0);
+    const uint32_t sF_u = __shfl_sync(0xffffffffu, smem_u32(sF), 0);
+    const uint32_t sW_u = __shfl_sync(0xffffffffu, smem_u32(sW), 0);
+    const uint32_t bars_u = __shfl_sync(0xffffffffu, smem_u32(bars), 0);
+    const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
+    if (elect_one_sync()) {
+      if (!kPair || rank_u == 0) {
+        constexpr int kM = kPair ? 256 : 128;
+        constexpr int kNn = kPair ? 256 : 128;
+        const uint32_t idesc = make_idesc_f16(kM, kNn, kFmt);
+        const uint32_t idesc_view = make_idesc_f16(kM, 128, kFmt);
+        int st = 0;
+        uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
+        for (int round = 0; round < rounds; ++round)
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int nh = kPair ? 1 : num_halves(l), ns = num_slabs(l);
+            const uint32_t id = l == 9 ? idesc_view : idesc;
+            for (int slot = 0; slot < 2; ++slot) {
+              if (slot == 0) {
+                mbar_wait_fast(bars_u + 6 * 8, ph_ready0);
+                ph_ready0 ^= 1;
+              } else {
+                mbar_wait_fast(bars_u + 7 * 8, ph_ready1);
+                ph_ready1 ^= 1;
               }
-              __syncwarp();
+              tc_fence_after();
+              const uint32_t a_base = sA_u + slot * kABytes;
+              const uint32_t f_base = sF_u + slot * kFBytes;
+              for (int h = 0; h < nh; ++h) {
+                const uint32_t d_tmem = tm_u + slot * 256 + h * 128;
+                for (int s = 0; s < ns; ++s) {
+                  mbar_wait_fast(bars_u + st * 8, wph);  // w_full[st] (pair: both halves landed)
+                  tc_fence_after();
+                  const bool tail = slab_is_tail(l, s);
+                  const bool from_feat = (l == 0) || (l == 5 && s >= 4);
+                  const int fs = (l == 0) ? s : s - 4;
+                  const uint32_t a_addr =
+                      from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
+                  const uint32_t b_addr = sW_u + st * kStageBytes;
+                  if (tail) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      const uint64_t ad = make_sw64_desc(a_addr + j * 32), bd = make_sw64_desc(b_addr + j * 32);
+                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const uint64_t ad = make_sw128_desc(a_addr + j * 32), bd = make_sw128_desc(b_addr + j * 32);
+                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                    }
+                  }
+                  // stage reusable (in both CTAs) once these MMAs have read it
+                  if (kPair) umma_commit_pair(&w_empty[st]);
+                  else umma_commit(&w_empty[st]);
+                  if (++st == kStages) {
+                    st = 0;
+                    wph ^= 1;
+                  }
+                }
+              }
+              if (kPair) umma_commit_pair(&acc_full[slot]);  // accumulator of (l, slot) complete
+              else umma_commit(&acc_full[slot]);
+            }
+          }
+      } else {
+        // pair mode, non-leader CTA: relay "my half of stage st has landed" to the leader's w_full[st]
+        int st = 0;
+        uint32_t wph = 0;
+        const uint32_t leader_w_full = mapa_u32(bars_u, 0);
+        for (int round = 0; round < rounds; ++round)
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int ns = num_slabs(l);
+            for (int k = 0; k < 2 * ns; ++k) {
+              mbar_wait_fast(bars_u + st * 8, wph);
+              mbar_arrive_remote(leader_w_full + st * 8);
               if (++st == kStages) {
                 st = 0;
                 wph ^= 1;
               }
             }
-            if (lane == 0) umma_commit_pair(&acc_full[slot]);
-            __syncwarp();
-          }
-        }
-    } else if (kPair) {
-      // non-leader CTA: relay "my half of stage st has landed" to the leader's w_peer barrier
-      if (lane == 0) {
-        int st = 0;
-        uint32_t wph = 0;
-        for (int round = 0; round < rounds; ++round)
-          for (int l = 0; l < kNumLayers; ++l) {
-            const int ns = num_slabs(l);
-            for (int slot = 0; slot < 2; ++slot)
-              for (int s = 0; s < ns; ++s) {
-                mbar_wait(&w_full[st], wph);
-                mbar_arrive_cluster(mapa_u32(smem_u32(&w_peer[st]), 0));
-                if (++st == kStages) {
-                  st = 0;
-                  wph ^= 1;
-                }
-              }
           }
       }
-    } else {
-      const uint32_t idesc = make_idesc_f16(128, 128, kFmt);
-      int st = 0;
-      uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
-      for (int round = 0; round < rounds; ++round)
-        for (int l = 0; l < kNumLayers; ++l) {
-          const int nh = num_halves(l), ns = num_slabs(l);
-          for (int slot = 0; slot < 2; ++slot) {
-            if (slot == 0) {
-              mbar_wait(&a_ready[0], ph_ready0);
-              ph_ready0 ^= 1;
-            } else {
-              mbar_wait(&a_ready[1], ph_ready1);
-              ph_ready1 ^= 1;
-            }
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + slot * kABytes);
-            const uint32_t f_base = smem_u32(sF + slot * kFBytes);
-            for (int h = 0; h < nh; ++h) {
-              const uint32_t d_tmem = tmem_base + slot * 256 + h * 128;
-              for (int s = 0; s < ns; ++s) {
-                mbar_wait(&w_full[st], wph);
-                tc_fence_after();
-                const bool tail = slab_is_tail(l, s);
-                const bool from_feat = (l == 0) || (l == 5 && s >= 4);
-                const int fs = (l == 0) ? s : s - 4;
-                const uint32_t a_addr = from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
-                const uint32_t b_addr = smem_u32(sW + st * kStageBytes);
-                if (lane == 0) {
-                  if (tail) {
-  #pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                      umma_ss(d_tmem, make_sw64_desc(a_addr + j * 32), make_sw64_desc(b_addr + j * 32), idesc,
-                              (s > 0 || j > 0) ? 1u : 0u);
-                  } else {
-  #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      umma_ss(d_tmem, make_sw128_desc(a_addr + j * 32), make_sw128_desc(b_addr + j * 32), idesc,
-                              (s > 0 || j > 0) ? 1u : 0u);
-                  }
-                  umma_commit(&w_empty[st]);  // stage reusable once these MMAs have read it
-                }
-                __syncwarp();
-                if (++st == kStages) {
-                  st = 0;
-                  wph ^= 1;
-                }
-              }
-            }
-            if (lane == 0) umma_commit(&acc_full[slot]);  // accumulator of (l, slot) complete
-            __syncwarp();
-          }
-        }
     }
+    __syncwarp();
   } else {
     // ============================ slot workers ============================
     const int slot = (warp - 2) >> 2;
@@ -369,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       tc_fence_before();  // previous tile's TMEM reads are done before its accumulator is reused
       __syncwarp();
       if (lane == 0) {
-        if (kPair) mbar_arrive_cluster(a_ready_leader);
+        if (kPair) mbar_arrive_remote(a_ready_leader);
         else mbar_arrive(&a_ready[slot]);
       }
 
@@ -384,6 +346,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           for (int c0 = 0; c0 < kWidth; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(t_acc + c0, v);
+            float bv[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) bv[e] = c_small.bias[l][c0 + e];  // LDCs overlap the TMEM load
             tmem_ld_wait();
             uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
 #pragma unroll
@@ -392,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int c = c0 + j * 8 + e;
-                float y = __uint_as_float(v[j * 8 + e]) + c_small.bias[l][c];
+                float y = __uint_as_float(v[j * 8 + e]) + bv[j * 8 + e];
                 if (l < 8) y = fmaxf(y, 0.f);
                 if (l == 7) dens = fmaf(y, c_small.w_density[c], dens);  // density_layer on fp32 h7
                 x[e] = y;
@@ -404,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (kPair) mbar_arrive_cluster(a_ready_leader);
+            if (kPair) mbar_arrive_remote(a_ready_leader);
             else mbar_arrive(&a_ready[slot]);
           }
         } else {

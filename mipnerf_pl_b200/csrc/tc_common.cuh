@@ -177,6 +177,34 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp (the compiler keeps uniform-datapath operands uniform under it)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// lean wait for single-thread roles (no spin counter in the hot loop; the kernel-level watchdog is
+// the bounded waits of the worker warps)
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar_addr),
+      "r"(parity)
+      : "memory");
+}
+// remote arrive with the default (release, cta-scope) semantics CUTLASS uses for pair barriers
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 // ---- CTA-pair (cta_group::2) and cluster-scope variants ---------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
