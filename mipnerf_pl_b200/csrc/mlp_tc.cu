@@ -44,15 +44,14 @@ constexpr int kCond = 128;      // view layer width
 constexpr int kFeat = 96;       // IPE width
 constexpr int kViewDim = 27;
 constexpr int kNumLayers = 10;  // 8 trunk + extra_layer + view layer
+constexpr int kNumGroups = 11;  // MMA groups per tile: layer 5 is split into its h-part and its skip part
 constexpr int kThreads = 320;
-constexpr int kStages = 3;
+constexpr int kStages = 6;
 constexpr uint32_t kStageBytes = 16384;  // [128 x 64] 16-bit, SW128
 constexpr uint32_t kTailBytes = 8192;    // [128 x 32] 16-bit, SW64
 constexpr uint32_t kABytes = 65536;      // 4 slabs
-constexpr uint32_t kFBytes = kStageBytes + kTailBytes;
 constexpr uint32_t kSmemA = 0;
-constexpr uint32_t kSmemF = kSmemA + 2 * kABytes;
-constexpr uint32_t kSmemW = kSmemF + 2 * kFBytes;
+constexpr uint32_t kSmemW = kSmemA + 2 * kABytes;
 constexpr uint32_t kSmemMisc = kSmemW + kStages * kStageBytes;
 constexpr uint32_t kMiscBytes = 128 + 16 + 2 * 128 * 4 + 8 * 4 + 2 * 4 * 8 * 4;
 constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // + slack for 1024-B alignment
@@ -92,6 +91,19 @@ __host__ __device__ constexpr int num_halves(int l) { return l == 9 ? 1 : 2; }
 // slab s of layer l: is it the 32-wide SW64 tail?
 __host__ __device__ constexpr bool slab_is_tail(int l, int s) { return (l == 0 && s == 1) || (l == 5 && s == 5); }
 
+// MMA groups of one tile, in issue order.  Group 5 = layer 5 over h4 (K 0..255), group 6 = layer 5 over
+// the re-computed IPE features (K 256..351, accumulating onto group 5): the skip connection without
+// a resident feature buffer.
+__host__ __device__ constexpr int group_layer(int g) { return g < 6 ? g : g - 1; }
+__host__ __device__ constexpr int group_slab_begin(int g) { return g == 6 ? 4 : 0; }
+__host__ __device__ constexpr int group_slab_end(int g) { return g == 0 ? 2 : (g == 6 ? 6 : 4); }
+__host__ __device__ constexpr uint32_t slab_bytes(int l, int s) { return slab_is_tail(l, s) ? kTailBytes : kStageBytes; }
+__host__ __device__ constexpr uint32_t slab_offset(int l, int s) {
+  uint32_t o = 0;
+  for (int i = 0; i < s; ++i) o += slab_bytes(l, i);
+  return o;
+}
+
 struct LevelParams {
   const uint8_t* wimage;
   const float* origins;
@@ -121,19 +133,17 @@ __device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
 }
 
 template <int kFmt, bool kPair>
-__global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
+__global__ void __maxnreg__(200) mlp_level_kernel(const LevelParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem + kSmemA;
-  uint8_t* sF = smem + kSmemF;
   uint8_t* sW = smem + kSmemW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemMisc);
-  uint64_t* w_full = bars;         // [kStages]  producer -> MMA   (tx bytes)
-  uint64_t* w_empty = bars + 3;    // [kStages]  MMA -> producer   (tcgen05.commit)
-  uint64_t* a_ready = bars + 6;    // [2]        workers -> MMA    (128 arrivals)
-  uint64_t* acc_full = bars + 8;   // [2]        MMA -> workers    (tcgen05.commit)
-  uint64_t* w_peer = bars + 10;    // [kStages]  pair mode, leader: the peer CTA's half of the stage landed
+  uint64_t* w_full = bars;                   // [kStages]  producer (+ peer relay) -> MMA   (tx bytes)
+  uint64_t* w_empty = bars + kStages;        // [kStages]  MMA -> producer   (tcgen05.commit)
+  uint64_t* a_ready = bars + 2 * kStages;    // [2]        worker warps -> MMA
+  uint64_t* acc_full = bars + 2 * kStages + 2;  // [2]     MMA -> workers    (tcgen05.commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 128);
   float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 144);  // [2][128]
   float* cs = vb_s + 256;                                          // [2][4]   scan carries
@@ -145,7 +155,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&w_full[i], (kPair && rank == 0) ? 2 : 1);  // leader: own producer + the peer's relay
       mbar_init(&w_empty[i], 1);
-      mbar_init(&w_peer[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_ready[s], kPair ? 8 : 4);  // one arrive per worker warp (of both CTAs in pair mode)
@@ -170,29 +179,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       int st = 0;
       uint32_t ph = 0;
       for (int round = 0; round < rounds; ++round)
-        for (int l = 0; l < kNumLayers; ++l) {
-          // pair mode: this CTA streams only half `rank` of the layer (64 rows for the view layer)
-          const uint8_t* lbase =
-              !kPair ? p.wimage + layer_offset(l)
-                     : (l == 9 ? p.wimage + kViewPairOffset + rank * 4 * kViewPairStage
-                               : p.wimage + layer_offset(l) + rank * (layer_bytes(l) / 2));
-          const int nh = kPair ? 1 : num_halves(l), ns = num_slabs(l);
-          for (int slot = 0; slot < 2; ++slot) {
-            const uint8_t* src = lbase;
-            for (int h = 0; h < nh; ++h)
-              for (int s = 0; s < ns; ++s) {
-                const uint32_t bytes =
-                    (kPair && l == 9) ? kViewPairStage : (slab_is_tail(l, s) ? kTailBytes : kStageBytes);
+        for (int g = 0; g < kNumGroups; ++g) {
+          const int l = group_layer(g);
+          const int s0 = group_slab_begin(g), s1 = group_slab_end(g);
+          const int nh = kPair ? 1 : num_halves(l);
+          for (int slot = 0; slot < 2; ++slot)
+            for (int h = 0; h < nh; ++h) {
+              // pair mode: this CTA streams only half `rank` of the layer (64 rows for the view layer)
+              const uint8_t* hbase =
+                  (kPair && l == 9) ? p.wimage + kViewPairOffset + rank * 4 * kViewPairStage
+                                    : p.wimage + layer_offset(l) + (kPair ? rank : (uint32_t)h) * (layer_bytes(l) / 2);
+              for (int s = s0; s < s1; ++s) {
+                const uint32_t bytes = (kPair && l == 9) ? kViewPairStage : slab_bytes(l, s);
+                const uint8_t* src = hbase + ((kPair && l == 9) ? s * kViewPairStage : slab_offset(l, s));
                 mbar_wait(&w_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&w_full[st], bytes);
                 bulk_g2s(sW + st * kStageBytes, src, bytes, &w_full[st]);
-                src += bytes;
                 if (++st == kStages) {
                   st = 0;
                   ph ^= 1;
                 }
               }
-          }
+            }
         }
     }
   } else if (warp == 1) {
@@ -201,7 +209,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     // (shuffled bases, loop counters) so the tcgen05 operands stay in uniform registers.
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA), 0);
-    const uint32_t sF_u = __shfl_sync(0xffffffffu, smem_u32(sF), 0);
     const uint32_t sW_u = __shfl_sync(0xffffffffu, smem_u32(sW), 0);
     const uint32_t bars_u = __shfl_sync(0xffffffffu, smem_u32(bars), 0);
     const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
@@ -214,44 +221,45 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         int st = 0;
         uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
         for (int round = 0; round < rounds; ++round)
-          for (int l = 0; l < kNumLayers; ++l) {
-            const int nh = kPair ? 1 : num_halves(l), ns = num_slabs(l);
+          for (int g = 0; g < kNumGroups; ++g) {
+            const int l = group_layer(g);
+            const int s0 = group_slab_begin(g), s1 = group_slab_end(g);
+            const int nh = kPair ? 1 : num_halves(l);
             const uint32_t id = l == 9 ? idesc_view : idesc;
             for (int slot = 0; slot < 2; ++slot) {
               if (slot == 0) {
-                mbar_wait_fast(bars_u + 6 * 8, ph_ready0);
+                mbar_wait_fast(bars_u + (2 * kStages) * 8, ph_ready0);
                 ph_ready0 ^= 1;
               } else {
-                mbar_wait_fast(bars_u + 7 * 8, ph_ready1);
+                mbar_wait_fast(bars_u + (2 * kStages + 1) * 8, ph_ready1);
                 ph_ready1 ^= 1;
               }
               tc_fence_after();
               const uint32_t a_base = sA_u + slot * kABytes;
-              const uint32_t f_base = sF_u + slot * kFBytes;
               for (int h = 0; h < nh; ++h) {
                 const uint32_t d_tmem = tm_u + slot * 256 + h * 128;
-                for (int s = 0; s < ns; ++s) {
+                for (int s = s0; s < s1; ++s) {
                   mbar_wait_fast(bars_u + st * 8, wph);  // w_full[st] (pair: both halves landed)
                   tc_fence_after();
                   const bool tail = slab_is_tail(l, s);
-                  const bool from_feat = (l == 0) || (l == 5 && s >= 4);
-                  const int fs = (l == 0) ? s : s - 4;
-                  const uint32_t a_addr =
-                      from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
+                  // feature slabs (layer 0, and the skip part of layer 5) sit in A slabs 0 / 1
+                  const int as = (l == 5 && s >= 4) ? s - 4 : s;
+                  const uint32_t a_addr = a_base + as * kStageBytes;
                   const uint32_t b_addr = sW_u + st * kStageBytes;
+                  const bool first = (s == 0);  // group 6 (s starts at 4) accumulates onto group 5
                   if (tail) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       const uint64_t ad = make_sw64_desc(a_addr + j * 32), bd = make_sw64_desc(b_addr + j * 32);
-                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
-                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
+                      else umma_ss(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
                     }
                   } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const uint64_t ad = make_sw128_desc(a_addr + j * 32), bd = make_sw128_desc(b_addr + j * 32);
-                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
-                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
+                      else umma_ss(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
                     }
                   }
                   // stage reusable (in both CTAs) once these MMAs have read it
@@ -273,8 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         uint32_t wph = 0;
         const uint32_t leader_w_full = mapa_u32(bars_u, 0);
         for (int round = 0; round < rounds; ++round)
-          for (int l = 0; l < kNumLayers; ++l) {
-            const int ns = num_slabs(l);
+          for (int g = 0; g < kNumGroups; ++g) {
+            const int ns = group_slab_end(g) - group_slab_begin(g);
             for (int k = 0; k < 2 * ns; ++k) {
               mbar_wait_fast(bars_u + st * 8, wph);
               mbar_arrive_remote(leader_w_full + st * 8);
@@ -293,7 +301,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     const int q = warp & 3;  // TMEM lane quarter this warp may access == sample quarter
     const int row = q * 32 + lane;
     uint8_t* myA = sA + slot * kABytes;
-    uint8_t* myF = sF + slot * kFBytes;
     const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
     uint32_t ph_acc = 0;
     const uint32_t a_ready_leader = kPair ? mapa_u32(smem_u32(&a_ready[slot]), 0) : 0u;
@@ -303,30 +310,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       const bool valid = tile < p.num_rays;
       const int64_t ray = valid ? tile : p.num_rays - 1;
       // ---- conical-frustum Gaussian of sample `row` and its 96 IPE features -> feature tile
-      const RayGeom g = load_ray_geom(p.origins, p.directions, p.radii, ray);
       const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
-      float mean[3], cov[3];
+      float mean[3], cov[3], dnorm;
       {
+        const RayGeom g = load_ray_geom(p.origins, p.directions, p.radii, ray);
         float tm, tv, rv;
         frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
         lift_gaussian(g, tm, tv, rv, mean, cov);
         if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
+        dnorm = sqrtf(g.d[0] * g.d[0] + g.d[1] * g.d[1] + g.d[2] * g.d[2]);
       }
       vb_s[slot * 128 + row] = __ldg(p.view_bias + ray * kCond + row);
+      // 96 IPE features -> A slabs 0 (K 0..63, SW128) and 1 (K 64..95, SW64); cheap enough (MUFU,
+      // underflowed degrees skipped) to be re-run for the skip connection instead of being kept resident
+      auto write_features = [&]() {
 #pragma unroll
-      for (int gi = 0; gi < 6; ++gi) {
-        float fsin[8], fcos[8];
+        for (int gi = 0; gi < 6; ++gi) {
+          float fsin[8], fcos[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
-          ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
+          for (int e = 0; e < 8; ++e) {
+            const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
+            ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
+          }
+          store8<kFmt>(myA + sw128_offset(row, gi * 8), fsin);  // K = f
+          if (gi < 2)
+            store8<kFmt>(myA + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
+          else
+            store8<kFmt>(myA + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
         }
-        store8<kFmt>(myF + sw128_offset(row, gi * 8), fsin);  // K = f
-        if (gi < 2)
-          store8<kFmt>(myF + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
-        else
-          store8<kFmt>(myF + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
-      }
+      };
+      write_features();
       fence_proxy_async_smem();
       tc_fence_before();  // previous tile's TMEM reads are done before its accumulator is reused
       __syncwarp();
@@ -336,11 +349,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
 
       float dens = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-      for (int l = 0; l < kNumLayers; ++l) {
+      for (int g = 0; g < kNumGroups; ++g) {
+        const int l = group_layer(g);
         mbar_wait(&acc_full[slot], ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
-        if (l < 9) {
+        if (g == 5) {
+          // layer 5, h-part done reading A: re-create the features there for the skip part
+          write_features();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (kPair) mbar_arrive_remote(a_ready_leader);
+            else mbar_arrive(&a_ready[slot]);
+          }
+        } else if (l < 9) {
           // trunk / bottleneck epilogue: +bias, ReLU (trunk only), 16-bit pack -> next A operand
 #pragma unroll 1
           for (int c0 = 0; c0 < kWidth; c0 += 32) {
@@ -395,7 +418,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       const float cr = rgb_activation(rgb0 + c_small.b_color[0], p.rgb_scale, p.rgb_padding);
       const float cg = rgb_activation(rgb1 + c_small.b_color[1], p.rgb_scale, p.rgb_padding);
       const float cb = rgb_activation(rgb2 + c_small.b_color[2], p.rgb_scale, p.rgb_padding);
-      const float dnorm = sqrtf(g.d[0] * g.d[0] + g.d[1] * g.d[1] + g.d[2] * g.d[2]);
       const float dd = density * ((t1 - t0) * dnorm);
       float incl = dd;
 #pragma unroll
