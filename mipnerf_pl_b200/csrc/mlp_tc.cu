@@ -133,7 +133,7 @@ __device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
 }
 
 template <int kFmt, bool kPair>
-__global__ void __maxnreg__(200) mlp_level_kernel(const LevelParams p) {
+__global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -369,9 +369,9 @@ __global__ void __maxnreg__(200) mlp_level_kernel(const LevelParams p) {
           for (int c0 = 0; c0 < kWidth; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(t_acc + c0, v);
-            float bv[32];
+            float bv[16];  // first half of the biases: LDCs overlap the TMEM load
 #pragma unroll
-            for (int e = 0; e < 32; ++e) bv[e] = c_small.bias[l][c0 + e];  // LDCs overlap the TMEM load
+            for (int e = 0; e < 16; ++e) bv[e] = c_small.bias[l][c0 + e];
             tmem_ld_wait();
             uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
 #pragma unroll
@@ -380,7 +380,7 @@ __global__ void __maxnreg__(200) mlp_level_kernel(const LevelParams p) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int c = c0 + j * 8 + e;
-                float y = __uint_as_float(v[j * 8 + e]) + bv[j * 8 + e];
+                float y = __uint_as_float(v[j * 8 + e]) + (j < 2 ? bv[j * 8 + e] : c_small.bias[l][c]);
                 if (l < 8) y = fmaxf(y, 0.f);
                 if (l == 7) dens = fmaf(y, c_small.w_density[c], dens);  // density_layer on fp32 h7
                 x[e] = y;

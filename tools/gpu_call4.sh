@@ -9,4 +9,4 @@ except Exception as e: print('bench failed', e); print(open('gpurun_out/bench_bf
 PY
 echo "== bench bf16 single"; MIPNERF_B200_TC_VARIANT=single timeout 300 python bench.py --steps 20 --warmup 5 --precision bf16 --no-cpu-baseline > gpurun_out/bench_bf16_single.json 2>/dev/null; python -c "
 import json; d=json.load(open('gpurun_out/bench_bf16_single.json')); print(d['value'], d['roofline']['frac'])"
-echo "== pytest parity"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu4.txt
+echo "== pytest parity"; timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -40 | tee gpurun_out/pytest_gpu4.txt | grep -E "Error|passed|failed" 
