@@ -12,7 +12,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmipnerf_b200.so"
-LIB_PATH = os.path.join(_HERE, LIB_NAME)
+LIB_PATH = os.environ.get("MIPNERF_B200_LIB") or os.path.join(_HERE, LIB_NAME)  # env: experiment builds
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
 FP32, BF16, FP16 = 0, 1, 2

@@ -29,7 +29,14 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """variant != "": an experiment build `libmipnerf_b200.<variant>.so` compiled with extra -D flags
+    (selected at run time with MIPNERF_B200_LIB=<path>)."""
+    global OBJ, OUT
+    if variant:
+        OBJ = os.path.join(HERE, "build", variant)
+        OUT = os.path.join(HERE, f"libmipnerf_b200.{variant}.so")
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(HERE, "..", "include", "mipnerf_b200.h"))
@@ -39,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+                        ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,4 +66,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = ""
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    if "--variant" in sys.argv:
+        var = sys.argv[sys.argv.index("--variant") + 1]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, defines=defs))

@@ -46,7 +46,10 @@ constexpr int kViewDim = 27;
 constexpr int kNumLayers = 10;  // 8 trunk + extra_layer + view layer
 constexpr int kNumGroups = 11;  // MMA groups per tile: layer 5 is split into its h-part and its skip part
 constexpr int kThreads = 320;
-constexpr int kStages = 6;
+#ifndef MIPNERF_TC_STAGES
+#define MIPNERF_TC_STAGES 6
+#endif
+constexpr int kStages = MIPNERF_TC_STAGES;
 constexpr uint32_t kStageBytes = 16384;  // [128 x 64] 16-bit, SW128
 constexpr uint32_t kTailBytes = 8192;    // [128 x 32] 16-bit, SW64
 constexpr uint32_t kABytes = 65536;      // 4 slabs
@@ -130,6 +133,64 @@ template <int kFmt>
 __device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
   *reinterpret_cast<uint4*>(dst) = make_uint4(pack2<kFmt>(x[0], x[1]), pack2<kFmt>(x[2], x[3]),
                                               pack2<kFmt>(x[4], x[5]), pack2<kFmt>(x[6], x[7]));
+}
+
+// Epilogue of trunk layer / bottleneck L (compile-time so that every bias is an immediate
+// constant-bank operand): TMEM accumulator row -> +bias -> ReLU (L < 8) -> 16-bit -> A operand
+// slabs, software-pipelined over 32-column TMEM loads.  L == 7 also accumulates the density head.
+template <int kFmt, int L>
+__device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int row, float& dens) {
+  uint32_t v[2][32];
+  tmem_ld32(t_acc, v[0]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    tmem_ld_wait();  // chunk k has landed
+    if (k < 7) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) & 1]);  // next chunk in flight while we work
+    const int c0 = 32 * k;
+    uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + j * 8 + 2 * e;
+        const float a = __uint_as_float(v[k & 1][j * 8 + 2 * e]) + c_small.bias[L][c];
+        const float b = __uint_as_float(v[k & 1][j * 8 + 2 * e + 1]) + c_small.bias[L][c + 1];
+        if (L == 7) {  // density_layer on the fp32 (un-rounded) h7        (models/mip_nerf.py:98)
+          dens = fmaf(fmaxf(a, 0.f), c_small.w_density[c], dens);
+          dens = fmaf(fmaxf(b, 0.f), c_small.w_density[c + 1], dens);
+        }
+        w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
+      }
+      *reinterpret_cast<uint4*>(slab + sw128_offset(row, (c0 & 63) + j * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// view layer epilogue + colour head (models/mip_nerf.py:108-110); vb = per-ray view-direction bias
+template <int kFmt>
+__device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __restrict__ vb, float& rgb0,
+                                              float& rgb1, float& rgb2) {
+  uint32_t v[2][32];
+  tmem_ld32(t_acc, v[0]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    tmem_ld_wait();
+    if (k < 3) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) & 1]);
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(vb + 32 * k + e);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = 32 * k + e + i;
+        const float y = fmaxf(__uint_as_float(v[k & 1][e + i]) + bb[i], 0.f);
+        rgb0 = fmaf(y, c_small.w_color[0][c], rgb0);
+        rgb1 = fmaf(y, c_small.w_color[1][c], rgb1);
+        rgb2 = fmaf(y, c_small.w_color[2][c], rgb2);
+      }
+    }
+  }
 }
 
 template <int kFmt, bool kPair>
@@ -364,29 +425,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
             else mbar_arrive(&a_ready[slot]);
           }
         } else if (l < 9) {
-          // trunk / bottleneck epilogue: +bias, ReLU (trunk only), 16-bit pack -> next A operand
-#pragma unroll 1
-          for (int c0 = 0; c0 < kWidth; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_acc + c0, v);
-            float bv[16];  // first half of the biases: LDCs overlap the TMEM load
-#pragma unroll
-            for (int e = 0; e < 16; ++e) bv[e] = c_small.bias[l][c0 + e];
-            tmem_ld_wait();
-            uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int c = c0 + j * 8 + e;
-                float y = __uint_as_float(v[j * 8 + e]) + (j < 2 ? bv[j * 8 + e] : c_small.bias[l][c]);
-                if (l < 8) y = fmaxf(y, 0.f);
-                if (l == 7) dens = fmaf(y, c_small.w_density[c], dens);  // density_layer on fp32 h7
-                x[e] = y;
-              }
-              store8<kFmt>(slab + sw128_offset(row, (c0 & 63) + j * 8), x);
-            }
+          switch (l) {
+            case 0: epilogue_trunk<kFmt, 0>(t_acc, myA, row, dens); break;
+            case 1: epilogue_trunk<kFmt, 1>(t_acc, myA, row, dens); break;
+            case 2: epilogue_trunk<kFmt, 2>(t_acc, myA, row, dens); break;
+            case 3: epilogue_trunk<kFmt, 3>(t_acc, myA, row, dens); break;
+            case 4: epilogue_trunk<kFmt, 4>(t_acc, myA, row, dens); break;
+            case 5: epilogue_trunk<kFmt, 5>(t_acc, myA, row, dens); break;
+            case 6: epilogue_trunk<kFmt, 6>(t_acc, myA, row, dens); break;
+            case 7: epilogue_trunk<kFmt, 7>(t_acc, myA, row, dens); break;
+            default: epilogue_trunk<kFmt, 8>(t_acc, myA, row, dens); break;
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -396,21 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
             else mbar_arrive(&a_ready[slot]);
           }
         } else {
-          // view layer epilogue + colour head (models/mip_nerf.py:108-110)
-#pragma unroll 1
-          for (int c0 = 0; c0 < kCond; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(t_acc + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int c = c0 + e;
-              const float y = fmaxf(__uint_as_float(v[e]) + vb_s[slot * 128 + c], 0.f);
-              rgb0 = fmaf(y, c_small.w_color[0][c], rgb0);
-              rgb1 = fmaf(y, c_small.w_color[1][c], rgb1);
-              rgb2 = fmaf(y, c_small.w_color[2][c], rgb2);
-            }
-          }
+          epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2);
         }
       }
       // ---- activations + compositing over the ray's 128 samples (4 warps of this slot)

@@ -281,6 +281,14 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
   }
 }
+// same with ReLU fused into the conversion (cvt.rn.relu.*x2.f32): max(x,0) then round
+template <int kFmt>
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t d;
+  if (kFmt == 1) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 template <int kFmt>
 __host__ __device__ __forceinline__ uint16_t to16(float x) {
   if (kFmt == 1) {
