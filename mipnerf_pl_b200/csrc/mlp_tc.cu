@@ -12,8 +12,10 @@
 //   * warp 0    : weight producer — cp.async.bulk of pre-swizzled [128 x 64] operand stages
 //   * warp 1    : MMA issuer     — tcgen05.mma kind::f16, M=128, N=128 (two N halves per layer)
 //   * warps 2-5 : slot 0 workers, warps 6-9: slot 1 workers — thread = sample row = TMEM lane:
-//                 IPE -> st.shared (SW128 A operand), epilogues (tcgen05.ld, +bias, ReLU, 16-bit
-//                 pack), density/colour heads on CUDA cores, 128-thread compositing scan.
+//                 epilogues (tcgen05.ld, +bias, ReLU, 16-bit pack -> st.shared SW128 A operand),
+//                 density/colour heads on CUDA cores, 128-thread compositing scan.
+//   * warps 10-11: IPE warps (one per slot) — Gaussians + 96 features of the slot's NEXT ray,
+//                 written into the feature tile while the current ray is still in the MLP.
 //   * layer-5 skip connection = extra K slabs read from the feature tile (no concat), the
 //     per-ray view-direction term of the view layer is a per-ray bias vector (pre-kernel).
 // CTA-pair mode (kPair, default): the grid is launched as 2-CTA clusters and the MMA is
@@ -23,7 +25,8 @@
 // epilogue warps of both CTAs arrive on the leader's a_ready barrier (remote mbarrier arrive);
 // tcgen05.commit multicasts stage-free / accumulator-full to both CTAs.
 // A operand: 4 SW128 slabs (64 KB) per slot, overwritten in place layer after layer; features:
-// SW128 slab (K 0..63) + SW64 slab (K 64..95) per slot; weight ring: 3 x 16 KB.
+// SW128 slab (K 0..63) + SW64 slab (K 64..95) per slot; weight ring: 3 x 16 KB (measured: deeper
+// rings do not help, the per-slot epilogue chain is the critical path).
 #include "mlp_tc.h"
 
 #include <cstdlib>
@@ -44,17 +47,18 @@ constexpr int kCond = 128;      // view layer width
 constexpr int kFeat = 96;       // IPE width
 constexpr int kViewDim = 27;
 constexpr int kNumLayers = 10;  // 8 trunk + extra_layer + view layer
-constexpr int kNumGroups = 11;  // MMA groups per tile: layer 5 is split into its h-part and its skip part
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;   // 12 warps: producer, MMA, 2x4 epilogue workers, 2 IPE warps
 #ifndef MIPNERF_TC_STAGES
-#define MIPNERF_TC_STAGES 6
+#define MIPNERF_TC_STAGES 3
 #endif
 constexpr int kStages = MIPNERF_TC_STAGES;
 constexpr uint32_t kStageBytes = 16384;  // [128 x 64] 16-bit, SW128
 constexpr uint32_t kTailBytes = 8192;    // [128 x 32] 16-bit, SW64
 constexpr uint32_t kABytes = 65536;      // 4 slabs
+constexpr uint32_t kFBytes = kStageBytes + kTailBytes;  // feature tile: SW128 slab (K 0..63) + SW64 slab (K 64..95)
 constexpr uint32_t kSmemA = 0;
-constexpr uint32_t kSmemW = kSmemA + 2 * kABytes;
+constexpr uint32_t kSmemF = kSmemA + 2 * kABytes;
+constexpr uint32_t kSmemW = kSmemF + 2 * kFBytes;
 constexpr uint32_t kSmemMisc = kSmemW + kStages * kStageBytes;
 constexpr uint32_t kMiscBytes = 128 + 16 + 2 * 128 * 4 + 8 * 4 + 2 * 4 * 8 * 4;
 constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // + slack for 1024-B alignment
@@ -94,18 +98,45 @@ __host__ __device__ constexpr int num_halves(int l) { return l == 9 ? 1 : 2; }
 // slab s of layer l: is it the 32-wide SW64 tail?
 __host__ __device__ constexpr bool slab_is_tail(int l, int s) { return (l == 0 && s == 1) || (l == 5 && s == 5); }
 
-// MMA groups of one tile, in issue order.  Group 5 = layer 5 over h4 (K 0..255), group 6 = layer 5 over
-// the re-computed IPE features (K 256..351, accumulating onto group 5): the skip connection without
-// a resident feature buffer.
-__host__ __device__ constexpr int group_layer(int g) { return g < 6 ? g : g - 1; }
-__host__ __device__ constexpr int group_slab_begin(int g) { return g == 6 ? 4 : 0; }
-__host__ __device__ constexpr int group_slab_end(int g) { return g == 0 ? 2 : (g == 6 ? 6 : 4); }
 __host__ __device__ constexpr uint32_t slab_bytes(int l, int s) { return slab_is_tail(l, s) ? kTailBytes : kStageBytes; }
 __host__ __device__ constexpr uint32_t slab_offset(int l, int s) {
   uint32_t o = 0;
   for (int i = 0; i < s; ++i) o += slab_bytes(l, i);
   return o;
 }
+
+#ifdef MIPNERF_TC_TRACE
+// debug build only: (clock64, event) pairs of CTA 0.  Each traced thread (one per role) owns a
+// private region with a register cursor, so an event costs one clock read + one fire-and-forget store.
+__device__ unsigned long long* g_trace = nullptr;
+constexpr int kTraceRegion = 15000;
+struct Tracer {
+  unsigned long long* base = nullptr;
+  int n = 0;
+  __device__ void init(int region) {
+    base = (blockIdx.x == 0 && g_trace) ? g_trace + 8 + 2ull * region * kTraceRegion : nullptr;
+  }
+  __device__ __forceinline__ void ev(uint32_t code) {
+    if (base && n < kTraceRegion) {
+      base[2 * n] = clock64();
+      base[2 * n + 1] = code;
+      ++n;
+    }
+  }
+  __device__ void finish(int region) {
+    if (base) g_trace[region] = n;
+  }
+};
+#define TRACER_DECL(region) Tracer tracer; tracer.init(region)
+#define TRACE(code) tracer.ev(code)
+#define TRACER_DONE(region) tracer.finish(region)
+#else
+#define TRACER_DECL(region) ((void)0)
+#define TRACE(code) ((void)0)
+#define TRACER_DONE(region) ((void)0)
+#endif
+// event codes: role<<24 | kind<<16 | g<<8 | slot/stage
+#define EV(role, kind, g, x) (((uint32_t)(role) << 24) | ((uint32_t)(kind) << 16) | ((uint32_t)(g) << 8) | (uint32_t)(x))
 
 struct LevelParams {
   const uint8_t* wimage;
@@ -141,11 +172,18 @@ __device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
 template <int kFmt, int L>
 __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int row, float& dens) {
   uint32_t v[2][32];
+#ifdef MIPNERF_EXP_NO_LDTM
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[0][i] = v[1][i] = (uint32_t)(row + i);
+#else
   tmem_ld32(t_acc, v[0]);
+#endif
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
+#ifndef MIPNERF_EXP_NO_LDTM
     tmem_ld_wait();  // chunk k has landed
     if (k < 7) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) & 1]);  // next chunk in flight while we work
+#endif
     const int c0 = 32 * k;
     uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
 #pragma unroll
@@ -162,6 +200,9 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
         }
         w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
       }
+#ifdef MIPNERF_EXP_NO_STS
+      if (w[0] == 0x12345678u && w[1] == w[2] && w[3] == 7u)  // keep the math alive, (almost) never store
+#endif
       *reinterpret_cast<uint4*>(slab + sw128_offset(row, (c0 & 63) + j * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
@@ -199,27 +240,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem + kSmemA;
+  uint8_t* sF = smem + kSmemF;
   uint8_t* sW = smem + kSmemW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemMisc);
-  uint64_t* w_full = bars;                   // [kStages]  producer (+ peer relay) -> MMA   (tx bytes)
-  uint64_t* w_empty = bars + kStages;        // [kStages]  MMA -> producer   (tcgen05.commit)
-  uint64_t* a_ready = bars + 2 * kStages;    // [2]        worker warps -> MMA
-  uint64_t* acc_full = bars + 2 * kStages + 2;  // [2]     MMA -> workers    (tcgen05.commit)
+  uint64_t* w_full = bars;                      // [kStages] producer (+ peer relay) -> MMA   (tx bytes)
+  uint64_t* w_empty = bars + kStages;           // [kStages] MMA -> producer                  (tcgen05.commit)
+  uint64_t* a_ready = bars + 2 * kStages;       // [2] worker warps -> MMA: A operand written, accumulator drained
+  uint64_t* acc_full = bars + 2 * kStages + 2;  // [2] MMA -> workers                          (tcgen05.commit)
+  uint64_t* f_ready = bars + 2 * kStages + 4;   // [2] IPE warp -> MMA: feature tile of the next ray written
+  uint64_t* f_free = bars + 2 * kStages + 6;    // [2] MMA -> IPE warp: layer 5 has read the feature tile
+  static_assert((2 * kStages + 8) * 8 <= 128, "barrier block");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 128);
-  float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 144);  // [2][128]
+  float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 144);  // [2][128] per-ray view-layer bias
   float* cs = vb_s + 256;                                          // [2][4]   scan carries
   float* ps = cs + 8;                                              // [2][4][8] partial sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = !kPair || rank == 0;
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&w_full[i], (kPair && rank == 0) ? 2 : 1);  // leader: own producer + the peer's relay
+      mbar_init(&w_full[i], (kPair && leader) ? 2 : 1);  // leader: own producer + the peer's relay
       mbar_init(&w_empty[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_ready[s], kPair ? 8 : 4);  // one arrive per worker warp (of both CTAs in pair mode)
       mbar_init(&acc_full[s], 1);
+      mbar_init(&f_ready[s], kPair ? 2 : 1);  // one arrive per IPE warp (of both CTAs)
+      mbar_init(&f_free[s], 1);
     }
     fence_mbar_init();
   }
@@ -233,16 +281,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int rounds = p.rounds;
+  auto tile_of = [&](int round, int slot) -> int64_t {
+    return kPair ? ((((int64_t)round * (gridDim.x >> 1) + (blockIdx.x >> 1)) * 2 + slot) * 2 + rank)
+                 : (((int64_t)round * gridDim.x + blockIdx.x) * 2 + slot);
+  };
 
   if (warp == 0) {
     // ============================ weight producer ============================
     if (lane == 0) {
+      TRACER_DECL(0);
       int st = 0;
       uint32_t ph = 0;
       for (int round = 0; round < rounds; ++round)
-        for (int g = 0; g < kNumGroups; ++g) {
-          const int l = group_layer(g);
-          const int s0 = group_slab_begin(g), s1 = group_slab_end(g);
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int ns = num_slabs(l);
           const int nh = kPair ? 1 : num_halves(l);
           for (int slot = 0; slot < 2; ++slot)
             for (int h = 0; h < nh; ++h) {
@@ -250,12 +302,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
               const uint8_t* hbase =
                   (kPair && l == 9) ? p.wimage + kViewPairOffset + rank * 4 * kViewPairStage
                                     : p.wimage + layer_offset(l) + (kPair ? rank : (uint32_t)h) * (layer_bytes(l) / 2);
-              for (int s = s0; s < s1; ++s) {
+              uint32_t off = 0;
+              for (int s = 0; s < ns; ++s) {
                 const uint32_t bytes = (kPair && l == 9) ? kViewPairStage : slab_bytes(l, s);
-                const uint8_t* src = hbase + ((kPair && l == 9) ? s * kViewPairStage : slab_offset(l, s));
                 mbar_wait(&w_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&w_full[st], bytes);
-                bulk_g2s(sW + st * kStageBytes, src, bytes, &w_full[st]);
+                bulk_g2s(sW + st * kStageBytes, hbase + off, bytes, &w_full[st]);
+                TRACE(EV(0, 0, l, st));
+                off += bytes;
                 if (++st == kStages) {
                   st = 0;
                   ph ^= 1;
@@ -263,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
               }
             }
         }
+      TRACER_DONE(0);
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
@@ -270,24 +325,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     // (shuffled bases, loop counters) so the tcgen05 operands stay in uniform registers.
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA), 0);
+    const uint32_t sF_u = __shfl_sync(0xffffffffu, smem_u32(sF), 0);
     const uint32_t sW_u = __shfl_sync(0xffffffffu, smem_u32(sW), 0);
     const uint32_t bars_u = __shfl_sync(0xffffffffu, smem_u32(bars), 0);
     const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
     if (elect_one_sync()) {
       if (!kPair || rank_u == 0) {
+        TRACER_DECL(1);
         constexpr int kM = kPair ? 256 : 128;
         constexpr int kNn = kPair ? 256 : 128;
         const uint32_t idesc = make_idesc_f16(kM, kNn, kFmt);
         const uint32_t idesc_view = make_idesc_f16(kM, 128, kFmt);
         int st = 0;
-        uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0;
+        uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0, ph_f0 = 0, ph_f1 = 0;
         for (int round = 0; round < rounds; ++round)
-          for (int g = 0; g < kNumGroups; ++g) {
-            const int l = group_layer(g);
-            const int s0 = group_slab_begin(g), s1 = group_slab_end(g);
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int ns = num_slabs(l);
             const int nh = kPair ? 1 : num_halves(l);
             const uint32_t id = l == 9 ? idesc_view : idesc;
             for (int slot = 0; slot < 2; ++slot) {
+              if (l == 0) {  // the ray's feature tile (written ahead of time by the IPE warp)
+                if (slot == 0) {
+                  mbar_wait_fast(bars_u + (2 * kStages + 4) * 8, ph_f0);
+                  ph_f0 ^= 1;
+                } else {
+                  mbar_wait_fast(bars_u + (2 * kStages + 5) * 8, ph_f1);
+                  ph_f1 ^= 1;
+                }
+              }
               if (slot == 0) {
                 mbar_wait_fast(bars_u + (2 * kStages) * 8, ph_ready0);
                 ph_ready0 ^= 1;
@@ -296,31 +361,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                 ph_ready1 ^= 1;
               }
               tc_fence_after();
+              TRACE(EV(1, 0, l, slot));
               const uint32_t a_base = sA_u + slot * kABytes;
+              const uint32_t f_base = sF_u + slot * kFBytes;
               for (int h = 0; h < nh; ++h) {
                 const uint32_t d_tmem = tm_u + slot * 256 + h * 128;
-                for (int s = s0; s < s1; ++s) {
+                for (int s = 0; s < ns; ++s) {
                   mbar_wait_fast(bars_u + st * 8, wph);  // w_full[st] (pair: both halves landed)
                   tc_fence_after();
+                  TRACE(EV(1, 1, l, slot * 16 + s));
                   const bool tail = slab_is_tail(l, s);
-                  // feature slabs (layer 0, and the skip part of layer 5) sit in A slabs 0 / 1
-                  const int as = (l == 5 && s >= 4) ? s - 4 : s;
-                  const uint32_t a_addr = a_base + as * kStageBytes;
+                  const bool from_feat = (l == 0) || (l == 5 && s >= 4);
+                  const int fs = (l == 0) ? s : s - 4;
+                  const uint32_t a_addr =
+                      from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
                   const uint32_t b_addr = sW_u + st * kStageBytes;
-                  const bool first = (s == 0);  // group 6 (s starts at 4) accumulates onto group 5
                   if (tail) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                       const uint64_t ad = make_sw64_desc(a_addr + j * 32), bd = make_sw64_desc(b_addr + j * 32);
-                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
-                      else umma_ss(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
+                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
                     }
                   } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                       const uint64_t ad = make_sw128_desc(a_addr + j * 32), bd = make_sw128_desc(b_addr + j * 32);
-                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
-                      else umma_ss(d_tmem, ad, bd, id, (!first || j > 0) ? 1u : 0u);
+                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
                     }
                   }
                   // stage reusable (in both CTAs) once these MMAs have read it
@@ -334,16 +402,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
               }
               if (kPair) umma_commit_pair(&acc_full[slot]);  // accumulator of (l, slot) complete
               else umma_commit(&acc_full[slot]);
+              if (l == 5) {  // last reader of this ray's feature tile: hand it back to the IPE warp(s)
+                if (kPair) umma_commit_pair(&f_free[slot]);
+                else umma_commit(&f_free[slot]);
+              }
+              TRACE(EV(1, 2, l, slot));
             }
           }
+        TRACER_DONE(1);
       } else {
         // pair mode, non-leader CTA: relay "my half of stage st has landed" to the leader's w_full[st]
         int st = 0;
         uint32_t wph = 0;
         const uint32_t leader_w_full = mapa_u32(bars_u, 0);
         for (int round = 0; round < rounds; ++round)
-          for (int g = 0; g < kNumGroups; ++g) {
-            const int ns = group_slab_end(g) - group_slab_begin(g);
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int ns = num_slabs(l);
             for (int k = 0; k < 2 * ns; ++k) {
               mbar_wait_fast(bars_u + st * 8, wph);
               mbar_arrive_remote(leader_w_full + st * 8);
@@ -356,35 +430,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
     }
     __syncwarp();
-  } else {
-    // ============================ slot workers ============================
-    const int slot = (warp - 2) >> 2;
-    const int q = warp & 3;  // TMEM lane quarter this warp may access == sample quarter
-    const int row = q * 32 + lane;
-    uint8_t* myA = sA + slot * kABytes;
-    const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
-    uint32_t ph_acc = 0;
-    const uint32_t a_ready_leader = kPair ? mapa_u32(smem_u32(&a_ready[slot]), 0) : 0u;
+  } else if (warp >= 10) {
+    // ============================ IPE warps (one per slot) ============================
+    // Conical-frustum Gaussians + 96 IPE features of the slot's NEXT ray, written into the feature
+    // tile as soon as layer 5 of the current ray has read it: off the per-ray critical path.
+    const int slot = warp - 10;
+    uint8_t* myF = sF + slot * kFBytes;
+    const uint32_t f_ready_leader = kPair ? mapa_u32(smem_u32(&f_ready[slot]), 0) : 0u;
+    uint32_t ph_free = 0;
+#ifdef MIPNERF_TC_TRACE
+    Tracer tracer;
+    if (slot == 0 && lane == 0) tracer.init(2);
+#endif
     for (int round = 0; round < rounds; ++round) {
-      const int64_t tile = kPair ? ((((int64_t)round * (gridDim.x >> 1) + (blockIdx.x >> 1)) * 2 + slot) * 2 + rank)
-                                 : (((int64_t)round * gridDim.x + blockIdx.x) * 2 + slot);
-      const bool valid = tile < p.num_rays;
-      const int64_t ray = valid ? tile : p.num_rays - 1;
-      // ---- conical-frustum Gaussian of sample `row` and its 96 IPE features -> feature tile
-      const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
-      float mean[3], cov[3], dnorm;
-      {
-        const RayGeom g = load_ray_geom(p.origins, p.directions, p.radii, ray);
-        float tm, tv, rv;
+      const int64_t tile = tile_of(round, slot);
+      const int64_t ray = tile < p.num_rays ? tile : p.num_rays - 1;
+      mbar_wait(&f_free[slot], ph_free ^ 1);  // first pass falls through (fresh barrier)
+      ph_free ^= 1;
+      TRACE(EV(3, 0, 0, slot));
+      const RayGeom g = load_ray_geom(p.origins, p.directions, p.radii, ray);
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 32 + lane;
+        const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+        float mean[3], cov[3], tm, tv, rv;
         frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
         lift_gaussian(g, tm, tv, rv, mean, cov);
         if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
-        dnorm = sqrtf(g.d[0] * g.d[0] + g.d[1] * g.d[1] + g.d[2] * g.d[2]);
-      }
-      vb_s[slot * 128 + row] = __ldg(p.view_bias + ray * kCond + row);
-      // 96 IPE features -> A slabs 0 (K 0..63, SW128) and 1 (K 64..95, SW64); cheap enough (MUFU,
-      // underflowed degrees skipped) to be re-run for the skip connection instead of being kept resident
-      auto write_features = [&]() {
 #pragma unroll
         for (int gi = 0; gi < 6; ++gi) {
           float fsin[8], fcos[8];
@@ -393,38 +465,66 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
             const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
             ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
           }
-          store8<kFmt>(myA + sw128_offset(row, gi * 8), fsin);  // K = f
+          store8<kFmt>(myF + sw128_offset(row, gi * 8), fsin);  // K = f
           if (gi < 2)
-            store8<kFmt>(myA + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
+            store8<kFmt>(myF + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
           else
-            store8<kFmt>(myA + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
+            store8<kFmt>(myF + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
         }
-      };
-      write_features();
+      }
       fence_proxy_async_smem();
-      tc_fence_before();  // previous tile's TMEM reads are done before its accumulator is reused
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair) mbar_arrive_remote(f_ready_leader);
+        else mbar_arrive(&f_ready[slot]);
+      }
+      TRACE(EV(3, 1, 0, slot));
+    }
+#ifdef MIPNERF_TC_TRACE
+    if (slot == 0 && lane == 0) tracer.finish(2);
+#endif
+  } else {
+    // ============================ slot workers ============================
+    const int slot = (warp - 2) >> 2;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access == sample quarter
+    const int row = q * 32 + lane;
+    uint8_t* myA = sA + slot * kABytes;
+    const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
+    uint32_t ph_acc = 0;
+#ifdef MIPNERF_TC_TRACE
+    Tracer tracer;
+    if (q == 0 && lane == 0 && slot == 1) tracer.init(3);
+#endif
+    const uint32_t a_ready_leader = kPair ? mapa_u32(smem_u32(&a_ready[slot]), 0) : 0u;
+    auto arrive_a_ready = [&]() {
       __syncwarp();
       if (lane == 0) {
         if (kPair) mbar_arrive_remote(a_ready_leader);
         else mbar_arrive(&a_ready[slot]);
       }
+    };
+    arrive_a_ready();  // accumulator of this slot is free for the first ray
+    for (int round = 0; round < rounds; ++round) {
+      const int64_t tile = tile_of(round, slot);
+      const bool valid = tile < p.num_rays;
+      const int64_t ray = valid ? tile : p.num_rays - 1;
+      const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+      float dnorm;
+      {
+        const float dx = __ldg(p.directions + ray * 3), dy = __ldg(p.directions + ray * 3 + 1),
+                    dz = __ldg(p.directions + ray * 3 + 2);
+        dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+      }
+      vb_s[slot * 128 + row] = __ldg(p.view_bias + ray * kCond + row);  // read in the view epilogue
+      TRACE(EV(2, 0, 0, slot));
 
       float dens = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-      for (int g = 0; g < kNumGroups; ++g) {
-        const int l = group_layer(g);
+      for (int l = 0; l < kNumLayers; ++l) {
         mbar_wait(&acc_full[slot], ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
-        if (g == 5) {
-          // layer 5, h-part done reading A: re-create the features there for the skip part
-          write_features();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (kPair) mbar_arrive_remote(a_ready_leader);
-            else mbar_arrive(&a_ready[slot]);
-          }
-        } else if (l < 9) {
+        TRACE(EV(2, 2, l, slot));
+        if (l < 9) {
           switch (l) {
             case 0: epilogue_trunk<kFmt, 0>(t_acc, myA, row, dens); break;
             case 1: epilogue_trunk<kFmt, 1>(t_acc, myA, row, dens); break;
@@ -436,15 +536,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
             case 7: epilogue_trunk<kFmt, 7>(t_acc, myA, row, dens); break;
             default: epilogue_trunk<kFmt, 8>(t_acc, myA, row, dens); break;
           }
+          TRACE(EV(2, 3, l, slot));
           fence_proxy_async_smem();
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (kPair) mbar_arrive_remote(a_ready_leader);
-            else mbar_arrive(&a_ready[slot]);
-          }
+          arrive_a_ready();
+          TRACE(EV(2, 4, l, slot));
         } else {
+          named_bar_sync(1 + slot, 128);  // vb_s of this ray visible to the whole slot
           epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2);
+          tc_fence_before();
+          arrive_a_ready();  // accumulator drained: the next ray's layer 0 may start while we composite
+          TRACE(EV(2, 3, l, slot));
         }
       }
       // ---- activations + compositing over the ray's 128 samples (4 warps of this slot)
@@ -474,6 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         dst[0] = pr, dst[1] = pg, dst[2] = pb, dst[3] = pw, dst[4] = pd;
       }
       named_bar_sync(1 + slot, 128);
+      TRACE(EV(2, 5, 0, slot));
       if (row == 0 && valid) {
         float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         for (int qq = 0; qq < 4; ++qq)
@@ -490,7 +593,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         p.distance[ray] = d;
         p.acc[ray] = s[3];
       }
+      named_bar_sync(1 + slot, 128);  // row 0 has consumed ps / everyone cs before the next ray reuses them
     }
+#ifdef MIPNERF_TC_TRACE
+    if (q == 0 && lane == 0 && slot == 1) tracer.finish(3);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -627,6 +734,19 @@ cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef MIPNERF_TC_TRACE
+int set_trace_ptr(unsigned long long* ptr);
+}  // namespace mipnerf
+extern "C" int mipnerf_b200_debug_set_trace_buffer(void* dev_ptr) {
+  unsigned long long* ptr = static_cast<unsigned long long*>(dev_ptr);
+  return mipnerf::set_trace_ptr(ptr);
+}
+namespace mipnerf {
+int set_trace_ptr(unsigned long long* ptr) {
+  return cudaMemcpyToSymbol(g_trace, &ptr, sizeof(ptr)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 bool tc_supported(const mipnerf_b200_config* c, int precision) {
   return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16) && c->num_samples == kN &&

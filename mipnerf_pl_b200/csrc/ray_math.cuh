@@ -105,15 +105,12 @@ __device__ __forceinline__ void ipe_pair<false>(float m, float v, int l, float& 
 
 template <>
 __device__ __forceinline__ void ipe_pair<true>(float m, float v, int l, float& f_sin, float& f_cos) {
+  // branch-free (8 pairs interleave): the damping factor is 2^(max(arg*log2e, -126)), i.e. <= 1.2e-38
+  // where the reference underflows to 0 — far below the 16-bit operand rounding this path feeds.
   const float scale = __int_as_float((127 + l) << 23);
   const float scale_sq = __int_as_float((127 + 2 * l) << 23);
-  const float e_arg = -0.5f * v * scale_sq;
-  if (e_arg < -104.0f) {
-    f_sin = 0.0f;
-    f_cos = 0.0f;
-    return;
-  }
-  const float e = __expf(e_arg);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf(v * (scale_sq * -0.72134752044448170368f), -126.0f)));
   const float y = m * scale;
   f_sin = e * sin_reduced_fast(y);
   f_cos = e * sin_reduced_fast(__fadd_rn(y, MIPNERF_HALF_PI_F32));

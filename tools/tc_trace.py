@@ -1,0 +1,94 @@
+"""Timeline of CTA 0 of the fused level kernel (trace build): who waits for whom.
+
+    MIPNERF_B200_LIB=.../libmipnerf_b200.trace.so python tools/tc_trace.py [pair|single]
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+variant = sys.argv[1] if len(sys.argv) > 1 else "pair"
+os.environ["MIPNERF_B200_TC_VARIANT"] = variant
+import mipnerf_pl_b200 as mp  # noqa: E402
+from mipnerf_pl_b200 import _cabi  # noqa: E402
+
+lib = _cabi.lib()
+dev = "cuda:0"
+model = mp.MipNerf(precision="bf16")
+model.load_state_dict(mp.make_state_dict(0))
+model = model.to(dev).eval()
+rays = mp.namedtuple_map(lambda t: t.to(dev), mp.random_ray_batch(4096, seed=0))
+for _ in range(3):
+    model(rays, False, True)
+torch.cuda.synchronize()
+REG = 15000
+buf = torch.zeros(8 + 2 * 4 * REG, dtype=torch.int64, device=dev)
+fn = C.CDLL(_cabi.LIB_PATH).mipnerf_b200_debug_set_trace_buffer
+fn.argtypes = [C.c_void_p]
+assert fn(buf.data_ptr()) == 0
+model.num_levels = 1          # one launch (coarse level) is enough for the timeline
+model(rays, False, True)
+torch.cuda.synchronize()
+fn(None)
+raw = buf.cpu().numpy()
+parts = []
+for r in range(4):
+    cnt = int(raw[r])
+    parts.append(raw[8 + 2 * r * REG: 8 + 2 * r * REG + 2 * cnt].reshape(-1, 2))
+ev = np.concatenate(parts)
+n = len(ev)
+t0 = ev[:, 0].min()
+ev = ev[np.argsort(ev[:, 0])]
+print(f"{n} events, span {(ev[-1, 0] - t0)} cycles")
+role = ev[:, 1] >> 24
+kind = (ev[:, 1] >> 16) & 0xff
+g = (ev[:, 1] >> 8) & 0xff
+x = ev[:, 1] & 0xff
+t = ev[:, 0] - t0
+
+def sel(r, k, gg=None, xx=None):
+    m = (role == r) & (kind == k)
+    if gg is not None:
+        m &= g == gg
+    if xx is not None:
+        m &= x == xx
+    return t[m]
+
+# steady-state statistics over the whole launch
+for slot in (1,):
+    acc = {gg: sel(2, 2, gg, slot) for gg in range(11)}          # worker: accumulator of group gg arrived
+    epi = {gg: sel(2, 3, gg, slot) for gg in range(11)}          # worker: epilogue compute finished
+    arr = {gg: sel(2, 4, gg, slot) for gg in range(11)}          # worker: arrived on a_ready
+    mma_go = {gg: sel(1, 0, gg, slot) for gg in range(11)}       # MMA: a_ready observed
+    mma_done = {gg: sel(1, 2, gg, slot) for gg in range(11)}     # MMA: all MMAs of the group issued + commit
+    print(f"--- slot {slot}: mean cycles per step over {len(acc[1])} tiles")
+    for gg in range(11):
+        if len(acc[gg]) and len(epi[gg]) == len(acc[gg]):
+            e = (epi[gg] - acc[gg]).mean()
+            f = (arr[gg] - epi[gg]).mean() if len(arr[gg]) == len(epi[gg]) else float('nan')
+        else:
+            e = f = float('nan')
+        # time from worker arrive (group gg done) to MMA observing it for group gg+1
+        nxt = gg + 1
+        if nxt < 11 and len(mma_go[nxt]) == len(arr[gg]) and len(arr[gg]):
+            h1 = (mma_go[nxt] - arr[gg]).mean()
+        else:
+            h1 = float('nan')
+        iss = (mma_done[gg] - mma_go[gg]).mean() if len(mma_done[gg]) == len(mma_go[gg]) and len(mma_go[gg]) else float('nan')
+        # MMA issue end -> worker sees accumulator
+        h2 = (acc[gg] - mma_done[gg]).mean() if len(acc[gg]) == len(mma_done[gg]) and len(acc[gg]) else float('nan')
+        print(f"g{gg:2d}: mma issue span {iss:8.0f} | commit->worker wake {h2:8.0f} | epilogue {e:8.0f} | fence+arrive {f:6.0f} | arrive->mma sees (next g) {h1:8.0f}")
+a, b = sel(3, 0), sel(3, 1)
+print("IPE warp: features of one ray take", (b - a[:len(b)]).mean() if len(b) else None, "cycles")
+tile_start = sel(2, 0, None, 1)
+if len(tile_start) > 2:
+    print("tile period slot 0:", np.diff(tile_start).mean())
+# first 120 events of round 1 as a raw timeline
+names = {(3, 0): "I start", (3, 1): "I done", (0, 0): "P issue", (1, 0): "M a_ready", (1, 1): "M w_full", (1, 2): "M commit", (2, 0): "W tile", (2, 1): "W feat",
+         (2, 2): "W acc", (2, 3): "W epi", (2, 4): "W arrive", (2, 5): "W comp"}
+start = np.searchsorted(t, tile_start[2]) if len(tile_start) > 2 else 0
+for i in range(start, min(start + 150, len(t))):
+    print(f"{t[i] - t[start]:8d} {names.get((role[i], kind[i]), '?'):10s} g={g[i]:2d} x={x[i]}")
