@@ -49,18 +49,19 @@ constexpr int kViewDim = 27;
 constexpr int kNumLayers = 10;  // 8 trunk + extra_layer + view layer
 constexpr int kThreads = 384;   // 12 warps: producer, MMA, 2x4 epilogue workers, 2 IPE warps
 #ifndef MIPNERF_TC_STAGES
-#define MIPNERF_TC_STAGES 3
+#define MIPNERF_TC_STAGES 6
 #endif
 constexpr int kStages = MIPNERF_TC_STAGES;
-constexpr uint32_t kStageBytes = 16384;  // [128 x 64] 16-bit, SW128
-constexpr uint32_t kTailBytes = 8192;    // [128 x 32] 16-bit, SW64
+constexpr uint32_t kStageBytes = 16384;  // A-operand slab: [128 x 64] 16-bit, SW128
+constexpr uint32_t kTailBytes = 8192;    // feature tail slab: [128 x 32] 16-bit, SW64
+constexpr uint32_t kWStage = 8192;       // weight stage: [128 x 32] 16-bit, SW64 (K = 32 = two MMA steps)
 constexpr uint32_t kABytes = 65536;      // 4 slabs
 constexpr uint32_t kFBytes = kStageBytes + kTailBytes;  // feature tile: SW128 slab (K 0..63) + SW64 slab (K 64..95)
 constexpr uint32_t kSmemA = 0;
 constexpr uint32_t kSmemF = kSmemA + 2 * kABytes;
 constexpr uint32_t kSmemW = kSmemF + 2 * kFBytes;
-constexpr uint32_t kSmemMisc = kSmemW + kStages * kStageBytes;
-constexpr uint32_t kMiscBytes = 128 + 16 + 2 * 128 * 4 + 8 * 4 + 2 * 4 * 8 * 4;
+constexpr uint32_t kSmemMisc = kSmemW + kStages * kWStage;
+constexpr uint32_t kMiscBytes = 256 + 16 + 2 * 128 * 4 + 8 * 4 + 2 * 4 * 8 * 4;
 constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // + slack for 1024-B alignment
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
 
@@ -74,36 +75,22 @@ struct SmallParams {
 };
 __constant__ SmallParams c_small;
 
-// byte offsets of each layer's stage sequence inside the packed image
-__host__ __device__ constexpr uint32_t layer_bytes(int l) {
-  return l == 0 ? 2u * (kStageBytes + kTailBytes)
-         : l == 5 ? 2u * (4u * kStageBytes + kStageBytes + kTailBytes)
-         : l == 9 ? 4u * kStageBytes
-                  : 8u * kStageBytes;
-}
+// Packed weight image: per layer, per N-half (rows h*128..), K-slabs of 32 as [128 x 64 B] SW64 stages.
+// number of 32-wide K slabs of layer l (96, 256, .., 352 = [h | x], .., view layer uses the first 256)
+__host__ __device__ constexpr int num_k32(int l) { return l == 0 ? 3 : (l == 5 ? 11 : 8); }
+__host__ __device__ constexpr int num_halves(int l) { return l == 9 ? 1 : 2; }
+__host__ __device__ constexpr uint32_t layer_bytes(int l) { return (uint32_t)num_halves(l) * num_k32(l) * kWStage; }
 __host__ __device__ constexpr uint32_t layer_offset(int l) {
   uint32_t o = 0;
   for (int i = 0; i < l; ++i) o += layer_bytes(i);
   return o;
 }
 constexpr uint32_t kImageStageBytes = layer_offset(kNumLayers);
-// pair mode splits the 128-wide view layer into two 64-row halves: 2 x 4 stages of [64 x 64] (8 KB)
+// pair mode splits the 128-wide view layer into two 64-row halves: 2 x 8 stages of [64 x 32] (4 KB)
 constexpr uint32_t kViewPairOffset = kImageStageBytes;
-constexpr uint32_t kViewPairStage = 8192;
-constexpr size_t kSmallOffset = ((size_t)kViewPairOffset + 2 * 4 * kViewPairStage + 255) / 256 * 256;
+constexpr uint32_t kViewPairStage = 4096;
+constexpr size_t kSmallOffset = ((size_t)kViewPairOffset + 2 * 8 * kViewPairStage + 255) / 256 * 256;
 constexpr size_t kImageBytes = kSmallOffset + ((sizeof(SmallParams) + 255) / 256 * 256);
-
-__host__ __device__ constexpr int num_slabs(int l) { return l == 0 ? 2 : (l == 5 ? 6 : 4); }
-__host__ __device__ constexpr int num_halves(int l) { return l == 9 ? 1 : 2; }
-// slab s of layer l: is it the 32-wide SW64 tail?
-__host__ __device__ constexpr bool slab_is_tail(int l, int s) { return (l == 0 && s == 1) || (l == 5 && s == 5); }
-
-__host__ __device__ constexpr uint32_t slab_bytes(int l, int s) { return slab_is_tail(l, s) ? kTailBytes : kStageBytes; }
-__host__ __device__ constexpr uint32_t slab_offset(int l, int s) {
-  uint32_t o = 0;
-  for (int i = 0; i < s; ++i) o += slab_bytes(l, i);
-  return o;
-}
 
 #ifdef MIPNERF_TC_TRACE
 // debug build only: (clock64, event) pairs of CTA 0.  Each traced thread (one per role) owns a
@@ -249,9 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   uint64_t* acc_full = bars + 2 * kStages + 2;  // [2] MMA -> workers                          (tcgen05.commit)
   uint64_t* f_ready = bars + 2 * kStages + 4;   // [2] IPE warp -> MMA: feature tile of the next ray written
   uint64_t* f_free = bars + 2 * kStages + 6;    // [2] MMA -> IPE warp: layer 5 has read the feature tile
-  static_assert((2 * kStages + 8) * 8 <= 128, "barrier block");
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 128);
-  float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 144);  // [2][128] per-ray view-layer bias
+  static_assert((2 * kStages + 8) * 8 <= 256, "barrier block");
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 256);
+  float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 272);  // [2][128] per-ray view-layer bias
   float* cs = vb_s + 256;                                          // [2][4]   scan carries
   float* ps = cs + 8;                                              // [2][4][8] partial sums
 
@@ -294,22 +281,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       uint32_t ph = 0;
       for (int round = 0; round < rounds; ++round)
         for (int l = 0; l < kNumLayers; ++l) {
-          const int ns = num_slabs(l);
+          const int ns = num_k32(l);
           const int nh = kPair ? 1 : num_halves(l);
+          const uint32_t bytes = (kPair && l == 9) ? kViewPairStage : kWStage;
           for (int slot = 0; slot < 2; ++slot)
             for (int h = 0; h < nh; ++h) {
               // pair mode: this CTA streams only half `rank` of the layer (64 rows for the view layer)
-              const uint8_t* hbase =
-                  (kPair && l == 9) ? p.wimage + kViewPairOffset + rank * 4 * kViewPairStage
-                                    : p.wimage + layer_offset(l) + (kPair ? rank : (uint32_t)h) * (layer_bytes(l) / 2);
-              uint32_t off = 0;
+              const uint8_t* src =
+                  (kPair && l == 9) ? p.wimage + kViewPairOffset + rank * 8 * kViewPairStage
+                                    : p.wimage + layer_offset(l) + (kPair ? rank : (uint32_t)h) * (layer_bytes(l) / num_halves(l));
               for (int s = 0; s < ns; ++s) {
-                const uint32_t bytes = (kPair && l == 9) ? kViewPairStage : slab_bytes(l, s);
                 mbar_wait(&w_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&w_full[st], bytes);
-                bulk_g2s(sW + st * kStageBytes, hbase + off, bytes, &w_full[st]);
+                bulk_g2s(sW + st * kWStage, src, bytes, &w_full[st]);
                 TRACE(EV(0, 0, l, st));
-                off += bytes;
+                src += bytes;
                 if (++st == kStages) {
                   st = 0;
                   ph ^= 1;
@@ -340,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0, ph_f0 = 0, ph_f1 = 0;
         for (int round = 0; round < rounds; ++round)
           for (int l = 0; l < kNumLayers; ++l) {
-            const int ns = num_slabs(l);
+            const int ns = num_k32(l);
             const int nh = kPair ? 1 : num_halves(l);
             const uint32_t id = l == 9 ? idesc_view : idesc;
             for (int slot = 0; slot < 2; ++slot) {
@@ -370,26 +356,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                   mbar_wait_fast(bars_u + st * 8, wph);  // w_full[st] (pair: both halves landed)
                   tc_fence_after();
                   TRACE(EV(1, 1, l, slot * 16 + s));
-                  const bool tail = slab_is_tail(l, s);
-                  const bool from_feat = (l == 0) || (l == 5 && s >= 4);
-                  const int fs = (l == 0) ? s : s - 4;
-                  const uint32_t a_addr =
-                      from_feat ? (f_base + (fs == 0 ? 0u : kStageBytes)) : (a_base + s * kStageBytes);
-                  const uint32_t b_addr = sW_u + st * kStageBytes;
-                  if (tail) {
+                  // A side of K-slab s (32 wide): activations live in 64-wide SW128 slabs, the features in
+                  // one SW128 slab (K 0..63) + one SW64 slab (K 64..95)
+                  const int fs = (l == 0) ? s : (l == 5 ? s - 8 : -1);  // >= 0: K-slab fs of the feature tile
+                  const bool a_sw64 = fs == 2;
+                  const uint32_t a_addr = fs < 0 ? a_base + (s >> 1) * kStageBytes + (s & 1) * 64
+                                                 : (fs < 2 ? f_base + fs * 64 : f_base + kStageBytes);
+                  const uint32_t b_addr = sW_u + st * kWStage;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                      const uint64_t ad = make_sw64_desc(a_addr + j * 32), bd = make_sw64_desc(b_addr + j * 32);
-                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
-                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
-                    }
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const uint64_t ad = make_sw128_desc(a_addr + j * 32), bd = make_sw128_desc(b_addr + j * 32);
-                      if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
-                      else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
-                    }
+                  for (int j = 0; j < 2; ++j) {
+                    const uint64_t ad = a_sw64 ? make_sw64_desc(a_addr + j * 32) : make_sw128_desc(a_addr + j * 32);
+                    const uint64_t bd = make_sw64_desc(b_addr + j * 32);
+                    if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                    else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
                   }
                   // stage reusable (in both CTAs) once these MMAs have read it
                   if (kPair) umma_commit_pair(&w_empty[st]);
@@ -417,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         const uint32_t leader_w_full = mapa_u32(bars_u, 0);
         for (int round = 0; round < rounds; ++round)
           for (int l = 0; l < kNumLayers; ++l) {
-            const int ns = num_slabs(l);
+            const int ns = num_k32(l);
             for (int k = 0; k < 2 * ns; ++k) {
               mbar_wait_fast(bars_u + st * 8, wph);
               mbar_arrive_remote(leader_w_full + st * 8);
@@ -779,31 +758,27 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
     const mipnerf_b200_linear& lin = w->linears[li];
     uint8_t* dst = img + layer_offset(l);
     for (int h = 0; h < num_halves(l); ++h)
-      for (int s = 0; s < num_slabs(l); ++s) {
-        const bool tail = slab_is_tail(l, s);
-        const int kcount = tail ? 32 : 64;
-        int kbase = s * 64;
-        if (l == 5 && s >= 4) kbase = kWidth + (s - 4) * 64;  // [h | x] concat order (mip_nerf.py:96-97)
-        const int threads = 128 * kcount;
+      for (int s = 0; s < num_k32(l); ++s) {
+        // K order of layer 5 is the reference's concat [h (256) | x (96)]   (mip_nerf.py:96-97)
         if (precision == MIPNERF_B200_BF16)
-          pack_stage_kernel<1><<<(threads + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, kbase,
-                                                                    kcount, dst, 128);
+          pack_stage_kernel<1><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32, 32,
+                                                                      dst, 128);
         else
-          pack_stage_kernel<0><<<(threads + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, kbase,
-                                                                    kcount, dst, 128);
-        dst += tail ? kTailBytes : kStageBytes;
+          pack_stage_kernel<0><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32, 32,
+                                                                      dst, 128);
+        dst += kWStage;
       }
   }
   {  // pair-mode view layer: two 64-row halves
     const mipnerf_b200_linear& lin = w->linears[10];
     uint8_t* dst = img + kViewPairOffset;
     for (int r = 0; r < 2; ++r)
-      for (int s = 0; s < 4; ++s) {
+      for (int s = 0; s < 8; ++s) {
         if (precision == MIPNERF_B200_BF16)
-          pack_stage_kernel<1><<<(64 * 64 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 64, 64,
+          pack_stage_kernel<1><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
                                                                      dst, 64);
         else
-          pack_stage_kernel<0><<<(64 * 64 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 64, 64,
+          pack_stage_kernel<0><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
                                                                      dst, 64);
         dst += kViewPairStage;
       }

@@ -86,6 +86,23 @@ print("IPE warp: features of one ray take", (b - a[:len(b)]).mean() if len(b) el
 tile_start = sel(2, 0, None, 1)
 if len(tile_start) > 2:
     print("tile period slot 0:", np.diff(tile_start).mean())
+# per-layer cadence of slot 1: accumulator-ready times relative to the previous layer's
+accs = [sel(2, 2, l, 1) for l in range(10)]
+if all(len(a) == len(accs[0]) for a in accs) and len(accs[0]) > 3:
+    A = np.stack(accs, 1)[1:-1]          # drop first/last tile
+    d = np.diff(A, axis=1)
+    print("slot 1: acc(l) - acc(l-1), l=1..9:", np.round(d.mean(0)).astype(int).tolist())
+    nxt = np.stack(accs, 1)[2:, 0] - A[:, 9][:len(np.stack(accs, 1)[2:, 0])]
+    print("slot 1: acc(0, next ray) - acc(9):", int(nxt.mean()), " tile period:", int(np.diff(np.stack(accs,1)[:,0]).mean()))
+    comp = sel(2, 5, None, 1); v_epi = sel(2, 3, 9, 1)
+    if len(comp) == len(v_epi):
+        print("view epilogue end -> composite done:", int((comp - v_epi).mean()))
+    i0, i1 = sel(3, 0), sel(3, 1)
+    f5 = sel(1, 2, 5, 0)
+    print("IPE start after layer-5 commit (slot 0):", int((i0[1:len(f5)+1] - f5[:len(i0)-1]).mean()) if len(i0) > 1 else None)
+    g0_ready = sel(1, 0, 0, 0)
+    if len(g0_ready) == len(i1):
+        print("MMA starts layer 0 (slot 0) after IPE done by:", np.round((g0_ready[1:] - i1[:-1])).astype(int).tolist()[:8])
 # first 120 events of round 1 as a raw timeline
 names = {(3, 0): "I start", (3, 1): "I done", (0, 0): "P issue", (1, 0): "M a_ready", (1, 1): "M w_full", (1, 2): "M commit", (2, 0): "W tile", (2, 1): "W feat",
          (2, 2): "W acc", (2, 3): "W epi", (2, 4): "W arrive", (2, 5): "W comp"}
