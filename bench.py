@@ -66,7 +66,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -141,8 +141,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -200,11 +200,16 @@ def main():
     barrier()
 
     # ---- value: device-timed steps, L2 flushed between them -------------------------------------
-    _cabi.profile_snapshot(reset=True)
-    lib.mipnerf_b200_profile_enable(1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.6)                      # nvidia-smi needs ~0.5 s before its first sample
+        for _ in range(args.warmup):         # keep the GPU under load while the sampler spins up
+            step()
+        torch.cuda.synchronize()
+        sampler.rows.clear()
+    _cabi.profile_snapshot(reset=True)
+    lib.mipnerf_b200_profile_enable(1)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()

@@ -22,10 +22,12 @@ from mipnerf_pl_b200.weights import make_state_dict  # noqa: E402
 # ~6e-7 abs on comp_rgb/acc; the floors grant 3-4x that.  (The kernels evaluate alpha as -expm1(-x),
 # i.e. they sit next to the exact value.)  Individual fine-level weights additionally trade mass
 # between neighbouring intervals when a resampled fencepost moves by an ulp (|dw| ~ sigma*T*|dt|), so
-# they are compared on their [0,1] probability scale: 1e-4 * max(|w|, 0.05), i.e. 5e-6 absolute for
-# thin intervals (observed 3e-6 on the x40-density stress weights, 7e-7 on xavier).
+# they are compared on their [0,1] probability scale: coarse weights (exact fenceposts) with floor 0.01,
+# fine weights with floor 0.1, i.e. 1e-5 absolute (observed: 6e-6 on the x40-density stress weights with
+# randomized sampling, 7e-7 on xavier).
 RTOL = 1e-4
-FLOORS = {"comp_rgb": 0.02, "acc": 0.02, "distance": 0.2, "weights": 0.05, "t_samples": 1e-2}
+FLOORS = {"comp_rgb": 0.02, "acc": 0.02, "distance": 0.2, "weights": 0.01, "t_samples": 1e-2}
+FINE_WEIGHTS_FLOOR = 0.1
 
 
 def golden(name):
@@ -58,11 +60,12 @@ def assert_close(a, b, floor, rtol=RTOL, what=""):
     return e
 
 
-def assert_level_close(got, want, rtol=RTOL, what=""):
+def assert_level_close(got, want, rtol=RTOL, what="", level=0):
     """got/want: (comp_rgb, distance, acc, weights, t_samples)."""
     errs = {}
     for name, g, w in zip(("comp_rgb", "distance", "acc", "weights", "t_samples"), got, want):
-        errs[name] = assert_close(g, w, FLOORS[name], rtol, f"{what}{name}")
+        floor = FINE_WEIGHTS_FLOOR if (name == "weights" and level > 0) else FLOORS[name]
+        errs[name] = assert_close(g, w, floor, rtol, f"{what}{name}")
     return errs
 
 

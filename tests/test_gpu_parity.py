@@ -162,7 +162,7 @@ def test_forward_fp32_vs_golden(name, kind, cfg):
     want = golden_levels(g)
     assert len(ret) == len(want)
     for lvl, (got, ref) in enumerate(zip(ret, want)):
-        assert_level_close(got[:5], ref, what=f"{name} level {lvl} ")
+        assert_level_close(got[:5], ref, what=f"{name} level {lvl} ", level=lvl)
         if lvl > 0:
             mism = float((got[5].cpu().numpy() != g[f"l{lvl}_inds"]).mean())
             # indices downstream of an fp32 MLP that sums in another order: equal except where a cdf
@@ -179,7 +179,7 @@ def test_forward_fp32_vs_oracle(kind):
     model = build_model(kind, 4)
     got = model(mp.namedtuple_map(lambda t: t.to(DEV), rays), False, True)
     for lvl in range(2):
-        assert_level_close(got[lvl], want[lvl], what=f"{kind} level {lvl} ")
+        assert_level_close(got[lvl], want[lvl], what=f"{kind} level {lvl} ", level=lvl)
 
 
 def test_render_image_vs_oracle():

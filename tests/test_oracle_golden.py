@@ -38,7 +38,7 @@ def test_forward_matches_reference(name, kind, cfg):
     want = golden_levels(g)
     assert len(ret) == len(want)
     for lvl, (got, ref) in enumerate(zip(ret, want)):
-        assert_level_close(got, ref, what=f"{name} level {lvl} ")
+        assert_level_close(got, ref, what=f"{name} level {lvl} ", level=lvl)
         bit_equal(got[4], ref[4], f"{name} level {lvl} t_samples")   # fenceposts: bit-exact
         if lvl > 0:
             bit_equal(dbg[lvl]["inds"], g[f"l{lvl}_inds"], f"{name} level {lvl} inds")
