@@ -257,6 +257,23 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(e2e_s.item())
 
+    # ---- 800x800 frame (BASELINE configs[3]): rows sharded over the ranks, rays generated on device,
+    #      one all_gather of the rendered pixels; device-timed, max over ranks
+    pose = mp.spheric_pose(0.5)
+    mp.render_frame(model, pose, 800, 800, True, world=world, rank=rank)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_frames = 3
+    f0.record()
+    for _ in range(n_frames):
+        mp.render_frame(model, pose, 800, 800, True, world=world, rank=rank)
+    f1.record()
+    barrier()
+    frame_ms = torch.tensor([f0.elapsed_time(f1) / n_frames], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(frame_ms, op=dist.ReduceOp.MAX)
+    frame_ms = float(frame_ms.item())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -278,8 +295,19 @@ def main():
         flops_per_launch = flops_step / launches_per_step if dominant in mlp_kernels else 0.0
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops"]
+        traffic = None   # dram read+write bytes per launch from the committed ncu --set full capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_mlp_level_pair_summary.json")) as f:
+                m = json.load(f)["metrics"]
+            rd = [float(v) for v in m["dram__bytes_read.sum"]["launches"]]
+            wr = [float(v) for v in m["dram__bytes_write.sum"]["launches"]]
+            scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+            traffic = (sum(rd) / len(rd)) * scale[m["dram__bytes_read.sum"]["unit"]] + \
+                      (sum(wr) / len(wr)) * scale[m["dram__bytes_write.sum"]["unit"]]
+        except Exception:  # noqa: BLE001
+            pass
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None,
+                    "frac": achieved / peak, "traffic": traffic if dominant == "mlp_level_tc" else None,
                     "peak_source": f"{peaks['_source']} MEASURED_PEAKS.json bf16_tflops (burst)",
                     "launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
                     "share_of_step": ms_l / max(total_ms, 1e-9),
@@ -310,6 +338,9 @@ def main():
         "kernel_launches": {k: v[0] for k, v in prof.items() if v[0]},
         "kernel_ms": {k: round(v[1], 4) for k, v in prof.items() if v[2]},
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "frame": {"height": 800, "width": 800, "rays": 640000, "ms": frame_ms, "rays_per_s": 640000 / (frame_ms * 1e-3),
+                  "what": "render_frame: on-device ray generation, both levels, rows sharded over ranks, "
+                          "all_gather of coarse+fine RGB and distance"},
     }
     print(json.dumps(line))
     if world > 1:

@@ -107,6 +107,14 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
                          mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* Pinhole rays of rows [row0,row0+rows) of an H x W frame generated on the device, replacing the
+ * host NumPy loaders (datasets/datasets.py:214-263, render_video.py:29-105).  `c2w_host` is a HOST
+ * pointer to the row-major [3,4] camera-to-world matrix; outputs are [rows*W, 3|1] device buffers. */
+int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, float focal, float near,
+                               float far, int row0, int rows, float* origins, float* directions,
+                               float* viewdirs, float* radii, float* near_out, float* far_out,
+                               void* stream);
+
 /* ---- per-stage entry points (unit parity against the functions of models/mip.py) ---- */
 
 /* sample_along_rays (models/mip.py:127-165): t_samples [B,N+1], means/covs [B,N,3] (nullable). */

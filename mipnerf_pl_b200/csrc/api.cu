@@ -314,6 +314,18 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
   return MIPNERF_B200_OK;
 }
 
+int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, float focal, float near, float far,
+                               int row0, int rows, float* origins, float* directions, float* viewdirs,
+                               float* radii, float* near_out, float* far_out, void* stream) {
+  if (!c2w_host || height < 2 || width < 1 || !(focal > 0.f) || row0 < 0 || rows < 0 || row0 + rows > height)
+    return fail(MIPNERF_B200_EINVAL, "bad frame geometry");
+  if (rows > 0 && (!origins || !directions || !viewdirs || !radii || !near_out || !far_out))
+    return fail(MIPNERF_B200_EINVAL, "NULL output");
+  CUDA_TRY(mipnerf::launch_generate_rays(c2w_host, height, width, focal, near, far, row0, rows, origins, directions,
+                                         viewdirs, radii, near_out, far_out, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
 int mipnerf_b200_sample_along_rays(const mipnerf_b200_rays* rays, int num_samples, int randomized,
                                    int disparity, const float* t_rand, float* t_samples, float* means,
                                    float* covs, void* stream) {

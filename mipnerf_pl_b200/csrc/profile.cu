@@ -26,7 +26,8 @@ State& state() {
   return s;
 }
 const char* const kNames[kKernCount] = {"coarse_t",  "cast_rays", "ipe",          "pos_enc",      "linear_f32",
-                                        "composite", "resample",  "pack_weights", "mlp_level_tc", "mlp_tc"};
+                                        "composite", "resample",  "pack_weights", "mlp_level_tc", "mlp_tc",
+                                        "generate_rays"};
 
 }  // namespace
 

@@ -18,6 +18,7 @@ enum KernelId : int {
   kKernPackWeights,
   kKernMlpLevelTc,   // fused tcgen05 level kernel (IPE + MLP + compositing)
   kKernMlpTc,        // tcgen05 MLP on explicit features
+  kKernRayGen,       // on-device pinhole ray generation
   kKernCount
 };
 

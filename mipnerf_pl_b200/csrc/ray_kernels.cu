@@ -14,6 +14,8 @@
 
 namespace mipnerf {
 
+static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
 // ---------------------------------------------------------------------------------------------
 // coarse fenceposts: one thread per (ray, j)
 // ---------------------------------------------------------------------------------------------
@@ -341,9 +343,63 @@ __global__ void resample_kernel(const float* __restrict__ bins, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Blender-style pinhole rays for rows [row0, row0+rows) of an H x W frame, straight into HBM
+// (datasets/datasets.py:214-263, render_video.py:29-105): one thread per pixel.
+//   camera dir = ((x - W/2 + .5)/f, -(y - H/2 + .5)/f, -1);  direction = R . dir;  origin = c2w[:,3]
+//   radius = |d(x,y) - d(x,y+1)| * 2/sqrt(12)  (last row repeats the previous one)
+// ---------------------------------------------------------------------------------------------
+struct Pose {
+  float m[12];  // row-major [3,4] camera-to-world
+};
+__device__ __forceinline__ void pixel_dir(const Pose& c, float x, float y, float w, float h, float focal,
+                                          float d[3]) {
+  const float cx = __fdiv_rn(__fadd_rn(__fsub_rn(x, __fmul_rn(w, 0.5f)), 0.5f), focal);
+  const float cy = -__fdiv_rn(__fadd_rn(__fsub_rn(y, __fmul_rn(h, 0.5f)), 0.5f), focal);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d[i] = c.m[i * 4 + 0] * cx + c.m[i * 4 + 1] * cy - c.m[i * 4 + 2];
+}
+__global__ void generate_rays_kernel(const Pose c, int height, int width, float focal, float near_v, float far_v,
+                                     int row0, int rows, float* __restrict__ origins,
+                                     float* __restrict__ directions, float* __restrict__ viewdirs,
+                                     float* __restrict__ radii, float* __restrict__ near_o,
+                                     float* __restrict__ far_o) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)rows * width) return;
+  const int y = row0 + (int)(idx / width), x = (int)(idx % width);
+  float d[3], dn[3];
+  pixel_dir(c, (float)x, (float)y, (float)width, (float)height, focal, d);
+  // neighbour one row down; the last row reuses the distance between rows H-2 and H-1
+  const int ya = y < height - 1 ? y : height - 2;
+  float da[3];
+  pixel_dir(c, (float)x, (float)ya, (float)width, (float)height, focal, da);
+  pixel_dir(c, (float)x, (float)(ya + 1), (float)width, (float)height, focal, dn);
+  const float dx = da[0] - dn[0], dy = da[1] - dn[1], dz = da[2] - dn[2];
+  const float inv = rsqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    origins[idx * 3 + i] = c.m[i * 4 + 3];
+    directions[idx * 3 + i] = d[i];
+    viewdirs[idx * 3 + i] = d[i] * inv;
+  }
+  radii[idx] = sqrtf(dx * dx + dy * dy + dz * dz) * 0.57735026918962576f;  // 2/sqrt(12)
+  near_o[idx] = near_v;
+  far_o[idx] = far_v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+cudaError_t launch_generate_rays(const float* c2w_host, int height, int width, float focal, float near_v,
+                                 float far_v, int row0, int rows, float* origins, float* directions,
+                                 float* viewdirs, float* radii, float* near_o, float* far_o, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  Pose c;
+  for (int i = 0; i < 12; ++i) c.m[i] = c2w_host[i];
+  LaunchScope scope(kKernRayGen, st);
+  generate_rays_kernel<<<blocks_for((int64_t)rows * width, 256), 256, 0, st>>>(
+      c, height, width, focal, near_v, far_v, row0, rows, origins, directions, viewdirs, radii, near_o, far_o);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_coarse_t(const float* near, const float* far, const float* t_rand, float* t_out,
                             int64_t num_rays, int n, int randomized, int disparity, cudaStream_t st) {

@@ -242,3 +242,28 @@ def test_edge_cases_and_errors():
     # float64 radii (NumPy>=2 promotion in the reference loader) are cast at the boundary
     r64 = one._replace(radii=one.radii.double())
     assert torch.equal(model(r64, False, True)[1][0], model(one, False, True)[1][0])
+
+
+def test_generate_rays_matches_host_loader():
+    c2w = mp.spheric_pose(1.3)
+    host = mp.rays_to_torch(mp.blender_rays(c2w, 800, 800), flatten=True)
+    r0, r1 = 395, 403
+    got = mp.generate_rays(c2w, 800, 800, rows=(r0, r1), device=DEV)
+    sl = slice(r0 * 800, r1 * 800)
+    for name in ("origins", "directions", "viewdirs", "radii", "near", "far"):
+        a, b = getattr(got, name).cpu(), getattr(host, name)[sl]
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), name
+    last = mp.generate_rays(c2w, 800, 800, rows=(799, 800), device=DEV)     # last row repeats the radius above it
+    assert torch.allclose(last.radii.cpu(), host.radii[799 * 800:], rtol=2e-6)
+
+
+def test_render_frame_equals_forward_on_host_rays():
+    c2w = mp.spheric_pose(0.4)
+    h = w = 40
+    model = build_model("trained_like", 3, precision="bf16")
+    coarse, fine, dist_map = mp.render_frame(model, c2w, h, w)
+    host = mp.namedtuple_map(lambda t: t.to(DEV), mp.rays_to_torch(mp.blender_rays(c2w, h, w), flatten=True))
+    ret = model(host, False, True)
+    assert coarse.shape == (h, w, 3) and dist_map.shape == (h, w)
+    assert torch.allclose(fine.reshape(-1, 3), ret[1][0], atol=2e-3)
+    assert torch.allclose(coarse.reshape(-1, 3), ret[0][0], atol=2e-3)
