@@ -204,9 +204,10 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.6)                      # nvidia-smi needs ~0.5 s before its first sample
-        for _ in range(args.warmup):         # keep the GPU under load while the sampler spins up
-            step()
-        torch.cuda.synchronize()
+    for _ in range(args.warmup):             # every rank (step() holds a collective): GPU under load
+        step()                               # while the sampler spins up
+    barrier()
+    if rank == 0:
         sampler.rows.clear()
     _cabi.profile_snapshot(reset=True)
     lib.mipnerf_b200_profile_enable(1)
