@@ -158,6 +158,7 @@ __device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
 // slabs, software-pipelined over 32-column TMEM loads.  L == 7 also accumulates the density head.
 template <int kFmt, int L>
 __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int row, float& dens) {
+  float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent chains for the density head
   uint32_t v[2][32];
 #ifdef MIPNERF_EXP_NO_LDTM
 #pragma unroll
@@ -179,12 +180,11 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = c0 + j * 8 + 2 * e;
-        const float a = __uint_as_float(v[k & 1][j * 8 + 2 * e]) + c_small.bias[L][c];
-        const float b = __uint_as_float(v[k & 1][j * 8 + 2 * e + 1]) + c_small.bias[L][c + 1];
-        if (L == 7) {  // density_layer on the fp32 (un-rounded) h7        (models/mip_nerf.py:98)
-          dens = fmaf(fmaxf(a, 0.f), c_small.w_density[c], dens);
-          dens = fmaf(fmaxf(b, 0.f), c_small.w_density[c + 1], dens);
-        }
+        float a = __uint_as_float(v[k & 1][j * 8 + 2 * e]), b = __uint_as_float(v[k & 1][j * 8 + 2 * e + 1]);
+        fadd2(a, b, c_small.bias[L][c], c_small.bias[L][c + 1]);  // one FADD2 for the pair
+        if (L == 7)  // density_layer on the fp32 (un-rounded) h7        (models/mip_nerf.py:98)
+          ffma2(dpart[2 * e], dpart[2 * e + 1], fmaxf(a, 0.f), fmaxf(b, 0.f), c_small.w_density[c],
+                c_small.w_density[c + 1]);
         w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
       }
 #ifdef MIPNERF_EXP_NO_STS
@@ -193,12 +193,15 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
       *reinterpret_cast<uint4*>(slab + sw128_offset(row, (c0 & 63) + j * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
+  if (L == 7)
+    dens = ((dpart[0] + dpart[1]) + (dpart[2] + dpart[3])) + ((dpart[4] + dpart[5]) + (dpart[6] + dpart[7]));
 }
 
 // view layer epilogue + colour head (models/mip_nerf.py:108-110); vb = per-ray view-direction bias
 template <int kFmt>
 __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __restrict__ vb, float& rgb0,
                                               float& rgb1, float& rgb2) {
+  float acc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // independent chains
   uint32_t v[2][32];
   tmem_ld32(t_acc, v[0]);
 #pragma unroll
@@ -210,15 +213,20 @@ __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __res
       const float4 b4 = *reinterpret_cast<const float4*>(vb + 32 * k + e);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 4; i += 2) {
         const int c = 32 * k + e + i;
-        const float y = fmaxf(__uint_as_float(v[k & 1][e + i]) + bb[i], 0.f);
-        rgb0 = fmaf(y, c_small.w_color[0][c], rgb0);
-        rgb1 = fmaf(y, c_small.w_color[1][c], rgb1);
-        rgb2 = fmaf(y, c_small.w_color[2][c], rgb2);
+        float y0 = __uint_as_float(v[k & 1][e + i]), y1 = __uint_as_float(v[k & 1][e + i + 1]);
+        fadd2(y0, y1, bb[i], bb[i + 1]);
+        y0 = fmaxf(y0, 0.f), y1 = fmaxf(y1, 0.f);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          ffma2(acc[ch][i], acc[ch][i + 1], y0, y1, c_small.w_color[ch][c], c_small.w_color[ch][c + 1]);
       }
     }
   }
+  rgb0 = (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]);
+  rgb1 = (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]);
+  rgb2 = (acc[2][0] + acc[2][1]) + (acc[2][2] + acc[2][3]);
 }
 
 template <int kFmt, bool kPair>
@@ -419,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     uint32_t ph_free = 0;
 #ifdef MIPNERF_TC_TRACE
     Tracer tracer;
-    if (slot == 0 && lane == 0) tracer.init(2);
+    (void)0;
 #endif
     for (int round = 0; round < rounds; ++round) {
       const int64_t tile = tile_of(round, slot);
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       TRACE(EV(3, 1, 0, slot));
     }
 #ifdef MIPNERF_TC_TRACE
-    if (slot == 0 && lane == 0) tracer.finish(2);
+    (void)0;
 #endif
   } else {
     // ============================ slot workers ============================
@@ -472,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     uint32_t ph_acc = 0;
 #ifdef MIPNERF_TC_TRACE
     Tracer tracer;
-    if (q == 0 && lane == 0 && slot == 1) tracer.init(3);
+    if (q == 0 && lane == 0) tracer.init(2 + slot);
 #endif
     const uint32_t a_ready_leader = kPair ? mapa_u32(smem_u32(&a_ready[slot]), 0) : 0u;
     auto arrive_a_ready = [&]() {
@@ -575,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       named_bar_sync(1 + slot, 128);  // row 0 has consumed ps / everyone cs before the next ray reuses them
     }
 #ifdef MIPNERF_TC_TRACE
-    if (q == 0 && lane == 0 && slot == 1) tracer.finish(3);
+    if (q == 0 && lane == 0) tracer.finish(2 + slot);
 #endif
   }
   tc_fence_before();

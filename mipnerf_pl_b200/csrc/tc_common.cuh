@@ -270,6 +270,24 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (FADD2 / FFMA2 on sm_100a): two IEEE fp32 ops per issue slot ----------------
+__device__ __forceinline__ void fadd2(float& a, float& b, float ca, float cb) {
+  uint64_t x, y, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(ca), "f"(cb));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+}
+// (acc_a, acc_b) += (xa, xb) * (wa, wb)
+__device__ __forceinline__ void ffma2(float& acc_a, float& acc_b, float xa, float xb, float wa, float wb) {
+  uint64_t x, w, c, r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(xa), "f"(xb));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(wa), "f"(wb));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc_a), "f"(acc_b));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(w), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc_a), "=f"(acc_b) : "l"(r));
+}
+
 // ---- 16-bit operand conversion (kFmt: 0 = fp16, 1 = bf16), low half = first element ---------------------
 template <int kFmt>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {

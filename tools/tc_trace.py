@@ -58,7 +58,7 @@ def sel(r, k, gg=None, xx=None):
     return t[m]
 
 # steady-state statistics over the whole launch
-for slot in (1,):
+for slot in (0, 1):
     acc = {gg: sel(2, 2, gg, slot) for gg in range(11)}          # worker: accumulator of group gg arrived
     epi = {gg: sel(2, 3, gg, slot) for gg in range(11)}          # worker: epilogue compute finished
     arr = {gg: sel(2, 4, gg, slot) for gg in range(11)}          # worker: arrived on a_ready
