@@ -47,6 +47,9 @@ constexpr int kCond = 128;      // view layer width
 constexpr int kFeat = 96;       // IPE width
 constexpr int kViewDim = 27;
 constexpr int kNumLayers = 10;  // 8 trunk + extra_layer + view layer
+#ifndef MIPNERF_TC_DEFAULT_VARIANT
+#define MIPNERF_TC_DEFAULT_VARIANT 1
+#endif
 constexpr int kThreads = 384;   // 12 warps: producer, MMA, 2x4 epilogue workers, 2 IPE warps
 #ifndef MIPNERF_TC_STAGES
 #define MIPNERF_TC_STAGES 6
@@ -132,6 +135,7 @@ struct LevelParams {
   const float* radii;
   const float* t;          // [B,129] fenceposts of this level
   const float* view_bias;  // [B,128]  b_view + W_view[:,256:] . pos_enc(viewdir)
+  uint8_t* feat_scratch;   // v2 kernel: per-CTA pre-swizzled feature slabs in global memory (L2 resident)
   float* comp_rgb;
   float* distance;
   float* acc;
@@ -595,6 +599,361 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   }
 }
 
+
+// =================================================================================================
+// v2 ("shared weight stream"): same tile / slot / epilogue structure as mlp_level_kernel<.,true>, but
+//   * every weight stage is consumed by BOTH slots before it is released (the producer streams each
+//     layer once per round instead of once per slot: half the L2->SMEM weight traffic, half the
+//     supply rate the ring has to sustain);
+//   * the ring has 12 x 8 KB stages; the 48 KB for that come from not keeping feature tiles in SMEM:
+//     the IPE warps write the (pre-swizzled, 16-bit) feature K-slabs of the next ray to a per-CTA
+//     global scratch (L2 resident) and the producer streams them through the same ring as A-operand
+//     stages for layer 0 and for the skip part of layer 5 (group 6 accumulates onto group 5; the
+//     workers are not involved in that split).
+// =================================================================================================
+constexpr int kStages2 = 12;
+constexpr int kNumGroups2 = 11;
+constexpr uint32_t kSmemW2 = 2 * kABytes;
+constexpr uint32_t kSmemMisc2 = kSmemW2 + kStages2 * kWStage;
+constexpr uint32_t kMisc2Bytes = 512 + 16 + 2 * 128 * 4 + 8 * 4 + 2 * 4 * 8 * 4;
+constexpr uint32_t kSmemTotal2 = kSmemMisc2 + kMisc2Bytes + 1024;
+static_assert(kSmemTotal2 <= 232448, "exceeds 227 KB of shared memory per CTA");
+constexpr uint32_t kFeatSlotBytes = 3 * kWStage;                 // K 0..31 | 32..63 | 64..95, [128 x 64 B] SW64 each
+constexpr uint32_t kFeatScratchPerCta = 2 * 2 * kFeatSlotBytes;  // 2 slots x 2 (ray parity)
+constexpr int kMaxCtas2 = 192;
+
+__host__ __device__ constexpr int g2_layer(int g) { return g < 6 ? g : g - 1; }
+__host__ __device__ constexpr int g2_nw(int g) { return (g == 0 || g == 6) ? 3 : 8; }
+__host__ __device__ constexpr int g2_wslab0(int g) { return g == 6 ? 8 : 0; }
+__host__ __device__ constexpr bool g2_feat(int g) { return g == 0 || g == 6; }
+
+template <int kFmt>
+__global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem + kSmemA;
+  uint8_t* sW = smem + kSmemW2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemMisc2);
+  uint64_t* w_full = bars;                       // [12] producer (+ peer relay) -> MMA
+  uint64_t* w_empty = bars + kStages2;           // [12] MMA -> producer (after the LAST use of the stage)
+  uint64_t* a_ready = bars + 2 * kStages2;       // [2]
+  uint64_t* acc_full = bars + 2 * kStages2 + 2;  // [2]
+  uint64_t* f_ready = bars + 2 * kStages2 + 4;   // [2] IPE warp -> producer: feature slabs of the ray are in the scratch
+  uint64_t* f_free = bars + 2 * kStages2 + 6;    // [2] MMA -> IPE warp: group 6 has consumed the ray's feature stages
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc2 + 512);
+  float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc2 + 528);
+  float* cs = vb_s + 256;
+  float* ps = cs + 8;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (tid == 0) {
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(&w_full[i], leader ? 2 : 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_ready[s], 8);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&f_ready[s], 1);
+      mbar_init(&f_free[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int rounds = p.rounds;
+  uint8_t* my_scratch = p.feat_scratch + (size_t)blockIdx.x * kFeatScratchPerCta;
+  auto tile_of = [&](int round, int slot) -> int64_t {
+    return (((int64_t)round * (gridDim.x >> 1) + (blockIdx.x >> 1)) * 2 + slot) * 2 + rank;
+  };
+
+  if (warp == 0) {
+    // ============================ producer: weights once per round + per-slot feature slabs ============
+    if (lane == 0) {
+      TRACER_DECL(0);
+      int pos = 0;
+      uint32_t fill_mask = 0, ph_fr0 = 0, ph_fr1 = 0;
+      auto fill = [&](int st, const void* src, uint32_t bytes, int tag) {
+        mbar_wait(&w_empty[st], ((fill_mask >> st) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&w_full[st], bytes);
+        bulk_g2s(sW + st * kWStage, src, bytes, &w_full[st]);
+        fill_mask ^= 1u << st;
+        TRACE(EV(0, 0, tag, st));
+      };
+      for (int round = 0; round < rounds; ++round)
+        for (int g = 0; g < kNumGroups2; ++g) {
+          const int l = g2_layer(g), nw = g2_nw(g);
+          const uint32_t bytes = l == 9 ? kViewPairStage : kWStage;
+          const uint8_t* src = l == 9 ? p.wimage + kViewPairOffset + rank * 8 * kViewPairStage
+                                      : p.wimage + layer_offset(l) + rank * (layer_bytes(l) / 2) + g2_wslab0(g) * kWStage;
+          for (int i = 0; i < nw; ++i) fill((pos + i) % kStages2, src + i * bytes, bytes, g);
+          if (g2_feat(g)) {
+            for (int slot = 0; slot < 2; ++slot) {
+              if (g == 0) {  // the IPE warp has published this ray's slabs
+                if (slot == 0) {
+                  mbar_wait(&f_ready[0], ph_fr0);
+                  ph_fr0 ^= 1;
+                } else {
+                  mbar_wait(&f_ready[1], ph_fr1);
+                  ph_fr1 ^= 1;
+                }
+              }
+              const uint8_t* fsrc = my_scratch + (slot * 2 + (round & 1)) * kFeatSlotBytes;
+              for (int i = 0; i < 3; ++i) fill((pos + nw + slot * 3 + i) % kStages2, fsrc + i * kWStage, kWStage, g);
+            }
+          }
+          pos = (pos + nw + (g2_feat(g) ? 6 : 0)) % kStages2;
+        }
+      TRACER_DONE(0);
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader) / stage relay (peer) ============================
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sA_u = __shfl_sync(0xffffffffu, smem_u32(sA), 0);
+    const uint32_t sW_u = __shfl_sync(0xffffffffu, smem_u32(sW), 0);
+    const uint32_t bars_u = __shfl_sync(0xffffffffu, smem_u32(bars), 0);
+    const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
+    if (elect_one_sync()) {
+      if (rank_u == 0) {
+        TRACER_DECL(1);
+        const uint32_t idesc = make_idesc_f16(256, 256, kFmt);
+        const uint32_t idesc_view = make_idesc_f16(256, 128, kFmt);
+        int pos = 0;
+        uint32_t full_mask = 0, ph_ready0 = 0, ph_ready1 = 0;
+        for (int round = 0; round < rounds; ++round)
+          for (int g = 0; g < kNumGroups2; ++g) {
+            const int l = g2_layer(g), nw = g2_nw(g);
+            const bool feat = g2_feat(g);
+            const uint32_t id = l == 9 ? idesc_view : idesc;
+            for (int slot = 0; slot < 2; ++slot) {
+              if (g != 6) {  // group 6 continues group 5's accumulation: same A-operand epoch
+                if (slot == 0) {
+                  mbar_wait_fast(bars_u + (2 * kStages2) * 8, ph_ready0);
+                  ph_ready0 ^= 1;
+                } else {
+                  mbar_wait_fast(bars_u + (2 * kStages2 + 1) * 8, ph_ready1);
+                  ph_ready1 ^= 1;
+                }
+                tc_fence_after();
+              }
+              TRACE(EV(1, 0, g, slot));
+              const uint32_t a_base = sA_u + slot * kABytes;
+              const uint32_t d_tmem = tm_u + slot * 256;
+              for (int i = 0; i < nw; ++i) {
+                const int stw = (pos + i) % kStages2;
+                int stf = 0;
+                if (slot == 0) mbar_wait_fast(bars_u + stw * 8, (full_mask >> stw) & 1u);
+                if (feat) {
+                  stf = (pos + nw + slot * 3 + i) % kStages2;
+                  mbar_wait_fast(bars_u + stf * 8, (full_mask >> stf) & 1u);
+                }
+                tc_fence_after();
+                TRACE(EV(1, 1, g, slot * 16 + i));
+                const uint32_t a_addr = feat ? sW_u + stf * kWStage : a_base + (i >> 1) * kStageBytes + (i & 1) * 64;
+                const uint32_t b_addr = sW_u + stw * kWStage;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint64_t ad = feat ? make_sw64_desc(a_addr + j * 32) : make_sw128_desc(a_addr + j * 32);
+                  const uint64_t bd = make_sw64_desc(b_addr + j * 32);
+                  umma_ss_pair(d_tmem, ad, bd, id, (g == 6 || i > 0 || j > 0) ? 1u : 0u);
+                }
+                if (feat) {  // the ray's private feature stage: free right away
+                  umma_commit_pair(&w_empty[stf]);
+                  full_mask ^= 1u << stf;
+                }
+                if (slot == 1) {  // second (last) use of the shared weight stage
+                  umma_commit_pair(&w_empty[stw]);
+                  full_mask ^= 1u << stw;
+                }
+              }
+              if (g != 5) umma_commit_pair(&acc_full[slot]);
+              if (g == 6) umma_commit_pair(&f_free[slot]);
+              TRACE(EV(1, 2, g, slot));
+            }
+            pos = (pos + nw + (feat ? 6 : 0)) % kStages2;
+          }
+        TRACER_DONE(1);
+      } else {
+        // peer CTA: relay "stage landed here" to the leader's w_full, in the producer's fill order
+        int pos = 0;
+        uint32_t mask = 0;
+        const uint32_t leader_w_full = mapa_u32(bars_u, 0);
+        auto relay = [&](int st) {
+          mbar_wait_fast(bars_u + st * 8, (mask >> st) & 1u);
+          mbar_arrive_remote(leader_w_full + st * 8);
+          mask ^= 1u << st;
+        };
+        for (int round = 0; round < rounds; ++round)
+          for (int g = 0; g < kNumGroups2; ++g) {
+            const int nw = g2_nw(g);
+            const int n = nw + (g2_feat(g) ? 6 : 0);
+            for (int i = 0; i < n; ++i) relay((pos + i) % kStages2);
+            pos = (pos + n) % kStages2;
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 10) {
+    // ============================ IPE warps: feature slabs of the slot's next ray -> global scratch ====
+    const int slot = warp - 10;
+    for (int round = 0; round < rounds; ++round) {
+      const int64_t tile = tile_of(round, slot);
+      const int64_t ray = tile < p.num_rays ? tile : p.num_rays - 1;
+      // run at most one ray ahead: start once the previous ray's group 6 has consumed its feature stages
+      // (keeps the single-count f_ready barrier from seeing two arrivals in one producer wait)
+      if (round >= 1) mbar_wait(&f_free[slot], (uint32_t)((round - 1) & 1));
+      uint8_t* dst = my_scratch + (slot * 2 + (round & 1)) * kFeatSlotBytes;
+      const RayGeom g = load_ray_geom(p.origins, p.directions, p.radii, ray);
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 32 + lane;
+        const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+        float mean[3], cov[3], tm, tv, rv;
+        frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
+        lift_gaussian(g, tm, tv, rv, mean, cov);
+        if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
+#pragma unroll
+        for (int gi = 0; gi < 6; ++gi) {
+          float fsin[8], fcos[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
+            ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
+          }
+          const int ks = gi * 8, kc = 48 + gi * 8;  // K of the sin / cos halves
+          store8<kFmt>(dst + (ks >> 5) * kWStage + sw64_offset(row, ks & 31), fsin);
+          store8<kFmt>(dst + (kc >> 5) * kWStage + sw64_offset(row, kc & 31), fcos);
+        }
+      }
+      __threadfence();                                     // slabs visible device-wide ...
+      asm volatile("fence.proxy.async;" ::: "memory");      // ... and to the TMA engine (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&f_ready[slot]);
+    }
+  } else {
+    // ============================ slot workers (as in v1; 10 accumulator hand-offs per ray) ============
+    const int slot = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint8_t* myA = sA + slot * kABytes;
+    const uint32_t t_acc = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
+    uint32_t ph_acc = 0;
+#ifdef MIPNERF_TC_TRACE
+    Tracer tracer;
+    if (q == 0 && lane == 0) tracer.init(2 + slot);
+#endif
+    const uint32_t a_ready_leader = mapa_u32(smem_u32(&a_ready[slot]), 0);
+    auto arrive_a_ready = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(a_ready_leader);
+    };
+    arrive_a_ready();
+    for (int round = 0; round < rounds; ++round) {
+      const int64_t tile = tile_of(round, slot);
+      const bool valid = tile < p.num_rays;
+      const int64_t ray = valid ? tile : p.num_rays - 1;
+      const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+      float dnorm;
+      {
+        const float dx = __ldg(p.directions + ray * 3), dy = __ldg(p.directions + ray * 3 + 1),
+                    dz = __ldg(p.directions + ray * 3 + 2);
+        dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+      }
+      vb_s[slot * 128 + row] = __ldg(p.view_bias + ray * kCond + row);
+      TRACE(EV(2, 0, 0, slot));
+      float dens = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+      for (int l = 0; l < kNumLayers; ++l) {
+        mbar_wait(&acc_full[slot], ph_acc);
+        ph_acc ^= 1;
+        tc_fence_after();
+        TRACE(EV(2, 2, l, slot));
+        if (l < 9) {
+          switch (l) {
+            case 0: epilogue_trunk<kFmt, 0>(t_acc, myA, row, dens); break;
+            case 1: epilogue_trunk<kFmt, 1>(t_acc, myA, row, dens); break;
+            case 2: epilogue_trunk<kFmt, 2>(t_acc, myA, row, dens); break;
+            case 3: epilogue_trunk<kFmt, 3>(t_acc, myA, row, dens); break;
+            case 4: epilogue_trunk<kFmt, 4>(t_acc, myA, row, dens); break;
+            case 5: epilogue_trunk<kFmt, 5>(t_acc, myA, row, dens); break;
+            case 6: epilogue_trunk<kFmt, 6>(t_acc, myA, row, dens); break;
+            case 7: epilogue_trunk<kFmt, 7>(t_acc, myA, row, dens); break;
+            default: epilogue_trunk<kFmt, 8>(t_acc, myA, row, dens); break;
+          }
+          TRACE(EV(2, 3, l, slot));
+          fence_proxy_async_smem();
+          tc_fence_before();
+          arrive_a_ready();
+          TRACE(EV(2, 4, l, slot));
+        } else {
+          named_bar_sync(1 + slot, 128);
+          epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2);
+          tc_fence_before();
+          arrive_a_ready();
+          TRACE(EV(2, 3, l, slot));
+        }
+      }
+      const float density = density_activation(dens + c_small.b_density, p.density_bias);
+      const float cr = rgb_activation(rgb0 + c_small.b_color[0], p.rgb_scale, p.rgb_padding);
+      const float cg = rgb_activation(rgb1 + c_small.b_color[1], p.rgb_scale, p.rgb_padding);
+      const float cb = rgb_activation(rgb2 + c_small.b_color[2], p.rgb_scale, p.rgb_padding);
+      const float dd = density * ((t1 - t0) * dnorm);
+      float incl = dd;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0.f;
+      if (lane == 31) cs[slot * 4 + q] = incl;
+      named_bar_sync(1 + slot, 128);
+      float before = 0.f;
+      for (int qq = 0; qq < q; ++qq) before += cs[slot * 4 + qq];
+      const float w = -expm1f(-dd) * expf(-(before + excl));
+      if (valid) p.weights[ray * kN + row] = w;
+      float pr = warp_sum(w * cr), pg = warp_sum(w * cg), pb = warp_sum(w * cb), pw = warp_sum(w),
+            pd = warp_sum(w * (0.5f * (t0 + t1)));
+      if (lane == 0) {
+        float* dst = ps + (slot * 4 + q) * 8;
+        dst[0] = pr, dst[1] = pg, dst[2] = pb, dst[3] = pw, dst[4] = pd;
+      }
+      named_bar_sync(1 + slot, 128);
+      TRACE(EV(2, 5, 0, slot));
+      if (row == 0 && valid) {
+        float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int qq = 0; qq < 4; ++qq)
+          for (int k = 0; k < 5; ++k) s[k] += ps[(slot * 4 + qq) * 8 + k];
+        const float t_first = __ldg(p.t + ray * (kN + 1)), t_last = __ldg(p.t + ray * (kN + 1) + kN);
+        float d = s[4];
+        if (isnan(d)) d = 0.f;
+        else if (isinf(d)) d = d > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        d = fminf(fmaxf(d, t_first), t_last);
+        const float bg = p.white_bkgd ? 1.0f - s[3] : 0.f;
+        p.comp_rgb[ray * 3 + 0] = s[0] + bg;
+        p.comp_rgb[ray * 3 + 1] = s[1] + bg;
+        p.comp_rgb[ray * 3 + 2] = s[2] + bg;
+        p.distance[ray] = d;
+        p.acc[ray] = s[3];
+      }
+      named_bar_sync(1 + slot, 128);
+    }
+#ifdef MIPNERF_TC_TRACE
+    if (q == 0 && lane == 0) tracer.finish(2 + slot);
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // view-direction term of the view layer as a per-ray bias: vb[r][n] = b[n] + W[n][256:283] . venc[r]
 __global__ void view_bias_kernel(const float* __restrict__ venc, const float* __restrict__ w,
                                  const float* __restrict__ b, float* __restrict__ out, int64_t num_rays) {
@@ -640,6 +999,7 @@ __global__ void pack_small_params_kernel(const SmallSrc src, SmallParams* __rest
 
 struct TcScratch {
   float *venc, *vbias, *t[2], *w[2];
+  uint8_t* feat;  // v2 kernel: kMaxCtas2 x kFeatScratchPerCta
   size_t bytes;
 };
 constexpr int64_t kChunkRaysTc = 65536;
@@ -660,6 +1020,7 @@ TcScratch carve_tc(int64_t rays, void* base) {
     s.t[i] = take((size_t)rays * (kN + 1));
     s.w[i] = take((size_t)rays * kN);
   }
+  s.feat = reinterpret_cast<uint8_t*>(take((size_t)kMaxCtas2 * kFeatScratchPerCta / sizeof(float)));
   s.bytes = off;
   return s;
 }
@@ -707,13 +1068,57 @@ cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// MIPNERF_B200_TC_VARIANT=single selects the 1-CTA kernel (cta_group::1); default is the CTA pair.
-bool use_pair_variant() {
-  const char* v = getenv("MIPNERF_B200_TC_VARIANT");
-  return !(v && v[0] == 's');
+bool g_attr_set2[2] = {false, false};
+
+template <int kFmt>
+cudaError_t launch_level_v2(const LevelParams& p, cudaStream_t st) {
+  auto kern = mlp_level_kernel_v2<kFmt>;
+  if (!g_attr_set2[kFmt]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal2);
+    if (e != cudaSuccess) return e;
+    g_attr_set2[kFmt] = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  LevelParams q = p;
+  LaunchScope scope(kKernMlpLevelTc, st);
+  const int64_t quads = (p.num_rays + 3) / 4;
+  int max_pairs = g_num_sms / 2;
+  if (max_pairs > kMaxCtas2 / 2) max_pairs = kMaxCtas2 / 2;
+  const int pairs = (int)(quads < max_pairs ? quads : max_pairs);
+  q.rounds = (int)((p.num_rays + 4 * (int64_t)pairs - 1) / (4 * (int64_t)pairs));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemTotal2;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, q);
 }
 
+// MIPNERF_B200_TC_VARIANT: "shared" = CTA pair + shared weight stream (v2), "pair" = CTA pair (v1),
+// "single" = 1-CTA kernel (cta_group::1).
+int tc_variant() {
+  const char* v = getenv("MIPNERF_B200_TC_VARIANT");
+  if (v && v[0] == 's' && v[1] == 'i') return 0;
+  if (v && v[0] == 's' && v[1] == 'h') return 2;
+  if (v && v[0] == 'p') return 1;
+  return MIPNERF_TC_DEFAULT_VARIANT;
+}
+bool use_pair_variant() { return tc_variant() != 0; }
+
 cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
+  if (tc_variant() == 2)
+    return precision == MIPNERF_B200_BF16 ? launch_level_v2<1>(p, st) : launch_level_v2<0>(p, st);
   const bool pair = use_pair_variant();
   if (precision == MIPNERF_B200_BF16)
     return pair ? launch_level_t<1, true>(p, st) : launch_level_t<1, false>(p, st);
@@ -843,6 +1248,7 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
       p.origins = origins, p.directions = directions, p.radii = radii;
       p.t = t_cur;
       p.view_bias = s.vbias;
+      p.feat_scratch = s.feat;
       p.comp_rgb = outs[l].comp_rgb + off * 3;
       p.distance = outs[l].distance + off;
       p.acc = outs[l].acc + off;

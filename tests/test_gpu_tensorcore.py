@@ -20,9 +20,9 @@ DEV = "cuda:0"
 DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
 
-@pytest.fixture(autouse=True, params=["pair", "single"])
+@pytest.fixture(autouse=True, params=["shared", "pair", "single"])
 def tc_variant(request, monkeypatch):
-    """Both kernel variants: the CTA-pair kernel (cta_group::2, default) and the 1-CTA kernel."""
+    """All kernel variants: CTA pair + shared weight stream (v2), CTA pair (v1), 1-CTA kernel."""
     monkeypatch.setenv("MIPNERF_B200_TC_VARIANT", request.param)
     return request.param
 

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
-variant = sys.argv[1] if len(sys.argv) > 1 else "pair"
+variant = sys.argv[1] if len(sys.argv) > 1 else "shared"
 os.environ["MIPNERF_B200_TC_VARIANT"] = variant
 import mipnerf_pl_b200 as mp  # noqa: E402
 from mipnerf_pl_b200 import _cabi  # noqa: E402
