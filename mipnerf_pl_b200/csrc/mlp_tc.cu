@@ -627,6 +627,49 @@ __host__ __device__ constexpr int g2_nw(int g) { return (g == 0 || g == 6) ? 3 :
 __host__ __device__ constexpr int g2_wslab0(int g) { return g == 6 ? 8 : 0; }
 __host__ __device__ constexpr bool g2_feat(int g) { return g == 0 || g == 6; }
 
+// position in the 12-stage ring + the mbarrier parity of that stage's current fill (fill #n goes to
+// stage n % 12 with parity (n / 12) & 1, so both follow by add-and-wrap, no division, no masks)
+struct RingPos {
+  uint32_t st, par;
+};
+__device__ __forceinline__ RingPos ring_at(RingPos b, uint32_t off) {  // off < kStages2
+  RingPos r{b.st + off, b.par};
+  if (r.st >= (uint32_t)kStages2) {
+    r.st -= kStages2;
+    r.par ^= 1u;
+  }
+  return r;
+}
+
+// MMAs of one (group, slot): kNw weight stages (shared by both slots: waited for by slot 0, released
+// after slot 1) and, for the feature groups, the slot's 3 private feature stages as the A operand.
+template <int kNw, bool kFeat, int kSlot>
+__device__ __forceinline__ void v2_issue(RingPos base, uint32_t bars_u, uint32_t sW_u, uint32_t a_base,
+                                         uint32_t d_tmem, uint32_t idesc, bool accumulate_all) {
+#pragma unroll
+  for (int i = 0; i < kNw; ++i) {
+    const RingPos w = ring_at(base, i);
+    if (kSlot == 0) mbar_wait_fast(bars_u + w.st * 8, w.par);
+    uint32_t a_lo, a_hi, f_empty = 0;
+    if (kFeat) {
+      const RingPos f = ring_at(base, kNw + kSlot * 3 + i);
+      mbar_wait_fast(bars_u + f.st * 8, f.par);
+      a_lo = desc_lo(sW_u + f.st * kWStage);
+      a_hi = kDescHiSw64;
+      f_empty = bars_u + (kStages2 + f.st) * 8;
+    } else {
+      a_lo = desc_lo(a_base + (i >> 1) * kStageBytes + (i & 1) * 64);
+      a_hi = kDescHiSw128;
+    }
+    tc_fence_after();
+    const uint32_t b_lo = desc_lo(sW_u + w.st * kWStage);
+    umma_ss_pair_lohi(d_tmem, a_lo, a_hi, b_lo, kDescHiSw64, idesc, (accumulate_all || i > 0) ? 1u : 0u);
+    umma_ss_pair_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, kDescHiSw64, idesc, 1u);
+    if (kFeat) umma_commit_pair_addr(f_empty);                                       // private stage: free now
+    if (kSlot == 1) umma_commit_pair_addr(bars_u + (kStages2 + w.st) * 8);  // last use of the shared stage
+  }
+}
+
 template <int kFmt>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -678,14 +721,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
     // ============================ producer: weights once per round + per-slot feature slabs ============
     if (lane == 0) {
       TRACER_DECL(0);
-      int pos = 0;
-      uint32_t fill_mask = 0, ph_fr0 = 0, ph_fr1 = 0;
-      auto fill = [&](int st, const void* src, uint32_t bytes, int tag) {
-        mbar_wait(&w_empty[st], ((fill_mask >> st) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&w_full[st], bytes);
-        bulk_g2s(sW + st * kWStage, src, bytes, &w_full[st]);
-        fill_mask ^= 1u << st;
-        TRACE(EV(0, 0, tag, st));
+      RingPos cur{0u, 0u};
+      uint32_t ph_fr0 = 0, ph_fr1 = 0;
+      auto fill = [&](const void* src, uint32_t bytes, int tag) {  // fills happen in ring order
+        mbar_wait(&w_empty[cur.st], cur.par ^ 1u);
+        mbar_arrive_expect_tx(&w_full[cur.st], bytes);
+        bulk_g2s(sW + cur.st * kWStage, src, bytes, &w_full[cur.st]);
+        TRACE(EV(0, 0, tag, cur.st));
+        cur = ring_at(cur, 1u);
       };
       for (int round = 0; round < rounds; ++round)
         for (int g = 0; g < kNumGroups2; ++g) {
@@ -693,7 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
           const uint32_t bytes = l == 9 ? kViewPairStage : kWStage;
           const uint8_t* src = l == 9 ? p.wimage + kViewPairOffset + rank * 8 * kViewPairStage
                                       : p.wimage + layer_offset(l) + rank * (layer_bytes(l) / 2) + g2_wslab0(g) * kWStage;
-          for (int i = 0; i < nw; ++i) fill((pos + i) % kStages2, src + i * bytes, bytes, g);
+          for (int i = 0; i < nw; ++i) fill(src + i * bytes, bytes, g);
           if (g2_feat(g)) {
             for (int slot = 0; slot < 2; ++slot) {
               if (g == 0) {  // the IPE warp has published this ray's slabs
@@ -706,10 +749,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
                 }
               }
               const uint8_t* fsrc = my_scratch + (slot * 2 + (round & 1)) * kFeatSlotBytes;
-              for (int i = 0; i < 3; ++i) fill((pos + nw + slot * 3 + i) % kStages2, fsrc + i * kWStage, kWStage, g);
+              for (int i = 0; i < 3; ++i) fill(fsrc + i * kWStage, kWStage, g);
             }
           }
-          pos = (pos + nw + (g2_feat(g) ? 6 : 0)) % kStages2;
         }
       TRACER_DONE(0);
     }
@@ -725,77 +767,53 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
         TRACER_DECL(1);
         const uint32_t idesc = make_idesc_f16(256, 256, kFmt);
         const uint32_t idesc_view = make_idesc_f16(256, 128, kFmt);
-        int pos = 0;
-        uint32_t full_mask = 0, ph_ready0 = 0, ph_ready1 = 0;
+        RingPos base{0u, 0u};
+        uint32_t ph_ready0 = 0, ph_ready1 = 0;
+        const uint32_t acc_full_u = bars_u + (2 * kStages2 + 2) * 8, f_free_u = bars_u + (2 * kStages2 + 6) * 8;
         for (int round = 0; round < rounds; ++round)
           for (int g = 0; g < kNumGroups2; ++g) {
-            const int l = g2_layer(g), nw = g2_nw(g);
+            const int l = g2_layer(g);
             const bool feat = g2_feat(g);
             const uint32_t id = l == 9 ? idesc_view : idesc;
-            for (int slot = 0; slot < 2; ++slot) {
-              if (g != 6) {  // group 6 continues group 5's accumulation: same A-operand epoch
-                if (slot == 0) {
-                  mbar_wait_fast(bars_u + (2 * kStages2) * 8, ph_ready0);
-                  ph_ready0 ^= 1;
-                } else {
-                  mbar_wait_fast(bars_u + (2 * kStages2 + 1) * 8, ph_ready1);
-                  ph_ready1 ^= 1;
-                }
-                tc_fence_after();
-              }
-              TRACE(EV(1, 0, g, slot));
-              const uint32_t a_base = sA_u + slot * kABytes;
-              const uint32_t d_tmem = tm_u + slot * 256;
-              for (int i = 0; i < nw; ++i) {
-                const int stw = (pos + i) % kStages2;
-                int stf = 0;
-                if (slot == 0) mbar_wait_fast(bars_u + stw * 8, (full_mask >> stw) & 1u);
-                if (feat) {
-                  stf = (pos + nw + slot * 3 + i) % kStages2;
-                  mbar_wait_fast(bars_u + stf * 8, (full_mask >> stf) & 1u);
-                }
-                tc_fence_after();
-                TRACE(EV(1, 1, g, slot * 16 + i));
-                const uint32_t a_addr = feat ? sW_u + stf * kWStage : a_base + (i >> 1) * kStageBytes + (i & 1) * 64;
-                const uint32_t b_addr = sW_u + stw * kWStage;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const uint64_t ad = feat ? make_sw64_desc(a_addr + j * 32) : make_sw128_desc(a_addr + j * 32);
-                  const uint64_t bd = make_sw64_desc(b_addr + j * 32);
-                  umma_ss_pair(d_tmem, ad, bd, id, (g == 6 || i > 0 || j > 0) ? 1u : 0u);
-                }
-                if (feat) {  // the ray's private feature stage: free right away
-                  umma_commit_pair(&w_empty[stf]);
-                  full_mask ^= 1u << stf;
-                }
-                if (slot == 1) {  // second (last) use of the shared weight stage
-                  umma_commit_pair(&w_empty[stw]);
-                  full_mask ^= 1u << stw;
-                }
-              }
-              if (g != 5) umma_commit_pair(&acc_full[slot]);
-              if (g == 6) umma_commit_pair(&f_free[slot]);
-              TRACE(EV(1, 2, g, slot));
+            // ---- slot 0
+            if (g != 6) {  // group 6 continues group 5's accumulation: same A-operand epoch
+              mbar_wait_fast(bars_u + (2 * kStages2) * 8, ph_ready0);
+              ph_ready0 ^= 1;
+              tc_fence_after();
             }
-            pos = (pos + nw + (feat ? 6 : 0)) % kStages2;
+            TRACE(EV(1, 0, g, 0));
+            if (feat) v2_issue<3, true, 0>(base, bars_u, sW_u, sA_u, tm_u, id, g == 6);
+            else v2_issue<8, false, 0>(base, bars_u, sW_u, sA_u, tm_u, id, false);
+            if (g != 5) umma_commit_pair_addr(acc_full_u);
+            if (g == 6) umma_commit_pair_addr(f_free_u);
+            TRACE(EV(1, 2, g, 0));
+            // ---- slot 1
+            if (g != 6) {
+              mbar_wait_fast(bars_u + (2 * kStages2 + 1) * 8, ph_ready1);
+              ph_ready1 ^= 1;
+              tc_fence_after();
+            }
+            TRACE(EV(1, 0, g, 1));
+            if (feat) v2_issue<3, true, 1>(base, bars_u, sW_u, sA_u + kABytes, tm_u + 256, id, g == 6);
+            else v2_issue<8, false, 1>(base, bars_u, sW_u, sA_u + kABytes, tm_u + 256, id, false);
+            if (g != 5) umma_commit_pair_addr(acc_full_u + 8);
+            if (g == 6) umma_commit_pair_addr(f_free_u + 8);
+            TRACE(EV(1, 2, g, 1));
+            base = ring_at(base, feat ? 9u : 8u);
           }
         TRACER_DONE(1);
       } else {
         // peer CTA: relay "stage landed here" to the leader's w_full, in the producer's fill order
-        int pos = 0;
-        uint32_t mask = 0;
+        RingPos cur{0u, 0u};
         const uint32_t leader_w_full = mapa_u32(bars_u, 0);
-        auto relay = [&](int st) {
-          mbar_wait_fast(bars_u + st * 8, (mask >> st) & 1u);
-          mbar_arrive_remote(leader_w_full + st * 8);
-          mask ^= 1u << st;
-        };
         for (int round = 0; round < rounds; ++round)
           for (int g = 0; g < kNumGroups2; ++g) {
-            const int nw = g2_nw(g);
-            const int n = nw + (g2_feat(g) ? 6 : 0);
-            for (int i = 0; i < n; ++i) relay((pos + i) % kStages2);
-            pos = (pos + n) % kStages2;
+            const int n = g2_feat(g) ? 9 : 8;
+            for (int i = 0; i < n; ++i) {
+              mbar_wait_fast(bars_u + cur.st * 8, cur.par);
+              mbar_arrive_remote(leader_w_full + cur.st * 8);
+              cur = ring_at(cur, 1u);
+            }
           }
       }
     }

@@ -261,6 +261,28 @@ __device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t adesc, ui
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the descriptors given as {lo, hi} 32-bit halves (hi is a per-layout constant, lo = addr>>4 | 1<<16)
+__device__ __forceinline__ void umma_ss_pair_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t kDescHiSw128 = 0x40004040u;  // SBO 1024 B, version 1, SWIZZLE_128B
+constexpr uint32_t kDescHiSw64 = 0x80004020u;   // SBO  512 B, version 1, SWIZZLE_64B
+__device__ __forceinline__ void umma_commit_pair_addr(uint32_t bar_addr) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          bar_addr),
+      "h"((uint16_t)3)
+      : "memory");
+}
 // arrive on the mbarrier at this shared-memory offset in BOTH CTAs once all prior MMAs completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(
