@@ -164,18 +164,11 @@ template <int kFmt, int L>
 __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int row, float& dens) {
   float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent chains for the density head
   uint32_t v[2][32];
-#ifdef MIPNERF_EXP_NO_LDTM
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[0][i] = v[1][i] = (uint32_t)(row + i);
-#else
   tmem_ld32(t_acc, v[0]);
-#endif
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-#ifndef MIPNERF_EXP_NO_LDTM
     tmem_ld_wait();  // chunk k has landed
     if (k < 7) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) & 1]);  // next chunk in flight while we work
-#endif
     const int c0 = 32 * k;
     uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
 #pragma unroll
@@ -191,9 +184,6 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
                 c_small.w_density[c + 1]);
         w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
       }
-#ifdef MIPNERF_EXP_NO_STS
-      if (row == 0)  // experiment: 1/128 of the stores (results are garbage; timing only)
-#endif
       *reinterpret_cast<uint4*>(slab + sw128_offset(row, (c0 & 63) + j * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }

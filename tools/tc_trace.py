@@ -30,8 +30,16 @@ fn = C.CDLL(_cabi.LIB_PATH).mipnerf_b200_debug_set_trace_buffer
 fn.argtypes = [C.c_void_p]
 assert fn(buf.data_ptr()) == 0
 model.num_levels = 1          # one launch (coarse level) is enough for the timeline
-model(rays, False, True)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for _ in range(20):           # steady clocks
+    model(rays, False, True)
+buf.zero_()
 torch.cuda.synchronize()
+e0.record()
+model(rays, False, True)
+e1.record()
+torch.cuda.synchronize()
+launch_ms = e0.elapsed_time(e1)
 fn(None)
 raw = buf.cpu().numpy()
 parts = []
@@ -42,7 +50,7 @@ ev = np.concatenate(parts)
 n = len(ev)
 t0 = ev[:, 0].min()
 ev = ev[np.argsort(ev[:, 0])]
-print(f"{n} events, span {(ev[-1, 0] - t0)} cycles")
+print(f"{n} events, span {(ev[-1, 0] - t0)} cycles; forward call {launch_ms:.4f} ms -> >= {(ev[-1, 0] - t0) / launch_ms / 1e3:.0f} MHz effective SM clock")
 role = ev[:, 1] >> 24
 kind = (ev[:, 1] >> 16) & 0xff
 g = (ev[:, 1] >> 8) & 0xff
