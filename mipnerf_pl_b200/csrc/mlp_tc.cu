@@ -962,19 +962,43 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
   if (warp == 0) tmem_dealloc_pair(tmem_base, 512);
 }
 
-// view-direction term of the view layer as a per-ray bias: vb[r][n] = b[n] + W[n][256:283] . venc[r]
-__global__ void view_bias_kernel(const float* __restrict__ venc, const float* __restrict__ w,
-                                 const float* __restrict__ b, float* __restrict__ out, int64_t num_rays) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= num_rays * kCond) return;
-  const int64_t ray = idx / kCond;
-  const int n = (int)(idx % kCond);
-  float acc = __ldg(b + n);
-  const float* wr = w + (size_t)n * (kWidth + kViewDim) + kWidth;
-  const float* v = venc + ray * kViewDim;
+// view-direction term of the view layer as a per-ray bias: vb[r][n] = b[n] + W[n][256:283] . pos_enc(viewdir[r])
+// (models/mip.py:353-363 + the `cat([bottleneck, viewenc])` half of view_layers.0, models/mip_nerf.py:106-108).
+// Block = 128 threads (thread n = output n keeps its 27 weights in registers) x 16 rays whose 27-wide
+// encodings are computed once into shared memory.
+constexpr int kVbRays = 16;
+__global__ void __launch_bounds__(kCond) view_bias_kernel(const float* __restrict__ viewdirs,
+                                                          const float* __restrict__ w, const float* __restrict__ b,
+                                                          float* __restrict__ out, int64_t num_rays) {
+  __shared__ float venc[kVbRays][kViewDim + 1];
+  const int n = threadIdx.x;
+  const int64_t ray0 = (int64_t)blockIdx.x * kVbRays;
+  for (int idx = n; idx < kVbRays * kViewDim; idx += kCond) {
+    const int r = idx / kViewDim, f = idx % kViewDim;
+    const int64_t ray = ray0 + r < num_rays ? ray0 + r : num_rays - 1;
+    float v;
+    if (f < 3) {
+      v = __ldg(viewdirs + ray * 3 + f);  // append_identity
+    } else {
+      const int g = f - 3, is_cos = g >= 12, h = is_cos ? g - 12 : g;  // scale-major, then xyz
+      const float y = __fmul_rn(__ldg(viewdirs + ray * 3 + h % 3), __int_as_float((127 + h / 3) << 23));
+      v = sinf(is_cos ? __fadd_rn(y, MIPNERF_HALF_PI_F32) : y);
+    }
+    venc[r][f] = v;
+  }
+  float wr[kViewDim];
 #pragma unroll
-  for (int k = 0; k < kViewDim; ++k) acc = fmaf(__ldg(wr + k), __ldg(v + k), acc);
-  out[idx] = acc;
+  for (int k = 0; k < kViewDim; ++k) wr[k] = __ldg(w + (size_t)n * (kWidth + kViewDim) + kWidth + k);
+  const float bias = __ldg(b + n);
+  __syncthreads();
+#pragma unroll 4
+  for (int r = 0; r < kVbRays; ++r) {
+    if (ray0 + r >= num_rays) break;
+    float acc = bias;
+#pragma unroll
+    for (int k = 0; k < kViewDim; ++k) acc = fmaf(wr[k], venc[r][k], acc);
+    out[(ray0 + r) * kCond + n] = acc;
+  }
 }
 
 // ---- weight packing ---------------------------------------------------------------------------
@@ -1232,11 +1256,10 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
     const float* origins = rays->origins + off * 3;
     const float* directions = rays->directions + off * 3;
     const float* radii = rays->radii + off;
-    if ((e = launch_pos_enc(rays->viewdirs + off * 3, s.venc, cnt, 0, c->deg_view, 1, st)) != cudaSuccess) return e;
     {
       LaunchScope scope(kKernPosEnc, st);
-      view_bias_kernel<<<(unsigned)((cnt * kCond + 255) / 256), 256, 0, st>>>(s.venc, view.weight, view.bias, s.vbias,
-                                                                              cnt);
+      view_bias_kernel<<<(unsigned)((cnt + kVbRays - 1) / kVbRays), kCond, 0, st>>>(rays->viewdirs + off * 3, view.weight,
+                                                                                  view.bias, s.vbias, cnt);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     const float *t_prev = nullptr, *w_prev = nullptr;

@@ -80,6 +80,12 @@ class MLP(torch.nn.Module):
         self.color_layer = torch.nn.Linear(net_width_condition, num_rgb_channels)
         self._packed = {}  # precision -> (versions, tensor)
 
+    def __getstate__(self):  # ctypes marshalling caches are per-process
+        d = self.__dict__.copy()
+        d.pop("_ws_cache", None)
+        d["_packed"] = {}
+        return d
+
     # ---- marshalling --------------------------------------------------------------------------
     def linears(self) -> List[torch.nn.Linear]:
         """state_dict order expected by mipnerf_b200_weights."""
@@ -87,7 +93,18 @@ class MLP(torch.nn.Module):
                 [seq[0] for seq in self.view_layers] + [self.color_layer])
 
     def _weights_struct(self, cfg: "_cabi.Config", precision: int, device):
+        """(struct, keep-alive list), cached until a parameter is modified / moved / re-typed."""
         lins = self.linears()
+        key = (precision, str(device), tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version,
+                                               l.weight.dtype) for l in lins))
+        hit = self.__dict__.get("_ws_cache")
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        ws, keep = self._weights_struct_uncached(cfg, precision, device, lins)
+        self.__dict__["_ws_cache"] = (key, ws, keep)
+        return ws, keep
+
+    def _weights_struct_uncached(self, cfg, precision, device, lins):
         arr = (_cabi.Linear * len(lins))()
         keep = []
         for i, l in enumerate(lins):
@@ -237,12 +254,15 @@ class MipNerf(torch.nn.Module):
         ws, wkeep = self.mlp._weights_struct(cfg, prec, dev)
         outs = (_cabi.LevelOut * self.num_levels)()
         ret = []
+        per_ray = 3 + 1 + 1 + n + (n + 1)
+        flat = torch.empty(self.num_levels * b * per_ray, device=dev)   # one allocation, 5 views per level
         for lvl in range(self.num_levels):
-            comp = torch.empty(b, 3, device=dev)
-            dist = torch.empty(b, device=dev)
-            acc = torch.empty(b, device=dev)
-            w = torch.empty(b, n, device=dev)
-            t = torch.empty(b, n + 1, device=dev)
+            o = lvl * b * per_ray
+            comp = flat[o:o + 3 * b].view(b, 3)
+            dist = flat[o + 3 * b:o + 4 * b]
+            acc = flat[o + 4 * b:o + 5 * b]
+            w = flat[o + 5 * b:o + (5 + n) * b].view(b, n)
+            t = flat[o + (5 + n) * b:o + per_ray * b].view(b, n + 1)
             inds = torch.empty(b, n + 1, device=dev, dtype=torch.int64) if (return_inds and lvl > 0) else None
             outs[lvl] = _cabi.LevelOut(comp.data_ptr(), dist.data_ptr(), acc.data_ptr(), w.data_ptr(),
                                        t.data_ptr(), _ptr(inds))
@@ -253,9 +273,11 @@ class MipNerf(torch.nn.Module):
             _cabi.check(lib.mipnerf_b200_forward(C.byref(cfg), C.byref(ws), C.byref(rs), 0, None, None, 0, prec,
                                                  outs, None, 0, None), "MipNerf.forward")
         scratch = _Workspace.get(dev, nbytes)
-        with torch.cuda.device(dev):
-            _cabi.check(lib.mipnerf_b200_forward(
-                C.byref(cfg), C.byref(ws), C.byref(rs), int(bool(randomized)), _ptr(t_rand), _ptr(u_jitter),
-                int(bool(white_bkgd)), prec, outs, scratch.data_ptr(), scratch.numel(), _stream(dev)),
-                "MipNerf.forward")
+        args = (C.byref(cfg), C.byref(ws), C.byref(rs), int(bool(randomized)), _ptr(t_rand), _ptr(u_jitter),
+                int(bool(white_bkgd)), prec, outs, scratch.data_ptr(), scratch.numel(), _stream(dev))
+        if dev.index is None or dev.index == torch.cuda.current_device():
+            _cabi.check(lib.mipnerf_b200_forward(*args), "MipNerf.forward")
+        else:
+            with torch.cuda.device(dev):
+                _cabi.check(lib.mipnerf_b200_forward(*args), "MipNerf.forward")
         return ret
