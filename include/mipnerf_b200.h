@@ -107,6 +107,11 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
                          mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* distloss (models/mip.py:8-20), forward value per ray: weights [B,N], samples [B,N+1] (sorted) ->
+ * per_ray_loss [B] = (1/3) sum_i d_i w_i^2 + sum_ij w_i w_j |m_i - m_j|; the reference's scalar is its mean. */
+int mipnerf_b200_distloss(const float* weights, const float* samples, int64_t num_rays, int num_samples,
+                          float* per_ray_loss, void* stream);
+
 /* Pinhole rays of rows [row0,row0+rows) of an H x W frame generated on the device, replacing the
  * host NumPy loaders (datasets/datasets.py:214-263, render_video.py:29-105).  `c2w_host` is a HOST
  * pointer to the row-major [3,4] camera-to-world matrix; outputs are [rows*W, 3|1] device buffers. */

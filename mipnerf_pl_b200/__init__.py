@@ -9,7 +9,7 @@ from .rays import (Rays, Rays_keys, namedtuple_map, rearrange_render_image, blen
 from .mip_nerf import MLP, MipNerf
 from .nerf_system import MipNeRFSystem, default_hparams, calc_psnr
 from .ops import (sample_along_rays, resample_along_rays, cast_rays, integrated_pos_enc, pos_enc,
-                  sorted_piecewise_constant_pdf, volumetric_rendering)
+                  sorted_piecewise_constant_pdf, volumetric_rendering, distloss)
 from .weights import make_state_dict
 from .render import generate_rays, render_frame, render_sharded, shard_bounds, shard_rows, gather_rows
 
@@ -17,6 +17,6 @@ __all__ = [
     "Rays", "Rays_keys", "namedtuple_map", "rearrange_render_image", "blender_rays", "spheric_pose",
     "random_ray_batch", "rays_to_torch", "MLP", "MipNerf", "MipNeRFSystem", "default_hparams", "calc_psnr",
     "sample_along_rays", "resample_along_rays", "cast_rays", "integrated_pos_enc", "pos_enc",
-    "sorted_piecewise_constant_pdf", "volumetric_rendering", "make_state_dict", "generate_rays", "render_frame",
+    "sorted_piecewise_constant_pdf", "volumetric_rendering", "distloss", "make_state_dict", "generate_rays", "render_frame",
     "render_sharded", "shard_bounds", "shard_rows", "gather_rows",
 ]

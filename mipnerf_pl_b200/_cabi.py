@@ -62,6 +62,7 @@ _SIGNATURES = {
     "mipnerf_b200_pack_weights": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.c_int, _V, C.c_size_t, _V]),
     "mipnerf_b200_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.c_int,
                                        _V, _V, C.c_int, C.c_int, C.POINTER(LevelOut), _V, C.c_size_t, _V]),
+    "mipnerf_b200_distloss": (C.c_int, [_V, _V, C.c_int64, C.c_int, _V, _V]),
     "mipnerf_b200_generate_rays": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                              _V, _V, _V, _V, _V, _V, _V]),
     "mipnerf_b200_sample_along_rays": (C.c_int, [C.POINTER(RaysStruct), C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V]),

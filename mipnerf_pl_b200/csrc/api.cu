@@ -314,6 +314,14 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
   return MIPNERF_B200_OK;
 }
 
+int mipnerf_b200_distloss(const float* weights, const float* samples, int64_t num_rays, int num_samples,
+                          float* per_ray_loss, void* stream) {
+  if (num_rays < 0 || num_samples < 1) return fail(MIPNERF_B200_EINVAL, "bad sizes");
+  if (num_rays > 0 && (!weights || !samples || !per_ray_loss)) return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  CUDA_TRY(mipnerf::launch_distloss(weights, samples, per_ray_loss, num_rays, num_samples, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
 int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, float focal, float near, float far,
                                int row0, int rows, float* origins, float* directions, float* viewdirs,
                                float* radii, float* near_out, float* far_out, void* stream) {

@@ -8,6 +8,8 @@
 namespace mipnerf {
 
 // ---- ray_kernels.cu ----
+cudaError_t launch_distloss(const float* weights, const float* t, float* out, int64_t num_rays, int n,
+                            cudaStream_t st);
 cudaError_t launch_generate_rays(const float* c2w_host, int height, int width, float focal, float near_v,
                                  float far_v, int row0, int rows, float* origins, float* directions,
                                  float* viewdirs, float* radii, float* near_o, float* far_o, cudaStream_t st);

@@ -19,6 +19,7 @@ enum KernelId : int {
   kKernMlpLevelTc,   // fused tcgen05 level kernel (IPE + MLP + compositing)
   kKernMlpTc,        // tcgen05 MLP on explicit features
   kKernRayGen,       // on-device pinhole ray generation
+  kKernDistloss,
   kKernCount
 };
 

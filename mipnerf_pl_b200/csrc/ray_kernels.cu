@@ -343,6 +343,49 @@ __global__ void resample_kernel(const float* __restrict__ bins, const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// distloss (models/mip.py:8-20), per ray:  (1/3) sum_i d_i w_i^2  +  sum_ij w_i w_j |m_i - m_j|.
+// The reference builds two [B,N,N] tensors; midpoints are sorted (fenceposts are), so
+//   sum_ij w_i w_j |m_i - m_j| = 2 sum_i w_i (m_i W_<i - M_<i),  W_<i = sum_{j<i} w_j,  M_<i = sum_{j<i} w_j m_j
+// which is two warp scans.  Warp per ray, fp64 accumulation.
+// ---------------------------------------------------------------------------------------------
+__global__ void distloss_kernel(const float* __restrict__ weights, const float* __restrict__ t,
+                                float* __restrict__ out, int64_t num_rays, int n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ray >= num_rays) return;
+  const float* w = weights + ray * n;
+  const float* tr = t + ray * (n + 1);
+  const int per = (n + 31) / 32;
+  double uni = 0.0, bi = 0.0, w_run = 0.0, m_run = 0.0;
+  // pass 1: lane totals over its contiguous chunk
+  for (int p = 0; p < per; ++p) {
+    const int i = lane * per + p;
+    if (i < n) {
+      const double wi = w[i], mi = 0.5 * ((double)tr[i] + (double)tr[i + 1]);
+      w_run += wi;
+      m_run += wi * mi;
+    }
+  }
+  double tot;
+  double w_before = warp_excl_scan_f64(w_run, lane, tot);
+  double m_before = warp_excl_scan_f64(m_run, lane, tot);
+  for (int p = 0; p < per; ++p) {
+    const int i = lane * per + p;
+    if (i < n) {
+      const double wi = w[i], t0 = tr[i], t1 = tr[i + 1], mi = 0.5 * (t0 + t1);
+      uni += (t1 - t0) * wi * wi;
+      bi += wi * (mi * w_before - m_before);
+      w_before += wi;
+      m_before += wi * mi;
+    }
+  }
+  double v = uni / 3.0 + 2.0 * bi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) out[ray] = (float)v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Blender-style pinhole rays for rows [row0, row0+rows) of an H x W frame, straight into HBM
 // (datasets/datasets.py:214-263, render_video.py:29-105): one thread per pixel.
 //   camera dir = ((x - W/2 + .5)/f, -(y - H/2 + .5)/f, -1);  direction = R . dir;  origin = c2w[:,3]
@@ -396,6 +439,14 @@ cudaError_t launch_generate_rays(const float* c2w_host, int height, int width, f
   LaunchScope scope(kKernRayGen, st);
   generate_rays_kernel<<<blocks_for((int64_t)rows * width, 256), 256, 0, st>>>(
       c, height, width, focal, near_v, far_v, row0, rows, origins, directions, viewdirs, radii, near_o, far_o);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_distloss(const float* weights, const float* t, float* out, int64_t num_rays, int n,
+                            cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  LaunchScope scope(kKernDistloss, st);
+  distloss_kernel<<<blocks_for(num_rays, 4), 128, 0, st>>>(weights, t, out, num_rays, n);
   return cudaGetLastError();
 }
 

@@ -196,3 +196,17 @@ def volumetric_rendering(rgb, density, t_samples, dirs, white_bkgd):
             comp.data_ptr(), dist.data_ptr(), acc.data_ptr(), w.data_ptr(), _stream(dev)),
             "volumetric_rendering")
     return comp, dist, acc, w
+
+
+def distloss(weight, samples):
+    """Distortion loss value (models/mip.py:8-20): weight [B,N], samples [B,N+1] -> scalar.
+    Forward only (the training backward is SURVEY §8f N2); O(N) per ray instead of the
+    reference's two [B,N,N] temporaries."""
+    dev = _dev(weight)
+    w, t = _f32(weight), _f32(samples)
+    b, n = w.shape
+    out = torch.empty(b, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().mipnerf_b200_distloss(w.data_ptr(), t.data_ptr(), b, n, out.data_ptr(), _stream(dev)),
+                    "distloss")
+    return out.mean()

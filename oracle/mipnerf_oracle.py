@@ -178,6 +178,16 @@ def volumetric_rendering(rgb, density, t_samples, dirs, white_bkgd):
     return comp_rgb, distance, acc, weights
 
 
+def distloss(weight, samples):
+    """Distortion loss (models/mip.py:8-20): weight [B,N], samples [B,N+1] -> scalar."""
+    interval = samples[:, 1:] - samples[:, :-1]
+    mid = (samples[:, 1:] + samples[:, :-1]) * 0.5
+    loss_uni = (1 / 3) * (interval * weight.pow(2)).sum(-1).mean()
+    ww = weight.unsqueeze(-1) * weight.unsqueeze(-2)
+    mm = (mid.unsqueeze(-1) - mid.unsqueeze(-2)).abs()
+    return loss_uni + (ww * mm).sum((-1, -2)).mean()
+
+
 def blurpool_weights(weights, resample_padding):
     """Max-then-average blur + constant (models/mip.py:252-257)."""
     wp = torch.cat([weights[..., :1], weights, weights[..., -1:]], dim=-1)

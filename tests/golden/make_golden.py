@@ -187,6 +187,9 @@ def stages_case():
         out.update({f"{tag}_comp": comp.numpy(), f"{tag}_dist": dist.numpy(), f"{tag}_acc": acc.numpy(),
                     f"{tag}_weights": w.numpy()})
     out.update(vr_rgb=rgb.numpy(), vr_density=dens.numpy(), vr_t=t.numpy())
+    # distloss on the white-background compositing weights
+    out["distloss_value"] = np.array(float(ref_mip.distloss(w, t)), dtype=np.float64)
+    out["distloss_weights"] = w.numpy()
     # MLP.forward
     model = RefMipNerf()
     model.load_state_dict(make_state_dict(seed=2))

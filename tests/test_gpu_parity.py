@@ -270,3 +270,15 @@ def test_render_frame_equals_forward_on_host_rays():
     assert coarse.shape == (h, w, 3) and dist_map.shape == (h, w)
     assert torch.allclose(fine.reshape(-1, 3), ret[1][0], atol=2e-3)
     assert torch.allclose(coarse.reshape(-1, 3), ret[0][0], atol=2e-3)
+
+
+def test_distloss_vs_golden_and_oracle():
+    g = golden("stages.npz")
+    val = mp.distloss(cuda(g["distloss_weights"]), cuda(g["vr_t"]))
+    assert abs(float(val) - float(g["distloss_value"])) <= 1e-4 * abs(float(g["distloss_value"]))
+    gen = torch.Generator().manual_seed(3)
+    t = torch.sort(2 + 4 * torch.rand(300, 129, generator=gen), dim=-1).values
+    w = torch.rand(300, 128, generator=gen) ** 3
+    want = oracle.distloss(w, t)
+    got = mp.distloss(w.to(DEV), t.to(DEV))
+    assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))

@@ -129,3 +129,20 @@ def test_weights_generator_is_deterministic():
     assert all(torch.equal(a[k], b[k]) for k in a)
     x = make_state_dict(0)["mlp.layers.0.0.weight"]
     assert abs(float(x.abs().max()) - (6 / (96 + 256)) ** 0.5) < 1e-3
+
+
+def test_bench_reference_arm_prints_contract_json():
+    """`bench.py --impl reference` (the CPU arm the driver runs first) needs no GPU and prints one JSON line
+    with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

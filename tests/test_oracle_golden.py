@@ -102,6 +102,8 @@ def test_stage_functions():
         assert_close(comp, g[f"{tag}_comp"], 1e-3, what=tag + " comp")
         assert_close(dist, g[f"{tag}_dist"], 1e-2, what=tag + " dist")
         assert_close(acc, g[f"{tag}_acc"], 1e-3, what=tag + " acc")
+    got = oracle.distloss(torch.from_numpy(g["distloss_weights"]), tt)
+    assert abs(float(got) - float(g["distloss_value"])) <= 1e-6 * abs(float(g["distloss_value"]))
     params = make_state_dict(seed=2)
     raw_rgb, raw_density = oracle.mlp_forward(params, torch.from_numpy(g["mlp_x"]), torch.from_numpy(g["mlp_venc"]))
     assert_close(raw_rgb, g["mlp_raw_rgb"], 1e-2, what="mlp raw_rgb")
