@@ -399,7 +399,11 @@ int mipnerf_b200_mlp_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_
       return fail(MIPNERF_B200_EUNSUPPORTED, "tensor-core MLP: default 8x256 model, 128 samples/ray only");
     if (!w->packed || w->packed_precision != precision)
       return fail(MIPNERF_B200_EINVAL, "weights->packed missing or packed for another precision");
-    cudaError_t e = mipnerf::tc_mlp_forward(cfg, w, x, view_enc, num_rays, precision, raw_rgb, raw_density, st);
+    if (!workspace || workspace_bytes < mipnerf::tc_mlp_workspace_bytes(num_rays))
+      return fail(MIPNERF_B200_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes,
+                  mipnerf::tc_mlp_workspace_bytes(num_rays));
+    cudaError_t e = mipnerf::tc_mlp_forward(cfg, w, x, view_enc, num_rays, precision, raw_rgb, raw_density, workspace,
+                                            st);
     if (e != cudaSuccess) return fail(MIPNERF_B200_ECUDA, "tc_mlp_forward: %s", cudaGetErrorString(e));
     return MIPNERF_B200_OK;
   }
@@ -428,7 +432,7 @@ size_t mipnerf_b200_mlp_workspace_bytes(const mipnerf_b200_config* cfg, int64_t 
   mipnerf_b200_config c2 = *cfg;
   c2.num_samples = 32;
   if (check_config(&c2, &d) != MIPNERF_B200_OK) return 0;
-  if (precision != MIPNERF_B200_FP32) return 256;
+  if (precision != MIPNERF_B200_FP32) return mipnerf::tc_mlp_workspace_bytes(num_rays);
   c2.num_samples = samples_per_ray;
   int64_t per = (kChunkRaysFp32 * 128) / samples_per_ray;
   if (per < 1) per = 1;

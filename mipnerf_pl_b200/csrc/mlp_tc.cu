@@ -135,6 +135,9 @@ struct LevelParams {
   const float* radii;
   const float* t;          // [B,129] fenceposts of this level
   const float* view_bias;  // [B,128]  b_view + W_view[:,256:] . pos_enc(viewdir)
+  const float* feat_in;    // MLP-only mode (mipnerf_b200_mlp_forward): [B,128,96] features supplied by the caller
+  float* raw_rgb_out;      // MLP-only mode: [B,128,3] / [B,128] raw heads instead of compositing
+  float* raw_density_out;
   uint8_t* feat_scratch;   // v2 kernel: per-CTA pre-swizzled feature slabs in global memory (L2 resident)
   float* comp_rgb;
   float* distance;
@@ -429,22 +432,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       mbar_wait(&f_free[slot], ph_free ^ 1);  // first pass falls through (fresh barrier)
       ph_free ^= 1;
       TRACE(EV(3, 0, 0, slot));
-      const RayGeom g = load_ray_geom(p.origins, p.directions, p.radii, ray);
+      RayGeom g{};
+      if (!p.feat_in) g = load_ray_geom(p.origins, p.directions, p.radii, ray);
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
         const int row = i * 32 + lane;
-        const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
-        float mean[3], cov[3], tm, tv, rv;
-        frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
-        lift_gaussian(g, tm, tv, rv, mean, cov);
-        if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
+        float mean[3] = {0.f, 0.f, 0.f}, cov[3] = {0.f, 0.f, 0.f};
+        const float* fin = nullptr;
+        if (p.feat_in) {
+          fin = p.feat_in + (ray * kN + row) * kFeat;  // MLP-only mode: the caller's encoding
+        } else {
+          const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+          float tm, tv, rv;
+          frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
+          lift_gaussian(g, tm, tv, rv, mean, cov);
+          if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
+        }
 #pragma unroll
         for (int gi = 0; gi < 6; ++gi) {
           float fsin[8], fcos[8];
+          if (fin) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
-            ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
+            for (int e = 0; e < 8; ++e) {
+              fsin[e] = __ldg(fin + gi * 8 + e);
+              fcos[e] = __ldg(fin + 48 + gi * 8 + e);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
+              ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
+            }
           }
           store8<kFmt>(myF + sw128_offset(row, gi * 8), fsin);  // K = f
           if (gi < 2)
@@ -489,9 +507,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       const int64_t tile = tile_of(round, slot);
       const bool valid = tile < p.num_rays;
       const int64_t ray = valid ? tile : p.num_rays - 1;
-      const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
-      float dnorm;
-      {
+      float t0 = 0.f, t1 = 0.f, dnorm = 0.f;
+      if (!p.raw_rgb_out) {
+        t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
         const float dx = __ldg(p.directions + ray * 3), dy = __ldg(p.directions + ray * 3 + 1),
                     dz = __ldg(p.directions + ray * 3 + 2);
         dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -529,6 +547,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           arrive_a_ready();  // accumulator drained: the next ray's layer 0 may start while we composite
           TRACE(EV(2, 3, l, slot));
         }
+      }
+      if (p.raw_rgb_out) {  // MLP-only mode: hand back the raw heads (models/mip_nerf.py:98,110)
+        if (valid) {
+          const int64_t sidx = ray * kN + row;
+          p.raw_rgb_out[sidx * 3 + 0] = rgb0 + c_small.b_color[0];
+          p.raw_rgb_out[sidx * 3 + 1] = rgb1 + c_small.b_color[1];
+          p.raw_rgb_out[sidx * 3 + 2] = rgb2 + c_small.b_color[2];
+          p.raw_density_out[sidx] = dens + c_small.b_density;
+        }
+        named_bar_sync(1 + slot, 128);  // vb_s is rewritten at the top of the next ray
+        continue;
       }
       // ---- activations + compositing over the ray's 128 samples (4 warps of this slot)
       const float density = density_activation(dens + c_small.b_density, p.density_bias);
@@ -966,12 +995,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
 // (models/mip.py:353-363 + the `cat([bottleneck, viewenc])` half of view_layers.0, models/mip_nerf.py:106-108).
 // Block = 128 threads (thread n = output n keeps its 27 weights in registers) x 16 rays whose 27-wide
 // encodings are computed once into shared memory.
+//
+// The same launch ("ray prologue") also writes the coarse fenceposts of level 0 (models/mip.py:143-160):
+// blocks past the view-bias range each produce kCoarsePerBlock values of t[B,129].  One launch instead
+// of two in front of the level-0 kernel.
 constexpr int kVbRays = 16;
-__global__ void __launch_bounds__(kCond) view_bias_kernel(const float* __restrict__ viewdirs,
-                                                          const float* __restrict__ w, const float* __restrict__ b,
-                                                          float* __restrict__ out, int64_t num_rays) {
+constexpr int kCoarsePerBlock = 8 * kCond;
+__global__ void __launch_bounds__(kCond) ray_prologue_kernel(const float* __restrict__ viewdirs,
+                                                             const float* __restrict__ w, const float* __restrict__ b,
+                                                             float* __restrict__ out, int64_t num_rays,
+                                                             unsigned vb_blocks, const float* __restrict__ near,
+                                                             const float* __restrict__ far,
+                                                             const float* __restrict__ t_rand, float* __restrict__ t_out,
+                                                             int disparity) {
   __shared__ float venc[kVbRays][kViewDim + 1];
   const int n = threadIdx.x;
+  if (blockIdx.x >= vb_blocks) {
+    const int64_t base = (int64_t)(blockIdx.x - vb_blocks) * kCoarsePerBlock, total = num_rays * (kN + 1);
+#pragma unroll 1
+    for (int i = 0; i < kCoarsePerBlock / kCond; ++i) {
+      const int64_t idx = base + i * kCond + n;
+      if (idx >= total) return;
+      const int64_t ray = idx / (kN + 1);
+      const int j = (int)(idx % (kN + 1));
+      t_out[idx] = coarse_fencepost(__ldg(near + ray), __ldg(far + ray), j, kN, disparity,
+                                    t_rand ? t_rand + idx : nullptr);
+    }
+    return;
+  }
   const int64_t ray0 = (int64_t)blockIdx.x * kVbRays;
   for (int idx = n; idx < kVbRays * kViewDim; idx += kCond) {
     const int r = idx / kViewDim, f = idx % kViewDim;
@@ -999,6 +1050,20 @@ __global__ void __launch_bounds__(kCond) view_bias_kernel(const float* __restric
     for (int k = 0; k < kViewDim; ++k) acc = fmaf(wr[k], venc[r][k], acc);
     out[(ray0 + r) * kCond + n] = acc;
   }
+}
+
+// MLP-only mode: same per-ray bias from a caller-supplied [B,27] view encoding
+__global__ void view_bias_from_enc_kernel(const float* __restrict__ venc, const float* __restrict__ w,
+                                          const float* __restrict__ b, float* __restrict__ out, int64_t num_rays) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * kCond) return;
+  const int64_t ray = idx / kCond;
+  const int n = (int)(idx % kCond);
+  float acc = __ldg(b + n);
+#pragma unroll
+  for (int k = 0; k < kViewDim; ++k)
+    acc = fmaf(__ldg(w + (size_t)n * (kWidth + kViewDim) + kWidth + k), __ldg(venc + ray * kViewDim + k), acc);
+  out[idx] = acc;
 }
 
 // ---- weight packing ---------------------------------------------------------------------------
@@ -1179,7 +1244,11 @@ bool tc_supported(const mipnerf_b200_config* c, int precision) {
          c->net_width_condition == kCond && c->skip_index == 4 && c->num_rgb_channels == 3 &&
          c->num_density_channels == 1;
 }
-bool tc_mlp_supported(const mipnerf_b200_config*, int, int) { return false; }
+bool tc_mlp_supported(const mipnerf_b200_config* c, int samples_per_ray, int precision) {
+  mipnerf_b200_config c2 = *c;
+  c2.num_samples = kN;
+  return samples_per_ray == kN && tc_supported(&c2, precision);
+}
 
 size_t tc_packed_bytes(const mipnerf_b200_config* c, int precision) {
   return tc_supported(c, precision) ? kImageBytes : 0;
@@ -1257,19 +1326,20 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
     const float* directions = rays->directions + off * 3;
     const float* radii = rays->radii + off;
     {
-      LaunchScope scope(kKernPosEnc, st);
-      view_bias_kernel<<<(unsigned)((cnt + kVbRays - 1) / kVbRays), kCond, 0, st>>>(rays->viewdirs + off * 3, view.weight,
-                                                                                  view.bias, s.vbias, cnt);
+      LaunchScope scope(kKernRayPrologue, st);
+      float* t0 = outs[0].t_samples ? outs[0].t_samples + off * (kN + 1) : s.t[0];
+      const unsigned vb_blocks = (unsigned)((cnt + kVbRays - 1) / kVbRays);
+      const unsigned ct_blocks = (unsigned)((cnt * (kN + 1) + kCoarsePerBlock - 1) / kCoarsePerBlock);
+      ray_prologue_kernel<<<vb_blocks + ct_blocks, kCond, 0, st>>>(
+          rays->viewdirs + off * 3, view.weight, view.bias, s.vbias, cnt, vb_blocks, rays->near + off, rays->far + off,
+          (randomized && t_rand) ? t_rand + off * (kN + 1) : nullptr, t0, c->disparity);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     const float *t_prev = nullptr, *w_prev = nullptr;
     for (int l = 0; l < c->num_levels; ++l) {
       float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (kN + 1) : s.t[l & 1];
       float* w_cur = outs[l].weights ? outs[l].weights + off * kN : s.w[l & 1];
-      if (l == 0)
-        e = launch_coarse_t(rays->near + off, rays->far + off, t_rand ? t_rand + off * (kN + 1) : nullptr, t_cur, cnt,
-                            kN, randomized, c->disparity, st);
-      else
+      if (l > 0)  // level 0's fenceposts came out of the ray prologue
         e = launch_resample(t_prev, w_prev, u_jitter ? u_jitter + off * (kN + 1) : nullptr, t_cur,
                             outs[l].inds ? outs[l].inds + off * (kN + 1) : nullptr, cnt, kN, kN + 1, randomized, 1,
                             c->resample_padding, st);
@@ -1297,9 +1367,35 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
   return cudaSuccess;
 }
 
-cudaError_t tc_mlp_forward(const mipnerf_b200_config*, const mipnerf_b200_weights*, const float*, const float*, int64_t,
-                           int, float*, float*, cudaStream_t) {
-  return cudaErrorNotSupported;
+cudaError_t tc_mlp_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights* w, const float* x,
+                           const float* view_enc, int64_t num_rays, int precision, float* raw_rgb, float* raw_density,
+                           void* workspace, cudaStream_t st) {
+  (void)c;
+  const uint8_t* img = static_cast<const uint8_t*>(w->packed);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_small, img + kSmallOffset, sizeof(SmallParams), 0,
+                                          cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return e;
+  float* vbias = static_cast<float*>(workspace);  // [num_rays, 128]
+  const mipnerf_b200_linear& view = w->linears[10];
+  {
+    LaunchScope scope(kKernPosEnc, st);
+    view_bias_from_enc_kernel<<<(unsigned)((num_rays * kCond + 255) / 256), 256, 0, st>>>(view_enc, view.weight,
+                                                                                           view.bias, vbias, num_rays);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  LevelParams p{};
+  p.wimage = img;
+  p.view_bias = vbias;
+  p.feat_in = x;
+  p.raw_rgb_out = raw_rgb;
+  p.raw_density_out = raw_density;
+  p.num_rays = num_rays;
+  // MLP-only mode lives in the v1 kernels (CTA pair unless MIPNERF_B200_TC_VARIANT=single)
+  const bool pair = tc_variant() != 0;
+  if (precision == MIPNERF_B200_BF16) return pair ? launch_level_t<1, true>(p, st) : launch_level_t<1, false>(p, st);
+  return pair ? launch_level_t<0, true>(p, st) : launch_level_t<0, false>(p, st);
 }
+
+size_t tc_mlp_workspace_bytes(int64_t num_rays) { return (size_t)(num_rays > 0 ? num_rays : 1) * kCond * sizeof(float); }
 
 }  // namespace mipnerf

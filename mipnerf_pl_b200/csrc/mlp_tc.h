@@ -21,6 +21,7 @@ cudaError_t tc_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weight
                        void* workspace, size_t workspace_bytes, cudaStream_t st);
 cudaError_t tc_mlp_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w, const float* x,
                            const float* view_enc, int64_t num_rays, int precision, float* raw_rgb,
-                           float* raw_density, cudaStream_t st);
+                           float* raw_density, void* workspace, cudaStream_t st);
+size_t tc_mlp_workspace_bytes(int64_t num_rays);
 
 }  // namespace mipnerf

@@ -20,6 +20,7 @@ enum KernelId : int {
   kKernMlpTc,        // tcgen05 MLP on explicit features
   kKernRayGen,       // on-device pinhole ray generation
   kKernDistloss,
+  kKernRayPrologue,  // view-direction bias + coarse fenceposts in front of the fused level kernels
   kKernCount
 };
 

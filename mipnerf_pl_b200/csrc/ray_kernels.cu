@@ -19,16 +19,6 @@ static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)(
 // ---------------------------------------------------------------------------------------------
 // coarse fenceposts: one thread per (ray, j)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float coarse_t(float near, float far, float s, int disparity) {
-  if (disparity) {
-    // 1 / (1/near*(1-s) + 1/far*s)        (models/mip.py:150)
-    const float a = __fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, s));
-    const float b = __fmul_rn(__fdiv_rn(1.0f, far), s);
-    return __fdiv_rn(1.0f, __fadd_rn(a, b));
-  }
-  return __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), s));  // near + (far-near)*s   (:153)
-}
-
 __global__ void coarse_t_kernel(const float* __restrict__ near, const float* __restrict__ far,
                                 const float* __restrict__ t_rand, float* __restrict__ t_out,
                                 int64_t num_rays, int n, int randomized, int disparity) {
@@ -37,17 +27,8 @@ __global__ void coarse_t_kernel(const float* __restrict__ near, const float* __r
   if (idx >= total) return;
   const int64_t ray = idx / (n + 1);
   const int j = (int)(idx % (n + 1));
-  const float nr = __ldg(near + ray), fr = __ldg(far + ray);
-  const float inv_n = 1.0f / (float)n;  // linspace(0,1,n+1)[j] == fl32(j/n) for the n we accept
-  auto tj = [&](int k) { return coarse_t(nr, fr, __fmul_rn((float)k, inv_n), disparity); };
-  float t = tj(j);
-  if (randomized) {
-    // mids / upper / lower (models/mip.py:156-160)
-    const float lower = j == 0 ? t : __fmul_rn(0.5f, __fadd_rn(t, tj(j - 1)));
-    const float upper = j == n ? t : __fmul_rn(0.5f, __fadd_rn(tj(j + 1), t));
-    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(t_rand + idx)));
-  }
-  t_out[idx] = t;
+  t_out[idx] = coarse_fencepost(__ldg(near + ray), __ldg(far + ray), j, n, disparity,
+                                randomized ? t_rand + idx : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

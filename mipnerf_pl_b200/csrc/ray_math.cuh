@@ -13,6 +13,33 @@ namespace mipnerf {
 
 #define MIPNERF_HALF_PI_F32 1.57079637050628662109375f  // fl32(0.5*pi) = 0x3FC90FDB (models/mip.py:350)
 #define MIPNERF_F32_EPS 1.1920928955078125e-07f          // torch.finfo(float32).eps
+// ---- coarse fenceposts (models/mip.py:143-160) -------------------------------------------------
+__device__ __forceinline__ float coarse_t(float near, float far, float s, int disparity) {
+  if (disparity) {
+    // 1 / (1/near*(1-s) + 1/far*s)        (models/mip.py:150)
+    const float a = __fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, s));
+    const float b = __fmul_rn(__fdiv_rn(1.0f, far), s);
+    return __fdiv_rn(1.0f, __fadd_rn(a, b));
+  }
+  return __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), s));  // near + (far-near)*s   (:153)
+}
+
+// fencepost j of n+1; `jitter` = &t_rand[ray][j] for the stratified draw, nullptr when deterministic
+__device__ __forceinline__ float coarse_fencepost(float nr, float fr, int j, int n, int disparity,
+                                                  const float* __restrict__ jitter) {
+  const float inv_n = 1.0f / (float)n;  // linspace(0,1,n+1)[j] == fl32(j/n) for the n we accept
+  float t = coarse_t(nr, fr, __fmul_rn((float)j, inv_n), disparity);
+  if (jitter) {
+    // mids / upper / lower (models/mip.py:156-160)
+    const float lower =
+        j == 0 ? t : __fmul_rn(0.5f, __fadd_rn(t, coarse_t(nr, fr, __fmul_rn((float)(j - 1), inv_n), disparity)));
+    const float upper =
+        j == n ? t : __fmul_rn(0.5f, __fadd_rn(coarse_t(nr, fr, __fmul_rn((float)(j + 1), inv_n), disparity), t));
+    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(jitter)));
+  }
+  return t;
+}
+
 
 struct RayGeom {
   float o[3];     // origin

@@ -103,3 +103,51 @@ def test_tc_full_batch_properties():
         assert torch.all(t[:, 1:] >= t[:, :-1])
         assert torch.allclose(rgb_w, black[lvl][0] + (1 - acc)[:, None], atol=1e-5)
         assert torch.allclose(w.sum(-1), acc, atol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_tc_mlp_stage_entry(precision):
+    """MLP.forward(x, view_enc, precision=...) alone (models/mip_nerf.py:75-111): the fused kernel in
+    MLP-only mode (features from the caller, raw heads out) against the oracle with the kernel's
+    operand rounding emulated, and against the fp32 oracle at the 16-bit bound."""
+    g = torch.Generator().manual_seed(31)
+    b = 37                                                            # odd: ragged last CTA pair
+    x = torch.rand(b, 128, 96, generator=g) * 2 - 1                   # IPE features live in [-1, 1]
+    venc = torch.randn(b, 27, generator=g)
+    params = make_state_dict(seed=6, kind="xavier")
+    mlp = mp.MLP(net_depth=8, net_width=256, net_depth_condition=1, net_width_condition=128,
+                 skip_index=4, num_rgb_channels=3, num_density_channels=1, activation="relu",
+                 xyz_dim=96, view_dim=27)
+    mlp.load_state_dict({k[len("mlp."):]: v for k, v in params.items()})
+    mlp = mlp.to(DEV).eval()
+    rgb, dens = mlp(x.to(DEV), venc.to(DEV), precision=precision)
+    torch.cuda.synchronize()
+    assert rgb.shape == (b, 128, 3) and dens.shape == (b, 128, 1)
+    want_rgb, want_dens = oracle.mlp_forward(params, x, venc, operand_dtype=DT[precision])
+    f32_rgb, f32_dens = oracle.mlp_forward(params, x, venc)
+    # Max-norm agreement with the emulation is NOT tight at the raw-head level: one 16-bit rounding that
+    # lands on the other side (fp32 accumulation order differs) perturbs every next-layer input by
+    # ~eps/16 and decorrelates that sample's later roundings, so a few samples differ by a full
+    # 16-bit-rounding error.  The median is what isolates kernel bugs (layout / barrier / head
+    # mistakes are O(1) everywhere); the max is held to the 16-bit bound.
+    med_tol, max_tol = (1e-3, 2e-2) if precision == "bf16" else (1.5e-4, 3e-3)
+    for name, got, want, ref in (("raw_rgb", rgb, want_rgb, f32_rgb), ("raw_density", dens, want_dens, f32_dens)):
+        scale = float(ref.abs().max())
+        d_emu = (got.cpu() - want).abs() / scale
+        e_f32 = float((got.cpu() - ref).abs().max()) / scale
+        print(f"{precision} {name}: err / max|ref|: median {float(d_emu.median()):.3e}, max {float(d_emu.max()):.3e} "
+              f"vs emulated oracle; max {e_f32:.3e} vs fp32")
+        assert float(d_emu.median()) <= med_tol, (name, float(d_emu.median()))
+        assert float(d_emu.max()) <= max_tol, (name, float(d_emu.max()))
+        assert e_f32 <= max_tol, (name, e_f32)
+    # fp32 entry on the same inputs agrees with the fp32 oracle at the fp32 bar
+    rgb32, dens32 = mlp(x.to(DEV), venc.to(DEV))
+    assert float((rgb32.cpu() - f32_rgb).abs().max()) <= 1e-4 * float(f32_rgb.abs().max())
+    assert float((dens32.cpu() - f32_dens).abs().max()) <= 1e-4 * float(f32_dens.abs().max())
+
+
+def test_tc_mlp_stage_entry_rejects_other_shapes():
+    mlp = mp.MLP(8, 256, 1, 128, 4, 3, 1, "relu", 96, 27).to(DEV)
+    x = torch.zeros(4, 64, 96, device=DEV)
+    with pytest.raises(NotImplementedError):
+        mlp(x, torch.zeros(4, 27, device=DEV), precision="bf16")     # 64 samples/ray: fp32 path only
