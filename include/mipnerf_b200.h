@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MIPNERF_B200_ABI_VERSION 1
+#define MIPNERF_B200_ABI_VERSION 2
 
 #define MIPNERF_B200_OK 0
 #define MIPNERF_B200_EINVAL (-1)       /* bad argument (NULL pointer, negative size, ...)            */
@@ -111,6 +111,51 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
  * per_ray_loss [B] = (1/3) sum_i d_i w_i^2 + sum_ij w_i w_j |m_i - m_j|; the reference's scalar is its mean. */
 int mipnerf_b200_distloss(const float* weights, const float* samples, int64_t num_rays, int num_samples,
                           float* per_ray_loss, void* stream);
+
+/* ---- training step (fp32 only in this round) ----------------------------------
+ * Gradient buffers, one per entry of mipnerf_b200_weights.linears (same order and shapes). */
+typedef struct mipnerf_b200_linear_grad {
+  float* weight_grad; /* [out_features, in_features] */
+  float* bias_grad;   /* [out_features]              */
+} mipnerf_b200_linear_grad;
+
+/* The loss of MipNeRFSystem.training_step (models/nerf_system.py:95-121):
+ *   loss = sum_l  level_mse_mult[l] * sum_r mask_r |comp_rgb_l,r - target_r|^2 / mask_sum
+ *               + level_dist_mult[l] * dist_scale * sum_r distloss_l,r
+ * (reference: mse_mult = {coarse_loss_mult, 1}, dist_mult = {0.01*coarse_loss_mult, 0.01},
+ * mask = rays.lossmult or ones, dist_scale = 1/B: the .mean() of models/mip.py:16,19).
+ * `mask_sum` and `dist_scale` are over the GLOBAL batch so that ray shards of one batch (chunks, ranks)
+ * produce gradients that simply add up. */
+typedef struct mipnerf_b200_loss {
+  const float* target_rgb;      /* [B,3] device                                                      */
+  const float* lossmult;        /* [B] device, or NULL for a mask of ones                            */
+  const float* mask_sum;        /* device scalar                                                     */
+  float dist_scale;
+  const float* level_mse_mult;  /* HOST [num_levels]                                                 */
+  const float* level_dist_mult; /* HOST [num_levels]                                                 */
+  float* per_ray_sqerr;         /* [num_levels, B] device, nullable: mask_r |comp_rgb - target|^2    */
+  float* per_ray_distloss;      /* [num_levels, B] device, nullable                                  */
+} mipnerf_b200_loss;
+
+size_t mipnerf_b200_train_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays);
+
+/* MipNerf.forward (outputs in `outs`, as mipnerf_b200_forward) followed by the backward pass of the loss
+ * above into `grads` (overwritten, or added to when `accumulate` != 0).  Replaces
+ * `loss = training_step(...); loss.backward()` (models/nerf_system.py:95-121 + autograd).  Fenceposts carry
+ * no gradient (stop_resample_grad=True semantics, models/mip.py:250-264).  precision must be FP32. */
+int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* weights,
+                                  const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                                  const float* u_jitter, int white_bkgd, int precision,
+                                  const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
+                                  const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.optim.Adam.step() for one flat fp32 tensor (models/nerf_system.py:70-72; amsgrad off, no weight
+ * decay): `step` is the 1-based step count after this update; the gradient is read as grad * grad_scale
+ * (1/world_size after a sum all-reduce). */
+int mipnerf_b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           double lr, double beta1, double beta2, double eps, int64_t step, double grad_scale,
+                           void* stream);
 
 /* Pinhole rays of rows [row0,row0+rows) of an H x W frame generated on the device, replacing the
  * host NumPy loaders (datasets/datasets.py:214-263, render_video.py:29-105).  `c2w_host` is a HOST

@@ -11,6 +11,7 @@ from .nerf_system import MipNeRFSystem, default_hparams, calc_psnr
 from .ops import (sample_along_rays, resample_along_rays, cast_rays, integrated_pos_enc, pos_enc,
                   sorted_piecewise_constant_pdf, volumetric_rendering, distloss)
 from .weights import make_state_dict
+from .train import FusedAdam, MipLRDecay, allreduce_grads, forward_backward, fused_loss, mip_lr
 from .render import generate_rays, render_frame, render_sharded, shard_bounds, shard_rows, gather_rows
 
 __all__ = [
@@ -18,5 +19,6 @@ __all__ = [
     "random_ray_batch", "rays_to_torch", "MLP", "MipNerf", "MipNeRFSystem", "default_hparams", "calc_psnr",
     "sample_along_rays", "resample_along_rays", "cast_rays", "integrated_pos_enc", "pos_enc",
     "sorted_piecewise_constant_pdf", "volumetric_rendering", "distloss", "make_state_dict", "generate_rays", "render_frame",
-    "render_sharded", "shard_bounds", "shard_rows", "gather_rows",
+    "render_sharded", "shard_bounds", "shard_rows", "gather_rows", "FusedAdam", "MipLRDecay", "allreduce_grads",
+    "forward_backward", "fused_loss", "mip_lr",
 ]

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmipnerf_b200.so"
 LIB_PATH = os.environ.get("MIPNERF_B200_LIB") or os.path.join(_HERE, LIB_NAME)  # env: experiment builds
 
+ABI_VERSION = 2
 OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
 FP32, BF16, FP16 = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
@@ -52,6 +53,17 @@ class LevelOut(C.Structure):
                 ("weights", C.c_void_p), ("t_samples", C.c_void_p), ("inds", C.c_void_p)]
 
 
+class LinearGrad(C.Structure):
+    _fields_ = [("weight_grad", C.c_void_p), ("bias_grad", C.c_void_p)]
+
+
+class Loss(C.Structure):
+    _fields_ = [("target_rgb", C.c_void_p), ("lossmult", C.c_void_p), ("mask_sum", C.c_void_p),
+                ("dist_scale", C.c_float), ("level_mse_mult", C.POINTER(C.c_float)),
+                ("level_dist_mult", C.POINTER(C.c_float)), ("per_ray_sqerr", C.c_void_p),
+                ("per_ray_distloss", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/mipnerf_b200.h declares.
 _V = C.c_void_p
 _SIGNATURES = {
@@ -63,6 +75,12 @@ _SIGNATURES = {
     "mipnerf_b200_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.c_int,
                                        _V, _V, C.c_int, C.c_int, C.POINTER(LevelOut), _V, C.c_size_t, _V]),
     "mipnerf_b200_distloss": (C.c_int, [_V, _V, C.c_int64, C.c_int, _V, _V]),
+    "mipnerf_b200_train_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int64]),
+    "mipnerf_b200_forward_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.c_int,
+                                                _V, _V, C.c_int, C.c_int, C.POINTER(Loss), C.POINTER(LevelOut),
+                                                C.POINTER(LinearGrad), C.c_int, C.c_int, _V, C.c_size_t, _V]),
+    "mipnerf_b200_adam_step": (C.c_int, [_V, _V, _V, _V, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_int64, C.c_double, _V]),
     "mipnerf_b200_generate_rays": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                              _V, _V, _V, _V, _V, _V, _V]),
     "mipnerf_b200_sample_along_rays": (C.c_int, [C.POINTER(RaysStruct), C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V]),
@@ -104,7 +122,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.mipnerf_b200_abi_version() != 1:
+        if handle.mipnerf_b200_abi_version() != ABI_VERSION:
             raise ImportError("libmipnerf_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -1,5 +1,6 @@
 // api.cu — the extern "C" surface declared in include/mipnerf_b200.h and the level loop of
 // MipNerf.forward (models/mip_nerf.py:172-248) expressed as kernel launches on one stream.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -311,6 +312,214 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
       w_prev = w_cur;
     }
   }
+  return MIPNERF_B200_OK;
+}
+
+// ---- training step -------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxTrainDepth = 16;
+struct TrainScratch {
+  float *enc, *venc, *h[kMaxTrainDepth], *bott, *v, *raw_rgb, *raw_density;
+  float *d_a, *d_b, *d_v, *d_raw_rgb, *d_raw_density, *part, *t[2], *w[2];
+  size_t bytes;
+};
+
+TrainScratch carve_train(const mipnerf_b200_config* c, const Dims& d, int64_t rays, void* base) {
+  TrainScratch s{};
+  const size_t m = (size_t)rays * c->num_samples;
+  size_t off = 0;
+  auto take = [&](size_t elems) {
+    float* p = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+    off += align_up(elems * sizeof(float));
+    return p;
+  };
+  s.enc = take(m * d.xyz_dim);
+  s.venc = take((size_t)rays * d.view_dim);
+  for (int i = 0; i < c->net_depth; ++i) s.h[i] = take(m * c->net_width);
+  s.bott = take(m * c->net_width);
+  s.v = take(m * c->net_width_condition);
+  s.raw_rgb = take(m * 3);
+  s.raw_density = take(m);
+  s.d_a = take(m * c->net_width);
+  s.d_b = take(m * c->net_width);
+  s.d_v = take(m * c->net_width_condition);
+  s.d_raw_rgb = take(m * 3);
+  s.d_raw_density = take(m);
+  const size_t max_n = c->net_width > c->net_width_condition ? c->net_width : c->net_width_condition;
+  const size_t max_k = (size_t)c->net_width + (d.xyz_dim > d.view_dim ? d.xyz_dim : d.view_dim) + 1;
+  s.part = take((size_t)mipnerf::kWgradMaxSlices * max_n * max_k);
+  for (int i = 0; i < 2; ++i) {
+    s.t[i] = take((size_t)rays * (c->num_samples + 1));
+    s.w[i] = take(m);
+  }
+  s.bytes = off;
+  return s;
+}
+
+int check_train_config(const mipnerf_b200_config* c) {
+  if (!c->use_viewdirs || c->net_depth_condition != 1)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "training: use_viewdirs=True with one view layer only");
+  if (c->net_depth > kMaxTrainDepth)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "training: net_depth <= %d", kMaxTrainDepth);
+  return MIPNERF_B200_OK;
+}
+
+inline bool takes_skip(const mipnerf_b200_config* c, int layer) {  // models/mip_nerf.py:40-42
+  return layer > 1 && (layer - 1) % c->skip_index == 0;
+}
+}  // namespace
+
+size_t mipnerf_b200_train_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays) {
+  Dims d;
+  if (check_config(cfg, &d) != MIPNERF_B200_OK || check_train_config(cfg) != MIPNERF_B200_OK || num_rays < 0)
+    return 0;
+  const int64_t r = num_rays < kChunkRaysFp32 ? num_rays : kChunkRaysFp32;
+  return carve_train(cfg, d, r > 0 ? r : 1, nullptr).bytes;
+}
+
+int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                                  const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                                  const float* u_jitter, int white_bkgd, int precision,
+                                  const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
+                                  const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  Dims d;
+  int rc;
+  if ((rc = check_config(cfg, &d))) return rc;
+  if ((rc = check_train_config(cfg))) return rc;
+  if ((rc = check_weights(cfg, d, w))) return rc;
+  if ((rc = check_rays(rays))) return rc;
+  if (precision != MIPNERF_B200_FP32)
+    return fail(MIPNERF_B200_EUNSUPPORTED, "training runs on the fp32 path only (tensor-core backward: next round)");
+  if (!outs || !loss || !grads) return fail(MIPNERF_B200_EINVAL, "outs / loss / grads is NULL");
+  if (num_grads != d.n_lin) return fail(MIPNERF_B200_EINVAL, "expected %d gradient pairs, got %d", d.n_lin, num_grads);
+  for (int i = 0; i < d.n_lin; ++i)
+    if (!grads[i].weight_grad || !grads[i].bias_grad) return fail(MIPNERF_B200_EINVAL, "grads[%d] has a NULL tensor", i);
+  if (!loss->level_mse_mult || !loss->level_dist_mult)
+    return fail(MIPNERF_B200_EINVAL, "loss multipliers are NULL");
+  if (rays->num_rays > 0 && (!loss->target_rgb || !loss->mask_sum || !rays->viewdirs))
+    return fail(MIPNERF_B200_EINVAL, "target_rgb / mask_sum / viewdirs is NULL");
+  if (randomized && (!t_rand || (cfg->num_levels > 1 && !u_jitter)))
+    return fail(MIPNERF_B200_EINVAL, "randomized=1 needs t_rand and u_jitter (the ABI takes the noise as input)");
+  for (int l = 0; l < cfg->num_levels; ++l)
+    if (rays->num_rays > 0 && (!outs[l].comp_rgb || !outs[l].distance || !outs[l].acc))
+      return fail(MIPNERF_B200_EINVAL, "outs[%d] misses comp_rgb/distance/acc", l);
+  const size_t need = mipnerf_b200_train_workspace_bytes(cfg, rays->num_rays);
+  if (rays->num_rays > 0 && (!workspace || workspace_bytes < need))
+    return fail(MIPNERF_B200_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = cfg->num_samples, depth = cfg->net_depth, W = cfg->net_width, Wc = cfg->net_width_condition;
+  const float rgb_scale = (float)(1.0 + 2.0 * (double)cfg->rgb_padding);
+  const int64_t B = rays->num_rays;
+  bool touched[kMaxTrainDepth + 8];
+  for (int i = 0; i < d.n_lin; ++i) touched[i] = accumulate != 0;
+  if (B == 0 && !accumulate)
+    for (int i = 0; i < d.n_lin; ++i) {
+      const mipnerf_b200_linear& l = w->linears[i];
+      CUDA_TRY(cudaMemsetAsync(grads[i].weight_grad, 0, sizeof(float) * l.in_features * l.out_features, st));
+      CUDA_TRY(cudaMemsetAsync(grads[i].bias_grad, 0, sizeof(float) * l.out_features, st));
+    }
+
+  for (int64_t off = 0; off < B; off += kChunkRaysFp32) {
+    const int64_t cnt = (B - off) < kChunkRaysFp32 ? (B - off) : kChunkRaysFp32;
+    const int64_t m = cnt * n;
+    const mipnerf_b200_rays rc_ = offset_rays(*rays, off, cnt);
+    const TrainScratch s = carve_train(cfg, d, cnt, workspace);
+    CUDA_TRY(mipnerf::launch_pos_enc(rc_.viewdirs, s.venc, cnt, 0, cfg->deg_view, 1, st));
+    auto wgrad = [&](int idx, const float* dy, const float* x1, int k1, const float* x2, int k2, int div) {
+      const mipnerf_b200_linear& l = w->linears[idx];
+      cudaError_t e = mipnerf::launch_wgrad_f32(dy, l.out_features, x1, k1, k1, x2, k2, k2, div, s.part,
+                                                grads[idx].weight_grad, grads[idx].bias_grad, touched[idx] ? 1 : 0,
+                                                m, st);
+      touched[idx] = true;
+      return e;
+    };
+    const float *t_prev = nullptr, *w_prev = nullptr;
+    for (int l = 0; l < cfg->num_levels; ++l) {
+      float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (n + 1) : s.t[l & 1];
+      float* w_cur = outs[l].weights ? outs[l].weights + off * n : s.w[l & 1];
+      // ---- forward of this level, every activation kept (models/mip_nerf.py:203-240)
+      if (l == 0) {
+        CUDA_TRY(mipnerf::launch_coarse_t(rc_.near, rc_.far, t_rand ? t_rand + off * (n + 1) : nullptr, t_cur,
+                                          cnt, n, randomized, cfg->disparity, st));
+      } else {
+        CUDA_TRY(mipnerf::launch_resample(t_prev, w_prev, u_jitter ? u_jitter + off * (n + 1) : nullptr, t_cur,
+                                          outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr, cnt, n, n + 1,
+                                          randomized, 1, cfg->resample_padding, st));
+      }
+      CUDA_TRY(mipnerf::launch_ipe_from_t(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc, cnt, n,
+                                          cfg->min_deg_point, cfg->max_deg_point, cfg->disable_integration, st));
+      for (int i = 0; i < depth; ++i) {
+        const mipnerf_b200_linear& li = w->linears[i];
+        const bool skip = takes_skip(cfg, i);
+        const float* in = i == 0 ? s.enc : s.h[i - 1];
+        const int k1 = i == 0 ? d.xyz_dim : W;
+        CUDA_TRY(mipnerf::launch_linear_f32(in, k1, k1, skip ? s.enc : nullptr, d.xyz_dim, skip ? d.xyz_dim : 0, 1,
+                                            li.weight, li.bias, s.h[i], W, m, W, 1, st));
+      }
+      const float* h_last = s.h[depth - 1];
+      const mipnerf_b200_linear& dl = w->linears[depth];
+      const mipnerf_b200_linear& el = w->linears[depth + 1];
+      const mipnerf_b200_linear& vl = w->linears[depth + 2];
+      const mipnerf_b200_linear& cl = w->linears[d.n_lin - 1];
+      CUDA_TRY(mipnerf::launch_linear_f32(h_last, W, W, nullptr, 0, 0, 1, dl.weight, dl.bias, s.raw_density, 1, m, 1,
+                                          0, st));
+      CUDA_TRY(mipnerf::launch_linear_f32(h_last, W, W, nullptr, 0, 0, 1, el.weight, el.bias, s.bott, W, m, W, 0, st));
+      CUDA_TRY(mipnerf::launch_linear_f32(s.bott, W, W, s.venc, d.view_dim, d.view_dim, n, vl.weight, vl.bias, s.v,
+                                          Wc, m, Wc, 1, st));
+      CUDA_TRY(mipnerf::launch_linear_f32(s.v, Wc, Wc, nullptr, 0, 0, 1, cl.weight, cl.bias, s.raw_rgb, 3, m, 3, 0,
+                                          st));
+      CUDA_TRY(mipnerf::launch_composite(s.raw_rgb, s.raw_density, t_cur, rc_.directions, outs[l].comp_rgb + off * 3,
+                                         outs[l].distance + off, outs[l].acc + off, w_cur, cnt, n, white_bkgd, 1,
+                                         cfg->density_bias, rgb_scale, cfg->rgb_padding, st));
+
+      // ---- backward of this level (its fenceposts are constants, so levels are independent here)
+      CUDA_TRY(mipnerf::launch_render_backward(
+          s.raw_rgb, s.raw_density, t_cur, rc_.directions, loss->target_rgb + off * 3,
+          loss->lossmult ? loss->lossmult + off : nullptr, loss->mask_sum, loss->level_mse_mult[l],
+          loss->level_dist_mult[l] * loss->dist_scale, white_bkgd, cfg->density_bias, rgb_scale, cfg->rgb_padding,
+          s.d_raw_rgb, s.d_raw_density, loss->per_ray_sqerr ? loss->per_ray_sqerr + (int64_t)l * B + off : nullptr,
+          loss->per_ray_distloss ? loss->per_ray_distloss + (int64_t)l * B + off : nullptr, cnt, n, st));
+      // colour head, view layer                                          (models/mip_nerf.py:106-110)
+      CUDA_TRY(wgrad(d.n_lin - 1, s.d_raw_rgb, s.v, Wc, nullptr, 0, 1));
+      CUDA_TRY(mipnerf::launch_color_dgrad(s.d_raw_rgb, cl.weight, s.v, s.d_v, m, Wc, st));
+      CUDA_TRY(wgrad(depth + 2, s.d_v, s.bott, W, s.venc, d.view_dim, n));
+      CUDA_TRY(mipnerf::launch_dgrad_f32(s.d_v, Wc, vl.weight, W + d.view_dim, nullptr, nullptr, nullptr, s.d_a, m, W,
+                                         st));
+      // bottleneck + density head share h_last                           (models/mip_nerf.py:98-101)
+      CUDA_TRY(wgrad(depth + 1, s.d_a, h_last, W, nullptr, 0, 1));
+      CUDA_TRY(wgrad(depth, s.d_raw_density, h_last, W, nullptr, 0, 1));
+      CUDA_TRY(mipnerf::launch_dgrad_f32(s.d_a, W, el.weight, W, s.d_raw_density, dl.weight, h_last, s.d_b, m, W, st));
+      // trunk                                                            (models/mip_nerf.py:93-97)
+      float *cur = s.d_b, *other = s.d_a;
+      for (int i = depth - 1; i >= 0; --i) {
+        const bool skip = takes_skip(cfg, i);
+        const float* in = i == 0 ? s.enc : s.h[i - 1];
+        const int k1 = i == 0 ? d.xyz_dim : W;
+        CUDA_TRY(wgrad(i, cur, in, k1, skip ? s.enc : nullptr, skip ? d.xyz_dim : 0, 1));
+        if (i > 0) {
+          CUDA_TRY(mipnerf::launch_dgrad_f32(cur, W, w->linears[i].weight, k1 + (skip ? d.xyz_dim : 0), nullptr,
+                                             nullptr, s.h[i - 1], other, m, W, st));
+          float* tmp = cur;
+          cur = other;
+          other = tmp;
+        }
+      }
+      t_prev = t_cur;
+      w_prev = w_cur;
+    }
+  }
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                           double lr, double beta1, double beta2, double eps, int64_t step, double grad_scale,
+                           void* stream) {
+  if (n < 0 || step < 1) return fail(MIPNERF_B200_EINVAL, "bad n / step");
+  if (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq)) return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  CUDA_TRY(mipnerf::launch_adam(param, grad, exp_avg, exp_avg_sq, n, (float)beta1, (float)beta2, (float)eps,
+                                (float)(lr / bc1), (float)sqrt(bc2), (float)grad_scale, (cudaStream_t)stream));
   return MIPNERF_B200_OK;
 }
 

@@ -39,4 +39,26 @@ cudaError_t launch_linear_f32(const float* x1, int ld1, int k1, const float* x2,
                               int x2_row_div, const float* w, const float* bias, float* y, int ldy,
                               int64_t m, int n, int relu, cudaStream_t st);
 
+// ---- train_kernels.cu (fp32 training step: backward + Adam) ----
+constexpr int kWgradMaxSlices = 128;
+int wgrad_num_slices(int64_t m);
+cudaError_t launch_render_backward(const float* raw_rgb, const float* raw_dens, const float* t, const float* dirs,
+                                   const float* target, const float* lossmult, const float* mask_sum,
+                                   float mse_mult, float dist_mult, int white_bkgd, float density_bias,
+                                   float rgb_scale, float rgb_padding, float* d_raw_rgb, float* d_raw_dens,
+                                   float* sqerr_out, float* dist_out, int64_t num_rays, int n, cudaStream_t st);
+cudaError_t launch_color_dgrad(const float* d_rgb, const float* wc, const float* v, float* d_v, int64_t m,
+                               int k_dim, cudaStream_t st);
+// dX[m,k] = (act[m,k] > 0 or act == NULL) * (dY[m,:n_dim] @ W[:n_dim, :k_dim] (row stride ldw) + r1[m] * r1w[k])
+cudaError_t launch_dgrad_f32(const float* dy, int n_dim, const float* w, int ldw, const float* r1,
+                             const float* r1w, const float* act, float* dx, int64_t m, int k_dim,
+                             cudaStream_t st);
+// dW[n_dim, k1+k2] (+)= dY^T @ [X1 | X2[row / x2_row_div]],  db[n_dim] (+)= colsum(dY); `part` holds
+// wgrad_num_slices(m) * n_dim * (k1+k2+1) floats of per-slice partial sums.
+cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
+                             int ld2, int k2, int x2_row_div, float* part, float* dw, float* db,
+                             int accumulate, int64_t m, cudaStream_t st);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
+                        float eps, float step_size, float bc2_sqrt, float grad_scale, cudaStream_t st);
+
 }  // namespace mipnerf

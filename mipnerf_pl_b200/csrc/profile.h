@@ -21,6 +21,10 @@ enum KernelId : int {
   kKernRayGen,       // on-device pinhole ray generation
   kKernDistloss,
   kKernRayPrologue,  // view-direction bias + coarse fenceposts in front of the fused level kernels
+  kKernRenderBackward,
+  kKernDgrad,
+  kKernWgrad,
+  kKernAdam,
   kKernCount
 };
 

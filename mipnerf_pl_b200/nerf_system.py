@@ -6,8 +6,8 @@ Kept: constructor from the flat dotted `hparams` dict, `forward`, `render_image`
 (`state_dict` + `hyper_parameters`).  pytorch-lightning is not part of this image,
 so when it cannot be imported a minimal stand-in base class provides
 `save_hyperparameters` / `hparams` / `log` / `load_from_checkpoint`.
-Training (`training_step`, optimiser, dataloaders) is out of scope for this tier:
-it needs the backward pass.
+`training_step` / `configure_optimizers` run on the library's fp32 backward and Adam kernels
+(mipnerf_pl_b200/train.py); dataloaders are row N4.
 """
 from __future__ import annotations
 
@@ -96,9 +96,29 @@ class MipNeRFSystem(_Base):
     def forward(self, batch_rays: Rays, randomized: bool, white_bkgd: bool):
         return self.mip_nerf(batch_rays, randomized, white_bkgd)  # num_levels results
 
-    def training_step(self, batch, batch_nb):
-        raise NotImplementedError("training needs the backward pass of the fused kernels "
-                                  "(SURVEY.md §8f row N2); this build covers the forward/render path")
+    def configure_optimizers(self):
+        """models/nerf_system.py:70-76: Adam(lr_init) + MipLRDecay stepped every optimiser step."""
+        from .train import FusedAdam, MipLRDecay
+        optimizer = FusedAdam(self.mip_nerf.parameters(), lr=self.hparams['optimizer.lr_init'])
+        scheduler = MipLRDecay(optimizer, self.hparams['optimizer.lr_init'], self.hparams['optimizer.lr_final'],
+                               self.hparams['optimizer.max_steps'], self.hparams['optimizer.lr_delay_steps'],
+                               self.hparams['optimizer.lr_delay_mult'])
+        return [optimizer], [{'scheduler': scheduler, 'interval': 'step'}]
+
+    def training_step(self, batch, batch_nb, *, t_rand=None, u_jitter=None):
+        """models/nerf_system.py:95-121.  The returned loss carries a grad_fn: forward and backward both ran
+        in the library (mipnerf_b200_forward_backward); `loss.backward()` hands the gradients to autograd."""
+        from .train import fused_loss
+        rays, rgbs = batch
+        loss, info = fused_loss(self.mip_nerf, rays, rgbs, self.train_randomized, self.white_bkgd,
+                                coarse_loss_mult=self.hparams['loss.coarse_loss_mult'],
+                                disable_multiscale_loss=self.hparams['loss.disable_multiscale_loss'],
+                                t_rand=t_rand, u_jitter=u_jitter)
+        with torch.no_grad():
+            psnr_fine = calc_psnr(info["ret"][-1][0], rgbs[..., :3])
+        self.log('train/loss', loss.detach())
+        self.log('train/psnr', psnr_fine, prog_bar=True)
+        return loss
 
     def validation_step(self, batch, batch_nb):
         """models/nerf_system.py:123-142 (image logging only when a logger is attached)."""

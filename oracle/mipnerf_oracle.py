@@ -68,16 +68,29 @@ def rowsum_f32(x: torch.Tensor) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(s[..., None]))
 
 
+class _CumsumF32(torch.autograd.Function):
+    """Forward: the bit pattern of torch.cumsum(float32) on CPU; backward: its adjoint (reversed cumsum),
+    so the oracle's training_loss differentiates through the transmittance like autograd does in the
+    reference (models/mip.py:385)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        a = x.detach().cpu().numpy().astype(np.float64)
+        return torch.from_numpy(np.cumsum(a, axis=-1).astype(np.float32)).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.flip(torch.cumsum(torch.flip(g, [-1]), dim=-1), [-1])
+
+
 def cumsum_f32(x: torch.Tensor) -> torch.Tensor:
     """torch.cumsum(x, -1) on CPU fp32: float64 running sum, rounded per prefix
     (models/mip.py:189, :385)."""
-    a = x.detach().cpu().numpy().astype(np.float64)
-    return torch.from_numpy(np.cumsum(a, axis=-1).astype(np.float32))
+    if x.dtype == torch.float64:        # float64 referee runs of the oracle (tests only)
+        return torch.cumsum(x, dim=-1)
+    return _CumsumF32.apply(x)
 
 
-# --------------------------------------------------------------------------
-# models/mip.py
-# --------------------------------------------------------------------------
 def conical_frustum_moments(t0, t1, radii):
     """Stable conical-frustum moments (models/mip.py:65-72).
     t0, t1: [B, N]; radii: [B, 1] -> t_mean, t_var, r_var each [B, N]."""
@@ -310,14 +323,18 @@ def mlp_forward(params: Dict[str, torch.Tensor], x, view_enc, net_depth=8, skip_
 
 def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white_bkgd: bool,
             config: Optional[dict] = None, t_rand=None, u_jitter=None,
-            return_debug=False, operand_dtype=None) -> List[Tuple[torch.Tensor, ...]]:
+            return_debug=False, operand_dtype=None, grad=False) -> List[Tuple[torch.Tensor, ...]]:
     """MipNerf.forward (models/mip_nerf.py:172-248): list over levels of
-    (comp_rgb [B,3], distance [B], acc [B], weights [B,N], t_samples [B,N+1])."""
+    (comp_rgb [B,3], distance [B], acc [B], weights [B,N], t_samples [B,N+1]).
+    `grad=True` keeps the autograd graph (training); the resampler then runs under no_grad on detached
+    weights, which is what stop_resample_grad=True does (models/mip.py:250-264)."""
     cfg = dict(DEFAULT_CONFIG)
     cfg.update(config or {})
     ret, debug = [], []
     t, weights = None, None
-    with torch.no_grad():
+    if grad:
+        assert cfg["stop_resample_grad"], "oracle restates the default stop_resample_grad=True only"
+    with (torch.enable_grad() if grad else torch.no_grad()):
         for level in range(cfg["num_levels"]):
             inds = None
             if level == 0:
@@ -325,10 +342,11 @@ def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white
                     rays.origins, rays.directions, rays.radii, cfg["num_samples"], rays.near,
                     rays.far, randomized, cfg["disparity"], cfg["ray_shape"], t_rand=t_rand)
             else:
-                t, (means, covs), inds = resample_along_rays(
-                    rays.origins, rays.directions, rays.radii, t, weights, randomized,
-                    cfg["ray_shape"], cfg["stop_resample_grad"], cfg["resample_padding"],
-                    u_jitter=u_jitter, return_inds=True)
+                with torch.no_grad():
+                    t, (means, covs), inds = resample_along_rays(
+                        rays.origins, rays.directions, rays.radii, t.detach(), weights.detach(), randomized,
+                        cfg["ray_shape"], cfg["stop_resample_grad"], cfg["resample_padding"],
+                        u_jitter=u_jitter, return_inds=True)
             if cfg["disable_integration"]:
                 covs = torch.zeros_like(covs)
             enc = integrated_pos_enc(means, covs, cfg["min_deg_point"], cfg["max_deg_point"])
@@ -343,6 +361,31 @@ def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white
             debug.append(dict(means=means, covs=covs, enc=enc, raw_rgb=raw_rgb,
                               raw_density=raw_density, inds=inds))
     return (ret, debug) if return_debug else ret
+
+
+def training_loss(params: Dict[str, torch.Tensor], rays: Rays, rgbs, randomized: bool, white_bkgd: bool,
+                  coarse_loss_mult=0.1, disable_multiscale_loss=False, config=None, t_rand=None, u_jitter=None):
+    """MipNeRFSystem.training_step's loss (models/nerf_system.py:95-111) with the autograd graph over
+    `params` kept: (loss, [mse per level], [distloss per level], ret)."""
+    ret = forward(params, rays, randomized, white_bkgd, config, t_rand=t_rand, u_jitter=u_jitter, grad=True)
+    mask = torch.ones_like(rays.lossmult) if disable_multiscale_loss else rays.lossmult
+    losses, dls = [], []
+    for (rgb, _, _, weights, t_samples) in ret:
+        losses.append((mask * (rgb - rgbs[..., :3]) ** 2).sum() / mask.sum())
+        dls.append(distloss(weights, t_samples))
+    loss = coarse_loss_mult * (sum(losses[:-1]) + 0.01 * sum(dls[:-1])) + losses[-1] + 0.01 * dls[-1]
+    return loss, losses, dls, ret
+
+
+def mip_lr(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1.0):
+    """MipLRDecay.get_lr (utils/lr_schedule.py:51-60) at `last_epoch == step`."""
+    import numpy as np
+    if lr_delay_steps > 0:
+        delay_rate = lr_delay_mult + (1 - lr_delay_mult) * np.sin(0.5 * np.pi * np.clip(step / lr_delay_steps, 0, 1))
+    else:
+        delay_rate = 1.0
+    tt = np.clip(step / max_steps, 0, 1)
+    return float(delay_rate * np.exp(np.log(lr_init) * (1 - tt) + np.log(lr_final) * tt))
 
 
 def render_image(params, rays: Rays, height: int, width: int, chunk_size: int, randomized=False,

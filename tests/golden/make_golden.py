@@ -202,7 +202,85 @@ def stages_case():
     save("stages.npz", **out)
 
 
+GRAD_STRIDE = 37  # the gradient digest keeps every 37th element of each tensor (+ norms and sums)
+
+
+def training_case():
+    """Loss and parameter gradients of MipNeRFSystem.training_step (models/nerf_system.py:95-111) computed by
+    the reference MipNerf + reference distloss + torch autograd; Adam/MipLRDecay trajectories from
+    torch.optim.Adam and the reference's utils/lr_schedule.py.  pytorch_lightning is not installed, so the
+    ten lines of loss arithmetic are restated here around the reference's own modules."""
+    from utils.lr_schedule import MipLRDecay as RefMipLRDecay  # reference
+    out = {}
+    for tag, seed, randomized, white, disable_ms in (("a", 7, False, True, False), ("b", 8, True, False, True)):
+        b = 48
+        rays = random_ray_batch(b, seed=seed, multiscale=True)
+        g = torch.Generator().manual_seed(100 + seed)
+        rgbs = torch.rand(b, 3, generator=g)
+        model = RefMipNerf()
+        model.load_state_dict(make_state_dict(seed=seed, kind="trained_like"))
+        model.train()
+        n = model.num_samples
+        if randomized:
+            torch.manual_seed(4321 + seed)
+            out[f"{tag}_t_rand"] = torch.rand(b, n + 1).numpy()
+            out[f"{tag}_u_jitter"] = torch.empty(b, n + 1).uniform_(to=(1 / (n + 1) - F32_EPS)).numpy()
+            torch.manual_seed(4321 + seed)
+        ret = model(to_ref_rays(rays), randomized, white)
+        mask = torch.ones_like(rays.lossmult) if disable_ms else rays.lossmult
+        losses, dls = [], []
+        for (rgb, _, _, weights, t_samples) in ret:
+            losses.append((mask * (rgb - rgbs[..., :3]) ** 2).sum() / mask.sum())
+            dls.append(ref_mip.distloss(weights, t_samples))
+        loss = 0.1 * (losses[0] + 0.01 * dls[0]) + losses[1] + 0.01 * dls[-1]
+        loss.backward()
+        out.update({f"{tag}_{k}": v for k, v in rays_dict(rays).items()})
+        out[f"{tag}_rgbs"] = rgbs.numpy()
+        out[f"{tag}_loss"] = np.array([float(loss)] + [float(x) for x in losses] + [float(x) for x in dls])
+        out[f"{tag}_meta"] = np.array([seed, int(randomized), int(white), int(disable_ms)], dtype=np.int64)
+        for name, prm in model.named_parameters():
+            gr = prm.grad.reshape(-1)
+            out[f"{tag}_grad_{name}"] = gr[::GRAD_STRIDE].numpy()
+            out[f"{tag}_gnorm_{name}"] = np.array([float(gr.double().norm()), float(gr.double().sum())])
+    # Adam + MipLRDecay: 4 steps on one tensor, lr from the reference scheduler
+    g = torch.Generator().manual_seed(9)
+    p = torch.nn.Parameter(torch.randn(1000, generator=g))
+    grads = torch.randn(4, 1000, generator=g) * torch.tensor([1e-3, 1.0, 1e3, 1e-6])[:, None]
+    opt = torch.optim.Adam([p], lr=5e-4)
+    sched = RefMipLRDecay(opt, 5e-4, 5e-6, 10, 4, 0.01)
+    out["adam_p0"] = p.detach().clone().numpy()
+    out["adam_grads"] = grads.numpy()
+    lrs, traj = [], []
+    for i in range(4):
+        lrs.append(opt.param_groups[0]["lr"])
+        p.grad = grads[i].clone()
+        opt.step()
+        sched.step()
+        traj.append(p.detach().clone().numpy())
+    out["adam_lrs"] = np.array(lrs)
+    out["adam_traj"] = np.stack(traj)
+    steps = [0, 1, 10, 1249, 2500, 2501, 100000, 999999, 1000000, 1500000]
+    dummy = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    ref_s = RefMipLRDecay(dummy, 5e-4, 5e-6, 1000000, 2500, 0.01)
+    vals = []
+    for st in steps:
+        ref_s.last_epoch = st
+        vals.append(ref_s.get_lr()[0])
+    out["lr_steps"] = np.array(steps, dtype=np.int64)
+    out["lr_values"] = np.array(vals, dtype=np.float64)
+    nodelay = RefMipLRDecay(dummy, 1e-3, 1e-5, 100, 0, 1.0)
+    vals = []
+    for st in (0, 50, 100):
+        nodelay.last_epoch = st
+        vals.append(nodelay.get_lr()[0])
+    out["lr_nodelay_values"] = np.array(vals, dtype=np.float64)
+    save("training.npz", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "training":   # regenerate only training.npz
+        training_case()
+        sys.exit(0)
     forward_case("forward_xavier.npz", 40, seed=0, weights_kind="xavier", randomized=False, white_bkgd=True)
     forward_case("forward_trained_like.npz", 40, seed=1, weights_kind="trained_like", randomized=False,
                  white_bkgd=False, multiscale=True)
@@ -212,6 +290,7 @@ if __name__ == "__main__":
                  num_samples=64, num_levels=1)
     resampler_case()
     stages_case()
+    training_case()
     with open(os.path.join(HERE, "VERSIONS.txt"), "w") as f:
         f.write(f"torch {torch.__version__}\nnumpy {np.__version__}\nreference {REF} (hjxwhy/mipnerf_pl @ 6c07452)\n"
                 f"cpu_capability {torch.backends.cpu.get_cpu_capability()}\n")

@@ -55,3 +55,33 @@ def test_shard_bounds_cover_everything():
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
     assert shard_rows(800, 8, 3) == (300, 400)
+
+
+def _grad_worker(rank, world, port, out_dir):
+    """allreduce_grads: DDP's mean over ranks of every parameter gradient, as ONE flat all-reduce."""
+    from mipnerf_pl_b200.train import allreduce_grads
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3)
+        shapes = [(256, 96), (256,), (1, 256), (3, 128), (3,)]
+        per_rank = [[torch.randn(*s, generator=g) for s in shapes] for _ in range(world)]
+        params = [torch.nn.Parameter(torch.zeros(*s)) for s in shapes] + [torch.nn.Parameter(torch.zeros(2))]
+        for p, gr in zip(params, per_rank[rank]):
+            p.grad = gr.clone()                              # the last parameter has no gradient: skipped
+        allreduce_grads(params)
+        want = [sum(per_rank[r][i] for r in range(world)) / world for i in range(len(shapes))]
+        ok = all(torch.allclose(p.grad, w, rtol=0, atol=1e-6) for p, w in zip(params, want)) and params[-1].grad is None
+        allreduce_grads(params, average=False)
+        ok = ok and all(torch.allclose(p.grad, w * world, rtol=0, atol=1e-5) for p, w in zip(params, want))
+        torch.save(ok, os.path.join(out_dir, f"gok{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allreduce_grads_world2(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp_.spawn(_grad_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(torch.load(tmp_path / f"gok{r}.pt") for r in range(world))

@@ -44,7 +44,7 @@ def build_model(kind, seed, precision="fp32", **kw):
 def test_native_library_is_loaded():
     from mipnerf_pl_b200 import _cabi
     lib = _cabi.lib()
-    assert lib.mipnerf_b200_abi_version() == 1
+    assert lib.mipnerf_b200_abi_version() == _cabi.ABI_VERSION
     with open("/proc/self/maps") as f:
         assert "libmipnerf_b200.so" in f.read()
 
