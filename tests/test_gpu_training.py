@@ -45,7 +45,11 @@ def test_forward_backward_matches_reference_autograd(tag):
     torch.cuda.synchronize()
     got = np.array([float(out["loss"])] + [float(x) for x in out["mse"]] + [float(x) for x in out["distloss"]])
     print(f"case {tag}: loss/mse/distloss {got} vs reference {g[f'{tag}_loss']}")
-    np.testing.assert_allclose(got, g[f"{tag}_loss"], rtol=2e-5)
+    levels = len(out["mse"])
+    np.testing.assert_allclose(got[:1 + levels], g[f"{tag}_loss"][:1 + levels], rtol=2e-5)      # loss, MSEs
+    # distloss of near-empty rays is a sum of products of thin-medium weights, whose fp32 values in the
+    # reference carry ~1e-4 relative cancellation noise (tests/test_reference_roundoff.py)
+    np.testing.assert_allclose(got[1 + levels:], g[f"{tag}_loss"][1 + levels:], rtol=3e-4)
     errs = grad_errors_vs_golden(named_grads(model), g, tag)
     print(f"case {tag}: per-tensor gradient error vs reference autograd "
           f"{ {k.replace('mlp.', ''): float(f'{v:.1e}') for k, v in errs.items() if k.endswith('weight')} } "
