@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frame", action="store_true", help="skip the 800x800 frame metric (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -260,20 +261,22 @@ def main():
 
     # ---- 800x800 frame (BASELINE configs[3]): rows sharded over the ranks, rays generated on device,
     #      one all_gather of the rendered pixels; device-timed, max over ranks
-    pose = mp.spheric_pose(0.5)
-    mp.render_frame(model, pose, 800, 800, True, world=world, rank=rank)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_frames = 3
-    f0.record()
-    for _ in range(n_frames):
+    frame_ms = None
+    if not args.no_frame:
+        pose = mp.spheric_pose(0.5)
         mp.render_frame(model, pose, 800, 800, True, world=world, rank=rank)
-    f1.record()
-    barrier()
-    frame_ms = torch.tensor([f0.elapsed_time(f1) / n_frames], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(frame_ms, op=dist.ReduceOp.MAX)
-    frame_ms = float(frame_ms.item())
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_frames = 3
+        f0.record()
+        for _ in range(n_frames):
+            mp.render_frame(model, pose, 800, 800, True, world=world, rank=rank)
+        f1.record()
+        barrier()
+        frame_ms = torch.tensor([f0.elapsed_time(f1) / n_frames], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(frame_ms, op=dist.ReduceOp.MAX)
+        frame_ms = float(frame_ms.item())
 
     if rank != 0:
         if world > 1:
@@ -343,9 +346,10 @@ def main():
         "kernel_launches": {k: v[0] for k, v in prof.items() if v[0]},
         "kernel_ms": {k: round(v[1], 4) for k, v in prof.items() if v[2]},
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "frame": {"height": 800, "width": 800, "rays": 640000, "ms": frame_ms, "rays_per_s": 640000 / (frame_ms * 1e-3),
-                  "what": "render_frame: on-device ray generation, both levels, rows sharded over ranks, "
-                          "all_gather of coarse+fine RGB and distance"},
+        "frame": None if frame_ms is None else {
+            "height": 800, "width": 800, "rays": 640000, "ms": frame_ms, "rays_per_s": 640000 / (frame_ms * 1e-3),
+            "what": "render_frame: on-device ray generation, both levels, rows sharded over ranks, "
+                    "all_gather of coarse+fine RGB and distance"},
     }
     print(json.dumps(line))
     if world > 1:
