@@ -34,6 +34,7 @@
 #include "kernels.h"
 #include "profile.h"
 #include "ray_math.cuh"
+#include "ray_resample.cuh"
 #include "tc_common.cuh"
 
 namespace mipnerf {
@@ -65,7 +66,8 @@ constexpr uint32_t kSmemF = kSmemA + 2 * kABytes;
 constexpr uint32_t kSmemW = kSmemF + 2 * kFBytes;
 constexpr uint32_t kSmemMisc = kSmemW + kStages * kWStage;
 constexpr uint32_t kMiscBytes = 256 + 16 + 2 * 128 * 4 + 8 * 4 + 2 * 4 * 8 * 4;
-constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024;  // + slack for 1024-B alignment
+constexpr uint32_t kSmemTotal = kSmemMisc + kMiscBytes + 1024 + 64;  // + slack for 1024-B alignment (when the base
+                                                                       // is aligned, the slack holds the resampler scratch)
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 // Biases and the two CUDA-core heads, broadcast-read by every thread: constant bank.
@@ -93,7 +95,11 @@ constexpr uint32_t kImageStageBytes = layer_offset(kNumLayers);
 constexpr uint32_t kViewPairOffset = kImageStageBytes;
 constexpr uint32_t kViewPairStage = 4096;
 constexpr size_t kSmallOffset = ((size_t)kViewPairOffset + 2 * 8 * kViewPairStage + 255) / 256 * 256;
-constexpr size_t kImageBytes = kSmallOffset + ((sizeof(SmallParams) + 255) / 256 * 256);
+// view-direction part of the view layer, transposed for coalesced per-ray reads by the IPE warps:
+// fp32 [27][128] weights W_view[n, 256 + k] as [k][n], then the 128 biases
+constexpr size_t kViewDirOffset = kSmallOffset + ((sizeof(SmallParams) + 255) / 256 * 256);
+constexpr size_t kViewDirBytes = (size_t)(kViewDim + 1) * kCond * sizeof(float);
+constexpr size_t kImageBytes = kViewDirOffset + ((kViewDirBytes + 255) / 256 * 256);
 
 #ifdef MIPNERF_TC_TRACE
 // debug build only: (clock64, event) pairs of CTA 0.  Each traced thread (one per role) owns a
@@ -133,8 +139,24 @@ struct LevelParams {
   const float* origins;
   const float* directions;
   const float* radii;
-  const float* t;          // [B,129] fenceposts of this level
-  const float* view_bias;  // [B,128]  b_view + W_view[:,256:] . pos_enc(viewdir)
+  float* t;                // [B,129] fenceposts of this level (read; written first when t_mode != 0)
+  float* view_bias;        // [B,128]  b_view + W_view[:,256:] . pos_enc(viewdir) (written first when vb_mode != 0)
+  // Fused ray prologue (v1 kernels): the IPE warps produce the fenceposts / view bias of the slot's next ray
+  // themselves instead of reading what a separate launch left in HBM.
+  int t_mode;              // 0: read p.t; 1: coarse fenceposts from near/far (models/mip.py:143-160);
+                           // 2: resample t_prev / w_prev (models/mip.py:232-280)
+  int vb_mode;             // 0: read p.view_bias; 1: compute it from viewdirs and the fp32 view-layer weights
+  const float* near;       // t_mode 1
+  const float* far;
+  const float* t_rand;     // t_mode 1, randomized: [B,129] uniforms, else nullptr
+  int disparity;
+  const float* t_prev;     // t_mode 2: previous level's fenceposts [B,129] and weights [B,128]
+  const float* w_prev;
+  const float* u_jitter;   // t_mode 2, randomized: [B,129], else nullptr
+  int64_t* inds;           // t_mode 2: optional searchsorted indices [B,129]
+  int randomized;
+  float resample_padding;
+  const float* viewdirs;   // vb_mode 1: [B,3]; the weights come from the packed image (kViewDirOffset)
   const float* feat_in;    // MLP-only mode (mipnerf_b200_mlp_forward): [B,128,96] features supplied by the caller
   float* raw_rgb_out;      // MLP-only mode: [B,128,3] / [B,128] raw heads instead of compositing
   float* raw_density_out;
@@ -420,20 +442,95 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     // tile as soon as layer 5 of the current ray has read it: off the per-ray critical path.
     const int slot = warp - 10;
     uint8_t* myF = sF + slot * kFBytes;
+    // One (kN+1)-float array per slot for the in-kernel resampler, carved out of the alignment slack at the end of
+    // the dynamic allocation when the runtime placed the buffer favourably (it does: 1024-aligned base).
+    float* early_scratch = nullptr;
+    {
+      const uint32_t used = (uint32_t)(smem - smem_raw) + kSmemMisc + kMiscBytes;
+      const uint32_t need = 2u * (kN + 1) * (uint32_t)sizeof(float);
+      if (used + need <= kSmemTotal)
+        early_scratch = reinterpret_cast<float*>(smem + kSmemMisc + kMiscBytes) + slot * (kN + 1);
+    }
     const uint32_t f_ready_leader = kPair ? mapa_u32(smem_u32(&f_ready[slot]), 0) : 0u;
     uint32_t ph_free = 0;
 #ifdef MIPNERF_TC_TRACE
     Tracer tracer;
-    (void)0;
+    if (slot == 0 && lane == 0) tracer.init(4);
 #endif
     for (int round = 0; round < rounds; ++round) {
       const int64_t tile = tile_of(round, slot);
       const int64_t ray = tile < p.num_rays ? tile : p.num_rays - 1;
+      TRACE(EV(3, 2, 0, slot));
+      // ---- ray prologue of the NEXT ray of this slot.  None of it touches the feature tile, so it runs while
+      //      layers 0..5 of the current ray are still reading that tile (this warp would be idle otherwise).
+      RayGeom g{};
+      if (!p.feat_in) g = load_ray_geom(p.origins, p.directions, p.radii, ray);
+      float* t_ray = p.t + ray * (kN + 1);
+      if (p.t_mode == 1) {
+        // coarse fenceposts (bit-identical to coarse_t_kernel)
+        const float nr = __ldg(p.near + ray), fr = __ldg(p.far + ray);
+        for (int j = lane; j <= kN; j += 32)
+          __stcg(t_ray + j, coarse_fencepost(nr, fr, j, kN, p.disparity,
+                                             p.t_rand ? p.t_rand + ray * (kN + 1) + j : nullptr));
+      } else if (p.t_mode == 2 && early_scratch) {
+        resample_warp_lean<true>(p.t_prev + ray * (kN + 1), p.w_prev + ray * kN, kN, kN + 1, p.randomized,
+                                 p.u_jitter ? p.u_jitter + ray * (kN + 1) : nullptr, p.resample_padding, early_scratch,
+                                 t_ray, p.inds ? p.inds + ray * (kN + 1) : nullptr, lane);
+      }
+      if (p.vb_mode == 1) {
+        // per-ray view-layer bias  b[n] + W[n, 256:283] . pos_enc(viewdir)   (models/mip.py:353-363,
+        // models/mip_nerf.py:106-108): lane f < 27 owns encoding element f, lane owns outputs n = lane + 32 j
+        float enc = 0.f;
+        if (lane < kViewDim) {
+          if (lane < 3) {
+            enc = __ldg(p.viewdirs + ray * 3 + lane);  // append_identity
+          } else {
+            const int gidx = lane - 3, is_cos = gidx >= 12, h = is_cos ? gidx - 12 : gidx;  // scale-major, then xyz
+            const float y = __fmul_rn(__ldg(p.viewdirs + ray * 3 + h % 3), __int_as_float((127 + h / 3) << 23));
+            enc = sinf(is_cos ? __fadd_rn(y, MIPNERF_HALF_PI_F32) : y);
+          }
+        }
+        const float* wt = reinterpret_cast<const float*>(p.wimage + kViewDirOffset);  // [27][128] | bias[128]
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = __ldg(wt + kViewDim * kCond + lane + 32 * j);
+#pragma unroll
+        for (int k = 0; k < kViewDim; ++k) {
+          const float e = __shfl_sync(0xffffffffu, enc, k);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = fmaf(__ldg(wt + k * kCond + lane + 32 * j), e, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) __stcg(p.view_bias + ray * kCond + lane + 32 * j, acc[j]);
+      }
+      // Stores above are consumed by this CTA's own warps only (this warp below, the slot's workers later):
+      // order them at CTA scope here, off the critical path, and fetch this lane's fenceposts now.
+      __threadfence_block();
+      __syncwarp();
+      const bool t_known = !p.feat_in && !(p.t_mode == 2 && !early_scratch);
+      float tq[4][2];  // [i][0|1] = t[i*32+lane], t[i*32+lane+1]
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tq[i][0] = t_known ? __ldcg(t_ray + i * 32 + lane) : 0.f;  // L2: may be our own stores
+        tq[i][1] = t_known ? __ldcg(t_ray + i * 32 + lane + 1) : 0.f;
+      }
+      TRACE(EV(3, 3, 0, slot));
       mbar_wait(&f_free[slot], ph_free ^ 1);  // first pass falls through (fresh barrier)
       ph_free ^= 1;
       TRACE(EV(3, 0, 0, slot));
-      RayGeom g{};
-      if (!p.feat_in) g = load_ray_geom(p.origins, p.directions, p.radii, ray);
+      if (p.t_mode == 2 && !early_scratch) {
+        // no spare shared memory: the feature tile this warp is about to fill doubles as the scratch
+        resample_warp_lean<true>(p.t_prev + ray * (kN + 1), p.w_prev + ray * kN, kN, kN + 1, p.randomized,
+                                 p.u_jitter ? p.u_jitter + ray * (kN + 1) : nullptr, p.resample_padding,
+                                 reinterpret_cast<float*>(myF), t_ray, p.inds ? p.inds + ray * (kN + 1) : nullptr, lane);
+        __threadfence_block();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tq[i][0] = __ldcg(t_ray + i * 32 + lane);
+          tq[i][1] = __ldcg(t_ray + i * 32 + lane + 1);
+        }
+      }
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
         const int row = i * 32 + lane;
@@ -442,7 +539,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         if (p.feat_in) {
           fin = p.feat_in + (ray * kN + row) * kFeat;  // MLP-only mode: the caller's encoding
         } else {
-          const float t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+          const float t0 = tq[0][0], t1 = tq[0][1];  // rotate: static register indexing in a rolled loop
+#pragma unroll
+          for (int r = 0; r < 3; ++r) tq[r][0] = tq[r + 1][0], tq[r][1] = tq[r + 1][1];
           float tm, tv, rv;
           frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
           lift_gaussian(g, tm, tv, rv, mean, cov);
@@ -480,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       TRACE(EV(3, 1, 0, slot));
     }
 #ifdef MIPNERF_TC_TRACE
-    (void)0;
+    if (slot == 0 && lane == 0) tracer.finish(4);
 #endif
   } else {
     // ============================ slot workers ============================
@@ -507,14 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       const int64_t tile = tile_of(round, slot);
       const bool valid = tile < p.num_rays;
       const int64_t ray = valid ? tile : p.num_rays - 1;
-      float t0 = 0.f, t1 = 0.f, dnorm = 0.f;
-      if (!p.raw_rgb_out) {
-        t0 = __ldg(p.t + ray * (kN + 1) + row), t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
-        const float dx = __ldg(p.directions + ray * 3), dy = __ldg(p.directions + ray * 3 + 1),
-                    dz = __ldg(p.directions + ray * 3 + 2);
-        dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
-      }
-      vb_s[slot * 128 + row] = __ldg(p.view_bias + ray * kCond + row);  // read in the view epilogue
+      float t0 = 0.f, t1 = 0.f, dnorm = 0.f, vb = 0.f;
       TRACE(EV(2, 0, 0, slot));
 
       float dens = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
@@ -523,6 +615,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         ph_acc ^= 1;
         tc_fence_after();
         TRACE(EV(2, 2, l, slot));
+        if (l == 8) {
+          // per-ray operands of the view epilogue / compositing: issued one epilogue early so the latency hides
+          // behind the bottleneck layer; read through L2 because in the fused-prologue modes they were stored
+          // by this CTA's IPE warp (ordered before us by f_ready -> MMA -> acc_full)
+          vb = __ldcg(p.view_bias + ray * kCond + row);
+          if (!p.raw_rgb_out) {
+            t0 = __ldcg(p.t + ray * (kN + 1) + row), t1 = __ldcg(p.t + ray * (kN + 1) + row + 1);
+            const float dx = __ldg(p.directions + ray * 3), dy = __ldg(p.directions + ray * 3 + 1),
+                        dz = __ldg(p.directions + ray * 3 + 2);
+            dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+          }
+        }
         if (l < 9) {
           switch (l) {
             case 0: epilogue_trunk<kFmt, 0>(t_acc, myA, row, dens); break;
@@ -541,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           arrive_a_ready();
           TRACE(EV(2, 4, l, slot));
         } else {
+          vb_s[slot * 128 + row] = vb;
           named_bar_sync(1 + slot, 128);  // vb_s of this ray visible to the whole slot
           epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2);
           tc_fence_before();
@@ -556,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           p.raw_rgb_out[sidx * 3 + 2] = rgb2 + c_small.b_color[2];
           p.raw_density_out[sidx] = dens + c_small.b_density;
         }
-        named_bar_sync(1 + slot, 128);  // vb_s is rewritten at the top of the next ray
+        named_bar_sync(1 + slot, 128);  // vb_s is rewritten before the next ray's view epilogue
         continue;
       }
       // ---- activations + compositing over the ray's 128 samples (4 warps of this slot)
@@ -591,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         for (int qq = 0; qq < 4; ++qq)
           for (int k = 0; k < 5; ++k) s[k] += ps[(slot * 4 + qq) * 8 + k];
-        const float t_first = __ldg(p.t + ray * (kN + 1)), t_last = __ldg(p.t + ray * (kN + 1) + kN);
+        const float t_first = __ldcg(p.t + ray * (kN + 1)), t_last = __ldcg(p.t + ray * (kN + 1) + kN);
         float d = s[4];
         if (isnan(d)) d = 0.f;
         else if (isinf(d)) d = d > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
@@ -1094,6 +1199,17 @@ __global__ void pack_small_params_kernel(const SmallSrc src, SmallParams* __rest
   if (i < 3) out->b_color[i] = src.b_color[i];
 }
 
+__global__ void pack_view_dir_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                     float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kViewDim * kCond) {
+    const int k = i / kCond, n = i % kCond;
+    out[i] = w[(size_t)n * (kWidth + kViewDim) + kWidth + k];
+  } else if (i < (kViewDim + 1) * kCond) {
+    out[i] = b[i - kViewDim * kCond];
+  }
+}
+
 struct TcScratch {
   float *venc, *vbias, *t[2], *w[2];
   uint8_t* feat;  // v2 kernel: kMaxCtas2 x kFeatScratchPerCta
@@ -1139,7 +1255,7 @@ cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   LevelParams q = p;
-  LaunchScope scope(kKernMlpLevelTc, st);
+  LaunchScope scope(p.feat_in ? kKernMlpTc : kKernMlpLevelTc, st);
   if (kPair) {
     const int64_t quads = (p.num_rays + 3) / 4;  // a CTA pair holds 4 rays (2 slots x 2 CTAs)
     const int pairs = (int)(quads < g_num_sms / 2 ? quads : g_num_sms / 2);
@@ -1212,6 +1328,12 @@ int tc_variant() {
   return MIPNERF_TC_DEFAULT_VARIANT;
 }
 bool use_pair_variant() { return tc_variant() != 0; }
+// MIPNERF_B200_TC_PROLOGUE=separate keeps the ray prologue / resampler as their own launches (A/B measurements);
+// default: produced inside the v1 level kernels.
+bool fused_prologue_enabled() {
+  const char* v = getenv("MIPNERF_B200_TC_PROLOGUE");
+  return tc_variant() != 2 && !(v && v[0] == 's');
+}
 
 cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
   if (tc_variant() == 2)
@@ -1306,6 +1428,8 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
   src.b_color = w->linears[11].bias;
   pack_small_params_kernel<<<(9 * kWidth + 255) / 256, 256, 0, st>>>(src,
                                                                       reinterpret_cast<SmallParams*>(img + kSmallOffset));
+  pack_view_dir_kernel<<<((kViewDim + 1) * kCond + 255) / 256, 256, 0, st>>>(
+      w->linears[10].weight, w->linears[10].bias, reinterpret_cast<float*>(img + kViewDirOffset));
   return cudaGetLastError();
 }
 
@@ -1325,7 +1449,10 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
     const float* origins = rays->origins + off * 3;
     const float* directions = rays->directions + off * 3;
     const float* radii = rays->radii + off;
-    {
+    // v1 kernels produce fenceposts and the view bias inside the level kernels (IPE warps); the shared-stream
+    // variant keeps the separate prologue / resample launches.
+    const bool fused_prologue = fused_prologue_enabled();
+    if (!fused_prologue) {
       LaunchScope scope(kKernRayPrologue, st);
       float* t0 = outs[0].t_samples ? outs[0].t_samples + off * (kN + 1) : s.t[0];
       const unsigned vb_blocks = (unsigned)((cnt + kVbRays - 1) / kVbRays);
@@ -1339,16 +1466,30 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
     for (int l = 0; l < c->num_levels; ++l) {
       float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (kN + 1) : s.t[l & 1];
       float* w_cur = outs[l].weights ? outs[l].weights + off * kN : s.w[l & 1];
-      if (l > 0)  // level 0's fenceposts came out of the ray prologue
-        e = launch_resample(t_prev, w_prev, u_jitter ? u_jitter + off * (kN + 1) : nullptr, t_cur,
-                            outs[l].inds ? outs[l].inds + off * (kN + 1) : nullptr, cnt, kN, kN + 1, randomized, 1,
-                            c->resample_padding, st);
-      if (e != cudaSuccess) return e;
+      const float* jit = (randomized && u_jitter) ? u_jitter + off * (kN + 1) : nullptr;
+      int64_t* inds = outs[l].inds ? outs[l].inds + off * (kN + 1) : nullptr;
+      if (l > 0 && !fused_prologue) {
+        e = launch_resample(t_prev, w_prev, jit, t_cur, inds, cnt, kN, kN + 1, randomized, 1, c->resample_padding, st);
+        if (e != cudaSuccess) return e;
+      }
       LevelParams p{};
       p.wimage = img;
       p.origins = origins, p.directions = directions, p.radii = radii;
       p.t = t_cur;
       p.view_bias = s.vbias;
+      if (fused_prologue) {
+        p.t_mode = l == 0 ? 1 : 2;
+        p.vb_mode = l == 0 ? 1 : 0;  // level 0 leaves the per-ray bias in s.vbias for the later levels
+        p.near = rays->near + off, p.far = rays->far + off;
+        p.t_rand = (randomized && t_rand) ? t_rand + off * (kN + 1) : nullptr;
+        p.disparity = c->disparity;
+        p.t_prev = t_prev, p.w_prev = w_prev;
+        p.u_jitter = jit;
+        p.inds = inds;
+        p.randomized = randomized;
+        p.resample_padding = c->resample_padding;
+        p.viewdirs = rays->viewdirs + off * 3;
+      }
       p.feat_scratch = s.feat;
       p.comp_rgb = outs[l].comp_rgb + off * 3;
       p.distance = outs[l].distance + off;

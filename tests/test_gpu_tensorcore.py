@@ -151,3 +151,29 @@ def test_tc_mlp_stage_entry_rejects_other_shapes():
     x = torch.zeros(4, 64, 96, device=DEV)
     with pytest.raises(NotImplementedError):
         mlp(x, torch.zeros(4, 27, device=DEV), precision="bf16")     # 64 samples/ray: fp32 path only
+
+
+@pytest.mark.parametrize("randomized", [False, True])
+def test_tc_fused_prologue_is_bit_exact(randomized):
+    """The fenceposts the level kernels produce themselves (coarse: near/far (+ stratified jitter); fine:
+    blur-pool + inverse CDF of the coarse weights) equal, bit for bit, what the stand-alone stage entry points
+    (which are pinned bit-exactly to the reference) return for the same inputs — searchsorted indices included."""
+    b = 203
+    rays = mp.namedtuple_map(lambda t: t.to(DEV), mp.random_ray_batch(b, seed=29, multiscale=True))
+    model = mp.MipNerf(precision="bf16")
+    model.load_state_dict(make_state_dict(seed=5, kind="trained_like"))
+    model = model.to(DEV).eval()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    t_rand = torch.rand(b, 129, device=DEV, generator=g) if randomized else None
+    u_jit = (torch.rand(b, 129, device=DEV, generator=g) * (1 / 129 - 1.2e-7)) if randomized else None
+    (c_rgb, _, _, w0, t0, _), (_, _, _, _, t1, inds1) = model(rays, randomized, True, t_rand=t_rand, u_jitter=u_jit,
+                                                              return_inds=True)
+    want_t0, _ = mp.sample_along_rays(rays.origins, rays.directions, rays.radii, 128, rays.near, rays.far,
+                                      randomized, False, "cone", t_rand=t_rand)
+    want_t1, _, want_inds = mp.resample_along_rays(rays.origins, rays.directions, rays.radii, t0, w0, randomized,
+                                                   "cone", True, 0.01, u_jitter=u_jit, return_inds=True)
+    torch.cuda.synchronize()
+    assert torch.equal(t0, want_t0)
+    assert torch.equal(t1, want_t1)
+    assert torch.equal(inds1, want_inds)
+    assert torch.isfinite(c_rgb).all()

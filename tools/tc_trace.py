@@ -1,6 +1,8 @@
 """Timeline of CTA 0 of the fused level kernel (trace build): who waits for whom.
 
-    MIPNERF_B200_LIB=.../libmipnerf_b200.trace.so python tools/tc_trace.py [pair|single]
+    MIPNERF_B200_LIB=.../libmipnerf_b200.trace.so python tools/tc_trace.py [pair|single|shared] [levels]
+
+levels = 1 traces the coarse launch, 2 the fine launch (the buffer keeps the last launch).
 """
 import ctypes as C
 import os
@@ -10,7 +12,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
-variant = sys.argv[1] if len(sys.argv) > 1 else "shared"
+variant = sys.argv[1] if len(sys.argv) > 1 else "pair"
+levels = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 os.environ["MIPNERF_B200_TC_VARIANT"] = variant
 import mipnerf_pl_b200 as mp  # noqa: E402
 from mipnerf_pl_b200 import _cabi  # noqa: E402
@@ -25,11 +28,12 @@ for _ in range(3):
     model(rays, False, True)
 torch.cuda.synchronize()
 REG = 15000
-buf = torch.zeros(8 + 2 * 4 * REG, dtype=torch.int64, device=dev)
+NREG = 5                      # producer, MMA issuer, workers slot 0 / 1, IPE warp slot 0
+buf = torch.zeros(8 + 2 * NREG * REG, dtype=torch.int64, device=dev)
 fn = C.CDLL(_cabi.LIB_PATH).mipnerf_b200_debug_set_trace_buffer
 fn.argtypes = [C.c_void_p]
 assert fn(buf.data_ptr()) == 0
-model.num_levels = 1          # one launch (coarse level) is enough for the timeline
+model.num_levels = levels     # the trace buffer keeps the LAST launch: 1 = coarse level, 2 = fine level
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for _ in range(20):           # steady clocks
     model(rays, False, True)
@@ -43,7 +47,7 @@ launch_ms = e0.elapsed_time(e1)
 fn(None)
 raw = buf.cpu().numpy()
 parts = []
-for r in range(4):
+for r in range(NREG):
     cnt = int(raw[r])
     parts.append(raw[8 + 2 * r * REG: 8 + 2 * r * REG + 2 * cnt].reshape(-1, 2))
 ev = np.concatenate(parts)
@@ -89,8 +93,13 @@ for slot in (0, 1):
         # MMA issue end -> worker sees accumulator
         h2 = (acc[gg] - mma_done[gg]).mean() if len(acc[gg]) == len(mma_done[gg]) and len(acc[gg]) else float('nan')
         print(f"g{gg:2d}: mma issue span {iss:8.0f} | commit->worker wake {h2:8.0f} | epilogue {e:8.0f} | fence+arrive {f:6.0f} | arrive->mma sees (next g) {h1:8.0f}")
-a, b = sel(3, 0), sel(3, 1)
-print("IPE warp: features of one ray take", (b - a[:len(b)]).mean() if len(b) else None, "cycles")
+a, b, r0, r1 = sel(3, 0), sel(3, 1), sel(3, 2), sel(3, 3)
+if len(b) > 3 and len(r0) == len(b) == len(r1) == len(a):
+    print(f"IPE warp (slot 0), mean cycles per ray: prologue before f_free {(r1 - r0)[1:].mean():.0f} | "
+          f"wait f_free {(a - r1)[1:].mean():.0f} | f_free -> features published {(b - a)[1:].mean():.0f} | "
+          f"idle until next round starts {(r0[1:] - b[:-1]).mean():.0f}")
+else:
+    print("IPE warp: events", len(r0), len(r1), len(a), len(b))
 tile_start = sel(2, 0, None, 1)
 if len(tile_start) > 2:
     print("tile period slot 0:", np.diff(tile_start).mean())
