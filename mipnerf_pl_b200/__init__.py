@@ -5,7 +5,7 @@ Importing the package never touches CUDA; the first op call loads
 libmipnerf_b200.so and raises if it is missing (no CPU fallback).
 """
 from .rays import (Rays, Rays_keys, namedtuple_map, rearrange_render_image, blender_rays, spheric_pose,
-                   random_ray_batch, rays_to_torch)
+                   random_ray_batch, rays_to_torch, RayStaging)
 from .mip_nerf import MLP, MipNerf
 from .nerf_system import MipNeRFSystem, default_hparams, calc_psnr
 from .ops import (sample_along_rays, resample_along_rays, cast_rays, integrated_pos_enc, pos_enc,
@@ -16,7 +16,7 @@ from .render import generate_rays, render_frame, render_sharded, shard_bounds, s
 
 __all__ = [
     "Rays", "Rays_keys", "namedtuple_map", "rearrange_render_image", "blender_rays", "spheric_pose",
-    "random_ray_batch", "rays_to_torch", "MLP", "MipNerf", "MipNeRFSystem", "default_hparams", "calc_psnr",
+    "random_ray_batch", "rays_to_torch", "RayStaging", "MLP", "MipNerf", "MipNeRFSystem", "default_hparams", "calc_psnr",
     "sample_along_rays", "resample_along_rays", "cast_rays", "integrated_pos_enc", "pos_enc",
     "sorted_piecewise_constant_pdf", "volumetric_rendering", "distloss", "make_state_dict", "generate_rays", "render_frame",
     "render_sharded", "shard_bounds", "shard_rows", "gather_rows", "FusedAdam", "MipLRDecay", "allreduce_grads",

@@ -24,6 +24,49 @@ def namedtuple_map(fn, tup):
     return type(tup)(*map(fn, tup))
 
 
+_FIELD_WIDTHS = (3, 3, 3, 1, 1, 1, 1)  # floats per ray of each Rays field: 13 in total (52 B/ray)
+
+
+class RayStaging:
+    """A ray batch in ONE pinned, field-major host buffer ([origins | directions | viewdirs | radii | lossmult |
+    near | far], 13*B floats) so that a step moves it to the GPU with a single host-to-device copy instead of
+    seven, and hands the kernels the same seven contiguous row-major tensors as views of one device buffer.
+    The reference's DataLoader does the equivalent with `pin_memory=True` + per-field `.to(device)`."""
+
+    def __init__(self, rays: Rays, pin: bool = True):
+        b = rays.origins.shape[0]
+        self.num_rays = b
+        self.host = torch.empty(13 * b, dtype=torch.float32, pin_memory=pin and torch.cuda.is_available())
+        self.fill(rays)
+        self._dev = {}
+
+    def _views(self, flat: torch.Tensor) -> Rays:
+        b, off, out = self.num_rays, 0, []
+        for w in _FIELD_WIDTHS:
+            out.append(flat[off:off + w * b].view(b, w))
+            off += w * b
+        return Rays(*out)
+
+    def fill(self, rays: Rays) -> None:
+        """Overwrite the host buffer with another batch of the same size."""
+        for dst, src in zip(self._views(self.host), rays):
+            dst.copy_(src.reshape(dst.shape))
+
+    @property
+    def host_rays(self) -> Rays:
+        return self._views(self.host)
+
+    def to(self, device, non_blocking: bool = True) -> Rays:
+        """One H2D copy on the current stream; returns Rays whose fields are views of the device buffer
+        (reused between calls: consume the rays before the next `to`)."""
+        device = torch.device(device)
+        buf = self._dev.get(device)
+        if buf is None:
+            buf = self._dev[device] = torch.empty(13 * self.num_rays, dtype=torch.float32, device=device)
+        buf.copy_(self.host, non_blocking=non_blocking)
+        return self._views(buf)
+
+
 def rearrange_render_image(rays: Rays, chunk_size: int = 4096) -> Tuple[List[Rays], torch.Tensor]:
     """[1,H,W,C] ray fields -> list of flat chunks + the lossmult mask
     (models/mip.py:404-421)."""

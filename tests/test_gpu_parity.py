@@ -282,3 +282,19 @@ def test_distloss_vs_golden_and_oracle():
     want = oracle.distloss(w, t)
     got = mp.distloss(w.to(DEV), t.to(DEV))
     assert abs(float(got) - float(want)) <= 1e-4 * abs(float(want))
+
+
+def test_ray_staging_single_copy_round_trip():
+    """RayStaging.to(): one H2D copy, seven contiguous views — the forward result is bit-identical to per-field copies."""
+    rays = mp.random_ray_batch(300, seed=8, multiscale=True)
+    st = mp.RayStaging(rays)
+    dev_rays = st.to(DEV)
+    for got, want in zip(dev_rays, rays):
+        assert got.is_contiguous() and torch.equal(got.cpu(), want.reshape(got.shape))
+    model = mp.MipNerf(precision="fp32")
+    model.load_state_dict(make_state_dict(seed=0, kind="xavier"))
+    model = model.to(DEV).eval()
+    a = model(dev_rays, False, True)
+    b = model(mp.namedtuple_map(lambda t: t.to(DEV), rays), False, True)
+    for (x, y) in zip(a[-1], b[-1]):
+        assert torch.equal(x, y)

@@ -145,3 +145,14 @@ def test_bench_reference_arm_prints_contract_json():
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_ray_staging_is_field_major_and_contiguous():
+    rays = mp.random_ray_batch(37, seed=2, multiscale=True)
+    st = mp.RayStaging(rays)
+    assert st.host.numel() == 13 * 37
+    for got, want in zip(st.host_rays, rays):
+        assert got.is_contiguous() and torch.equal(got, want.reshape(got.shape))
+    other = mp.random_ray_batch(37, seed=3)
+    st.fill(other)
+    assert torch.equal(st.host_rays.directions, other.directions)
