@@ -1211,7 +1211,7 @@ __global__ void pack_view_dir_kernel(const float* __restrict__ w, const float* _
 }
 
 struct TcScratch {
-  float *venc, *vbias, *t[2], *w[2];
+  float *vbias, *t[2], *w[2];
   uint8_t* feat;  // v2 kernel: kMaxCtas2 x kFeatScratchPerCta
   size_t bytes;
 };
@@ -1227,7 +1227,6 @@ TcScratch carve_tc(int64_t rays, void* base) {
     off += align_up(elems * sizeof(float));
     return p;
   };
-  s.venc = take((size_t)rays * kViewDim);
   s.vbias = take((size_t)rays * kCond);
   for (int i = 0; i < 2; ++i) {
     s.t[i] = take((size_t)rays * (kN + 1));

@@ -298,3 +298,30 @@ def test_ray_staging_single_copy_round_trip():
     b = model(mp.namedtuple_map(lambda t: t.to(DEV), rays), False, True)
     for (x, y) in zip(a[-1], b[-1]):
         assert torch.equal(x, y)
+
+
+def test_bench_line_contract():
+    """bench.py on the GPU prints ONE JSON line with the keys the driver reads (value, e2e, roofline, clocks,
+    gpu_launches ...), a tensor-bound roofline for the fused level kernel and non-zero launch counts."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "5", "--warmup", "3",
+                          "--no-cpu-baseline", "--no-frame"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["unit"] == "rays/s" and d["dtype"] == "bf16"
+    assert d["value"] > 1e5 and 0 < d["e2e"]["value"] <= d["value"] * 1.05
+    assert d["e2e"]["h2d_bytes_per_step"] == 4096 * 52 and d["e2e"]["d2h_bytes_per_step"] == 4096 * 28
+    assert d["gpu_launches"] == 2 * 5 and d["kernel_launches"] == {"mlp_level_tc": 10}
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["kernel"] == "mlp_level_tc" and 0.2 < r["frac"] < 1.0
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert "workload" in d["config"]
