@@ -4,25 +4,23 @@
 // reference's concatenations without materialising them —
 //   * skip connection  cat([h, inputs])            (models/mip_nerf.py:96-97)  div = 1
 //   * view condition   cat([bottleneck, viewenc])  (models/mip_nerf.py:106-107) div = samples/ray
-// Operands stay fp32 and products are accumulated with FFMA in k order, so the result is within
-// fp32 round-off of torch's sgemm; this path exists to demonstrate the 1e-4 parity bar, the
+// Operands stay fp32 and products are accumulated with FFMA in k order (tile engine: sgemm_tile.cuh), so the
+// result is within fp32 round-off of torch's sgemm; this path exists to demonstrate the 1e-4 parity bar, the
 // tensor-core path (mlp_tc.cu) is the fast one.
 #include "kernels.h"
 #include "profile.h"
+#include "sgemm_tile.cuh"
 
 namespace mipnerf {
 
-template <int BM, int BN, int BK>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTileThreads, 2)
 linear_f32_kernel(const float* __restrict__ x1, int ld1, int k1, const float* __restrict__ x2, int ld2,
                   int k2, int x2_row_div, const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ y, int ldy, int64_t m, int n, int relu) {
-  static_assert(BM == 128 && BN == 128, "micro-tile mapping assumes 128x128");
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+                  float* __restrict__ y, int ldy, int64_t m, int n, int relu, int vec_a, int vec_b) {
+  __shared__ __align__(16) TileSmem s;
   const int tid = threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.x * BM;
-  const int col0 = blockIdx.y * BN;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+  const int col0 = blockIdx.y * kTileN;
   const int K = k1 + k2;
   const int ty = tid >> 4, tx = tid & 15;
   float acc[8][8];
@@ -31,49 +29,50 @@ linear_f32_kernel(const float* __restrict__ x1, int ld1, int k1, const float* __
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (int kk = 0; kk < K; kk += BK) {
+  auto fetch_a = [&](int kk) {
+    return fetch_frag([&](int g) {
+      const int64_t row = row0 + (g >> 2);
+      const int k = kk + (g & 3) * 4;
+      if (row >= m || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k + 4 <= k1) return ld4(x1 + row * ld1 + k, 4, vec_a);
+      float e[4];
 #pragma unroll
-    for (int i = 0; i < BM * BK / 256; ++i) {
-      const int idx = tid + i * 256;
-      const int r = idx / BK, k = idx % BK;
-      const int64_t row = row0 + r;
-      const int kg = kk + k;
-      float v = 0.f;
-      if (row < m && kg < K)
-        v = kg < k1 ? __ldg(x1 + row * ld1 + kg) : __ldg(x2 + (row / x2_row_div) * ld2 + (kg - k1));
-      As[k][r] = v;
-    }
-#pragma unroll
-    for (int i = 0; i < BN * BK / 256; ++i) {
-      const int idx = tid + i * 256;
-      const int r = idx / BK, k = idx % BK;
-      const int col = col0 + r;
-      const int kg = kk + k;
-      Bs[k][r] = (col < n && kg < K) ? __ldg(w + (int64_t)col * K + kg) : 0.f;
-    }
+      for (int j = 0; j < 4; ++j) {  // straddles x1 | x2 (the concatenations) or the end of K
+        const int kg = k + j;
+        e[j] = kg < k1 ? __ldg(x1 + row * ld1 + kg)
+                       : (kg < K ? __ldg(x2 + (row / x2_row_div) * ld2 + (kg - k1)) : 0.f);
+      }
+      return make_float4(e[0], e[1], e[2], e[3]);
+    });
+  };
+  auto fetch_b = [&](int kk) {
+    return fetch_frag([&](int g) {
+      const int col = col0 + (g >> 2);
+      const int k = kk + (g & 3) * 4;
+      if (col >= n || k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return ld4(w + (int64_t)col * K + k, K - k, vec_b);
+    });
+  };
+
+  Frag fa = fetch_a(0), fb = fetch_b(0);
+  for (int kk = 0; kk < K; kk += kTileK) {
+    store_kcontig(s.a, fa);
+    store_kcontig(s.b, fb);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    if (kk + kTileK < K) {  // next tile's global loads fly during the FFMAs
+      fa = fetch_a(kk + kTileK);
+      fb = fetch_b(kk + kTileK);
     }
+    tile_fma(s, acc, ty, tx);
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int64_t row = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    const int64_t row = row0 + tile_row(i, ty);
     if (row >= m) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      const int col = col0 + tile_row(j, tx);
       if (col >= n) continue;
       float v = acc[i][j] + __ldg(bias + col);
       if (relu) v = fmaxf(v, 0.f);
@@ -131,8 +130,10 @@ cudaError_t launch_linear_f32(const float* x1, int ld1, int k1, const float* x2,
         x1, ld1, k1, x2, ld2, k2, x2_row_div, w, bias, y, ldy, m, n, relu);
   } else {
     dim3 grid((unsigned)((m + 127) / 128), (unsigned)((n + 127) / 128));
-    linear_f32_kernel<128, 128, 16><<<grid, 256, 0, st>>>(x1, ld1, k1, x2, ld2, k2, x2_row_div, w, bias, y,
-                                                          ldy, m, n, relu);
+    const int vec_a = aligned16(x1) && ld1 % 4 == 0;
+    const int vec_b = aligned16(w) && (k1 + k2) % 4 == 0;
+    linear_f32_kernel<<<grid, kTileThreads, 0, st>>>(x1, ld1, k1, x2, ld2, k2, x2_row_div, w, bias, y, ldy, m, n,
+                                                     relu, vec_a, vec_b);
   }
   return cudaGetLastError();
 }

@@ -280,7 +280,7 @@ __global__ void generate_rays_kernel(const Pose c, int height, int width, float 
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)rows * width) return;
   const int y = row0 + (int)(idx / width), x = (int)(idx % width);
-  float d[3], dn[3];
+  float d[3];
   pixel_dir(c, (float)x, (float)y, (float)width, (float)height, focal, d);
   // |d(x,y) - d(x,y+1)| is the rotated camera-space step (0, 1/f, 0): the same for every pixel (so
   // "the last row repeats the previous one" holds trivially) and free of the fp32 cancellation noise

@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include "profile.h"
 #include "ray_math.cuh"
+#include "sgemm_tile.cuh"
 
 namespace mipnerf {
 
@@ -207,60 +208,56 @@ cudaError_t launch_color_dgrad(const float* d_rgb, const float* wc, const float*
 // dgrad:  dX[m,k] = mask * ( sum_n dY[m,n] W[n*ldw + k]  +  r1[m] * r1w[k] ),  mask = act[m,k] > 0 (or 1)
 // 128 x 128 output tile, reduction over n in steps of 16, 8x8 micro-tiles (same mapping as linear_f32.cu).
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTileThreads, 2)
 dgrad_f32_kernel(const float* __restrict__ dy, int n_dim, const float* __restrict__ w, int ldw,
                  const float* __restrict__ r1, const float* __restrict__ r1w, const float* __restrict__ act,
-                 float* __restrict__ dx, int64_t m, int k_dim) {
-  constexpr int BM = 128, BN = 128, BK = 16;
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+                 float* __restrict__ dx, int64_t m, int k_dim, int vec_a, int vec_b) {
+  __shared__ __align__(16) TileSmem s;
   const int tid = threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.x * BM;
-  const int col0 = blockIdx.y * BN;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+  const int col0 = blockIdx.y * kTileN;
   const int ty = tid >> 4, tx = tid & 15;
   float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int nn = 0; nn < n_dim; nn += BK) {
-#pragma unroll
-    for (int i = 0; i < BM * BK / 256; ++i) {
-      const int idx = tid + i * 256;
-      const int r = idx / BK, k = idx % BK;
-      const int64_t row = row0 + r;
-      As[k][r] = (row < m && nn + k < n_dim) ? __ldg(dy + row * n_dim + nn + k) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < BN * BK / 256; ++i) {
-      const int idx = tid + i * 256;
-      const int k = idx / BN, c = idx % BN;
-      Bs[k][c] = (col0 + c < k_dim && nn + k < n_dim) ? __ldg(w + (int64_t)(nn + k) * ldw + col0 + c) : 0.f;
-    }
+  auto fetch_a = [&](int nn) {  // dY rows, contiguous along the reduction index n
+    return fetch_frag([&](int g) {
+      const int64_t row = row0 + (g >> 2);
+      const int nk = nn + (g & 3) * 4;
+      if (row >= m || nk >= n_dim) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return ld4(dy + row * n_dim + nk, n_dim - nk, vec_a);
+    });
+  };
+  auto fetch_b = [&](int nn) {  // W rows n, contiguous along the output column k
+    return fetch_frag([&](int g) {
+      const int nk = nn + (g >> 5);
+      const int c = col0 + (g & 31) * 4;
+      if (nk >= n_dim || c >= k_dim) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return ld4(w + (int64_t)nk * ldw + c, k_dim - c, vec_b);
+    });
+  };
+  Frag fa = fetch_a(0), fb = fetch_b(0);
+  for (int nn = 0; nn < n_dim; nn += kTileK) {
+    store_kcontig(s.a, fa);
+    store_rowcontig(s.b, fb);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    if (nn + kTileK < n_dim) {
+      fa = fetch_a(nn + kTileK);
+      fb = fetch_b(nn + kTileK);
     }
+    tile_fma(s, acc, ty, tx);
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int64_t row = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    const int64_t row = row0 + tile_row(i, ty);
     if (row >= m) continue;
     const float rv = r1 ? __ldg(r1 + row) : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col = col0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      const int col = col0 + tile_row(j, tx);
       if (col >= k_dim) continue;
       float v = acc[i][j];
       if (r1) v = fmaf(rv, __ldg(r1w + col), v);
@@ -276,7 +273,9 @@ cudaError_t launch_dgrad_f32(const float* dy, int n_dim, const float* w, int ldw
   if (m == 0 || k_dim == 0) return cudaSuccess;
   LaunchScope scope(kKernDgrad, st);
   dim3 grid((unsigned)((m + 127) / 128), (unsigned)((k_dim + 127) / 128));
-  dgrad_f32_kernel<<<grid, 256, 0, st>>>(dy, n_dim, w, ldw, r1, r1w, act, dx, m, k_dim);
+  const int vec_a = aligned16(dy) && n_dim % 4 == 0;
+  const int vec_b = aligned16(w) && ldw % 4 == 0;
+  dgrad_f32_kernel<<<grid, kTileThreads, 0, st>>>(dy, n_dim, w, ldw, r1, r1w, act, dx, m, k_dim, vec_a, vec_b);
   return cudaGetLastError();
 }
 
@@ -285,16 +284,14 @@ cudaError_t launch_dgrad_f32(const float* dy, int n_dim, const float* w, int ldw
 //   Xc = [X1 (k1 cols) | X2[m / x2_row_div] (k2 cols) | 1]   — the trailing ones column yields the bias grad.
 // Both operand tiles are read along their contiguous dimension (no transposes): the reduction index is the row.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTileThreads, 2)
 wgrad_f32_kernel(const float* __restrict__ dy, int n_dim, const float* __restrict__ x1, int ld1, int k1,
                  const float* __restrict__ x2, int ld2, int k2, int x2_row_div, float* __restrict__ part,
-                 int64_t m, int64_t slice_rows) {
-  constexpr int BM = 128, BN = 128, BK = 16;
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN + 4];
+                 int64_t m, int64_t slice_rows, int vec_a, int vec_b) {
+  __shared__ __align__(16) TileSmem s;
   const int tid = threadIdx.x;
   const int K = k1 + k2;
-  const int n0 = blockIdx.y * BM, kg0 = blockIdx.z * BN;
+  const int n0 = blockIdx.y * kTileM, kg0 = blockIdx.z * kTileN;
   const int64_t m_begin = (int64_t)blockIdx.x * slice_rows;
   const int64_t m_end = (m_begin + slice_rows) < m ? (m_begin + slice_rows) : m;
   const int ty = tid >> 4, tx = tid & 15;
@@ -303,52 +300,50 @@ wgrad_f32_kernel(const float* __restrict__ dy, int n_dim, const float* __restric
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int64_t m0 = m_begin; m0 < m_end; m0 += BK) {
+  auto fetch_a = [&](int64_t m0) {  // dY rows m0..m0+15, contiguous along n
+    return fetch_frag([&](int g) {
+      const int64_t row = m0 + (g >> 5);
+      const int nn = n0 + (g & 31) * 4;
+      if (row >= m_end || nn >= n_dim) return make_float4(0.f, 0.f, 0.f, 0.f);
+      return ld4(dy + row * n_dim + nn, n_dim - nn, vec_a);
+    });
+  };
+  auto fetch_b = [&](int64_t m0) {  // [X1 | X2[row / div] | 1] rows, contiguous along the column
+    return fetch_frag([&](int g) {
+      const int64_t row = m0 + (g >> 5);
+      const int kg = kg0 + (g & 31) * 4;
+      if (row >= m_end || kg > K) return make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kg + 4 <= k1) return ld4(x1 + row * ld1 + kg, 4, vec_b);
+      float e[4];
 #pragma unroll
-    for (int i = 0; i < BM * BK / 256; ++i) {
-      const int idx = tid + i * 256;
-      const int mm = idx / BM, r = idx % BM;
-      const int64_t row = m0 + mm;
-      As[mm][r] = (row < m_end && n0 + r < n_dim) ? __ldg(dy + row * n_dim + n0 + r) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < BN * BK / 256; ++i) {
-      const int idx = tid + i * 256;
-      const int mm = idx / BN, c = idx % BN;
-      const int64_t row = m0 + mm;
-      const int kg = kg0 + c;
-      float v = 0.f;
-      if (row < m_end) {
-        if (kg < k1) v = __ldg(x1 + row * ld1 + kg);
-        else if (kg < K) v = __ldg(x2 + (row / x2_row_div) * ld2 + (kg - k1));
-        else if (kg == K) v = 1.0f;
+      for (int j = 0; j < 4; ++j) {
+        const int c = kg + j;
+        e[j] = c < k1 ? __ldg(x1 + row * ld1 + c)
+                      : (c < K ? __ldg(x2 + (row / x2_row_div) * ld2 + (c - k1)) : (c == K ? 1.0f : 0.f));
       }
-      Bs[mm][c] = v;
-    }
+      return make_float4(e[0], e[1], e[2], e[3]);
+    });
+  };
+  Frag fa = fetch_a(m_begin), fb = fetch_b(m_begin);
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += kTileK) {
+    store_rowcontig(s.a, fa);
+    store_rowcontig(s.b, fb);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    if (m0 + kTileK < m_end) {
+      fa = fetch_a(m0 + kTileK);
+      fb = fetch_b(m0 + kTileK);
     }
+    tile_fma(s, acc, ty, tx);
     __syncthreads();
   }
   float* out = part + (size_t)blockIdx.x * n_dim * (K + 1);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int n = n0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    const int n = n0 + tile_row(i, ty);
     if (n >= n_dim) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int kg = kg0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      const int kg = kg0 + tile_row(j, tx);
       if (kg > K) continue;
       out[(size_t)n * (K + 1) + kg] = acc[i][j];
     }
@@ -388,7 +383,10 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
   slice_rows = (slice_rows + 15) / 16 * 16;
   LaunchScope scope(kKernWgrad, st);
   dim3 grid((unsigned)slices, (unsigned)((n_dim + 127) / 128), (unsigned)((K + 1 + 127) / 128));
-  wgrad_f32_kernel<<<grid, 256, 0, st>>>(dy, n_dim, x1, ld1, k1, x2, ld2, k2, x2_row_div, part, m, slice_rows);
+  const int vec_a = aligned16(dy) && n_dim % 4 == 0;
+  const int vec_b = aligned16(x1) && ld1 % 4 == 0;
+  wgrad_f32_kernel<<<grid, kTileThreads, 0, st>>>(dy, n_dim, x1, ld1, k1, x2, ld2, k2, x2_row_div, part, m, slice_rows,
+                                                  vec_a, vec_b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (K + 1), 256), 256, 0, st>>>(part, slices, n_dim, K, dw, db,
