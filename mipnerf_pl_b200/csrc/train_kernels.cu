@@ -280,8 +280,9 @@ cudaError_t launch_dgrad_f32(const float* dy, int n_dim, const float* w, int ldw
 }
 
 // -------------------------------------------------------------------------------------------------
-// wgrad partials:  part[s][n][kg] = sum_{m in slice s} dY[m,n] * Xc[m,kg],   kg in [0, K],
-//   Xc = [X1 (k1 cols) | X2[m / x2_row_div] (k2 cols) | 1]   — the trailing ones column yields the bias grad.
+// wgrad partials:  part[s][n][kg] = sum_{m in slice s} dY[m,n] * Xc[m,kg],  Xc = [X1 (k1 cols) | X2[m / x2_row_div]
+//   (k2 cols)];  column K of the partial holds the bias gradient (column sums of dY, accumulated from the staged
+//   dY tile by the first column block — no extra tile for a 'ones' column).
 // Both operand tiles are read along their contiguous dimension (no transposes): the reduction index is the row.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTileThreads, 2)
@@ -312,18 +313,18 @@ wgrad_f32_kernel(const float* __restrict__ dy, int n_dim, const float* __restric
     return fetch_frag([&](int g) {
       const int64_t row = m0 + (g >> 5);
       const int kg = kg0 + (g & 31) * 4;
-      if (row >= m_end || kg > K) return make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row >= m_end || kg >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
       if (kg + 4 <= k1) return ld4(x1 + row * ld1 + kg, 4, vec_b);
       float e[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = kg + j;
-        e[j] = c < k1 ? __ldg(x1 + row * ld1 + c)
-                      : (c < K ? __ldg(x2 + (row / x2_row_div) * ld2 + (c - k1)) : (c == K ? 1.0f : 0.f));
+        e[j] = c < k1 ? __ldg(x1 + row * ld1 + c) : (c < K ? __ldg(x2 + (row / x2_row_div) * ld2 + (c - k1)) : 0.f);
       }
       return make_float4(e[0], e[1], e[2], e[3]);
     });
   };
+  float bsum = 0.f;
   Frag fa = fetch_a(m_begin), fb = fetch_b(m_begin);
   for (int64_t m0 = m_begin; m0 < m_end; m0 += kTileK) {
     store_rowcontig(s.a, fa);
@@ -333,10 +334,15 @@ wgrad_f32_kernel(const float* __restrict__ dy, int n_dim, const float* __restric
       fa = fetch_a(m0 + kTileK);
       fb = fetch_b(m0 + kTileK);
     }
+    if (blockIdx.z == 0 && tid < kTileM) {  // bias gradient: column sums of the dY tile, first column block only
+#pragma unroll
+      for (int k = 0; k < kTileK; ++k) bsum += s.a[k][tid];
+    }
     tile_fma(s, acc, ty, tx);
     __syncthreads();
   }
   float* out = part + (size_t)blockIdx.x * n_dim * (K + 1);
+  if (blockIdx.z == 0 && tid < kTileM && n0 + tid < n_dim) out[(size_t)(n0 + tid) * (K + 1) + K] = bsum;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int n = n0 + tile_row(i, ty);
@@ -344,7 +350,7 @@ wgrad_f32_kernel(const float* __restrict__ dy, int n_dim, const float* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int kg = kg0 + tile_row(j, tx);
-      if (kg > K) continue;
+      if (kg >= K) continue;
       out[(size_t)n * (K + 1) + kg] = acc[i][j];
     }
   }
@@ -382,7 +388,7 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
   int64_t slice_rows = (m + slices - 1) / slices;
   slice_rows = (slice_rows + 15) / 16 * 16;
   LaunchScope scope(kKernWgrad, st);
-  dim3 grid((unsigned)slices, (unsigned)((n_dim + 127) / 128), (unsigned)((K + 1 + 127) / 128));
+  dim3 grid((unsigned)slices, (unsigned)((n_dim + 127) / 128), (unsigned)((K + 127) / 128));
   const int vec_a = aligned16(dy) && n_dim % 4 == 0;
   const int vec_b = aligned16(x1) && ld1 % 4 == 0;
   wgrad_f32_kernel<<<grid, kTileThreads, 0, st>>>(dy, n_dim, x1, ld1, k1, x2, ld2, k2, x2_row_div, part, m, slice_rows,

@@ -83,14 +83,19 @@ class MLP(torch.nn.Module):
     def __getstate__(self):  # ctypes marshalling caches are per-process
         d = self.__dict__.copy()
         d.pop("_ws_cache", None)
+        d.pop("_lin_cache", None)
         d["_packed"] = {}
         return d
 
     # ---- marshalling --------------------------------------------------------------------------
     def linears(self) -> List[torch.nn.Linear]:
-        """state_dict order expected by mipnerf_b200_weights."""
-        return ([seq[0] for seq in self.layers] + [self.density_layer, self.extra_layer] +
-                [seq[0] for seq in self.view_layers] + [self.color_layer])
+        """state_dict order expected by mipnerf_b200_weights (cached: the submodule tree is fixed after __init__)."""
+        lins = self.__dict__.get("_lin_cache")
+        if lins is None:
+            lins = ([seq[0] for seq in self.layers] + [self.density_layer, self.extra_layer] +
+                    [seq[0] for seq in self.view_layers] + [self.color_layer])
+            self.__dict__["_lin_cache"] = lins
+        return lins
 
     def _weights_struct(self, cfg: "_cabi.Config", precision: int, device):
         """(struct, keep-alive list), cached until a parameter is modified / moved / re-typed."""
