@@ -165,6 +165,17 @@ int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, flo
                                float* viewdirs, float* radii, float* near_out, float* far_out,
                                void* stream);
 
+/* Training rays from pixel ids, scene resident in HBM (replaces the per-pixel host arrays of
+ * datasets/datasets.py:116-168, 216-263 and the DataLoader's H2D copies):
+ *   cam_table [num_images, 24] = pix2cam (3x3 row-major, maps (x+.5, y+.5, 1) to a camera direction) |
+ *                                cam2world (3x4 row-major) | lossmult | near | far
+ *   offsets [num_images+1] first atlas row of each image; widths [num_images]; atlas [P,3] target colours
+ *   pixel_ids [count] atlas rows -> the seven Rays fields ([count,3|1]) and rgb [count,3] (nullable). */
+int mipnerf_b200_rays_from_pixels(const float* cam_table, const int64_t* offsets, const int32_t* widths,
+                                  int num_images, const int64_t* pixel_ids, int64_t count, const float* atlas,
+                                  float* origins, float* directions, float* viewdirs, float* radii,
+                                  float* lossmult, float* near_out, float* far_out, float* rgb, void* stream);
+
 /* ---- per-stage entry points (unit parity against the functions of models/mip.py) ---- */
 
 /* sample_along_rays (models/mip.py:127-165): t_samples [B,N+1], means/covs [B,N,3] (nullable). */

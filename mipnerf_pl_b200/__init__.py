@@ -12,6 +12,8 @@ from .ops import (sample_along_rays, resample_along_rays, cast_rays, integrated_
                   sorted_piecewise_constant_pdf, volumetric_rendering, distloss)
 from .weights import make_state_dict
 from .train import FusedAdam, MipLRDecay, allreduce_grads, forward_backward, fused_loss, mip_lr
+from .datasets import (Blender, Multicam, DeviceRayBank, Scene, dataset_dict, load_blender_scene, load_multicam_scene,
+                       image_rays, convert_blender_to_multiscale, write_synthetic_blender_scene)
 from .render import generate_rays, render_frame, render_sharded, shard_bounds, shard_rows, gather_rows
 
 __all__ = [
@@ -20,5 +22,7 @@ __all__ = [
     "sample_along_rays", "resample_along_rays", "cast_rays", "integrated_pos_enc", "pos_enc",
     "sorted_piecewise_constant_pdf", "volumetric_rendering", "distloss", "make_state_dict", "generate_rays", "render_frame",
     "render_sharded", "shard_bounds", "shard_rows", "gather_rows", "FusedAdam", "MipLRDecay", "allreduce_grads",
-    "forward_backward", "fused_loss", "mip_lr",
+    "forward_backward", "fused_loss", "mip_lr", "Blender", "Multicam", "DeviceRayBank", "Scene", "dataset_dict",
+    "load_blender_scene", "load_multicam_scene", "image_rays", "convert_blender_to_multiscale",
+    "write_synthetic_blender_scene",
 ]

@@ -543,6 +543,21 @@ int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, flo
   return MIPNERF_B200_OK;
 }
 
+int mipnerf_b200_rays_from_pixels(const float* cam_table, const int64_t* offsets, const int32_t* widths,
+                                  int num_images, const int64_t* pixel_ids, int64_t count, const float* atlas,
+                                  float* origins, float* directions, float* viewdirs, float* radii,
+                                  float* lossmult, float* near_out, float* far_out, float* rgb, void* stream) {
+  if (num_images < 1 || count < 0) return fail(MIPNERF_B200_EINVAL, "bad sizes");
+  if (!cam_table || !offsets || !widths) return fail(MIPNERF_B200_EINVAL, "NULL scene table");
+  if (count > 0 && (!pixel_ids || !origins || !directions || !viewdirs || !radii || !lossmult || !near_out || !far_out))
+    return fail(MIPNERF_B200_EINVAL, "NULL ray tensor");
+  if (rgb && !atlas) return fail(MIPNERF_B200_EINVAL, "rgb requested without a pixel atlas");
+  CUDA_TRY(mipnerf::launch_rays_from_pixels(cam_table, offsets, widths, num_images, pixel_ids, count, atlas, origins,
+                                            directions, viewdirs, radii, lossmult, near_out, far_out, rgb,
+                                            (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
 int mipnerf_b200_sample_along_rays(const mipnerf_b200_rays* rays, int num_samples, int randomized,
                                    int disparity, const float* t_rand, float* t_samples, float* means,
                                    float* covs, void* stream) {

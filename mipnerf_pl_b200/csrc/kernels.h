@@ -13,6 +13,10 @@ cudaError_t launch_distloss(const float* weights, const float* t, float* out, in
 cudaError_t launch_generate_rays(const float* c2w_host, int height, int width, float focal, float near_v,
                                  float far_v, int row0, int rows, float* origins, float* directions,
                                  float* viewdirs, float* radii, float* near_o, float* far_o, cudaStream_t st);
+cudaError_t launch_rays_from_pixels(const float* cam_table, const int64_t* offsets, const int32_t* widths,
+                                    int num_images, const int64_t* pixel_ids, int64_t count, const float* atlas,
+                                    float* origins, float* directions, float* viewdirs, float* radii,
+                                    float* lossmult, float* near_o, float* far_o, float* rgb, cudaStream_t st);
 cudaError_t launch_coarse_t(const float* near, const float* far, const float* t_rand, float* t_out,
                             int64_t num_rays, int n, int randomized, int disparity, cudaStream_t st);
 cudaError_t launch_cast_rays(const float* origins, const float* directions, const float* radii,

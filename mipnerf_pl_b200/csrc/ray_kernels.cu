@@ -299,8 +299,80 @@ __global__ void generate_rays_kernel(const Pose c, int height, int width, float 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Training rays straight from pixel ids (datasets/datasets.py:116-168, 216-263 without the
+// host-side per-pixel arrays).  The scene lives in HBM as a pixel atlas [P,3] + a camera table per image
+//   cam[24] = pix2cam (3x3 row-major) | cam2world (3x4 row-major) | lossmult | near | far,
+// `offsets[i]` = first atlas row of image i, `widths[i]` its width.  One thread per requested pixel:
+//   image = upper_bound(offsets, id) - 1, (x, y) from the in-image index,
+//   camera dir = pix2cam . (x+.5, y+.5, 1),  direction = R . dir,  origin = t,  viewdir = direction / |direction|,
+//   radius = |R . pix2cam[:,1]| * 2/sqrt(12)   (the y-neighbour distance of the reference, which is the same
+//   vector for every pixel of an image; see generate_rays_kernel for why it is evaluated analytically).
+// ---------------------------------------------------------------------------------------------
+__global__ void rays_from_pixels_kernel(const float* __restrict__ cam_table, const int64_t* __restrict__ offsets,
+                                        const int32_t* __restrict__ widths, int num_images,
+                                        const int64_t* __restrict__ pixel_ids, int64_t count,
+                                        const float* __restrict__ atlas, float* __restrict__ origins,
+                                        float* __restrict__ directions, float* __restrict__ viewdirs,
+                                        float* __restrict__ radii, float* __restrict__ lossmult,
+                                        float* __restrict__ near_o, float* __restrict__ far_o,
+                                        float* __restrict__ rgb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t id = __ldg(pixel_ids + i);
+  int lo = 0, hi = num_images;  // offsets[lo] <= id < offsets[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) <= id) lo = mid;
+    else hi = mid;
+  }
+  const float* cam = cam_table + (size_t)lo * 24;
+  const int64_t local = id - __ldg(offsets + lo);
+  const int w = __ldg(widths + lo);
+  const float px = (float)(local % w) + 0.5f, py = (float)(local / w) + 0.5f;
+  float k[9], m[12];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) k[j] = __ldg(cam + j);
+#pragma unroll
+  for (int j = 0; j < 12; ++j) m[j] = __ldg(cam + 9 + j);
+  const float cx = k[0] * px + k[1] * py + k[2], cy = k[3] * px + k[4] * py + k[5], cz = k[6] * px + k[7] * py + k[8];
+  float d[3], s[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    d[r] = m[r * 4 + 0] * cx + m[r * 4 + 1] * cy + m[r * 4 + 2] * cz;
+    s[r] = m[r * 4 + 0] * k[1] + m[r * 4 + 1] * k[4] + m[r * 4 + 2] * k[7];  // d(x, y+1) - d(x, y)
+  }
+  const float inv_norm = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    origins[i * 3 + r] = m[r * 4 + 3];
+    directions[i * 3 + r] = d[r];
+    viewdirs[i * 3 + r] = d[r] * inv_norm;
+  }
+  radii[i] = sqrtf(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) * 0.5773502691896258f;  // 2 / sqrt(12)
+  lossmult[i] = __ldg(cam + 21);
+  near_o[i] = __ldg(cam + 22);
+  far_o[i] = __ldg(cam + 23);
+  if (rgb) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[i * 3 + c] = __ldg(atlas + id * 3 + c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+cudaError_t launch_rays_from_pixels(const float* cam_table, const int64_t* offsets, const int32_t* widths,
+                                    int num_images, const int64_t* pixel_ids, int64_t count, const float* atlas,
+                                    float* origins, float* directions, float* viewdirs, float* radii,
+                                    float* lossmult, float* near_o, float* far_o, float* rgb, cudaStream_t st) {
+  if (count == 0) return cudaSuccess;
+  LaunchScope scope(kKernRayGen, st);
+  rays_from_pixels_kernel<<<blocks_for(count, 256), 256, 0, st>>>(cam_table, offsets, widths, num_images, pixel_ids,
+                                                                 count, atlas, origins, directions, viewdirs, radii,
+                                                                 lossmult, near_o, far_o, rgb);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_generate_rays(const float* c2w_host, int height, int width, float focal, float near_v,
                                  float far_v, int row0, int rows, float* origins, float* directions,
                                  float* viewdirs, float* radii, float* near_o, float* far_o, cudaStream_t st) {

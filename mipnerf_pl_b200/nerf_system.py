@@ -7,7 +7,7 @@ Kept: constructor from the flat dotted `hparams` dict, `forward`, `render_image`
 so when it cannot be imported a minimal stand-in base class provides
 `save_hyperparameters` / `hparams` / `log` / `load_from_checkpoint`.
 `training_step` / `configure_optimizers` run on the library's fp32 backward and Adam kernels
-(mipnerf_pl_b200/train.py); dataloaders are row N4.
+(mipnerf_pl_b200/train.py); `setup` / dataloaders use mipnerf_pl_b200/datasets.py (row N4).
 """
 from __future__ import annotations
 
@@ -95,6 +95,30 @@ class MipNeRFSystem(_Base):
 
     def forward(self, batch_rays: Rays, randomized: bool, white_bkgd: bool):
         return self.mip_nerf(batch_rays, randomized, white_bkgd)  # num_levels results
+
+    def setup(self, stage=None):
+        """models/nerf_system.py:56-68."""
+        from .datasets import dataset_dict
+        dataset = dataset_dict[self.hparams['dataset_name']]
+        self.train_dataset = dataset(data_dir=self.hparams['data_path'], split='train',
+                                     white_bkgd=self.hparams['train.white_bkgd'],
+                                     batch_type=self.hparams['train.batch_type'])
+        self.val_dataset = dataset(data_dir=self.hparams['data_path'], split='val',
+                                   white_bkgd=self.hparams['val.white_bkgd'],
+                                   batch_type=self.hparams['val.batch_type'])
+
+    def train_dataloader(self):
+        """models/nerf_system.py:78-83 (the reference's host path; `datasets.DeviceRayBank.sample` is the
+        device-resident alternative that needs no loader)."""
+        from torch.utils.data import DataLoader
+        return DataLoader(self.train_dataset, shuffle=True, num_workers=self.hparams['train.num_work'],
+                          batch_size=self.hparams['train.batch_size'], pin_memory=True)
+
+    def val_dataloader(self):
+        """models/nerf_system.py:85-93: one image (H*W rays) at a time."""
+        from torch.utils.data import DataLoader
+        return DataLoader(self.val_dataset, shuffle=False, num_workers=1, batch_size=1, pin_memory=True,
+                          persistent_workers=True)
 
     def configure_optimizers(self):
         """models/nerf_system.py:70-76: Adam(lr_init) + MipLRDecay stepped every optimiser step."""

@@ -277,9 +277,51 @@ def training_case():
     save("training.npz", **out)
 
 
+def datasets_case():
+    """The reference's own loaders (datasets/datasets.py Blender + Multicam) and multi-scale converter
+    (datasets/convert_blender_data.py) run on a tiny synthetic Blender-format scene; the scene is rebuilt
+    bit-identically by mipnerf_pl_b200.write_synthetic_blender_scene(root, 3, 16, 16, seed=5) in the tests."""
+    import json
+    import tempfile
+    from datasets.datasets import Blender as RefBlender, Multicam as RefMulticam  # reference
+    from datasets.convert_blender_data import convert_to_nerfdata  # reference
+    from mipnerf_pl_b200.datasets import write_synthetic_blender_scene  # ours: input generator only
+    root = tempfile.mkdtemp()
+    write_synthetic_blender_scene(root, 3, 16, 16, seed=5)
+    out = {}
+    for white in (True, False):
+        tag = "w" if white else "k"
+        ds = RefBlender(root, "train", white_bkgd=white)
+        out.update({f"blender_{tag}_train_{k}": np.asarray(getattr(ds.rays, k)) for k in RefRays._fields})
+        out[f"blender_{tag}_train_images"] = np.asarray(ds.images)
+    dv = RefBlender(root, "val", batch_type="single_image")
+    rays1, img1 = dv[0]
+    rays2, img2 = dv[0]          # val ignores the index and cycles
+    out.update({f"blender_val1_{k}": np.asarray(getattr(rays2, k)) for k in RefRays._fields})
+    out["blender_val1_image"] = np.asarray(img2)
+    out["blender_focal"] = np.array(dv.focal)
+    ms_root = root + "_ms"
+    convert_to_nerfdata(root, ms_root, 3)
+    meta = json.load(open(os.path.join(ms_root, "metadata.json")))["train"]
+    for k in ("pix2cam", "cam2world", "width", "height", "focal", "lossmult", "near", "far", "label"):
+        out[f"ms_meta_{k}"] = np.array(meta[k], dtype=np.float64)
+    out["ms_meta_file_path"] = np.array(meta["file_path"])
+    mt = RefMulticam(ms_root, "train")
+    out.update({f"ms_train_{k}": np.asarray(getattr(mt.rays, k)) for k in RefRays._fields})
+    out["ms_train_images"] = np.asarray(mt.images)
+    mv = RefMulticam(ms_root, "test", batch_type="single_image")
+    r, im = mv[4]
+    out.update({f"ms_test4_{k}": np.asarray(getattr(r, k)) for k in RefRays._fields})
+    out["ms_test4_image"] = np.asarray(im)
+    save("datasets.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "training":   # regenerate only training.npz
         training_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "datasets":   # regenerate only datasets.npz
+        datasets_case()
         sys.exit(0)
     forward_case("forward_xavier.npz", 40, seed=0, weights_kind="xavier", randomized=False, white_bkgd=True)
     forward_case("forward_trained_like.npz", 40, seed=1, weights_kind="trained_like", randomized=False,
@@ -291,6 +333,7 @@ if __name__ == "__main__":
     resampler_case()
     stages_case()
     training_case()
+    datasets_case()
     with open(os.path.join(HERE, "VERSIONS.txt"), "w") as f:
         f.write(f"torch {torch.__version__}\nnumpy {np.__version__}\nreference {REF} (hjxwhy/mipnerf_pl @ 6c07452)\n"
                 f"cpu_capability {torch.backends.cpu.get_cpu_capability()}\n")

@@ -60,6 +60,18 @@ def main():
             lambda: mp.generate_rays(pose, side, side, device=dev),
             side * side * 48),
     }
+    # device-resident training rays: 20 images of 800x800 random pixels + poses, one random batch of B pixel ids
+    import numpy as np
+    from mipnerf_pl_b200.datasets import DeviceRayBank, Scene
+    n_img, hw = 20, 800
+    k_inv = np.array([[1 / 1111.111, 0, -0.5 * hw / 1111.111], [0, -1 / 1111.111, 0.5 * hw / 1111.111], [0, 0, -1]],
+                     dtype=np.float32)
+    scene = Scene([np.zeros((hw, hw, 3), dtype=np.float32) for _ in range(n_img)], np.broadcast_to(k_inv, (n_img, 3, 3)),
+                  np.stack([mp.spheric_pose(0.3 * i) for i in range(n_img)]), 1.0, 2.0, 6.0)
+    bank = DeviceRayBank(scene, dev)
+    ids = torch.randint(0, bank.num_pixels, (B,), device=dev, generator=g)
+    cases["rays_from_pixels (DeviceRayBank: training rays + target rgb from pixel ids)"] = (
+        lambda: bank.rays(ids), B * (8 + 12 + 52 + 12))
     rows = []
     for name, (fn, nbytes) in cases.items():
         for _ in range(2):
