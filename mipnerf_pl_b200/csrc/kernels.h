@@ -44,8 +44,8 @@ cudaError_t launch_linear_f32(const float* x1, int ld1, int k1, const float* x2,
                               int64_t m, int n, int relu, cudaStream_t st);
 
 // ---- train_kernels.cu (fp32 training step: backward + Adam) ----
-constexpr int kWgradMaxSlices = 128;
-int wgrad_num_slices(int64_t m);
+constexpr int kWgradMaxSlices = 160;
+int wgrad_num_slices(int64_t m, int tiles);
 cudaError_t launch_render_backward(const float* raw_rgb, const float* raw_dens, const float* t, const float* dirs,
                                    const float* target, const float* lossmult, const float* mask_sum,
                                    float mse_mult, float dist_mult, int white_bkgd, float density_bias,
@@ -58,7 +58,7 @@ cudaError_t launch_dgrad_f32(const float* dy, int n_dim, const float* w, int ldw
                              const float* r1w, const float* act, float* dx, int64_t m, int k_dim,
                              cudaStream_t st);
 // dW[n_dim, k1+k2] (+)= dY^T @ [X1 | X2[row / x2_row_div]],  db[n_dim] (+)= colsum(dY); `part` holds
-// wgrad_num_slices(m) * n_dim * (k1+k2+1) floats of per-slice partial sums.
+// up to kWgradMaxSlices * n_dim * (k1+k2+1) floats of per-slice partial sums.
 cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
                              int ld2, int k2, int x2_row_div, float* part, float* dw, float* db,
                              int accumulate, int64_t m, cudaStream_t st);

@@ -368,10 +368,27 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, 
   *dst = accumulate ? *dst + acc : acc;
 }
 
-int wgrad_num_slices(int64_t m) {
+// Number of M-slices for a wgrad with `tiles` output tiles.  Small problems: one slice per 4096 rows.  Large ones:
+// fill whole waves of the grid (2 CTAs per SM resident) so the last wave is not mostly empty — 4 tiles x 74 slices
+// is exactly one wave of 296 CTAs on 148 SMs, where the old fixed 128 slices left the second wave 27 % full.
+int wgrad_num_slices(int64_t m, int tiles) {
   int64_t s = (m + 4095) / 4096;
   if (s < 1) s = 1;
   if (s > kWgradMaxSlices) s = kWgradMaxSlices;
+  static int resident = 0;
+  if (resident == 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident = 2 * sms;
+  }
+  if (tiles < 1) tiles = 1;
+  if (s * tiles > resident) {  // more than one wave anyway: round the slice count to whole waves
+    const int64_t waves = (s * tiles + resident - 1) / resident;
+    int64_t fit = waves * resident / tiles;
+    if (fit > kWgradMaxSlices) fit = (waves - 1 > 0 ? (waves - 1) * resident / tiles : kWgradMaxSlices);
+    if (fit >= 1 && fit <= kWgradMaxSlices) s = fit;
+  }
   return (int)s;
 }
 
@@ -384,7 +401,8 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
   }
   if (x2_row_div < 1) x2_row_div = 1;
   const int K = k1 + k2;
-  const int slices = wgrad_num_slices(m);
+  const int tiles = ((n_dim + 127) / 128) * ((K + 127) / 128);
+  const int slices = wgrad_num_slices(m, tiles);
   int64_t slice_rows = (m + slices - 1) / slices;
   slice_rows = (slice_rows + 15) / 16 * 16;
   LaunchScope scope(kKernWgrad, st);

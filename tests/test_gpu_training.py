@@ -120,6 +120,18 @@ def test_gradients_add_up_over_ray_shards_and_chunks():
         assert e <= 1e-5, (k, e)
 
 
+def test_gradients_are_bit_reproducible():
+    """Fixed-order wgrad reduction: two runs of the same step give identical bits (no atomics anywhere)."""
+    rays = to_dev(mp.random_ray_batch(1500, seed=31, multiscale=True))
+    rgbs = torch.rand(1500, 3, device=DEV)
+    model = gpu_model(4, "trained_like")
+    runs = []
+    for _ in range(2):
+        mp.forward_backward(model, rays, rgbs, False, True)
+        runs.append([p.grad.clone() for p in model.parameters()])
+    assert all(torch.equal(a, b) for a, b in zip(*runs))
+
+
 def test_fused_adam_matches_torch_adam():
     g = golden("training.npz")
     p = torch.nn.Parameter(torch.from_numpy(g["adam_p0"]).to(DEV))
