@@ -177,6 +177,13 @@ class MLP(torch.nn.Module):
         return raw_rgb, raw_density
 
 
+class LevelOutputs(list):
+    """What `MipNerf.forward` returns: the reference's list of per-level 5-tuples (models/mip_nerf.py:246), plus
+    `.pixels` — comp_rgb | distance | acc of every level as one contiguous [levels, 5*B] tensor (a view of the same
+    memory), for reading rendered pixels back to the host with a single copy."""
+    pixels: Optional[torch.Tensor] = None
+
+
 class MipNerf(torch.nn.Module):
     """models/mip_nerf.py:114-248 — same constructor (plus `precision`), same forward contract."""
 
@@ -258,16 +265,22 @@ class MipNerf(torch.nn.Module):
             t_rand = u_jitter = None
         ws, wkeep = self.mlp._weights_struct(cfg, prec, dev)
         outs = (_cabi.LevelOut * self.num_levels)()
-        ret = []
-        per_ray = 3 + 1 + 1 + n + (n + 1)
-        flat = torch.empty(self.num_levels * b * per_ray, device=dev)   # one allocation, 5 views per level
-        for lvl in range(self.num_levels):
-            o = lvl * b * per_ray
+        # One allocation for everything: the per-level pixel outputs (comp_rgb | distance | acc = 5 floats/ray) of
+        # all levels first, so that a caller that only wants pixels reads them back with ONE contiguous copy
+        # (`ret.pixels`, [levels, 5*B]); then weights / fenceposts per level.
+        levels = self.num_levels
+        flat = torch.empty(levels * b * (5 + n + n + 1), device=dev)
+        ret = LevelOutputs()
+        ret.pixels = flat[:levels * 5 * b].view(levels, 5 * b) if b > 0 else flat[:0].view(levels, 0)
+        tail = levels * 5 * b
+        for lvl in range(levels):
+            o = lvl * 5 * b
             comp = flat[o:o + 3 * b].view(b, 3)
             dist = flat[o + 3 * b:o + 4 * b]
             acc = flat[o + 4 * b:o + 5 * b]
-            w = flat[o + 5 * b:o + (5 + n) * b].view(b, n)
-            t = flat[o + (5 + n) * b:o + per_ray * b].view(b, n + 1)
+            q = tail + lvl * (2 * n + 1) * b
+            w = flat[q:q + n * b].view(b, n)
+            t = flat[q + n * b:q + (2 * n + 1) * b].view(b, n + 1)
             inds = torch.empty(b, n + 1, device=dev, dtype=torch.int64) if (return_inds and lvl > 0) else None
             outs[lvl] = _cabi.LevelOut(comp.data_ptr(), dist.data_ptr(), acc.data_ptr(), w.data_ptr(),
                                        t.data_ptr(), _ptr(inds))
