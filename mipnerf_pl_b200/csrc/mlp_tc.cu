@@ -1,23 +1,26 @@
 // mlp_tc.cu — the tensor-core path: one fused kernel per sampling level that does, per ray,
-//   fenceposts -> conical-frustum Gaussians -> IPE features        (models/mip.py:81-103, 322-350)
+//   fenceposts (coarse, or resampled from the previous level)      (models/mip.py:127-165, 168-280)
+//   -> conical-frustum Gaussians -> IPE features                   (models/mip.py:81-103, 322-350)
 //   -> 8x256 trunk + density / bottleneck / view / colour heads    (models/mip_nerf.py:75-111)
 //   -> activations + front-to-back alpha compositing               (models/mip_nerf.py:236-238, mip.py:366-401)
-// without any intermediate tensor touching HBM.  Per level the kernel reads 52 B of ray data and the
-// [B,129] fenceposts and writes comp_rgb/distance/acc/weights; the weights stream from L2.
+// without any intermediate tensor touching HBM.  Per level the kernel reads 52 B of ray data (+ the previous
+// level's fenceposts / weights for the resampler) and writes t_samples/comp_rgb/distance/acc/weights; the
+// weights stream from L2.  A forward is two launches of this kernel and nothing else.
 //
-// Mapping (sm_100a, 1 persistent CTA per SM, 320 threads):
+// Mapping (sm_100a, 1 persistent CTA per SM, 384 threads = 12 warps):
 //   * tile = one ray = 128 samples = UMMA M.  Each CTA keeps TWO rays in flight ("slots") so that
 //     while slot 0's epilogue warps turn an accumulator into the next layer's A operand, the tensor
 //     core runs slot 1's layer.  TMEM: 2 x 256 fp32 columns (the whole 512).
-//   * warp 0    : weight producer — cp.async.bulk of pre-swizzled [128 x 64] operand stages
-//   * warp 1    : MMA issuer     — tcgen05.mma kind::f16, M=128, N=128 (two N halves per layer)
+//   * warp 0    : weight producer — cp.async.bulk of pre-swizzled [128 x 32] (SW64, 8 KB) operand stages
+//   * warp 1    : MMA issuer (one elected lane around the whole issue loop) / relay in the peer CTA
 //   * warps 2-5 : slot 0 workers, warps 6-9: slot 1 workers — thread = sample row = TMEM lane:
-//                 epilogues (tcgen05.ld, +bias, ReLU, 16-bit pack -> st.shared SW128 A operand),
-//                 density/colour heads on CUDA cores, 128-thread compositing scan.
-//   * warps 10-11: IPE warps (one per slot) — Gaussians + 96 features of the slot's NEXT ray,
-//                 written into the feature tile while the current ray is still in the MLP.
+//                 epilogues (tcgen05.ld, packed FADD2 bias, cvt.relu 16-bit pack -> st.shared SW128 A operand),
+//                 density/colour heads on CUDA cores (FFMA2), 128-thread compositing scan.
+//   * warps 10-11: IPE warps (one per slot) — for the slot's NEXT ray: the ray prologue (coarse fenceposts or the
+//                 bit-exact inverse-CDF resampler, per-ray view-layer bias) while the current ray's layers 0..5
+//                 still read the feature tile, then Gaussians + 96 features into that tile once it is released.
 //   * layer-5 skip connection = extra K slabs read from the feature tile (no concat), the
-//     per-ray view-direction term of the view layer is a per-ray bias vector (pre-kernel).
+//     per-ray view-direction term of the view layer is a per-ray bias vector.
 // CTA-pair mode (kPair, default): the grid is launched as 2-CTA clusters and the MMA is
 // tcgen05.mma.cta_group::2 (M=256: rays of both CTAs, N=256): each CTA stages only ITS half of every
 // weight tile (N rows rank*128..), so L2->SMEM weight traffic and SMEM operand reads per SM halve.
@@ -25,8 +28,9 @@
 // epilogue warps of both CTAs arrive on the leader's a_ready barrier (remote mbarrier arrive);
 // tcgen05.commit multicasts stage-free / accumulator-full to both CTAs.
 // A operand: 4 SW128 slabs (64 KB) per slot, overwritten in place layer after layer; features:
-// SW128 slab (K 0..63) + SW64 slab (K 64..95) per slot; weight ring: 3 x 16 KB (measured: deeper
-// rings do not help, the per-slot epilogue chain is the critical path).
+// SW128 slab (K 0..63) + SW64 slab (K 64..95) per slot; weight ring: 6 x 8 KB.
+// Other modes of the same kernel: MLP-only (features from the caller, raw heads out: mipnerf_b200_mlp_forward),
+// separate prologue (MIPNERF_B200_TC_PROLOGUE=separate); mlp_level_kernel_v2 is the "shared weight stream" variant.
 #include "mlp_tc.h"
 
 #include <cstdlib>
