@@ -252,6 +252,45 @@ __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __res
   rgb2 = (acc[2][0] + acc[2][1]) + (acc[2][2] + acc[2][3]);
 }
 
+// Gaussian + 96 IPE features of one sample row of a ray (or, in MLP-only mode, the caller's features) into the
+// slot's feature tile: SW128 slab (K 0..63) + SW64 tail (K 64..95).
+template <int kFmt>
+__device__ __forceinline__ void ipe_row_group(const LevelParams& p, const RayGeom& g, int64_t ray, int row, float t0,
+                                              float t1, uint8_t* myF) {
+  float mean[3] = {0.f, 0.f, 0.f}, cov[3] = {0.f, 0.f, 0.f};
+  const float* fin = nullptr;
+  if (p.feat_in) {
+    fin = p.feat_in + (ray * kN + row) * kFeat;  // MLP-only mode: the caller's encoding
+  } else {
+    float tm, tv, rv;
+    frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
+    lift_gaussian(g, tm, tv, rv, mean, cov);
+    if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
+  }
+#pragma unroll
+  for (int gi = 0; gi < 6; ++gi) {
+    float fsin[8], fcos[8];
+    if (fin) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        fsin[e] = __ldg(fin + gi * 8 + e);
+        fcos[e] = __ldg(fin + 48 + gi * 8 + e);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
+        ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
+      }
+    }
+    store8<kFmt>(myF + sw128_offset(row, gi * 8), fsin);  // K = f
+    if (gi < 2)
+      store8<kFmt>(myF + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
+    else
+      store8<kFmt>(myF + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
+  }
+}
+
 template <int kFmt, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -537,42 +576,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
-        const int row = i * 32 + lane;
-        float mean[3] = {0.f, 0.f, 0.f}, cov[3] = {0.f, 0.f, 0.f};
-        const float* fin = nullptr;
-        if (p.feat_in) {
-          fin = p.feat_in + (ray * kN + row) * kFeat;  // MLP-only mode: the caller's encoding
-        } else {
-          const float t0 = tq[0][0], t1 = tq[0][1];  // rotate: static register indexing in a rolled loop
+        ipe_row_group<kFmt>(p, g, ray, i * 32 + lane, tq[0][0], tq[0][1], myF);
 #pragma unroll
-          for (int r = 0; r < 3; ++r) tq[r][0] = tq[r + 1][0], tq[r][1] = tq[r + 1][1];
-          float tm, tv, rv;
-          frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
-          lift_gaussian(g, tm, tv, rv, mean, cov);
-          if (p.disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
-        }
-#pragma unroll
-        for (int gi = 0; gi < 6; ++gi) {
-          float fsin[8], fcos[8];
-          if (fin) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              fsin[e] = __ldg(fin + gi * 8 + e);
-              fcos[e] = __ldg(fin + 48 + gi * 8 + e);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
-              ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
-            }
-          }
-          store8<kFmt>(myF + sw128_offset(row, gi * 8), fsin);  // K = f
-          if (gi < 2)
-            store8<kFmt>(myF + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
-          else
-            store8<kFmt>(myF + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
-        }
+        for (int r = 0; r < 3; ++r) tq[r][0] = tq[r + 1][0], tq[r][1] = tq[r + 1][1];  // rotate: static indexing
       }
       fence_proxy_async_smem();
       __syncwarp();
