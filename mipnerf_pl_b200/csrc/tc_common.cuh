@@ -79,8 +79,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// MIPNERF_TC_WAIT_HINT_NS: suspend-time hint of mbarrier.try_wait (how long the hardware may park the waiting
+// thread before the instruction returns false).  0 = no operand, the implementation's default time limit.
+#ifndef MIPNERF_TC_WAIT_HINT_NS
+#define MIPNERF_TC_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if MIPNERF_TC_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MIPNERF_TC_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -88,6 +102,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded spin: a protocol bug turns into a trap (reported as a launch failure) instead of a hang
@@ -190,6 +205,17 @@ __device__ __forceinline__ bool elect_one_sync() {
 // lean wait for single-thread roles (no spin counter in the hot loop; the kernel-level watchdog is
 // the bounded waits of the worker warps)
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar_addr, uint32_t parity) {
+#if MIPNERF_TC_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar_addr),
+      "r"(parity), "r"((uint32_t)MIPNERF_TC_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
@@ -199,6 +225,7 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar_addr, uint32_t parit
       "DONE_%=:\n\t}" ::"r"(bar_addr),
       "r"(parity)
       : "memory");
+#endif
 }
 // remote arrive with the default (release, cta-scope) semantics CUTLASS uses for pair barriers
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {

@@ -356,6 +356,55 @@ wgrad_f32_kernel(const float* __restrict__ dy, int n_dim, const float* __restric
   }
 }
 
+// wgrad for the two narrow heads (density: n = 1, colour: n = 3), where a 128-wide output tile would be 97-99 %
+// padding: thread = input column k (blockDim / k_dim row groups per block), each row's dY values are warp-uniform
+// loads, X is read once, coalesced — an HBM-bound pass.  Same partial layout as wgrad_f32_kernel.
+__global__ void __launch_bounds__(256)
+wgrad_small_n_kernel(const float* __restrict__ dy, int n_dim, const float* __restrict__ x, int k_dim,
+                     float* __restrict__ part, int64_t m, int64_t slice_rows) {
+  __shared__ float red[256][5];
+  const int tid = threadIdx.x;
+  const int groups = 256 / k_dim;          // k_dim in {128, 256}
+  const int grp = tid / k_dim, k = tid % k_dim;
+  const int64_t m_begin = (int64_t)blockIdx.x * slice_rows;
+  const int64_t m_end = (m_begin + slice_rows) < m ? (m_begin + slice_rows) : m;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  if (grp < groups) {
+    for (int64_t row = m_begin + grp; row < m_end; row += groups) {
+      const float xv = __ldg(x + row * k_dim + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < n_dim) {
+          const float d = __ldg(dy + row * n_dim + j);
+          acc[j] = fmaf(d, xv, acc[j]);
+          bsum[j] += d;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[tid][j] = acc[j];
+  __syncthreads();
+  float* out = part + (size_t)blockIdx.x * n_dim * (k_dim + 1);
+  if (tid < k_dim) {
+    for (int j = 0; j < n_dim; ++j) {
+      float v = 0.f;
+      for (int g2 = 0; g2 < groups; ++g2) v += red[g2 * k_dim + tid][j];
+      out[(size_t)j * (k_dim + 1) + tid] = v;
+    }
+  }
+  __syncthreads();
+  if (k == 0)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[grp][j] = bsum[j];
+  __syncthreads();
+  if (tid < n_dim) {
+    float v = 0.f;
+    for (int g2 = 0; g2 < groups; ++g2) v += red[g2][tid];
+    out[(size_t)tid * (k_dim + 1) + k_dim] = v;
+  }
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, int n_dim, int k_dim,
                                     float* __restrict__ dw, float* __restrict__ db, int accumulate) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,6 +450,22 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
   }
   if (x2_row_div < 1) x2_row_div = 1;
   const int K = k1 + k2;
+  if (n_dim <= 4 && k2 == 0 && ld1 == k1 && (k1 == 128 || k1 == 256)) {  // the density / colour heads
+    // many short slices (8 blocks per SM in flight): the partial buffer is sized for 160 slices of a 256 x 353
+    // layer, i.e. room for thousands of [n_dim <= 4] x [K+1 <= 257] partials
+    int64_t want = m / 512;
+    if (want < 1) want = 1;
+    if (want > 1184) want = 1184;
+    const int slices = (int)want;
+    int64_t rows = (m + slices - 1) / slices;
+    LaunchScope scope(kKernWgrad, st);
+    wgrad_small_n_kernel<<<slices, 256, 0, st>>>(dy, n_dim, x1, k1, part, m, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (K + 1), 256), 256, 0, st>>>(part, slices, n_dim, K, dw, db,
+                                                                                 accumulate);
+    return cudaGetLastError();
+  }
   const int tiles = ((n_dim + 127) / 128) * ((K + 127) / 128);
   const int slices = wgrad_num_slices(m, tiles);
   int64_t slice_rows = (m + slices - 1) / slices;
