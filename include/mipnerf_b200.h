@@ -142,13 +142,21 @@ size_t mipnerf_b200_train_workspace_bytes(const mipnerf_b200_config* cfg, int64_
 /* MipNerf.forward (outputs in `outs`, as mipnerf_b200_forward) followed by the backward pass of the loss
  * above into `grads` (overwritten, or added to when `accumulate` != 0).  Replaces
  * `loss = training_step(...); loss.backward()` (models/nerf_system.py:95-121 + autograd).  Fenceposts carry
- * no gradient (stop_resample_grad=True semantics, models/mip.py:250-264).  precision must be FP32. */
+ * no gradient (stop_resample_grad=True semantics, models/mip.py:250-264).  precision FP32: every GEMM in fp32 FFMA
+ * (the parity mode); BF16 / FP16: forward and dgrad GEMMs on tcgen05 with 16-bit operands, wgrad / heads / rendering
+ * in fp32 (default 8x256 architecture only). */
 int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* weights,
                                   const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
                                   const float* u_jitter, int white_bkgd, int precision,
                                   const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
                                   const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
                                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stand-alone tensor-core linear layer  y[m,n] = act(x[m,k] . weight[n,k]^T + bias)  (tcgen05, 16-bit operands, fp32
+ * accumulate; n in {128,256}, k in {96,128,256}): the GEMM the training step uses for its forward and dgrad passes in
+ * BF16 / FP16 mode.  `scratch` receives the packed weight image (n * ceil(k/64) * 128 bytes). */
+int mipnerf_b200_linear_tc(const float* x, const float* weight, const float* bias, float* y, int64_t m, int n,
+                           int k, int relu, int precision, void* scratch, size_t scratch_bytes, void* stream);
 
 /* torch.optim.Adam.step() for one flat fp32 tensor (models/nerf_system.py:70-72; amsgrad off, no weight
  * decay): `step` is the 1-based step count after this update; the gradient is read as grad * grad_scale

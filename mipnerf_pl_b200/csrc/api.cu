@@ -321,8 +321,12 @@ constexpr int kMaxTrainDepth = 16;
 struct TrainScratch {
   float *enc, *venc, *h[kMaxTrainDepth], *bott, *v, *raw_rgb, *raw_density;
   float *d_a, *d_b, *d_v, *d_raw_rgb, *d_raw_density, *part, *t[2], *w[2];
+  float* vrow;      // tensor-core mode: per-ray view-direction bias [rays, net_width_condition]
+  uint8_t* images;  // tensor-core mode: packed B operands (kTrainImages x kTrainImageBytes)
   size_t bytes;
 };
+constexpr int kTrainImages = 2 * kMaxTrainDepth + 8;
+constexpr size_t kTrainImageBytes = 131072;  // 256 x 256 x 16 bit
 
 TrainScratch carve_train(const mipnerf_b200_config* c, const Dims& d, int64_t rays, void* base) {
   TrainScratch s{};
@@ -352,8 +356,15 @@ TrainScratch carve_train(const mipnerf_b200_config* c, const Dims& d, int64_t ra
     s.t[i] = take((size_t)rays * (c->num_samples + 1));
     s.w[i] = take(m);
   }
+  s.vrow = take((size_t)rays * c->net_width_condition);
+  s.images = reinterpret_cast<uint8_t*>(take(kTrainImages * kTrainImageBytes / sizeof(float)));
   s.bytes = off;
   return s;
+}
+
+// Tensor-core GEMMs of the training step exist for the default widths only (linear_tc.cu).
+bool train_tc_supported(const mipnerf_b200_config* c, const Dims& d) {
+  return c->net_width == 256 && c->net_width_condition == 128 && d.xyz_dim == 96 && c->net_depth <= kMaxTrainDepth;
 }
 
 int check_train_config(const mipnerf_b200_config* c) {
@@ -389,8 +400,11 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
   if ((rc = check_train_config(cfg))) return rc;
   if ((rc = check_weights(cfg, d, w))) return rc;
   if ((rc = check_rays(rays))) return rc;
-  if (precision != MIPNERF_B200_FP32)
-    return fail(MIPNERF_B200_EUNSUPPORTED, "training runs on the fp32 path only (tensor-core backward: next round)");
+  const bool tc = precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16;
+  if (precision != MIPNERF_B200_FP32 && !tc) return fail(MIPNERF_B200_EINVAL, "precision %d", precision);
+  if (tc && !train_tc_supported(cfg, d))
+    return fail(MIPNERF_B200_EUNSUPPORTED,
+                "tensor-core training GEMMs: 8x256 trunk / 128 view layer / 96-d IPE only; use MIPNERF_B200_FP32");
   if (!outs || !loss || !grads) return fail(MIPNERF_B200_EINVAL, "outs / loss / grads is NULL");
   if (num_grads != d.n_lin) return fail(MIPNERF_B200_EINVAL, "expected %d gradient pairs, got %d", d.n_lin, num_grads);
   for (int i = 0; i < d.n_lin; ++i)
@@ -420,12 +434,41 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
       CUDA_TRY(cudaMemsetAsync(grads[i].bias_grad, 0, sizeof(float) * l.out_features, st));
     }
 
+  // ---- tensor-core mode: B operands of every forward / dgrad GEMM, packed once per call (the weights change every
+  //      optimiser step).  fwd[i] = W_i[:, :k_main], fwd_skip[i] = W_i[:, 256:352], bwd[i] = W_i[:, :256]^T;
+  //      slots depth / depth+1 hold the bottleneck and the view layer.
+  const uint8_t *img_fwd[kMaxTrainDepth + 2] = {nullptr}, *img_skip[kMaxTrainDepth] = {nullptr},
+                *img_bwd[kMaxTrainDepth + 2] = {nullptr};
+  if (tc && B > 0) {
+    uint8_t* base = carve_train(cfg, d, B < kChunkRaysFp32 ? B : kChunkRaysFp32, workspace).images;
+    int slot = 0;
+    auto pack = [&](const mipnerf_b200_linear& l, int off, int transposed, int nn, int kk, const uint8_t** out) {
+      uint8_t* dst = base + (size_t)(slot++) * kTrainImageBytes;
+      *out = dst;
+      return mipnerf::launch_pack_linear_image(l.weight, l.in_features, off, transposed, dst, nn, kk, precision, st);
+    };
+    for (int i = 0; i < depth; ++i) {
+      const mipnerf_b200_linear& l = w->linears[i];
+      CUDA_TRY(pack(l, 0, 0, W, i == 0 ? d.xyz_dim : W, &img_fwd[i]));
+      if (takes_skip(cfg, i)) CUDA_TRY(pack(l, W, 0, W, d.xyz_dim, &img_skip[i]));
+      if (i > 0) CUDA_TRY(pack(l, 0, 1, W, W, &img_bwd[i]));          // B[k_out][n] = W_i[n][k_out]
+    }
+    CUDA_TRY(pack(w->linears[depth + 1], 0, 0, W, W, &img_fwd[depth]));      // bottleneck
+    CUDA_TRY(pack(w->linears[depth + 1], 0, 1, W, W, &img_bwd[depth]));
+    CUDA_TRY(pack(w->linears[depth + 2], 0, 0, Wc, W, &img_fwd[depth + 1]));  // view layer, bottleneck columns
+    CUDA_TRY(pack(w->linears[depth + 2], 0, 1, W, Wc, &img_bwd[depth + 1]));
+  }
+
   for (int64_t off = 0; off < B; off += kChunkRaysFp32) {
     const int64_t cnt = (B - off) < kChunkRaysFp32 ? (B - off) : kChunkRaysFp32;
     const int64_t m = cnt * n;
     const mipnerf_b200_rays rc_ = offset_rays(*rays, off, cnt);
     const TrainScratch s = carve_train(cfg, d, cnt, workspace);
     CUDA_TRY(mipnerf::launch_pos_enc(rc_.viewdirs, s.venc, cnt, 0, cfg->deg_view, 1, st));
+    if (tc) {
+      const mipnerf_b200_linear& vl0 = w->linears[depth + 2];
+      CUDA_TRY(mipnerf::launch_view_bias_from_enc(s.venc, vl0.weight, vl0.bias, s.vrow, cnt, st));
+    }
     auto wgrad = [&](int idx, const float* dy, const float* x1, int k1, const float* x2, int k2, int div) {
       const mipnerf_b200_linear& l = w->linears[idx];
       cudaError_t e = mipnerf::launch_wgrad_f32(dy, l.out_features, x1, k1, k1, x2, k2, k2, div, s.part,
@@ -454,8 +497,18 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
         const bool skip = takes_skip(cfg, i);
         const float* in = i == 0 ? s.enc : s.h[i - 1];
         const int k1 = i == 0 ? d.xyz_dim : W;
-        CUDA_TRY(mipnerf::launch_linear_f32(in, k1, k1, skip ? s.enc : nullptr, d.xyz_dim, skip ? d.xyz_dim : 0, 1,
-                                            li.weight, li.bias, s.h[i], W, m, W, 1, st));
+        if (!tc) {
+          CUDA_TRY(mipnerf::launch_linear_f32(in, k1, k1, skip ? s.enc : nullptr, d.xyz_dim, skip ? d.xyz_dim : 0, 1,
+                                              li.weight, li.bias, s.h[i], W, m, W, 1, st));
+        } else if (!skip) {
+          CUDA_TRY(mipnerf::launch_linear_tc(in, k1, img_fwd[i], s.h[i], W, m, W, k1, li.bias, nullptr, 1, nullptr,
+                                             nullptr, nullptr, nullptr, 1, precision, st));
+        } else {  // cat([h, enc]) as two K passes: the second adds the first's partial sums, the bias and the ReLU
+          CUDA_TRY(mipnerf::launch_linear_tc(in, k1, img_fwd[i], s.h[i], W, m, W, k1, nullptr, nullptr, 1, nullptr,
+                                             nullptr, nullptr, nullptr, 0, precision, st));
+          CUDA_TRY(mipnerf::launch_linear_tc(s.enc, d.xyz_dim, img_skip[i], s.h[i], W, m, W, d.xyz_dim, li.bias, nullptr,
+                                             1, s.h[i], nullptr, nullptr, nullptr, 1, precision, st));
+        }
       }
       const float* h_last = s.h[depth - 1];
       const mipnerf_b200_linear& dl = w->linears[depth];
@@ -464,9 +517,16 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
       const mipnerf_b200_linear& cl = w->linears[d.n_lin - 1];
       CUDA_TRY(mipnerf::launch_linear_f32(h_last, W, W, nullptr, 0, 0, 1, dl.weight, dl.bias, s.raw_density, 1, m, 1,
                                           0, st));
-      CUDA_TRY(mipnerf::launch_linear_f32(h_last, W, W, nullptr, 0, 0, 1, el.weight, el.bias, s.bott, W, m, W, 0, st));
-      CUDA_TRY(mipnerf::launch_linear_f32(s.bott, W, W, s.venc, d.view_dim, d.view_dim, n, vl.weight, vl.bias, s.v,
-                                          Wc, m, Wc, 1, st));
+      if (!tc) {
+        CUDA_TRY(mipnerf::launch_linear_f32(h_last, W, W, nullptr, 0, 0, 1, el.weight, el.bias, s.bott, W, m, W, 0, st));
+        CUDA_TRY(mipnerf::launch_linear_f32(s.bott, W, W, s.venc, d.view_dim, d.view_dim, n, vl.weight, vl.bias, s.v,
+                                            Wc, m, Wc, 1, st));
+      } else {
+        CUDA_TRY(mipnerf::launch_linear_tc(h_last, W, img_fwd[depth], s.bott, W, m, W, W, el.bias, nullptr, 1, nullptr,
+                                           nullptr, nullptr, nullptr, 0, precision, st));
+        CUDA_TRY(mipnerf::launch_linear_tc(s.bott, W, img_fwd[depth + 1], s.v, Wc, m, Wc, W, nullptr, s.vrow, n, nullptr,
+                                           nullptr, nullptr, nullptr, 1, precision, st));
+      }
       CUDA_TRY(mipnerf::launch_linear_f32(s.v, Wc, Wc, nullptr, 0, 0, 1, cl.weight, cl.bias, s.raw_rgb, 3, m, 3, 0,
                                           st));
       CUDA_TRY(mipnerf::launch_composite(s.raw_rgb, s.raw_density, t_cur, rc_.directions, outs[l].comp_rgb + off * 3,
@@ -484,12 +544,20 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
       CUDA_TRY(wgrad(d.n_lin - 1, s.d_raw_rgb, s.v, Wc, nullptr, 0, 1));
       CUDA_TRY(mipnerf::launch_color_dgrad(s.d_raw_rgb, cl.weight, s.v, s.d_v, m, Wc, st));
       CUDA_TRY(wgrad(depth + 2, s.d_v, s.bott, W, s.venc, d.view_dim, n));
-      CUDA_TRY(mipnerf::launch_dgrad_f32(s.d_v, Wc, vl.weight, W + d.view_dim, nullptr, nullptr, nullptr, s.d_a, m, W,
-                                         st));
+      if (!tc)
+        CUDA_TRY(mipnerf::launch_dgrad_f32(s.d_v, Wc, vl.weight, W + d.view_dim, nullptr, nullptr, nullptr, s.d_a, m, W,
+                                           st));
+      else
+        CUDA_TRY(mipnerf::launch_linear_tc(s.d_v, Wc, img_bwd[depth + 1], s.d_a, W, m, W, Wc, nullptr, nullptr, 1,
+                                           nullptr, nullptr, nullptr, nullptr, 0, precision, st));
       // bottleneck + density head share h_last                           (models/mip_nerf.py:98-101)
       CUDA_TRY(wgrad(depth + 1, s.d_a, h_last, W, nullptr, 0, 1));
       CUDA_TRY(wgrad(depth, s.d_raw_density, h_last, W, nullptr, 0, 1));
-      CUDA_TRY(mipnerf::launch_dgrad_f32(s.d_a, W, el.weight, W, s.d_raw_density, dl.weight, h_last, s.d_b, m, W, st));
+      if (!tc)
+        CUDA_TRY(mipnerf::launch_dgrad_f32(s.d_a, W, el.weight, W, s.d_raw_density, dl.weight, h_last, s.d_b, m, W, st));
+      else
+        CUDA_TRY(mipnerf::launch_linear_tc(s.d_a, W, img_bwd[depth], s.d_b, W, m, W, W, nullptr, nullptr, 1, nullptr,
+                                           s.d_raw_density, dl.weight, h_last, 0, precision, st));
       // trunk                                                            (models/mip_nerf.py:93-97)
       float *cur = s.d_b, *other = s.d_a;
       for (int i = depth - 1; i >= 0; --i) {
@@ -498,8 +566,12 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
         const int k1 = i == 0 ? d.xyz_dim : W;
         CUDA_TRY(wgrad(i, cur, in, k1, skip ? s.enc : nullptr, skip ? d.xyz_dim : 0, 1));
         if (i > 0) {
-          CUDA_TRY(mipnerf::launch_dgrad_f32(cur, W, w->linears[i].weight, k1 + (skip ? d.xyz_dim : 0), nullptr,
-                                             nullptr, s.h[i - 1], other, m, W, st));
+          if (!tc)
+            CUDA_TRY(mipnerf::launch_dgrad_f32(cur, W, w->linears[i].weight, k1 + (skip ? d.xyz_dim : 0), nullptr,
+                                               nullptr, s.h[i - 1], other, m, W, st));
+          else
+            CUDA_TRY(mipnerf::launch_linear_tc(cur, W, img_bwd[i], other, W, m, W, W, nullptr, nullptr, 1, nullptr,
+                                               nullptr, nullptr, s.h[i - 1], 0, precision, st));
           float* tmp = cur;
           cur = other;
           other = tmp;
@@ -509,6 +581,22 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
       w_prev = w_cur;
     }
   }
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_linear_tc(const float* x, const float* weight, const float* bias, float* y, int64_t m, int n,
+                           int k, int relu, int precision, void* scratch, size_t scratch_bytes, void* stream) {
+  if (m < 0 || !mipnerf::linear_tc_shape_ok(n, k))
+    return fail(MIPNERF_B200_EUNSUPPORTED, "linear_tc: n in {128,256}, k in {96,128,256} (got n=%d k=%d)", n, k);
+  if (precision != MIPNERF_B200_BF16 && precision != MIPNERF_B200_FP16)
+    return fail(MIPNERF_B200_EINVAL, "linear_tc: precision must be BF16 or FP16");
+  if (m > 0 && (!x || !weight || !y)) return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  const size_t need = mipnerf::linear_tc_image_bytes(n, k);
+  if (!scratch || scratch_bytes < need) return fail(MIPNERF_B200_EWORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(mipnerf::launch_pack_linear_image(weight, k, 0, 0, scratch, n, k, precision, st));
+  CUDA_TRY(mipnerf::launch_linear_tc(x, k, scratch, y, n, m, n, k, bias, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
+                                     relu, precision, st));
   return MIPNERF_B200_OK;
 }
 

@@ -65,4 +65,21 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
                         float eps, float step_size, float bc2_sqrt, float grad_scale, cudaStream_t st);
 
+// ---- linear_tc.cu (tcgen05 linear layer for the training step's forward / dgrad GEMMs) ----
+size_t linear_tc_image_bytes(int n, int k);
+bool linear_tc_shape_ok(int n, int k);
+// B image of  W[:, off:off+k]  (transposed == 0, n rows)  or of  W[off:off+k, :n]^T  (transposed == 1)
+cudaError_t launch_pack_linear_image(const float* w, int ldw, int off, int transposed, void* image, int n, int k,
+                                     int precision, cudaStream_t st);
+// Y = [mask>0] * relu?( X[M,:k] . B^T + bias[col] + row_bias[row/row_div][col] + prev[row][col] + r1[row]*r1w[col] )
+cudaError_t launch_linear_tc(const float* x, int ldx, const void* image, float* y, int ldy, int64_t m, int n, int k,
+                             const float* bias, const float* row_bias, int row_div, const float* prev,
+                             const float* r1, const float* r1w, const float* mask, int relu, int precision,
+                             cudaStream_t st);
+
+// ---- mlp_tc.cu ----
+// out[ray][n] = b[n] + W[n, in_main : in_main + view_dim] . venc[ray]   (view-direction part of the view layer)
+cudaError_t launch_view_bias_from_enc(const float* venc, const float* w, const float* b, float* out,
+                                      int64_t num_rays, cudaStream_t st);
+
 }  // namespace mipnerf

@@ -1546,6 +1546,14 @@ cudaError_t tc_mlp_forward(const mipnerf_b200_config* c, const mipnerf_b200_weig
   return pair ? launch_level_t<0, true>(p, st) : launch_level_t<0, false>(p, st);
 }
 
+cudaError_t launch_view_bias_from_enc(const float* venc, const float* w, const float* b, float* out,
+                                      int64_t num_rays, cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  LaunchScope scope(kKernPosEnc, st);
+  view_bias_from_enc_kernel<<<(unsigned)((num_rays * kCond + 255) / 256), 256, 0, st>>>(venc, w, b, out, num_rays);
+  return cudaGetLastError();
+}
+
 size_t tc_mlp_workspace_bytes(int64_t num_rays) { return (size_t)(num_rays > 0 ? num_rays : 1) * kCond * sizeof(float); }
 
 }  // namespace mipnerf

@@ -25,6 +25,7 @@ enum KernelId : int {
   kKernDgrad,
   kKernWgrad,
   kKernAdam,
+  kKernLinearTc,     // stand-alone tcgen05 linear layer (training forward / dgrad)
   kKernCount
 };
 

@@ -1,5 +1,7 @@
 """Training step of `MipNeRFSystem` (models/nerf_system.py:70-76, 95-121) on the library's backward
-kernels (SURVEY.md §8f N2, fp32 in this round).
+kernels.  `MipNerf.precision` selects the arithmetic of the step: 'fp32' = every GEMM in fp32
+FFMA (the parity mode, gradients match the reference's autograd); 'bf16' / 'fp16' = forward and dgrad GEMMs on
+tcgen05 with 16-bit operands and fp32 accumulation, wgrad / heads / rendering in fp32.
 
 * `fused_loss(...)`       the reference's training loss as one differentiable scalar: forward + backward run
                           inside `mipnerf_b200_forward_backward`; `loss.backward()` only hands the stored
@@ -123,8 +125,7 @@ def _run(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white
          grad_tensors: Sequence[torch.Tensor], accumulate: bool, mask_sum, global_rays):
     if not model.stop_resample_grad:
         raise NotImplementedError("training kernels implement stop_resample_grad=True (the reference default)")
-    if model.precision != "fp32":
-        raise NotImplementedError("training runs on the fp32 path (tensor-core backward: SURVEY.md §8f N2, next)")
+    prec = _cabi.PRECISIONS[model.precision]   # fp32: the parity mode; bf16 / fp16: forward + dgrad GEMMs on tcgen05
     if model.ray_shape != "cone":
         raise NotImplementedError
     if randomized and model.density_noise > 0:
@@ -171,7 +172,7 @@ def _run(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white
     with torch.cuda.device(dev):
         _cabi.check(lib.mipnerf_b200_forward_backward(
             C.byref(cfg), C.byref(ws), C.byref(rs), int(bool(randomized)), _ptr(t_rand), _ptr(u_jitter),
-            int(bool(white_bkgd)), _cabi.FP32, C.byref(loss), outs, garr, len(lins), int(bool(accumulate)),
+            int(bool(white_bkgd)), prec, C.byref(loss), outs, garr, len(lins), int(bool(accumulate)),
             scratch.data_ptr() if nbytes else None, scratch.numel() if nbytes else 0, _stream(dev)),
             "forward_backward")
     mse = sqerr.sum(dim=1) / mask_sum                      # [levels]   (models/nerf_system.py:104-105)

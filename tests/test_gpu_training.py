@@ -192,3 +192,59 @@ def test_training_rejects_bad_arguments():
     small = mp.MipNerf(num_samples=64, num_levels=1).to(DEV)          # other shapes train too (fp32 path)
     out = mp.forward_backward(small, rays, torch.rand(8, 3, device=DEV), False, True)
     assert torch.isfinite(out["loss"]) and all(torch.isfinite(p.grad).all() for p in small.parameters())
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("fp16", 3e-3)])
+@pytest.mark.parametrize("n,k", [(256, 256), (256, 96), (128, 256), (256, 128)])
+def test_linear_tc_matches_fp32_linear(precision, tol, n, k):
+    """The stand-alone tcgen05 linear layer (training forward / dgrad GEMM): 700 rows (ragged last tile, several
+    tiles per CTA) against torch's fp32 linear on the SAME 16-bit-rounded operands (tight) and on the fp32 operands."""
+    import ctypes as C
+    from mipnerf_pl_b200 import _cabi
+    g = torch.Generator(device=DEV).manual_seed(n + k)
+    m = 700
+    x = torch.randn(m, k, device=DEV, generator=g)
+    w = torch.randn(n, k, device=DEV, generator=g) / k ** 0.5
+    b = torch.randn(n, device=DEV, generator=g)
+    y = torch.full((m, n), float("nan"), device=DEV)
+    scratch = torch.empty(n * ((k + 63) // 64) * 128, dtype=torch.uint8, device=DEV)
+    _cabi.check(_cabi.lib().mipnerf_b200_linear_tc(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), m, n, k, 1,
+                                                   _cabi.PRECISIONS[precision], scratch.data_ptr(), scratch.numel(),
+                                                   torch.cuda.current_stream().cuda_stream), "linear_tc")
+    torch.cuda.synchronize()
+    dt = torch.bfloat16 if precision == "bf16" else torch.float16
+    rounded = torch.relu(x.to(dt).double() @ w.to(dt).double().T + b.double())
+    exact = torch.relu(x.double() @ w.double().T + b.double())
+    scale = float(exact.abs().max())
+    assert float((y.double() - rounded).abs().max()) <= 2e-5 * scale * k ** 0.5
+    assert float((y.double() - exact).abs().max()) <= tol * scale
+
+
+@pytest.mark.parametrize("precision,loss_tol,grad_tol", [("bf16", 5e-3, 1.5e-1), ("fp16", 1e-3, 8e-2)])
+def test_tensor_core_training_mode_tracks_fp32(precision, loss_tol, grad_tol):
+    """precision='bf16'|'fp16': forward and dgrad GEMMs on tcgen05.  Loss and every gradient tensor stay within
+    the operand-rounding distance of the fp32 step (which is pinned to the reference's autograd).  That distance is
+    NOT the operand epsilon for the trunk: an activation perturbed by eps flips the ReLU masks of a fraction ~eps of
+    the units, each flip adds/removes a full-size term, so the gradient moves by ~sqrt(eps) (observed: 5e-2 for fp16
+    on layers.0, 6e-2 for bf16) — the same mechanism that limits the fp32 trunk bar to 2e-3."""
+    b = 200
+    rays = to_dev(mp.random_ray_batch(b, seed=41, multiscale=True))
+    rgbs = torch.rand(b, 3, device=DEV)
+    ref_model = gpu_model(6, "xavier")
+    ref = mp.forward_backward(ref_model, rays, rgbs, False, True)
+    g_ref = {k: p.grad.clone() for k, p in ref_model.named_parameters()}
+    model = gpu_model(6, "xavier", precision=precision)
+    out = mp.forward_backward(model, rays, rgbs, False, True)
+    torch.cuda.synchronize()
+    assert float(out["loss"]) == pytest.approx(float(ref["loss"]), rel=loss_tol)
+    errs = {k: float((p.grad - g_ref[k]).norm() / g_ref[k].norm()) for k, p in model.named_parameters()}
+    print(f"{precision}: per-tensor gradient distance to the fp32 step "
+          f"{ {k.replace('mlp.', ''): float(f'{v:.1e}') for k, v in errs.items() if k.endswith('weight')} }")
+    assert max(errs.values()) <= grad_tol, errs
+    # and it trains
+    opt = mp.FusedAdam(model.parameters(), lr=5e-4)
+    first = float(out["loss"])
+    for _ in range(8):
+        last = float(mp.forward_backward(model, rays, rgbs, False, True)["loss"])
+        opt.step()
+    assert last < first

@@ -78,8 +78,6 @@ def test_training_refuses_cpu_tensors_and_other_modes():
         mp.forward_backward(model, rays, torch.zeros(4, 3), False, True)
     with pytest.raises(NotImplementedError):
         mp.forward_backward(mp.MipNerf(stop_resample_grad=False), rays, torch.zeros(4, 3), False, True)
-    with pytest.raises(NotImplementedError):
-        mp.forward_backward(mp.MipNerf(precision="bf16"), rays, torch.zeros(4, 3), False, True)
 
 
 def test_system_configure_optimizers_shapes():

@@ -22,9 +22,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    model = mp.MipNerf()
+    model = mp.MipNerf(precision=args.precision)
     model.load_state_dict(mp.make_state_dict(seed=0, kind="xavier"))
     model = model.to(dev)
     opt = mp.FusedAdam(model.parameters(), lr=5e-4)
@@ -52,7 +53,7 @@ def main():
     prof = _cabi.profile_snapshot(reset=True)
     ms = e0.elapsed_time(e1) / args.steps
     flops = 3 * args.rays * FLOP_PER_RAY_FWD          # forward + dgrad + wgrad (dgrad of layer 0 is not needed)
-    print(json.dumps({"what": "fp32 training step (forward + backward + Adam), randomized, 128+128 samples",
+    print(json.dumps({"what": f"{args.precision} training step (forward + backward + Adam), randomized, 128+128 samples",
                       "rays": args.rays, "ms_per_step": ms, "rays_per_s": args.rays / (ms * 1e-3),
                       "approx_tflops": flops / (ms * 1e-3) / 1e12, "loss": float(out["loss"]),
                       "kernel_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in prof.items() if v[2]},
