@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -469,8 +470,22 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
       const mipnerf_b200_linear& vl0 = w->linears[depth + 2];
       CUDA_TRY(mipnerf::launch_view_bias_from_enc(s.venc, vl0.weight, vl0.bias, s.vrow, cnt, st));
     }
+    // tensor-core mode: wgrad partials on tcgen05 as well (transposing staging: 1.21 vs 1.33 ms per 256x256 layer, the
+    // staging is latency-bound).  MIPNERF_B200_WGRAD_TC=0 keeps wgrad on the fp32 FFMA tiles (A/B runs).
+    const char* wgrad_env = getenv("MIPNERF_B200_WGRAD_TC");
+    const bool wgrad_on_tc = !(wgrad_env && wgrad_env[0] == '0');
     auto wgrad = [&](int idx, const float* dy, const float* x1, int k1, const float* x2, int k2, int div) {
       const mipnerf_b200_linear& l = w->linears[idx];
+      if (tc && wgrad_on_tc && mipnerf::wgrad_tc_shape_ok(l.out_features)) {  // tensor-core partials + same reduction
+        int slices = 0;
+        cudaError_t e2 = mipnerf::launch_wgrad_tc_partials(dy, l.out_features, x1, k1, k1, x2, k2, k2, div, s.part, m,
+                                                           mipnerf::kWgradMaxSlices, precision, &slices, st);
+        if (e2 != cudaSuccess) return e2;
+        e2 = mipnerf::launch_wgrad_reduce(s.part, slices, l.out_features, k1 + k2, grads[idx].weight_grad,
+                                          grads[idx].bias_grad, touched[idx] ? 1 : 0, st);
+        touched[idx] = true;
+        return e2;
+      }
       cudaError_t e = mipnerf::launch_wgrad_f32(dy, l.out_features, x1, k1, k1, x2, k2, k2, div, s.part,
                                                 grads[idx].weight_grad, grads[idx].bias_grad, touched[idx] ? 1 : 0,
                                                 m, st);

@@ -77,6 +77,14 @@ cudaError_t launch_linear_tc(const float* x, int ldx, const void* image, float* 
                              const float* r1, const float* r1w, const float* mask, int relu, int precision,
                              cudaStream_t st);
 
+bool wgrad_tc_shape_ok(int n_dim);
+cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
+                                     int ld2, int k2, int x2_row_div, float* part, int64_t m, int max_slices,
+                                     int precision, int* slices_out, cudaStream_t st);
+// fixed-order reduction of [slices, n_dim, k_dim + 1] partials into dW / db (train_kernels.cu)
+cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_dim, float* dw, float* db,
+                                int accumulate, cudaStream_t st);
+
 // ---- mlp_tc.cu ----
 // out[ray][n] = b[n] + W[n, in_main : in_main + view_dim] . venc[ray]   (view-direction part of the view layer)
 cudaError_t launch_view_bias_from_enc(const float* venc, const float* w, const float* b, float* out,

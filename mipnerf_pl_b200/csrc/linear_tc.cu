@@ -189,6 +189,133 @@ __global__ void __launch_bounds__(128, 1) linear_tc_kernel(const LinearTcParams 
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad on the tensor core:  part[s][n][kg] = sum_{m in slice s} dY[m, n0+n] * Xc[m, kg0+kg],
+//   Xc = [X1 (k1 cols) | X2[m / x2_row_div] (k2 cols)], one CTA per (slice, 128-wide n tile, <=256-wide k tile).
+// The reduction index is the row m, so BOTH operands are needed "m-major"; they are transposed while staging:
+// thread t owns output row n = t of A (and columns t, t+128 of B), reads its column of dY / Xc for the 64 rows of a
+// slab (a warp reads 128 contiguous bytes per row: coalesced), and writes eight 16-byte chunks of 8 consecutive m
+// into the SW128 K-major slab.  4 MMAs (K = 16) per slab accumulate in TMEM over the whole slice; the bias gradient
+// (column sums of dY) falls out of the A staging.  Two CTAs fit per SM (48 KB of shared memory, 256 TMEM columns
+// each), so one CTA stages while the other's MMAs run.  Partials have the layout wgrad_reduce_kernel expects.
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradTcParams {
+  const float* dy;  // [M, n_dim]
+  int n_dim;
+  const float* x1;  // [M, ld1]
+  int ld1, k1;
+  const float* x2;  // [M / x2_row_div, ld2] or null
+  int ld2, k2, x2_row_div;
+  float* part;      // [slices, n_dim, K + 1]
+  int64_t m, slice_rows;
+};
+
+template <int kFmt>
+__global__ void __launch_bounds__(128, 2) wgrad_tc_kernel(const WgradTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;           // [128 n x 64 m] 16 KB
+  uint8_t* sB = sA + 16384;     // [nk   x 64 m] <= 32 KB
+  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(sB + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int K = p.k1 + p.k2;
+  const int n0 = blockIdx.y * 128, kg0 = blockIdx.z * 256;
+  int nk = K - kg0 < 256 ? K - kg0 : 256;  // valid output columns of this k tile
+  const int nk_mma = (nk + 15) & ~15;      // UMMA N: a multiple of 16 (padding columns are staged as zeros)
+  const int64_t m_begin = (int64_t)blockIdx.x * p.slice_rows;
+  const int64_t m_end = (m_begin + p.slice_rows) < p.m ? (m_begin + p.slice_rows) : p.m;
+
+  if (tid == 0) {
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_f16(128, nk_mma, kFmt);
+  uint32_t ph = 0, acc = 0;
+  float bsum = 0.f;
+  const int n = n0 + tid;
+  const bool n_ok = n < p.n_dim;
+  auto xcol = [&](int64_t row, int c) -> float {  // Xc[row][c], zero outside
+    if (c < p.k1) return __ldg(p.x1 + row * (int64_t)p.ld1 + c);
+    if (c < K) return __ldg(p.x2 + (row / p.x2_row_div) * (int64_t)p.ld2 + (c - p.k1));
+    return 0.f;
+  };
+  for (int64_t m0 = m_begin; m0 < m_end; m0 += 64) {
+    // ---- A: row n = tid, 64 consecutive m -> 8 chunks of 16 bytes
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int64_t row = m0 + half * 32 + i;
+        v[i] = (n_ok && row < m_end) ? __ldg(p.dy + row * (int64_t)p.n_dim + n) : 0.f;
+        bsum += v[i];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(sA + sw128_offset(tid, (half * 4 + c) * 8)) =
+            make_uint4(pack2<kFmt>(v[c * 8], v[c * 8 + 1]), pack2<kFmt>(v[c * 8 + 2], v[c * 8 + 3]),
+                       pack2<kFmt>(v[c * 8 + 4], v[c * 8 + 5]), pack2<kFmt>(v[c * 8 + 6], v[c * 8 + 7]));
+    }
+    // ---- B: rows (output columns) tid and tid + 128 of this k tile
+    for (int rb = tid; rb < nk_mma; rb += 128) {
+      const int col = kg0 + rb;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int64_t row = m0 + half * 32 + i;
+          v[i] = (rb < nk && row < m_end) ? xcol(row, col) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(sB + sw128_offset(rb, (half * 4 + c) * 8)) =
+              make_uint4(pack2<kFmt>(v[c * 8], v[c * 8 + 1]), pack2<kFmt>(v[c * 8 + 2], v[c * 8 + 3]),
+                         pack2<kFmt>(v[c * 8 + 4], v[c * 8 + 5]), pack2<kFmt>(v[c * 8 + 6], v[c * 8 + 7]));
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        umma_ss(tmem_base, make_sw128_desc(smem_u32(sA) + j * 32), make_sw128_desc(smem_u32(sB) + j * 32), idesc, acc);
+        acc = 1;
+      }
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, ph);  // the slab has been consumed: it may be overwritten
+    ph ^= 1;
+    tc_fence_after();
+  }
+  // ---- partial sums of this slice: accumulator row n = tid
+  float* out = p.part + (size_t)blockIdx.x * p.n_dim * (K + 1);
+  for (int c = 0; c < nk_mma; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    if (n_ok) {
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (c + q < nk) out[(size_t)n * (K + 1) + kg0 + c + q] = m_begin < m_end ? __uint_as_float(v[q]) : 0.f;
+    }
+  }
+  if (blockIdx.z == 0 && n_ok) out[(size_t)n * (K + 1) + K] = bsum;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 int g_sms = 0;
 bool g_attr[2] = {false, false};
 
@@ -241,6 +368,48 @@ cudaError_t launch_linear_tc(const float* x, int ldx, const void* image, float* 
   LaunchScope scope(kKernLinearTc, st);
   if (fmt) linear_tc_kernel<1><<<grid, 128, smem, st>>>(p);
   else linear_tc_kernel<0><<<grid, 128, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+bool wgrad_tc_shape_ok(int n_dim) { return n_dim == 128 || n_dim == 256; }
+
+// Partials only; the caller runs the fixed-order reduction (train_kernels.cu) afterwards.  Returns the slice count.
+cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
+                                     int ld2, int k2, int x2_row_div, float* part, int64_t m, int max_slices,
+                                     int precision, int* slices_out, cudaStream_t st) {
+  if (!x2) x2 = x1, ld2 = ld1, k2 = 0;
+  if (x2_row_div < 1) x2_row_div = 1;
+  const int K = k1 + k2;
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int n_tiles = (n_dim + 127) / 128, k_tiles = (K + 255) / 256;
+  int64_t slices = (2 * (int64_t)g_sms + n_tiles * k_tiles - 1) / (n_tiles * k_tiles);  // one wave of 2 CTAs per SM
+  const int64_t by_rows = (m + 63) / 64;
+  if (slices > by_rows) slices = by_rows;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  int64_t slice_rows = (m + slices - 1) / slices;
+  slice_rows = (slice_rows + 63) / 64 * 64;
+  const int fmt = precision == 1 ? 1 : 0;
+  static bool attr[2] = {false, false};
+  const size_t smem = 1024 + 16384 + 32768 + 64;
+  if (!attr[fmt]) {
+    cudaError_t e = fmt ? cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(wgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr[fmt] = true;
+  }
+  WgradTcParams p{};
+  p.dy = dy, p.n_dim = n_dim, p.x1 = x1, p.ld1 = ld1, p.k1 = k1, p.x2 = x2, p.ld2 = ld2, p.k2 = k2;
+  p.x2_row_div = x2_row_div, p.part = part, p.m = m, p.slice_rows = slice_rows;
+  dim3 grid((unsigned)slices, (unsigned)n_tiles, (unsigned)k_tiles);
+  LaunchScope scope(kKernWgradTc, st);
+  if (fmt) wgrad_tc_kernel<1><<<grid, 128, smem, st>>>(p);
+  else wgrad_tc_kernel<0><<<grid, 128, smem, st>>>(p);
+  *slices_out = (int)slices;
   return cudaGetLastError();
 }
 

@@ -26,6 +26,7 @@ enum KernelId : int {
   kKernWgrad,
   kKernAdam,
   kKernLinearTc,     // stand-alone tcgen05 linear layer (training forward / dgrad)
+  kKernWgradTc,      // tcgen05 wgrad partials
   kKernCount
 };
 

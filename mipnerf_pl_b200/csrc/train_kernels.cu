@@ -441,6 +441,14 @@ int wgrad_num_slices(int64_t m, int tiles) {
   return (int)s;
 }
 
+cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_dim, float* dw, float* db,
+                                int accumulate, cudaStream_t st) {
+  LaunchScope scope(kKernWgrad, st);
+  wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (k_dim + 1), 256), 256, 0, st>>>(part, slices, n_dim, k_dim, dw, db,
+                                                                                     accumulate);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
                              int ld2, int k2, int x2_row_div, float* part, float* dw, float* db,
                              int accumulate, int64_t m, cudaStream_t st) {
