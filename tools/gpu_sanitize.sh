@@ -1,7 +1,8 @@
 #!/bin/bash
 # compute-sanitizer memcheck / synccheck over every kernel family at small sizes: the three
 # tensor-core variants (deterministic + randomized: in-kernel prologue and resampler), the MLP-only stage entry,
-# the fp32 path, a frame, the distloss kernel and one fp32 training step (backward + Adam).
+# the fp32 path, a frame, the distloss kernel, one fp32 training step (backward + Adam) and the tensor-core
+# training mode (tcgen05 linear / wgrad kernels).
 mkdir -p gpurun_out
 cat > /tmp/san.py <<'PY'
 import torch, sys, os
@@ -28,6 +29,10 @@ tm = mp.MipNerf(); tm.load_state_dict(mp.make_state_dict(2)); tm = tm.to(dev)
 opt = mp.FusedAdam(tm.parameters(), lr=5e-4)
 o = mp.forward_backward(tm, rays, torch.rand(37, 3, device=dev), True, True, t_rand=t_rand, u_jitter=u_jit); opt.step()
 torch.cuda.synchronize(); print("train", float(o["loss"]))
+for prec in ("bf16", "fp16"):                      # tensor-core training mode: linear_tc + wgrad_tc kernels
+    tm = mp.MipNerf(precision=prec); tm.load_state_dict(mp.make_state_dict(2)); tm = tm.to(dev)
+    o = mp.forward_backward(tm, rays, torch.rand(37, 3, device=dev), False, True)
+    torch.cuda.synchronize(); print("train", prec, float(o["loss"]))
 PY
 for tool in memcheck synccheck; do
   echo "== $tool"; timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py 2>&1 | tail -20 | tee gpurun_out/sanitizer_$tool.txt
