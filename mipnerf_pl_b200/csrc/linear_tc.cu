@@ -10,9 +10,9 @@
 //     thread, fp32 -> 16-bit, SW128 K-major slabs: the layout and descriptors validated by mipnerf_b200_selftest_umma), one thread issues K/16 tcgen05.mma (M=128, N, K=16)
 //     and commits to an mbarrier, every thread then reads its accumulator row from TMEM and applies the epilogue
 //     straight to global memory:  + bias[col]  + row_bias[row / row_div][col]  + prev[row][col]  + r1[row]*r1w[col],
-//     ReLU, ReLU-mask by another activation (dgrad).
-// This is the simple serial pipeline (stage -> MMA -> epilogue per tile): the tensor core idles during staging and
-// epilogue, which is acceptable for a pass that is bound by its 1 GB of HBM traffic, not by its 69 GFLOP.
+//     ReLU, ReLU-mask by another activation (dgrad);
+//   * staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap (warp-specialised, two TMEM
+//     accumulators): the pass is bound by its 1 GB of HBM traffic, not by its 69 GFLOP.
 #include "kernels.h"
 #include "profile.h"
 #include "tc_common.cuh"
@@ -57,8 +57,20 @@ struct LinearTcParams {
   int relu;
 };
 
+__device__ __forceinline__ void named_bar(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// Warp-specialised pipeline, 256 threads:
+//   warps 4-7 ("stagers"): global -> registers -> 16-bit SW128 slabs of tile i+1 while the tensor core works on tile i
+//                          and the epilogue warps drain tile i-1; thread 128 also issues the MMAs of the staged tile;
+//   warps 0-3 ("epilogue"): thread = accumulator row (TMEM lane quarter = warp), TMEM -> epilogue -> global.
+// Two accumulator buffers in TMEM (2 x 256 columns), one A buffer in shared memory:
+//   a_free      MMA(i) has consumed the A slabs           (tcgen05.commit)   stagers may overwrite them
+//   acc_full[b] MMA(i) has written accumulator b = i & 1  (tcgen05.commit)   epilogue may read it
+//   acc_free[b] the epilogue has drained accumulator b    (4 warp arrives)   MMA(i+2) may overwrite it
 template <int kFmt>
-__global__ void __launch_bounds__(128, 1) linear_tc_kernel(const LinearTcParams p) {
+__global__ void __launch_bounds__(256, 1) linear_tc_kernel(const LinearTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);  // SW128 atoms need 1024-B alignment
@@ -67,126 +79,152 @@ __global__ void __launch_bounds__(128, 1) linear_tc_kernel(const LinearTcParams 
   uint8_t* sB = sA + (size_t)slabs * 16384;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)slabs * p.n * 128);
   uint64_t* bar_b = bars;
-  uint64_t* bar_mma = bars + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  uint64_t* a_free = bars + 1;
+  uint64_t* acc_full = bars + 2;  // [2]
+  uint64_t* acc_free = bars + 4;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(bar_b, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(a_free, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_free[b], 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (tid == 0) {  // the weights: once per CTA
-    mbar_arrive_expect_tx(bar_b, (uint32_t)(slabs * p.n * 128));
-    for (int s = 0; s < slabs; ++s)
-      bulk_g2s(sB + (size_t)s * p.n * 128, p.image + (size_t)s * p.n * 128, (uint32_t)(p.n * 128), bar_b);
-  }
-  const uint32_t idesc = make_idesc_f16(128, p.n, kFmt);
   const int64_t tiles = (p.m + 127) / 128;
-  uint32_t ph_mma = 0;
-  bool b_ready = false;
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t row = tile * 128 + tid;
-    const bool valid = row < p.m;
-    // ---- stage the tile of X, one 64-column slab at a time: 2048 float4 per slab = 16 per thread, consecutive
-    //      threads on consecutive 16-byte pieces (coalesced), all 16 loads in flight before the first conversion
-    const int64_t row0 = tile * 128;
-    for (int s = 0; s < slabs; ++s) {
-      float4 f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int idx = i * 128 + tid;
-        const int r = idx >> 4, k0 = s * 64 + (idx & 15) * 4;
-        f[i] = (row0 + r < p.m && k0 < p.k) ? __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * (int64_t)p.ldx + k0))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int idx = i * 128 + tid;
-        const int r = idx >> 4, q = idx & 15;
-        *reinterpret_cast<uint2*>(sA + (size_t)s * 16384 + sw128_offset(r, (q >> 1) * 8) + (q & 1) * 8) =
-            make_uint2(pack2<kFmt>(f[i].x, f[i].y), pack2<kFmt>(f[i].z, f[i].w));
-      }
+
+  if (warp >= 4) {
+    // ===================================== stagers (+ MMA issue by thread 128) =====================================
+    const int st = tid - 128;
+    if (st == 0) {  // the weights: once per CTA
+      mbar_arrive_expect_tx(bar_b, (uint32_t)(slabs * p.n * 128));
+      for (int s = 0; s < slabs; ++s)
+        bulk_g2s(sB + (size_t)s * p.n * 128, p.image + (size_t)s * p.n * 128, (uint32_t)(p.n * 128), bar_b);
     }
-    fence_proxy_async_smem();  // st.shared operand -> async proxy
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) {
-      if (!b_ready) {
-        mbar_wait(bar_b, 0);
-        b_ready = true;
-      }
-      uint32_t acc = 0;
+    const uint32_t idesc = make_idesc_f16(128, p.n, kFmt);
+    uint32_t ph_afree = 0, ph_accfree[2] = {0, 0};
+    bool b_ready = false;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int64_t row0 = tile * 128;
       for (int s = 0; s < slabs; ++s) {
-        const int steps = ((p.k - s * 64) < 64 ? (p.k - s * 64) : 64) / 16;
-        for (int j = 0; j < steps; ++j) {
-          umma_ss(tmem_base, make_sw128_desc(smem_u32(sA + (size_t)s * 16384) + j * 32),
-                  make_sw128_desc(smem_u32(sB + (size_t)s * p.n * 128) + j * 32), idesc, acc);
-          acc = 1;
+        float4 f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {  // 16 coalesced loads in flight per thread before anything else
+          const int idx = i * 128 + st;
+          const int r = idx >> 4, k0 = s * 64 + (idx & 15) * 4;
+          f[i] = (row0 + r < p.m && k0 < p.k)
+                     ? __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * (int64_t)p.ldx + k0))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (s == 0 && it > 0) {  // the previous tile's MMAs must be done with the A slabs
+          mbar_wait(a_free, ph_afree);
+          ph_afree ^= 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int idx = i * 128 + st;
+          const int r = idx >> 4, q = idx & 15;
+          *reinterpret_cast<uint2*>(sA + (size_t)s * 16384 + sw128_offset(r, (q >> 1) * 8) + (q & 1) * 8) =
+              make_uint2(pack2<kFmt>(f[i].x, f[i].y), pack2<kFmt>(f[i].z, f[i].w));
         }
       }
-      umma_commit(bar_mma);
-    }
-    __syncwarp();
-    mbar_wait(bar_mma, ph_mma);
-    ph_mma ^= 1;
-    tc_fence_after();
-    // ---- epilogue: this thread's accumulator row, 32 columns at a time
-    const float rv = (p.r1 && valid) ? __ldg(p.r1 + row) : 0.f;
-    for (int c = 0; c < p.n; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
-      tmem_ld_wait();
-      if (valid) {
-        float* yr = p.y + row * (int64_t)p.ldy + c;
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const int col = c + q;
-          float o[4] = {__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
-                        __uint_as_float(v[q + 3])};
-          auto add4 = [&](const float* src) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(src));
-            o[0] += t.x, o[1] += t.y, o[2] += t.z, o[3] += t.w;
-          };
-          if (p.bias) add4(p.bias + col);
-          if (p.row_bias) add4(p.row_bias + (row / p.row_div) * p.n + col);
-          if (p.prev) {  // may alias y (in-place second K pass): a plain coherent load, not the read-only path
-            const float4 t = *reinterpret_cast<const float4*>(p.prev + row * (int64_t)p.ldy + col);
-            o[0] += t.x, o[1] += t.y, o[2] += t.z, o[3] += t.w;
-          }
-          if (p.r1) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.r1w + col));
-            o[0] = fmaf(rv, t.x, o[0]), o[1] = fmaf(rv, t.y, o[1]), o[2] = fmaf(rv, t.z, o[2]), o[3] = fmaf(rv, t.w, o[3]);
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-          }
-          if (p.mask) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.mask + row * (int64_t)p.ldy + col));
-            if (!(t.x > 0.f)) o[0] = 0.f;
-            if (!(t.y > 0.f)) o[1] = 0.f;
-            if (!(t.z > 0.f)) o[2] = 0.f;
-            if (!(t.w > 0.f)) o[3] = 0.f;
-          }
-          *reinterpret_cast<float4*>(yr + q) = make_float4(o[0], o[1], o[2], o[3]);
+      fence_proxy_async_smem();  // st.shared operand -> async proxy
+      named_bar(1, 128);         // all four stager warps have written their part
+      if (st == 0) {
+        const int buf = it & 1;
+        if (!b_ready) {
+          mbar_wait(bar_b, 0);
+          b_ready = true;
         }
+        if (it >= 2) {  // accumulator `buf` was last used by tile it-2: wait until the epilogue drained it
+          mbar_wait(&acc_free[buf], ph_accfree[buf]);
+          ph_accfree[buf] ^= 1;
+        }
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int s = 0; s < slabs; ++s) {
+          const int steps = ((p.k - s * 64) < 64 ? (p.k - s * 64) : 64) / 16;
+          for (int j = 0; j < steps; ++j) {
+            umma_ss(tmem_base + buf * 256, make_sw128_desc(smem_u32(sA + (size_t)s * 16384) + j * 32),
+                    make_sw128_desc(smem_u32(sB + (size_t)s * p.n * 128) + j * 32), idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(a_free);
+        umma_commit(&acc_full[buf]);
       }
     }
-    tc_fence_before();
-    __syncthreads();  // accumulator drained and A tile consumed: the next tile may overwrite both
-    tc_fence_after();
+    if (st == 0 && !b_ready) mbar_wait(bar_b, 0);  // never leave with a bulk copy in flight
+  } else {
+    // ============================================== epilogue warps ==============================================
+    uint32_t ph_full[2] = {0, 0};
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int64_t row = tile * 128 + tid;
+      const bool valid = row < p.m;
+      const float rv = (p.r1 && valid) ? __ldg(p.r1 + row) : 0.f;
+      mbar_wait(&acc_full[buf], ph_full[buf]);
+      ph_full[buf] ^= 1;
+      tc_fence_after();
+      for (int c = 0; c < p.n; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * 256 + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          float* yr = p.y + row * (int64_t)p.ldy + c;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            const int col = c + q;
+            float o[4] = {__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]),
+                          __uint_as_float(v[q + 3])};
+            auto add4 = [&](const float* src) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+              o[0] += t.x, o[1] += t.y, o[2] += t.z, o[3] += t.w;
+            };
+            if (p.bias) add4(p.bias + col);
+            if (p.row_bias) add4(p.row_bias + (row / p.row_div) * p.n + col);
+            if (p.prev) {  // may alias y (in-place second K pass): a plain coherent load, not the read-only path
+              const float4 t = *reinterpret_cast<const float4*>(p.prev + row * (int64_t)p.ldy + col);
+              o[0] += t.x, o[1] += t.y, o[2] += t.z, o[3] += t.w;
+            }
+            if (p.r1) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.r1w + col));
+              o[0] = fmaf(rv, t.x, o[0]), o[1] = fmaf(rv, t.y, o[1]), o[2] = fmaf(rv, t.z, o[2]),
+              o[3] = fmaf(rv, t.w, o[3]);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+            }
+            if (p.mask) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.mask + row * (int64_t)p.ldy + col));
+              if (!(t.x > 0.f)) o[0] = 0.f;
+              if (!(t.y > 0.f)) o[1] = 0.f;
+              if (!(t.z > 0.f)) o[2] = 0.f;
+              if (!(t.w > 0.f)) o[3] = 0.f;
+            }
+            *reinterpret_cast<float4*>(yr + q) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[buf]);
+    }
   }
-  if (tid == 0 && !b_ready) mbar_wait(bar_b, 0);  // never leave with a bulk copy in flight
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -366,8 +404,8 @@ cudaError_t launch_linear_tc(const float* x, int ldx, const void* image, float* 
   const int64_t tiles = (m + 127) / 128;
   const int grid = (int)(tiles < g_sms ? tiles : g_sms);
   LaunchScope scope(kKernLinearTc, st);
-  if (fmt) linear_tc_kernel<1><<<grid, 128, smem, st>>>(p);
-  else linear_tc_kernel<0><<<grid, 128, smem, st>>>(p);
+  if (fmt) linear_tc_kernel<1><<<grid, 256, smem, st>>>(p);
+  else linear_tc_kernel<0><<<grid, 256, smem, st>>>(p);
   return cudaGetLastError();
 }
 
