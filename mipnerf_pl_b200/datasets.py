@@ -19,7 +19,6 @@ in two forms:
 """
 from __future__ import annotations
 
-import ctypes as C
 import json
 import os
 from typing import List, Optional, Sequence, Tuple
@@ -28,7 +27,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
-from .rays import Rays, Rays_keys, namedtuple_map
+from .rays import Rays, Rays_keys
 
 _RADIUS_SCALE = 2.0 / np.sqrt(12.0)
 

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import torch
 

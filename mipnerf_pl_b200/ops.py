@@ -13,12 +13,11 @@ Differences that the C ABI forces and that are visible here:
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 
 from . import _cabi
-from .rays import Rays
 
 F32_EPS = float(torch.finfo(torch.float32).eps)
 

@@ -30,8 +30,7 @@ explicitly so the oracle does not depend on the ISA torch dispatches to:
 from __future__ import annotations
 
 import collections
-import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
