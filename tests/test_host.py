@@ -156,3 +156,34 @@ def test_ray_staging_is_field_major_and_contiguous():
     other = mp.random_ray_batch(37, seed=3)
     st.fill(other)
     assert torch.equal(st.host_rays.directions, other.directions)
+
+
+def test_training_and_dataset_entry_points_validate_arguments_without_gpu(lib):
+    """Status codes of the training / dataset / tensor-core-linear entry points for bad arguments: every check
+    happens before the first launch, so this runs without a GPU."""
+    cfg = mp.MipNerf()._config()
+    # workspace sizing: bounded by the chunk, zero for shapes the training step does not cover
+    w4096 = lib.mipnerf_b200_train_workspace_bytes(C.byref(cfg), 4096)
+    assert w4096 > 5 << 30 and lib.mipnerf_b200_train_workspace_bytes(C.byref(cfg), 10 ** 7) == w4096
+    no_view = mp.MipNerf(use_viewdirs=False, mlp_net_width_condition=256)._config()
+    assert lib.mipnerf_b200_train_workspace_bytes(C.byref(no_view), 64) == 0
+    # forward_backward: config problems first, then NULL arguments
+    rc = lib.mipnerf_b200_forward_backward(C.byref(no_view), None, None, 0, None, None, 1, 0, None, None, None, 0, 0, None,
+                                           0, None)
+    assert rc == _cabi.EUNSUPPORTED and b"training" in lib.mipnerf_b200_last_error()
+    rc = lib.mipnerf_b200_forward_backward(C.byref(cfg), None, None, 0, None, None, 1, 0, None, None, None, 0, 0, None, 0,
+                                           None)
+    assert rc == _cabi.EINVAL
+    # adam: step is 1-based
+    assert lib.mipnerf_b200_adam_step(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == _cabi.EINVAL
+    assert lib.mipnerf_b200_adam_step(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == _cabi.OK
+    assert lib.mipnerf_b200_adam_step(None, None, None, None, 5, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == _cabi.EINVAL
+    # tensor-core linear: shapes / precision / scratch
+    assert lib.mipnerf_b200_linear_tc(None, None, None, None, 0, 64, 256, 0, _cabi.BF16, None, 0, None) == _cabi.EUNSUPPORTED
+    assert lib.mipnerf_b200_linear_tc(None, None, None, None, 0, 256, 256, 0, _cabi.FP32, None, 0, None) == _cabi.EINVAL
+    assert lib.mipnerf_b200_linear_tc(None, None, None, None, 0, 256, 256, 0, _cabi.BF16, None, 0, None) == _cabi.EWORKSPACE
+    # ray bank / distloss
+    assert lib.mipnerf_b200_rays_from_pixels(None, None, None, 0, None, 0, None, None, None, None, None, None, None, None,
+                                             None, None) == _cabi.EINVAL
+    assert lib.mipnerf_b200_distloss(None, None, -1, 128, None, None) == _cabi.EINVAL
+    assert lib.mipnerf_b200_distloss(None, None, 0, 128, None, None) == _cabi.OK
