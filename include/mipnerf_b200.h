@@ -112,7 +112,7 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
 int mipnerf_b200_distloss(const float* weights, const float* samples, int64_t num_rays, int num_samples,
                           float* per_ray_loss, void* stream);
 
-/* ---- training step (fp32 only in this round) ----------------------------------
+/* ---- training step -------------------------------------------------------------
  * Gradient buffers, one per entry of mipnerf_b200_weights.linears (same order and shapes). */
 typedef struct mipnerf_b200_linear_grad {
   float* weight_grad; /* [out_features, in_features] */

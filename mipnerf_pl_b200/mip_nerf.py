@@ -4,8 +4,9 @@ the sm_100a kernels of libmipnerf_b200.so through the C ABI.
 
 The modules own ordinary fp32 `torch.nn.Linear` parameters, so Lightning
 checkpoints of the reference (`mip_nerf.mlp.layers.{i}.0.weight`, ...) load with
-`load_state_dict` unchanged.  `forward` is inference-only (no autograd graph): the
-backward pass is row N2 of SURVEY.md §8(f).
+`load_state_dict` unchanged.  `forward` builds no autograd graph; training goes
+through `mipnerf_pl_b200.train` (`fused_loss` / `forward_backward`), where one library call runs forward and
+backward and hands the gradients to autograd or `param.grad`.
 """
 from __future__ import annotations
 

@@ -199,7 +199,7 @@ def volumetric_rendering(rgb, density, t_samples, dirs, white_bkgd):
 
 def distloss(weight, samples):
     """Distortion loss value (models/mip.py:8-20): weight [B,N], samples [B,N+1] -> scalar.
-    Forward only (the training backward is SURVEY §8f N2); O(N) per ray instead of the
+    Value only (its gradient is part of `train.forward_backward`); O(N) per ray instead of the
     reference's two [B,N,N] temporaries."""
     dev = _dev(weight)
     w, t = _f32(weight), _f32(samples)
