@@ -1,6 +1,6 @@
-// train_kernels.cu — backward pass and optimiser kernels of the training step (the tensor-core
-// mode swaps the fp32 GEMMs below for linear_tc.cu):
-// models/nerf_system.py:95-121 training_step, torch.optim.Adam of :70-76).
+// train_kernels.cu — backward pass and optimiser kernels of the training step (SURVEY.md §8f N2:
+// models/nerf_system.py:95-121 training_step, torch.optim.Adam of :70-76).  The tensor-core mode swaps the fp32
+// GEMMs below for the kernels of linear_tc.cu.
 //
 // What is differentiated: loss = sum_l  a_l * MSE_l(comp_rgb, target; lossmult mask) + b_l * distloss_l(weights, t)
 // with respect to the 24 MLP tensors.  Fenceposts carry no gradient (coarse ones are constants of near/far;
