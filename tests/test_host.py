@@ -187,3 +187,26 @@ def test_training_and_dataset_entry_points_validate_arguments_without_gpu(lib):
                                              None, None) == _cabi.EINVAL
     assert lib.mipnerf_b200_distloss(None, None, -1, 128, None, None) == _cabi.EINVAL
     assert lib.mipnerf_b200_distloss(None, None, 0, 128, None, None) == _cabi.OK
+
+
+def test_public_header_is_plain_c_and_links(tmp_path):
+    """include/mipnerf_b200.h is a C header (no torch / C++ types): a C99 translation unit that includes it compiles
+    with -Wall -Wextra -pedantic -Werror and links against the shared library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "mipnerf_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '  mipnerf_b200_config cfg; mipnerf_b200_loss loss; mipnerf_b200_linear_grad g;\n'
+                   '  (void)cfg; (void)loss; (void)g;\n'
+                   '  printf("%d %d\\n", mipnerf_b200_abi_version(), MIPNERF_B200_ABI_VERSION);\n'
+                   '  return mipnerf_b200_abi_version() == MIPNERF_B200_ABI_VERSION ? 0 : 1;\n}\n')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.join(ROOT, "mipnerf_pl_b200")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-l:libmipnerf_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["2", "2"], out
