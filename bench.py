@@ -97,28 +97,50 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def _oracle_setup():
+def _cpu_arm_setup():
+    """The CPU arm: the UNMODIFIED reference imported from baseline/_ref (tools/install_ref.py) when it is
+    installed (`kind` "reference"), else the oracle port (`kind` "port").  Returns (kind, forward) with
+    forward(state_dict, rays_tuple) -> list of per-level tuples, fp32, no_grad, randomized=False, white_bkgd=True."""
     import torch
     import mipnerf_pl_b200 as mp
-    from oracle import mipnerf_oracle as oracle  # allowed here: this IS the CPU arm
-    return torch, mp, oracle
+    try:
+        from baseline import ref_loader
+        RefMipNerf, RefRays, _ = ref_loader.load()
+        models = {}
+
+        def forward(sd, rays):
+            m = models.get(id(sd))
+            if m is None:
+                m = RefMipNerf()                      # models/mip_nerf.py:117-141 defaults == BASELINE configs[1]
+                m.load_state_dict(sd)
+                models[id(sd)] = m.eval()
+            with torch.no_grad():
+                return m(RefRays(*rays), False, True)
+        return "reference", forward
+    except ImportError:
+        from oracle import mipnerf_oracle as oracle  # allowed here: this IS the CPU arm
+
+        def forward(sd, rays):
+            return oracle.forward(sd, oracle.Rays(*rays), False, True)
+        return "port", forward
 
 
-def pick_cpu_threads():
+def pick_cpu_threads(forward):
     """The reference's CPU path uses torch intra-op threads; on a many-core host more threads is not faster
     (the per-ray ops are small).  Time one 128-ray forward at a few thread counts and keep the fastest, so the
     CPU arm is the reference at its best on this box, not at os.cpu_count()."""
-    torch, mp, oracle = _oracle_setup()
+    import torch
+    import mipnerf_pl_b200 as mp
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
-    rays = oracle.Rays(*mp.random_ray_batch(128, seed=1))
+    rays = mp.random_ray_batch(128, seed=1)
     sd = mp.make_state_dict(seed=0, kind="xavier")
     best, best_dt = cands[-1], float("inf")
     for c in cands:
         torch.set_num_threads(c)
-        oracle.forward(sd, rays, False, True)
+        forward(sd, rays)
         t0 = time.perf_counter()
-        oracle.forward(sd, rays, False, True)
+        forward(sd, rays)
         dt = time.perf_counter() - t0
         if dt < best_dt:
             best, best_dt = c, dt
@@ -126,41 +148,47 @@ def pick_cpu_threads():
     return best, 128 / best_dt
 
 
-def cpu_arm(num_rays, steps, warmup):
-    """The reference's CPU torch path (oracle port); returns (rays/s, s per step, threads used)."""
-    torch, mp, oracle = _oracle_setup()
-    rays = oracle.Rays(*mp.random_ray_batch(num_rays, seed=0))
+def cpu_arm(forward, num_rays, steps, warmup):
+    """Time the CPU arm; returns (rays/s, s per step, threads used)."""
+    import torch
+    import mipnerf_pl_b200 as mp
+    rays = mp.random_ray_batch(num_rays, seed=0)
     sd = mp.make_state_dict(seed=0, kind="xavier")
     for _ in range(warmup):
-        oracle.forward(sd, oracle.Rays(*[f[:min(256, num_rays)] for f in rays]), False, True)
+        forward(sd, type(rays)(*[f[:min(256, num_rays)] for f in rays]))
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        oracle.forward(sd, rays, False, True)
+        forward(sd, rays)
         times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
     return num_rays / dt, dt, torch.get_num_threads()
+
+
+CPU_ARM_WHAT = {"reference": "the unmodified reference MipNerf.forward (models/mip_nerf.py:172-248) imported from baseline/_ref",
+                "port": "fp32 torch-CPU oracle (port of models/mip_nerf.py:172-248; baseline/_ref not installed)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads, rate = pick_cpu_threads()
+    kind, forward = _cpu_arm_setup()
+    threads, rate = pick_cpu_threads(forward)
     steps = max(1, args.steps)
     # bounded sample per step: the whole K-step run should take ~90 s of CPU time on this box
     sample = int(min(BATCH, max(64, rate * 90.0 / steps)))
-    rps, dt, cores = cpu_arm(sample, steps, max(1, min(args.warmup, 2)))
+    rps, dt, cores = cpu_arm(forward, sample, steps, max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": "rays/sec (4096-ray batch, 128+128 samples)", "value": rps,
         "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "lego single-scale 800x800, 4096-ray batch, 128+128 samples (configs[1])",
-                   "step": f"CPU oracle forward on a {sample}-ray sample of the batch"},
-        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {BATCH} rays per step, fp32 torch-CPU oracle (port of "
-                                   f"models/mip_nerf.py:172-248), randomized=False, {cores} torch threads "
+                   "step": f"CPU forward ({kind}) on a {sample}-ray sample of the batch"},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} of {BATCH} rays per step, {CPU_ARM_WHAT[kind]}, fp32, "
+                                   f"randomized=False, {cores} torch threads "
                                    f"(fastest of a sweep up to {os.cpu_count()} host threads)"},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -350,11 +378,12 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        threads, rate = pick_cpu_threads()
+        kind, forward = _cpu_arm_setup()
+        threads, rate = pick_cpu_threads(forward)
         sample = int(min(B, max(256, rate * 10.0)))                  # ~10 s per timed run
-        rps, dt, cores = cpu_arm(sample, 2, 1)
-        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": f"{sample} of {B} rays (same rays/weights), 2 timed runs of the fp32 torch-CPU oracle on "
+        rps, dt, cores = cpu_arm(forward, sample, 2, 1)
+        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind,
+               "sample": f"{sample} of {B} rays (same rays/weights), 2 timed runs of {CPU_ARM_WHAT[kind]} on "
                          f"{cores} torch threads (fastest of a sweep up to {os.cpu_count()} host threads)"}
 
     line = {

@@ -1,0 +1,57 @@
+"""The CPU arm of bench.py is the UNMODIFIED reference when baseline/_ref is installed (tools/install_ref.py).
+Here: (1) the installed files are byte-identical to the manifest they were copied with, (2) the oracle port equals
+the reference bit for bit on the bench workload's rays and weights — so a box that only has the port (kind "port")
+times the same arithmetic."""
+import hashlib
+import json
+import os
+
+import pytest
+import torch
+
+from helpers import ROOT, make_state_dict, oracle
+
+import mipnerf_pl_b200 as mp
+
+ref_loader = pytest.importorskip("baseline.ref_loader")
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="baseline/_ref not installed on this box")
+
+
+def test_installed_reference_matches_manifest():
+    with open(os.path.join(ref_loader.REF_DIR, "MANIFEST.json")) as f:
+        man = json.load(f)
+    assert set(man["files"]) >= {"models/mip.py", "models/mip_nerf.py", "datasets/datasets.py"}
+    for rel, digest in man["files"].items():
+        with open(os.path.join(ref_loader.REF_DIR, rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == digest, rel
+    src = man["source"]
+    if os.path.isdir(src):   # build container: still identical to the upstream tree
+        for rel in man["files"]:
+            with open(os.path.join(src, rel), "rb") as a, open(os.path.join(ref_loader.REF_DIR, rel), "rb") as b:
+                assert a.read() == b.read(), rel
+
+
+@pytest.mark.parametrize("kind", ["xavier", "trained_like"])
+def test_port_equals_reference_bit_for_bit(kind):
+    RefMipNerf, RefRays, _ = ref_loader.load()
+    rays = mp.random_ray_batch(96, seed=0)
+    sd = make_state_dict(seed=0, kind=kind)
+    model = RefMipNerf()
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        want = model.eval()(RefRays(*rays), False, True)
+    got = oracle.forward(sd, oracle.Rays(*rays), False, True)
+    for lvl in range(2):
+        for k, name in enumerate(("comp_rgb", "distance", "acc", "weights", "t_samples")):
+            assert torch.equal(got[lvl][k], want[lvl][k]), (kind, lvl, name)
+
+
+def test_bench_cpu_arm_prefers_the_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    kind, forward = bench._cpu_arm_setup()
+    assert kind == "reference"
+    out = forward(make_state_dict(seed=0), mp.random_ray_batch(8, seed=0))
+    assert len(out) == 2 and out[1][0].shape == (8, 3)
