@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MIPNERF_B200_ABI_VERSION 2
+#define MIPNERF_B200_ABI_VERSION 3
 
 #define MIPNERF_B200_OK 0
 #define MIPNERF_B200_EINVAL (-1)       /* bad argument (NULL pointer, negative size, ...)            */
@@ -35,6 +35,12 @@ extern "C" {
 #define MIPNERF_B200_FP32 0 /* CUDA-core FFMA, fp32 operands: the 1e-4 parity mode                   */
 #define MIPNERF_B200_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM             */
 #define MIPNERF_B200_FP16 2 /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM             */
+/* Split-operand tensor-core modes: every GEMM operand x is carried as hi = fl16(x), lo = fl16(x - hi) and each
+ * K step issues hi.hi + lo.hi + hi.lo into the same fp32 TMEM accumulator (3x the MMAs).  FP16X3 keeps 22
+ * significant operand bits (|x| < 65504) and is the tensor-core mode that meets the reference's fp32 result
+ * to 1e-4 (models/mip_nerf.py:94-110 computes every nn.Linear in fp32); BF16X3 keeps 16 bits with fp32's range. */
+#define MIPNERF_B200_FP16X3 3
+#define MIPNERF_B200_BF16X3 4
 
 /* One torch.nn.Linear: weight [out_features, in_features] row-major, bias [out_features]. */
 typedef struct mipnerf_b200_linear {
@@ -178,7 +184,8 @@ int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, flo
  *   cam_table [num_images, 24] = pix2cam (3x3 row-major, maps (x+.5, y+.5, 1) to a camera direction) |
  *                                cam2world (3x4 row-major) | lossmult | near | far
  *   offsets [num_images+1] first atlas row of each image; widths [num_images]; atlas [P,3] target colours
- *   pixel_ids [count] atlas rows -> the seven Rays fields ([count,3|1]) and rgb [count,3] (nullable). */
+ *   pixel_ids [count] atlas rows (ids outside [0, offsets[num_images]) are clamped to the first / last row)
+ *   -> the seven Rays fields ([count,3|1]) and rgb [count,3] (nullable). */
 int mipnerf_b200_rays_from_pixels(const float* cam_table, const int64_t* offsets, const int32_t* widths,
                                   int num_images, const int64_t* pixel_ids, int64_t count, const float* atlas,
                                   float* origins, float* directions, float* viewdirs, float* radii,

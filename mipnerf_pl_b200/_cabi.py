@@ -14,10 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmipnerf_b200.so"
 LIB_PATH = os.environ.get("MIPNERF_B200_LIB") or os.path.join(_HERE, LIB_NAME)  # env: experiment builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
-FP32, BF16, FP16 = 0, 1, 2
-PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16}
+FP32, BF16, FP16, FP16X3, BF16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16, "fp16x3": FP16X3, "bf16x3": BF16X3}
 
 _f32p = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)

@@ -271,7 +271,7 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
     if (!mipnerf::tc_supported(cfg, precision))
       return fail(MIPNERF_B200_EUNSUPPORTED,
                   "tensor-core path supports only the default 8x256 / N=128 / deg 0..16 / deg_view 4 model "
-                  "with precision bf16|fp16; use MIPNERF_B200_FP32 for other shapes");
+                  "with precision bf16|fp16|fp16x3|bf16x3; use MIPNERF_B200_FP32 for other shapes");
     if (!w->packed || w->packed_precision != precision ||
         w->packed_bytes < mipnerf::tc_packed_bytes(cfg, precision))
       return fail(MIPNERF_B200_EINVAL, "weights->packed missing or packed for another precision");
@@ -365,7 +365,13 @@ TrainScratch carve_train(const mipnerf_b200_config* c, const Dims& d, int64_t ra
 
 // Tensor-core GEMMs of the training step exist for the default widths only (linear_tc.cu).
 bool train_tc_supported(const mipnerf_b200_config* c, const Dims& d) {
-  return c->net_width == 256 && c->net_width_condition == 128 && d.xyz_dim == 96 && c->net_depth <= kMaxTrainDepth;
+  if (!(c->net_width == 256 && c->net_width_condition == 128 && d.xyz_dim == 96 && c->net_depth <= kMaxTrainDepth))
+    return false;
+  // packed-operand slots the step needs (forward + skip + transposed dgrad images + bottleneck / view layer x 2):
+  // must fit the kTrainImages slots carved from the workspace
+  int slots = 4;
+  for (int i = 0; i < c->net_depth; ++i) slots += 1 + (i > 1 && (i - 1) % c->skip_index == 0 ? 1 : 0) + (i > 0 ? 1 : 0);
+  return slots <= kTrainImages;
 }
 
 int check_train_config(const mipnerf_b200_config* c) {
@@ -402,6 +408,9 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
   if ((rc = check_weights(cfg, d, w))) return rc;
   if ((rc = check_rays(rays))) return rc;
   const bool tc = precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16;
+  if (precision == MIPNERF_B200_FP16X3 || precision == MIPNERF_B200_BF16X3)
+    return fail(MIPNERF_B200_EUNSUPPORTED,
+                "training: the split-operand precisions are forward-only; use FP32 (parity) or BF16 / FP16");
   if (precision != MIPNERF_B200_FP32 && !tc) return fail(MIPNERF_B200_EINVAL, "precision %d", precision);
   if (tc && !train_tc_supported(cfg, d))
     return fail(MIPNERF_B200_EUNSUPPORTED,

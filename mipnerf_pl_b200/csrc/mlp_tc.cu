@@ -34,6 +34,7 @@
 #include "mlp_tc.h"
 
 #include <cstdlib>
+#include <mutex>
 
 #include "kernels.h"
 #include "profile.h"
@@ -104,6 +105,10 @@ constexpr size_t kSmallOffset = ((size_t)kViewPairOffset + 2 * 8 * kViewPairStag
 constexpr size_t kViewDirOffset = kSmallOffset + ((sizeof(SmallParams) + 255) / 256 * 256);
 constexpr size_t kViewDirBytes = (size_t)(kViewDim + 1) * kCond * sizeof(float);
 constexpr size_t kImageBytes = kViewDirOffset + ((kViewDirBytes + 255) / 256 * 256);
+// Split-operand ("x3") modes: a second stage image with the LOW halves of the weights (w - fl16(w), rounded to the
+// same 16-bit format), same internal layout as the stage part of the first image, appended after it.
+constexpr size_t kLoOffset = kImageBytes;
+constexpr size_t kLoBytes = ((size_t)kViewPairOffset + 2 * 8 * kViewPairStage + 255) / 256 * 256;
 
 #ifdef MIPNERF_TC_TRACE
 // debug build only: (clock64, event) pairs of CTA 0.  Each traced thread (one per role) owns a
@@ -186,10 +191,29 @@ __device__ __forceinline__ void store8(uint8_t* dst, const float (&x)[8]) {
                                               pack2<kFmt>(x[4], x[5]), pack2<kFmt>(x[6], x[7]));
 }
 
+template <int kFmt>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if (kFmt == 1) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+// x = hi + lo with hi = fl16(x), lo = fl16(x - hi): the two 16-bit operands of the split ("x3") modes
+template <int kFmt>
+__device__ __forceinline__ void store8_split(uint8_t* dst_hi, uint8_t* dst_lo, const float (&x)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = pack2<kFmt>(x[2 * e], x[2 * e + 1]);
+    const float2 f = unpack2<kFmt>(h[e]);
+    l[e] = pack2<kFmt>(x[2 * e] - f.x, x[2 * e + 1] - f.y);
+  }
+  *reinterpret_cast<uint4*>(dst_hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(dst_lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // Epilogue of trunk layer / bottleneck L (compile-time so that every bias is an immediate
 // constant-bank operand): TMEM accumulator row -> +bias -> ReLU (L < 8) -> 16-bit -> A operand
 // slabs, software-pipelined over 32-column TMEM loads.  L == 7 also accumulates the density head.
-template <int kFmt, int L>
+template <int kFmt, int L, bool kX3>
 __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int row, float& dens) {
   float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent chains for the density head
   uint32_t v[2][32];
@@ -202,7 +226,7 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
     uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t w[4];
+      uint32_t w[4], wl[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = c0 + j * 8 + 2 * e;
@@ -211,9 +235,18 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
         if (L == 7)  // density_layer on the fp32 (un-rounded) h7        (models/mip_nerf.py:98)
           ffma2(dpart[2 * e], dpart[2 * e + 1], fmaxf(a, 0.f), fmaxf(b, 0.f), c_small.w_density[c],
                 c_small.w_density[c + 1]);
-        w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
+        if (kX3) {  // hi = fl16(x), lo = fl16(x - hi): 22 (fp16) / 16 (bf16) significant bits reach the next layer
+          if (L < 8) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+          w[e] = pack2<kFmt>(a, b);
+          const float2 h = unpack2<kFmt>(w[e]);
+          wl[e] = pack2<kFmt>(a - h.x, b - h.y);
+        } else {
+          w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
+        }
       }
-      *reinterpret_cast<uint4*>(slab + sw128_offset(row, (c0 & 63) + j * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+      const uint32_t off = sw128_offset(row, (c0 & 63) + j * 8);
+      *reinterpret_cast<uint4*>(slab + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      if (kX3) *reinterpret_cast<uint4*>(slab + kABytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
   }
   if (L == 7)
@@ -254,7 +287,7 @@ __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __res
 
 // Gaussian + 96 IPE features of one sample row of a ray (or, in MLP-only mode, the caller's features) into the
 // slot's feature tile: SW128 slab (K 0..63) + SW64 tail (K 64..95).
-template <int kFmt>
+template <int kFmt, bool kX3>
 __device__ __forceinline__ void ipe_row_group(const LevelParams& p, const RayGeom& g, int64_t ray, int row, float t0,
                                               float t1, uint8_t* myF) {
   float mean[3] = {0.f, 0.f, 0.f}, cov[3] = {0.f, 0.f, 0.f};
@@ -283,16 +316,27 @@ __device__ __forceinline__ void ipe_row_group(const LevelParams& p, const RayGeo
         ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
       }
     }
-    store8<kFmt>(myF + sw128_offset(row, gi * 8), fsin);  // K = f
-    if (gi < 2)
-      store8<kFmt>(myF + sw128_offset(row, 48 + gi * 8), fcos);  // K = 48 + f < 64
-    else
-      store8<kFmt>(myF + kStageBytes + sw64_offset(row, (gi - 2) * 8), fcos);  // K = 64.. -> SW64 tail
+    const uint32_t o_sin = sw128_offset(row, gi * 8);                                     // K = f
+    const uint32_t o_cos = gi < 2 ? sw128_offset(row, 48 + gi * 8)                        // K = 48 + f < 64
+                                  : kStageBytes + sw64_offset(row, (gi - 2) * 8);         // K = 64.. -> SW64 tail
+    if (kX3) {  // low halves go to the second feature tile (the other slot's, unused in the split modes)
+      store8_split<kFmt>(myF + o_sin, myF + kFBytes + o_sin, fsin);
+      store8_split<kFmt>(myF + o_cos, myF + kFBytes + o_cos, fcos);
+    } else {
+      store8<kFmt>(myF + o_sin, fsin);
+      store8<kFmt>(myF + o_cos, fcos);
+    }
   }
 }
 
-template <int kFmt, bool kPair>
+// kX3 (split-operand parity modes, CTA pair only): ONE ray per CTA (slot 0); every activation / feature / weight is
+// carried as hi + lo 16-bit halves (A_lo and F_lo live where slot 1's tiles would be, W_lo stages alternate with W_hi
+// in the ring) and every K step issues  A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  into the same fp32 accumulator: 3x the MMAs,
+// ~2^-22 (fp16 halves) / 2^-16 (bf16 halves) relative operand error instead of 2^-11 / 2^-8.
+template <int kFmt, bool kPair, bool kX3>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
+  static_assert(!kX3 || kPair, "split-operand modes exist for the CTA-pair kernel only");
+  constexpr int kSlots = kX3 ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -339,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   const uint32_t tmem_base = *tmem_slot;
   const int rounds = p.rounds;
   auto tile_of = [&](int round, int slot) -> int64_t {
-    return kPair ? ((((int64_t)round * (gridDim.x >> 1) + (blockIdx.x >> 1)) * 2 + slot) * 2 + rank)
+    return kPair ? ((((int64_t)round * (gridDim.x >> 1) + (blockIdx.x >> 1)) * kSlots + slot) * 2 + rank)
                  : (((int64_t)round * gridDim.x + blockIdx.x) * 2 + slot);
   };
 
@@ -354,22 +398,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           const int ns = num_k32(l);
           const int nh = kPair ? 1 : num_halves(l);
           const uint32_t bytes = (kPair && l == 9) ? kViewPairStage : kWStage;
-          for (int slot = 0; slot < 2; ++slot)
+          for (int slot = 0; slot < kSlots; ++slot)
             for (int h = 0; h < nh; ++h) {
               // pair mode: this CTA streams only half `rank` of the layer (64 rows for the view layer)
               const uint8_t* src =
                   (kPair && l == 9) ? p.wimage + kViewPairOffset + rank * 8 * kViewPairStage
                                     : p.wimage + layer_offset(l) + (kPair ? rank : (uint32_t)h) * (layer_bytes(l) / num_halves(l));
               for (int s = 0; s < ns; ++s) {
-                mbar_wait(&w_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&w_full[st], bytes);
-                bulk_g2s(sW + st * kWStage, src, bytes, &w_full[st]);
-                TRACE(EV(0, 0, l, st));
-                src += bytes;
-                if (++st == kStages) {
-                  st = 0;
-                  ph ^= 1;
+#pragma unroll
+                for (int part = 0; part < (kX3 ? 2 : 1); ++part) {  // x3: W_hi stage, then the W_lo stage of the slab
+                  mbar_wait(&w_empty[st], ph ^ 1);
+                  mbar_arrive_expect_tx(&w_full[st], bytes);
+                  bulk_g2s(sW + st * kWStage, src + (part ? kLoOffset : 0), bytes, &w_full[st]);
+                  TRACE(EV(0, 0, l, st));
+                  if (++st == kStages) {
+                    st = 0;
+                    ph ^= 1;
+                  }
                 }
+                src += bytes;
               }
             }
         }
@@ -399,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
             const int ns = num_k32(l);
             const int nh = kPair ? 1 : num_halves(l);
             const uint32_t id = l == 9 ? idesc_view : idesc;
-            for (int slot = 0; slot < 2; ++slot) {
+            for (int slot = 0; slot < kSlots; ++slot) {
               if (l == 0) {  // the ray's feature tile (written ahead of time by the IPE warp)
                 if (slot == 0) {
                   mbar_wait_fast(bars_u + (2 * kStages + 4) * 8, ph_f0);
@@ -432,13 +479,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                   const bool a_sw64 = fs == 2;
                   const uint32_t a_addr = fs < 0 ? a_base + (s >> 1) * kStageBytes + (s & 1) * 64
                                                  : (fs < 2 ? f_base + fs * 64 : f_base + kStageBytes);
-                  const uint32_t b_addr = sW_u + st * kWStage;
+                  const uint32_t a_lo_addr = a_addr + (fs < 0 ? kABytes : kFBytes);  // x3: low halves of the A operand
+                  uint32_t b_addr = sW_u + st * kWStage;
 #pragma unroll
                   for (int j = 0; j < 2; ++j) {
                     const uint64_t ad = a_sw64 ? make_sw64_desc(a_addr + j * 32) : make_sw128_desc(a_addr + j * 32);
                     const uint64_t bd = make_sw64_desc(b_addr + j * 32);
                     if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
                     else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
+                  }
+                  if (kX3) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {  // A_lo . W_hi
+                      const uint64_t ad =
+                          a_sw64 ? make_sw64_desc(a_lo_addr + j * 32) : make_sw128_desc(a_lo_addr + j * 32);
+                      umma_ss_pair(d_tmem, ad, make_sw64_desc(b_addr + j * 32), id, 1u);
+                    }
+                    umma_commit_pair(&w_empty[st]);
+                    if (++st == kStages) {
+                      st = 0;
+                      wph ^= 1;
+                    }
+                    mbar_wait_fast(bars_u + st * 8, wph);  // the slab's W_lo stage
+                    tc_fence_after();
+                    b_addr = sW_u + st * kWStage;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {  // A_hi . W_lo
+                      const uint64_t ad = a_sw64 ? make_sw64_desc(a_addr + j * 32) : make_sw128_desc(a_addr + j * 32);
+                      umma_ss_pair(d_tmem, ad, make_sw64_desc(b_addr + j * 32), id, 1u);
+                    }
                   }
                   // stage reusable (in both CTAs) once these MMAs have read it
                   if (kPair) umma_commit_pair(&w_empty[st]);
@@ -485,6 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     // tile as soon as layer 5 of the current ray has read it: off the per-ray critical path.
     const int slot = warp - 10;
     uint8_t* myF = sF + slot * kFBytes;
+    const int my_rounds = slot < kSlots ? rounds : 0;  // x3: only slot 0 exists
     // One (kN+1)-float array per slot for the in-kernel resampler, carved out of the alignment slack at the end of
     // the dynamic allocation when the runtime placed the buffer favourably (it does: 1024-aligned base).
     float* early_scratch = nullptr;
@@ -500,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     Tracer tracer;
     if (slot == 0 && lane == 0) tracer.init(4);
 #endif
-    for (int round = 0; round < rounds; ++round) {
+    for (int round = 0; round < my_rounds; ++round) {
       const int64_t tile = tile_of(round, slot);
       const int64_t ray = tile < p.num_rays ? tile : p.num_rays - 1;
       TRACE(EV(3, 2, 0, slot));
@@ -576,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
 #pragma unroll 1
       for (int i = 0; i < 4; ++i) {
-        ipe_row_group<kFmt>(p, g, ray, i * 32 + lane, tq[0][0], tq[0][1], myF);
+        ipe_row_group<kFmt, kX3>(p, g, ray, i * 32 + lane, tq[0][0], tq[0][1], myF);
 #pragma unroll
         for (int r = 0; r < 3; ++r) tq[r][0] = tq[r + 1][0], tq[r][1] = tq[r + 1][1];  // rotate: static indexing
       }
@@ -611,8 +681,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         else mbar_arrive(&a_ready[slot]);
       }
     };
-    arrive_a_ready();  // accumulator of this slot is free for the first ray
-    for (int round = 0; round < rounds; ++round) {
+    const int my_rounds = slot < kSlots ? rounds : 0;  // x3: the second worker group has no slot
+    if (slot < kSlots) arrive_a_ready();  // accumulator of this slot is free for the first ray
+    for (int round = 0; round < my_rounds; ++round) {
       const int64_t tile = tile_of(round, slot);
       const bool valid = tile < p.num_rays;
       const int64_t ray = valid ? tile : p.num_rays - 1;
@@ -639,15 +710,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         }
         if (l < 9) {
           switch (l) {
-            case 0: epilogue_trunk<kFmt, 0>(t_acc, myA, row, dens); break;
-            case 1: epilogue_trunk<kFmt, 1>(t_acc, myA, row, dens); break;
-            case 2: epilogue_trunk<kFmt, 2>(t_acc, myA, row, dens); break;
-            case 3: epilogue_trunk<kFmt, 3>(t_acc, myA, row, dens); break;
-            case 4: epilogue_trunk<kFmt, 4>(t_acc, myA, row, dens); break;
-            case 5: epilogue_trunk<kFmt, 5>(t_acc, myA, row, dens); break;
-            case 6: epilogue_trunk<kFmt, 6>(t_acc, myA, row, dens); break;
-            case 7: epilogue_trunk<kFmt, 7>(t_acc, myA, row, dens); break;
-            default: epilogue_trunk<kFmt, 8>(t_acc, myA, row, dens); break;
+            case 0: epilogue_trunk<kFmt, 0, kX3>(t_acc, myA, row, dens); break;
+            case 1: epilogue_trunk<kFmt, 1, kX3>(t_acc, myA, row, dens); break;
+            case 2: epilogue_trunk<kFmt, 2, kX3>(t_acc, myA, row, dens); break;
+            case 3: epilogue_trunk<kFmt, 3, kX3>(t_acc, myA, row, dens); break;
+            case 4: epilogue_trunk<kFmt, 4, kX3>(t_acc, myA, row, dens); break;
+            case 5: epilogue_trunk<kFmt, 5, kX3>(t_acc, myA, row, dens); break;
+            case 6: epilogue_trunk<kFmt, 6, kX3>(t_acc, myA, row, dens); break;
+            case 7: epilogue_trunk<kFmt, 7, kX3>(t_acc, myA, row, dens); break;
+            default: epilogue_trunk<kFmt, 8, kX3>(t_acc, myA, row, dens); break;
           }
           TRACE(EV(2, 3, l, slot));
           fence_proxy_async_smem();
@@ -1028,15 +1099,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
         TRACE(EV(2, 2, l, slot));
         if (l < 9) {
           switch (l) {
-            case 0: epilogue_trunk<kFmt, 0>(t_acc, myA, row, dens); break;
-            case 1: epilogue_trunk<kFmt, 1>(t_acc, myA, row, dens); break;
-            case 2: epilogue_trunk<kFmt, 2>(t_acc, myA, row, dens); break;
-            case 3: epilogue_trunk<kFmt, 3>(t_acc, myA, row, dens); break;
-            case 4: epilogue_trunk<kFmt, 4>(t_acc, myA, row, dens); break;
-            case 5: epilogue_trunk<kFmt, 5>(t_acc, myA, row, dens); break;
-            case 6: epilogue_trunk<kFmt, 6>(t_acc, myA, row, dens); break;
-            case 7: epilogue_trunk<kFmt, 7>(t_acc, myA, row, dens); break;
-            default: epilogue_trunk<kFmt, 8>(t_acc, myA, row, dens); break;
+            case 0: epilogue_trunk<kFmt, 0, false>(t_acc, myA, row, dens); break;
+            case 1: epilogue_trunk<kFmt, 1, false>(t_acc, myA, row, dens); break;
+            case 2: epilogue_trunk<kFmt, 2, false>(t_acc, myA, row, dens); break;
+            case 3: epilogue_trunk<kFmt, 3, false>(t_acc, myA, row, dens); break;
+            case 4: epilogue_trunk<kFmt, 4, false>(t_acc, myA, row, dens); break;
+            case 5: epilogue_trunk<kFmt, 5, false>(t_acc, myA, row, dens); break;
+            case 6: epilogue_trunk<kFmt, 6, false>(t_acc, myA, row, dens); break;
+            case 7: epilogue_trunk<kFmt, 7, false>(t_acc, myA, row, dens); break;
+            default: epilogue_trunk<kFmt, 8, false>(t_acc, myA, row, dens); break;
           }
           TRACE(EV(2, 3, l, slot));
           fence_proxy_async_smem();
@@ -1183,12 +1254,19 @@ __global__ void view_bias_from_enc_kernel(const float* __restrict__ venc, const 
 
 // ---- weight packing ---------------------------------------------------------------------------
 template <int kFmt>
+__device__ __forceinline__ float from16(uint16_t h) {
+  if (kFmt == 1) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&h));
+  return __half2float(*reinterpret_cast<__half*>(&h));
+}
+// lo != 0: the low half  fl16(w - fl16(w))  of the split-operand modes instead of fl16(w)
+template <int kFmt>
 __global__ void pack_stage_kernel(const float* __restrict__ w, int in_features, int row0, int kbase, int kcount,
-                                  uint8_t* __restrict__ dst, int nrows) {
+                                  uint8_t* __restrict__ dst, int nrows, int lo) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nrows * kcount) return;
   const int i = idx / kcount, j = idx % kcount;
-  const float v = w[(size_t)(row0 + i) * in_features + kbase + j];
+  float v = w[(size_t)(row0 + i) * in_features + kbase + j];
+  if (lo) v = v - from16<kFmt>(to16<kFmt>(v));
   const uint32_t off = kcount == 64 ? sw128_offset(i, j) : sw64_offset(i, j);
   *reinterpret_cast<uint16_t*>(dst + off) = to16<kFmt>(v);
 }
@@ -1220,6 +1298,53 @@ __global__ void pack_view_dir_kernel(const float* __restrict__ w, const float* _
   }
 }
 
+// c_small is ONE constant bank per device, while the ABI lets callers run forwards of different models on different
+// streams.  SmallUpload serialises those users: it holds a host lock for the duration of the enqueue, makes the
+// stream wait for the previous user's kernels (on another stream) before overwriting the bank, and records an event
+// after this call's launches.  Same-stream callers (the normal case) pay one event record.  During stream capture the
+// cross-stream wait is skipped (a capture is single-stream by construction and the event lives outside the graph).
+constexpr int kMaxDevices = 64;
+struct SmallBankState {
+  cudaEvent_t done = nullptr;
+  cudaStream_t last = nullptr;
+  bool used = false;
+};
+std::mutex g_small_mu;
+SmallBankState g_small_state[kMaxDevices];
+
+class SmallUpload {
+ public:
+  SmallUpload(const uint8_t* img, cudaStream_t st) : lock_(g_small_mu), st_(st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    state_ = &g_small_state[dev % kMaxDevices];
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
+    capturing_ = cap != cudaStreamCaptureStatusNone;
+    if (!capturing_ && state_->used && state_->last != st) {
+      err_ = cudaStreamWaitEvent(st, state_->done, 0);
+      if (err_ != cudaSuccess) return;
+    }
+    err_ = cudaMemcpyToSymbolAsync(c_small, img + kSmallOffset, sizeof(SmallParams), 0, cudaMemcpyDeviceToDevice, st);
+  }
+  cudaError_t error() const { return err_; }
+  ~SmallUpload() {
+    if (capturing_ || err_ != cudaSuccess) return;
+    if (!state_->done && cudaEventCreateWithFlags(&state_->done, cudaEventDisableTiming) != cudaSuccess) return;
+    if (cudaEventRecord(state_->done, st_) == cudaSuccess) {
+      state_->last = st_;
+      state_->used = true;
+    }
+  }
+
+ private:
+  std::lock_guard<std::mutex> lock_;
+  cudaStream_t st_;
+  SmallBankState* state_ = nullptr;
+  bool capturing_ = false;
+  cudaError_t err_ = cudaSuccess;
+};
+
 struct TcScratch {
   float *vbias, *t[2], *w[2];
   uint8_t* feat;  // v2 kernel: kMaxCtas2 x kFeatScratchPerCta
@@ -1248,15 +1373,19 @@ TcScratch carve_tc(int64_t rays, void* base) {
 }
 
 int g_num_sms = 0;
-bool g_attr_set[2][2] = {{false, false}, {false, false}};
+bool g_attr_set[2][2][2] = {};
 
-template <int kFmt, bool kPair>
+// operand format (0 fp16, 1 bf16) and split flag of a tensor-core precision
+inline int fmt_of(int precision) { return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_BF16X3) ? 1 : 0; }
+inline bool is_x3(int precision) { return precision == MIPNERF_B200_FP16X3 || precision == MIPNERF_B200_BF16X3; }
+
+template <int kFmt, bool kPair, bool kX3 = false>
 cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
-  auto kern = mlp_level_kernel<kFmt, kPair>;
-  if (!g_attr_set[kFmt][kPair]) {
+  auto kern = mlp_level_kernel<kFmt, kPair, kX3>;
+  if (!g_attr_set[kFmt][kPair][kX3]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
     if (e != cudaSuccess) return e;
-    g_attr_set[kFmt][kPair] = true;
+    g_attr_set[kFmt][kPair][kX3] = true;
   }
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1266,9 +1395,10 @@ cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
   LevelParams q = p;
   LaunchScope scope(p.feat_in ? kKernMlpTc : kKernMlpLevelTc, st);
   if (kPair) {
-    const int64_t quads = (p.num_rays + 3) / 4;  // a CTA pair holds 4 rays (2 slots x 2 CTAs)
+    constexpr int64_t kPerPair = kX3 ? 2 : 4;  // rays a CTA pair holds at a time (slots x 2 CTAs)
+    const int64_t quads = (p.num_rays + kPerPair - 1) / kPerPair;
     const int pairs = (int)(quads < g_num_sms / 2 ? quads : g_num_sms / 2);
-    q.rounds = (int)((p.num_rays + 4 * (int64_t)pairs - 1) / (4 * (int64_t)pairs));
+    q.rounds = (int)((p.num_rays + kPerPair * (int64_t)pairs - 1) / (kPerPair * (int64_t)pairs));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kThreads);
@@ -1339,12 +1469,14 @@ int tc_variant() {
 bool use_pair_variant() { return tc_variant() != 0; }
 // MIPNERF_B200_TC_PROLOGUE=separate keeps the ray prologue / resampler as their own launches (A/B measurements);
 // default: produced inside the v1 level kernels.
-bool fused_prologue_enabled() {
+bool fused_prologue_enabled(int precision) {
   const char* v = getenv("MIPNERF_B200_TC_PROLOGUE");
-  return tc_variant() != 2 && !(v && v[0] == 's');
+  return (is_x3(precision) || tc_variant() != 2) && !(v && v[0] == 's');
 }
 
 cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
+  if (is_x3(precision))  // split-operand parity modes: the CTA-pair kernel, whatever variant is selected
+    return fmt_of(precision) ? launch_level_t<1, true, true>(p, st) : launch_level_t<0, true, true>(p, st);
   if (tc_variant() == 2)
     return precision == MIPNERF_B200_BF16 ? launch_level_v2<1>(p, st) : launch_level_v2<0>(p, st);
   const bool pair = use_pair_variant();
@@ -1369,7 +1501,8 @@ int set_trace_ptr(unsigned long long* ptr) {
 #endif
 
 bool tc_supported(const mipnerf_b200_config* c, int precision) {
-  return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16) && c->num_samples == kN &&
+  return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16 || is_x3(precision)) &&
+         c->num_samples == kN &&
          c->min_deg_point == 0 && c->max_deg_point == 16 && c->deg_view == 4 && c->use_viewdirs &&
          c->net_depth == 8 && c->net_width == kWidth && c->net_depth_condition == 1 &&
          c->net_width_condition == kCond && c->skip_index == 4 && c->num_rgb_channels == 3 &&
@@ -1382,7 +1515,7 @@ bool tc_mlp_supported(const mipnerf_b200_config* c, int samples_per_ray, int pre
 }
 
 size_t tc_packed_bytes(const mipnerf_b200_config* c, int precision) {
-  return tc_supported(c, precision) ? kImageBytes : 0;
+  return tc_supported(c, precision) ? kImageBytes + (is_x3(precision) ? kLoBytes : 0) : 0;
 }
 
 size_t tc_workspace_bytes(const mipnerf_b200_config* c, int64_t num_rays, int precision) {
@@ -1395,38 +1528,43 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
                             void* packed_out, cudaStream_t st) {
   if (!tc_supported(c, precision)) return cudaErrorNotSupported;
   uint8_t* img = static_cast<uint8_t*>(packed_out);
-  cudaError_t e = cudaMemsetAsync(img, 0, kImageBytes, st);
+  const bool bf = fmt_of(precision) == 1;
+  const int parts = is_x3(precision) ? 2 : 1;  // hi image, then (split modes) the lo stage image
+  cudaError_t e = cudaMemsetAsync(img, 0, kImageBytes + (parts == 2 ? kLoBytes : 0), st);
   if (e != cudaSuccess) return e;
   LaunchScope scope(kKernPackWeights, st);
-  for (int l = 0; l < kNumLayers; ++l) {
-    const int li = l < 8 ? l : (l == 8 ? 9 : 10);  // layers.l | extra_layer | view_layers.0
-    const mipnerf_b200_linear& lin = w->linears[li];
-    uint8_t* dst = img + layer_offset(l);
-    for (int h = 0; h < num_halves(l); ++h)
-      for (int s = 0; s < num_k32(l); ++s) {
-        // K order of layer 5 is the reference's concat [h (256) | x (96)]   (mip_nerf.py:96-97)
-        if (precision == MIPNERF_B200_BF16)
-          pack_stage_kernel<1><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32, 32,
-                                                                      dst, 128);
-        else
-          pack_stage_kernel<0><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32, 32,
-                                                                      dst, 128);
-        dst += kWStage;
-      }
-  }
-  {  // pair-mode view layer: two 64-row halves
-    const mipnerf_b200_linear& lin = w->linears[10];
-    uint8_t* dst = img + kViewPairOffset;
-    for (int r = 0; r < 2; ++r)
-      for (int s = 0; s < 8; ++s) {
-        if (precision == MIPNERF_B200_BF16)
-          pack_stage_kernel<1><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
-                                                                     dst, 64);
-        else
-          pack_stage_kernel<0><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
-                                                                     dst, 64);
-        dst += kViewPairStage;
-      }
+  for (int part = 0; part < parts; ++part) {
+    uint8_t* base = img + (part ? kLoOffset : 0);
+    for (int l = 0; l < kNumLayers; ++l) {
+      const int li = l < 8 ? l : (l == 8 ? 9 : 10);  // layers.l | extra_layer | view_layers.0
+      const mipnerf_b200_linear& lin = w->linears[li];
+      uint8_t* dst = base + layer_offset(l);
+      for (int h = 0; h < num_halves(l); ++h)
+        for (int s = 0; s < num_k32(l); ++s) {
+          // K order of layer 5 is the reference's concat [h (256) | x (96)]   (mip_nerf.py:96-97)
+          if (bf)
+            pack_stage_kernel<1><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32,
+                                                                        32, dst, 128, part);
+          else
+            pack_stage_kernel<0><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32,
+                                                                        32, dst, 128, part);
+          dst += kWStage;
+        }
+    }
+    {  // pair-mode view layer: two 64-row halves
+      const mipnerf_b200_linear& lin = w->linears[10];
+      uint8_t* dst = base + kViewPairOffset;
+      for (int r = 0; r < 2; ++r)
+        for (int s = 0; s < 8; ++s) {
+          if (bf)
+            pack_stage_kernel<1><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
+                                                                       dst, 64, part);
+          else
+            pack_stage_kernel<0><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
+                                                                       dst, 64, part);
+          dst += kViewPairStage;
+        }
+    }
   }
   SmallSrc src;
   for (int l = 0; l < 8; ++l) src.bias[l] = w->linears[l].bias;
@@ -1446,8 +1584,8 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
                        int randomized, const float* t_rand, const float* u_jitter, int white_bkgd, int precision,
                        mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   const uint8_t* img = static_cast<const uint8_t*>(w->packed);
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_small, img + kSmallOffset, sizeof(SmallParams), 0,
-                                          cudaMemcpyDeviceToDevice, st);
+  SmallUpload small(img, st);  // biases / heads -> constant bank, ordered against other streams' forwards
+  cudaError_t e = small.error();
   if (e != cudaSuccess) return e;
   const mipnerf_b200_linear& view = w->linears[10];
   const float rgb_scale = (float)(1.0 + 2.0 * (double)c->rgb_padding);
@@ -1460,7 +1598,7 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
     const float* radii = rays->radii + off;
     // v1 kernels produce fenceposts and the view bias inside the level kernels (IPE warps); the shared-stream
     // variant keeps the separate prologue / resample launches.
-    const bool fused_prologue = fused_prologue_enabled();
+    const bool fused_prologue = fused_prologue_enabled(precision);
     if (!fused_prologue) {
       LaunchScope scope(kKernRayPrologue, st);
       float* t0 = outs[0].t_samples ? outs[0].t_samples + off * (kN + 1) : s.t[0];
@@ -1522,8 +1660,8 @@ cudaError_t tc_mlp_forward(const mipnerf_b200_config* c, const mipnerf_b200_weig
                            void* workspace, cudaStream_t st) {
   (void)c;
   const uint8_t* img = static_cast<const uint8_t*>(w->packed);
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_small, img + kSmallOffset, sizeof(SmallParams), 0,
-                                          cudaMemcpyDeviceToDevice, st);
+  SmallUpload small(img, st);
+  cudaError_t e = small.error();
   if (e != cudaSuccess) return e;
   float* vbias = static_cast<float*>(workspace);  // [num_rays, 128]
   const mipnerf_b200_linear& view = w->linears[10];
@@ -1541,6 +1679,8 @@ cudaError_t tc_mlp_forward(const mipnerf_b200_config* c, const mipnerf_b200_weig
   p.raw_density_out = raw_density;
   p.num_rays = num_rays;
   // MLP-only mode lives in the v1 kernels (CTA pair unless MIPNERF_B200_TC_VARIANT=single)
+  if (is_x3(precision))
+    return fmt_of(precision) ? launch_level_t<1, true, true>(p, st) : launch_level_t<0, true, true>(p, st);
   const bool pair = tc_variant() != 0;
   if (precision == MIPNERF_B200_BF16) return pair ? launch_level_t<1, true>(p, st) : launch_level_t<1, false>(p, st);
   return pair ? launch_level_t<0, true>(p, st) : launch_level_t<0, false>(p, st);

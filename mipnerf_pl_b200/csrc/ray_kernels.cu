@@ -318,7 +318,10 @@ __global__ void rays_from_pixels_kernel(const float* __restrict__ cam_table, con
                                         float* __restrict__ rgb) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const int64_t id = __ldg(pixel_ids + i);
+  // ids outside the atlas are clamped to its first / last row (never read out of bounds); offsets[num_images] = P
+  const int64_t total = __ldg(offsets + num_images);
+  int64_t id = __ldg(pixel_ids + i);
+  id = id < 0 ? 0 : (id >= total ? total - 1 : id);
   int lo = 0, hi = num_images;  // offsets[lo] <= id < offsets[hi]
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;

@@ -24,17 +24,25 @@ __device__ __forceinline__ float coarse_t(float near, float far, float s, int di
   return __fadd_rn(near, __fmul_rn(__fsub_rn(far, near), s));  // near + (far-near)*s   (:153)
 }
 
+// torch.linspace(start, end, steps)[j] on CPU, float32: step = fl32((end-start)/(steps-1)); the first half counts up
+// from `start`, the second half DOWN from `end`, each element rounded once (ATen evaluates start + step*j in double,
+// which is exact before the final rounding, i.e. an fma).  For steps-1 a power of two both halves reduce to
+// fl32(j*step); for the other sample counts (96, 192) the second half differs from j*step by an ulp.
+__device__ __forceinline__ float linspace_f32(float start, float end, int steps, int j) {
+  const float step = __fdiv_rn(__fsub_rn(end, start), (float)(steps - 1));
+  return j < steps / 2 ? __fmaf_rn(step, (float)j, start) : __fmaf_rn(-step, (float)(steps - 1 - j), end);
+}
+
 // fencepost j of n+1; `jitter` = &t_rand[ray][j] for the stratified draw, nullptr when deterministic
 __device__ __forceinline__ float coarse_fencepost(float nr, float fr, int j, int n, int disparity,
                                                   const float* __restrict__ jitter) {
-  const float inv_n = 1.0f / (float)n;  // linspace(0,1,n+1)[j] == fl32(j/n) for the n we accept
-  float t = coarse_t(nr, fr, __fmul_rn((float)j, inv_n), disparity);
+  float t = coarse_t(nr, fr, linspace_f32(0.0f, 1.0f, n + 1, j), disparity);  // models/mip.py:143
   if (jitter) {
     // mids / upper / lower (models/mip.py:156-160)
     const float lower =
-        j == 0 ? t : __fmul_rn(0.5f, __fadd_rn(t, coarse_t(nr, fr, __fmul_rn((float)(j - 1), inv_n), disparity)));
+        j == 0 ? t : __fmul_rn(0.5f, __fadd_rn(t, coarse_t(nr, fr, linspace_f32(0.0f, 1.0f, n + 1, j - 1), disparity)));
     const float upper =
-        j == n ? t : __fmul_rn(0.5f, __fadd_rn(coarse_t(nr, fr, __fmul_rn((float)(j + 1), inv_n), disparity), t));
+        j == n ? t : __fmul_rn(0.5f, __fadd_rn(coarse_t(nr, fr, linspace_f32(0.0f, 1.0f, n + 1, j + 1), disparity), t));
     t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(jitter)));
   }
   return t;

@@ -97,9 +97,10 @@ __device__ __forceinline__ void resample_warp(const float* __restrict__ bins_g,
   __syncwarp();
   // u (:198-208), searchsorted(right=True) (:211), interpolation (:219-228)
   const float one_m_eps = 1.0f - MIPNERF_F32_EPS;
-  const float step = randomized ? (float)(1.0 / (double)ns) : __fdiv_rn(one_m_eps, (float)(ns - 1));
+  const float step = (float)(1.0 / (double)ns);  // randomized: arange(ns) * (1/ns)   (models/mip.py:198-200)
   for (int j = lane; j < ns; j += 32) {
-    float u = __fmul_rn((float)j, step);
+    // deterministic: torch.linspace(0, 1-eps, ns)   (models/mip.py:206-207)
+    float u = randomized ? __fmul_rn((float)j, step) : linspace_f32(0.0f, one_m_eps, ns, j);
     if (randomized) u = fminf(__fadd_rn(u, __ldg(jitter_g + j)), one_m_eps);
     int lo = 0, hi = nb + 1;
     while (lo < hi) {
@@ -214,9 +215,10 @@ __device__ __forceinline__ void resample_warp_lean(const float* __restrict__ bin
   }
   __syncwarp();
   const float one_m_eps = 1.0f - MIPNERF_F32_EPS;
-  const float step = randomized ? (float)(1.0 / (double)ns) : __fdiv_rn(one_m_eps, (float)(ns - 1));
+  const float step = (float)(1.0 / (double)ns);  // randomized: arange(ns) * (1/ns)   (models/mip.py:198-200)
   for (int j = lane; j < ns; j += 32) {
-    float u = __fmul_rn((float)j, step);
+    // deterministic: torch.linspace(0, 1-eps, ns)   (models/mip.py:206-207)
+    float u = randomized ? __fmul_rn((float)j, step) : linspace_f32(0.0f, one_m_eps, ns, j);
     if (randomized) u = fminf(__fadd_rn(u, __ldg(jitter_g + j)), one_m_eps);
     int lo = 0, hi = nb + 1;
     while (lo < hi) {

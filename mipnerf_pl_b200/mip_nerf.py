@@ -26,12 +26,14 @@ def _xavier_init(linear):
 
 
 class _Workspace:
-    """Per-device scratch handed to the library (torch owns every byte)."""
+    """Per-(device, stream) scratch handed to the library (torch owns every byte).  Keyed by the stream
+    the call is enqueued on, so forwards issued on different streams never share a scratch buffer."""
     _bufs = {}
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
-        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = None

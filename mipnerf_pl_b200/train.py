@@ -62,6 +62,13 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, grad_scale=grad_scale))
 
+    @staticmethod
+    def _step_count(st) -> int:
+        """Steps taken so far as a Python int: a state loaded from a torch.optim.Adam checkpoint (what the reference's
+        Lightning `trainer.fit(ckpt_path=...)` restores) keeps `step` as a float32 tensor."""
+        step = st["step"]
+        return step if isinstance(step, int) else int(float(step))
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -71,6 +78,7 @@ class FusedAdam(torch.optim.Optimizer):
         lib = _cabi.lib()
         for group in self.param_groups:
             b1, b2 = group["betas"]
+            grad_scale = float(group.get("grad_scale", 1.0))   # absent after loading a torch.optim.Adam state_dict
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -82,12 +90,12 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
+                st["step"] = self._step_count(st) + 1
                 with torch.cuda.device(dev):
                     _cabi.check(lib.mipnerf_b200_adam_step(
                         p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                         p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]), st["step"],
-                        float(group["grad_scale"]), _stream(dev)), "FusedAdam.step")
+                        grad_scale, _stream(dev)), "FusedAdam.step")
                 torch.autograd.graph.increment_version(p)  # written in place by the library: keep the
                 #                                            packed-weight caches (keyed on _version) honest
         return loss

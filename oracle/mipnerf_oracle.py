@@ -208,7 +208,8 @@ def blurpool_weights(weights, resample_padding):
 
 
 def deterministic_u(num_samples):
-    """torch.linspace(0, 1-eps, n) on CPU == fl32(j * fl32(fl32(1-eps)/(n-1)))
+    """torch.linspace(0, 1-eps, n) on CPU: step = fl32(fl32(1-eps)/(n-1)); first half fl32(step*j), second half
+    fl32(end - step*(n-1-j)) with one rounding (equal to fl32(j*step) when n-1 is a power of two)
     (models/mip.py:206-208)."""
     return torch.linspace(0.0, 1.0 - F32_EPS, num_samples)
 
@@ -275,34 +276,42 @@ DEFAULT_CONFIG = dict(
     mlp_num_density_channels=1)
 
 
-def _mlp_forward_16bit(params, x, view_enc, net_depth, skip_index, prefix, dt):
+def _mlp_forward_16bit(params, x, view_enc, net_depth, skip_index, prefix, dt, split=False):
     """MLP.forward with the operand rounding of the tensor-core kernels emulated (fp32 accumulate):
     trunk / bottleneck / view-layer GEMM operands (activations AND weights) rounded to `dt`;
     density head, view-direction term and colour head stay fp32 — exactly the split documented in
-    mipnerf_pl_b200/csrc/mlp_tc.cu.  Test infrastructure for the bf16/fp16 modes only."""
+    mipnerf_pl_b200/csrc/mlp_tc.cu.  `split=True` emulates the split-operand ("x3") modes: each operand is
+    hi = fl16(x), lo = fl16(x - hi) and the product is hi.hi + lo.hi + hi.lo.  Test infrastructure only."""
     def r(t):
         return t.to(dt).to(torch.float32)
+
+    def lin(a, w):
+        if not split:
+            return F.linear(r(a), r(w))
+        ah, wh = r(a), r(w)
+        al, wl = r(a - ah), r(w - wh)
+        return F.linear(ah, wh) + F.linear(al, wh) + F.linear(ah, wl)
     inputs = x
     for i in range(net_depth):
-        x = F.relu(F.linear(r(x), r(params[f"{prefix}layers.{i}.0.weight"]), params[f"{prefix}layers.{i}.0.bias"]))
+        x = F.relu(lin(x, params[f"{prefix}layers.{i}.0.weight"]) + params[f"{prefix}layers.{i}.0.bias"])
         if i % skip_index == 0 and i > 0:
             x = torch.cat([x, inputs], dim=-1)
     raw_density = F.linear(x, params[f"{prefix}density_layer.weight"], params[f"{prefix}density_layer.bias"])
-    bott = F.linear(r(x), r(params[f"{prefix}extra_layer.weight"]), params[f"{prefix}extra_layer.bias"])
+    bott = lin(x, params[f"{prefix}extra_layer.weight"]) + params[f"{prefix}extra_layer.bias"]
     wv, bv = params[f"{prefix}view_layers.0.0.weight"], params[f"{prefix}view_layers.0.0.bias"]
     k = bott.shape[-1]
-    v = F.relu(F.linear(r(bott), r(wv[:, :k])) + (F.linear(view_enc, wv[:, k:]) + bv)[:, None, :])
+    v = F.relu(lin(bott, wv[:, :k]) + (F.linear(view_enc, wv[:, k:]) + bv)[:, None, :])
     raw_rgb = F.linear(v, params[f"{prefix}color_layer.weight"], params[f"{prefix}color_layer.bias"])
     return raw_rgb, raw_density
 
 
 def mlp_forward(params: Dict[str, torch.Tensor], x, view_enc, net_depth=8, skip_index=4,
-                net_depth_condition=1, prefix="mlp.", operand_dtype=None):
+                net_depth_condition=1, prefix="mlp.", operand_dtype=None, operand_split=False):
     """MLP.forward (models/mip_nerf.py:75-111) over a state_dict-style mapping
     with the reference's key names (``mlp.layers.{i}.0.weight`` ...)."""
     if operand_dtype is not None:
         assert view_enc is not None and net_depth_condition == 1
-        return _mlp_forward_16bit(params, x, view_enc, net_depth, skip_index, prefix, operand_dtype)
+        return _mlp_forward_16bit(params, x, view_enc, net_depth, skip_index, prefix, operand_dtype, operand_split)
     inputs = x
     for i in range(net_depth):
         x = F.relu(F.linear(x, params[f"{prefix}layers.{i}.0.weight"], params[f"{prefix}layers.{i}.0.bias"]))
@@ -322,7 +331,7 @@ def mlp_forward(params: Dict[str, torch.Tensor], x, view_enc, net_depth=8, skip_
 
 def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white_bkgd: bool,
             config: Optional[dict] = None, t_rand=None, u_jitter=None,
-            return_debug=False, operand_dtype=None, grad=False) -> List[Tuple[torch.Tensor, ...]]:
+            return_debug=False, operand_dtype=None, grad=False, operand_split=False) -> List[Tuple[torch.Tensor, ...]]:
     """MipNerf.forward (models/mip_nerf.py:172-248): list over levels of
     (comp_rgb [B,3], distance [B], acc [B], weights [B,N], t_samples [B,N+1]).
     `grad=True` keeps the autograd graph (training); the resampler then runs under no_grad on detached
@@ -352,7 +361,7 @@ def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white
             view_enc = pos_enc(rays.viewdirs, 0, cfg["deg_view"], True) if cfg["use_viewdirs"] else None
             raw_rgb, raw_density = mlp_forward(params, enc, view_enc, cfg["mlp_net_depth"],
                                                cfg["mlp_skip_index"], cfg["mlp_net_depth_condition"],
-                                               operand_dtype=operand_dtype)
+                                               operand_dtype=operand_dtype, operand_split=operand_split)
             rgb = torch.sigmoid(raw_rgb) * (1 + 2 * cfg["rgb_padding"]) - cfg["rgb_padding"]
             density = F.softplus(raw_density + cfg["density_bias"])
             comp_rgb, distance, acc, weights = volumetric_rendering(rgb, density, t, rays.directions, white_bkgd)

@@ -156,6 +156,27 @@ def test_fused_adam_matches_torch_adam():
     torch.testing.assert_close(a.detach(), b_.detach(), rtol=1e-5, atol=1e-7)
 
 
+def test_fused_adam_resumes_from_torch_adam_state():
+    """Resume of a reference (torch.optim.Adam) run: the loaded state has a float32 tensor `step` and no
+    `grad_scale`; continuing with FusedAdam must track torch.optim.Adam continuing."""
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    a = torch.nn.Parameter(torch.randn(4097, device=DEV, generator=gen))
+    ref = torch.optim.Adam([a], lr=1e-3)
+    for _ in range(5):
+        a.grad = torch.randn(4097, device=DEV, generator=gen)
+        ref.step()
+    b_ = torch.nn.Parameter(a.detach().clone())
+    fused = mp.FusedAdam([b_], lr=1e-3)
+    fused.load_state_dict(ref.state_dict())
+    for _ in range(5):
+        gr = torch.randn(4097, device=DEV, generator=gen)
+        a.grad, b_.grad = gr.clone(), gr.clone()
+        ref.step()
+        fused.step()
+    assert fused.state[b_]["step"] == 10
+    torch.testing.assert_close(a.detach(), b_.detach(), rtol=1e-5, atol=1e-7)
+
+
 def test_training_steps_reduce_the_loss_and_refresh_packed_weights():
     torch.manual_seed(0)
     model = gpu_model(3, "xavier")

@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(lib):
     assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mipnerf_b200_abi_version() == _cabi.ABI_VERSION == 2
+    assert lib.mipnerf_b200_abi_version() == _cabi.ABI_VERSION == 3
 
 
 def test_ctypes_structs_match_header_layout():
@@ -144,7 +144,9 @@ def test_bench_reference_arm_prints_contract_json():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    have_ref = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "models", "mip_nerf.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0
 
 
 def test_ray_staging_is_field_major_and_contiguous():
@@ -209,4 +211,4 @@ def test_public_header_is_plain_c_and_links(tmp_path):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                     str(src), "-o", str(exe), "-L", libdir, "-l:libmipnerf_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.split() == ["2", "2"], out
+    assert out.returncode == 0 and out.stdout.split() == ["3", "3"], out

@@ -86,3 +86,23 @@ def test_system_configure_optimizers_shapes():
     assert isinstance(opt, mp.FusedAdam) and sched["interval"] == "step"
     assert opt.param_groups[0]["lr"] == pytest.approx(mp.mip_lr(0, 5e-4, 5e-6, 1000000, 2500, 0.01))
     assert sum(p.numel() for g_ in opt.param_groups for p in g_["params"]) == 612740
+
+
+def test_fused_adam_resumes_from_a_torch_adam_checkpoint():
+    """The reference resumes through Lightning, which restores torch.optim.Adam's state (float32 tensor `step`, no
+    `grad_scale` in the param group): loading it into FusedAdam must leave a state step() can consume."""
+    import mipnerf_pl_b200 as mp
+    p_ref = [torch.nn.Parameter(torch.ones(5, 3)), torch.nn.Parameter(torch.zeros(3))]
+    adam = torch.optim.Adam(p_ref, lr=5e-4)
+    for _ in range(3):
+        for p in p_ref:
+            p.grad = torch.full_like(p, 0.1)
+        adam.step()
+    p_new = [torch.nn.Parameter(p.detach().clone()) for p in p_ref]
+    fused = mp.FusedAdam(p_new, lr=5e-4)
+    fused.load_state_dict(adam.state_dict())
+    assert "grad_scale" not in fused.param_groups[0] or fused.param_groups[0]["grad_scale"] == 1.0
+    for p in p_new:
+        st = fused.state[p]
+        assert mp.FusedAdam._step_count(st) == 3
+        assert st["exp_avg"].shape == p.shape and st["exp_avg_sq"].shape == p.shape
