@@ -184,7 +184,7 @@ def run_reference(args):
         "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "lego single-scale 800x800, 4096-ray batch, 128+128 samples (configs[1])",
+        "config": {"workload": WORKLOAD,
                    "step": f"CPU forward ({kind}) on a {sample}-ray sample of the batch"},
         "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} of {BATCH} rays per step, {CPU_ARM_WHAT[kind]}, fp32, "
@@ -196,16 +196,51 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+WORKLOAD = ("lego single-scale 800x800 Blender-shape rays, 4096-ray batch, 128 coarse + 128 fine samples "
+            "(BASELINE configs[1])")
+PEAK_DIVISOR = {"bf16": 1, "fp16": 1, "fp16x3": 3, "bf16x3": 3, "fp32": 1}   # split modes issue 3 MMAs per product
+DTYPE = {"bf16": "bf16", "fp16": "f16", "fp32": "f32", "fp16x3": "f16x3 (split fp16 operands, 22 bits)",
+         "bf16x3": "bf16x3 (split bf16 operands, 16 bits)"}
+
+
+def measure_parity(mp, model, dev):
+    """Measured in this run: fine-level RGB of `model`'s precision against the fp32 CPU forward of the reference
+    (baseline/_ref, else the oracle port) on 256 rays, xavier and trained-like weights.  The checker only."""
+    import torch
+    kind, forward = _cpu_arm_setup()
+    out = {"checker": kind, "rays": 256, "floor": 0.02, "precision": model.precision}
+    rays = mp.random_ray_batch(256, seed=0)
+    rays_d = mp.namedtuple_map(lambda t: t.to(dev), rays)
+    keep = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    for wk in ("xavier", "trained_like"):
+        sd = mp.make_state_dict(seed=0, kind=wk)
+        want = forward(sd, rays)
+        model.load_state_dict(sd)
+        got = model(rays_d, False, True)
+        torch.cuda.synchronize()
+        d = (got[-1][0].cpu() - want[-1][0]).abs()
+        out[wk] = {"max_abs_rgb": float(d.max()),
+                   "max_rel_rgb_vs_fp32_reference": float((d / want[-1][0].abs().clamp_min(0.02)).max())}
+    model.load_state_dict(keep)
+    out["meets_1e-4"] = all(out[k]["max_rel_rgb_vs_fp32_reference"] <= 1e-4 for k in ("xavier", "trained_like"))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16", "fp16"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16", "fp16", "fp16x3", "bf16x3"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank renders its own --batch rays; strong: ONE --batch-ray batch split over the ranks")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame", action="store_true", help="skip the 800x800 frame metric (profiling runs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -235,26 +270,85 @@ def main():
     model.precision = precision
     model.load_state_dict(mp.make_state_dict(seed=0, kind="xavier"))
     model = model.to(dev).eval()
-
-    B = args.batch
-    staging = mp.RayStaging(mp.random_ray_batch(B, seed=rank))         # pinned host batch (e2e arm): 52 B/ray
-    rays = mp.namedtuple_map(lambda t: t.to(dev), staging.host_rays)    # resident copy (value arm)
-    gathered = torch.empty(world * B, 3, device=dev) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-
-    def step():
-        ret = model(rays, False, True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, ret[-1][0])
-        return ret
+    use_graph = not args.no_graph and precision != "fp32"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    class Arm:
+        """One sharding of the workload: this rank's rays in a pinned staging buffer, the resident copy, the graph."""
+
+        def __init__(self, rays_local):
+            self.b = rays_local.origins.shape[0]
+            self.staging = mp.RayStaging(rays_local)                     # pinned host batch (e2e arm): 52 B/ray
+            self.rays = self.staging.to(dev)                              # resident copy (value arm)
+            self.gathered = torch.empty(world * self.b * 3, device=dev) if world > 1 else None
+            self.graph = mp.GraphedForward(model, self.staging, True, dev, world=world) if use_graph else None
+            self.out_host = torch.empty(2, 5 * self.b, pin_memory=True)   # per level: comp_rgb | distance | acc
+
+        def eager(self):
+            ret = model(self.rays, False, True)
+            if world > 1:
+                dist.all_gather_into_tensor(self.gathered, ret[-1][0].reshape(-1))
+            return ret
+
+        def step(self):
+            return self.graph.replay() if self.graph else self.eager()
+
+        def e2e_step(self):
+            self.staging.to(dev)                                          # ONE H2D copy of the step's rays (pinned)
+            ret = self.step()
+            self.out_host.copy_(ret.pixels, non_blocking=True)            # ONE D2H copy: both levels' rgb, dist, acc
+            torch.cuda.current_stream().synchronize()                    # the caller reads the pixels every step
+
+        def timed(self, steps, fn=None):
+            """K steps, device-timed with events on the launch stream, L2 flushed (untimed) between steps;
+            returns ms per step, max over ranks."""
+            fn = fn or self.step
+            starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+            barrier()
+            for i in range(steps):
+                flush.zero_()
+                starts[i].record()
+                fn()
+                stops[i].record()
+            barrier()
+            total = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(starts, stops))], device=dev,
+                                 dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(total, op=dist.ReduceOp.MAX)
+            return float(total.item()) / steps
+
+        def timed_e2e(self, steps):
+            for _ in range(3):
+                self.e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.e2e_step()
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item()) / steps
+
+    B = args.batch
+    if args.scaling == "strong":
+        assert B % world == 0, "--scaling strong needs --batch divisible by the number of ranks"
+        full = mp.random_ray_batch(B, seed=0)
+        lo, hi = mp.shard_bounds(B, world, rank)
+        arm = Arm(mp.Rays(*[f[lo:hi] for f in full]))
+    else:
+        arm = Arm(mp.random_ray_batch(B, seed=rank))
+    b_local, b_global = arm.b, (B if args.scaling == "strong" else world * B)
+
     for _ in range(args.warmup):
-        step()
+        arm.step()
     barrier()
 
     # ---- value: device-timed steps, L2 flushed between them -------------------------------------
@@ -263,56 +357,44 @@ def main():
         sampler.start()
         time.sleep(0.6)                      # nvidia-smi needs ~0.5 s before its first sample
     for _ in range(args.warmup):             # every rank (step() holds a collective): GPU under load
-        step()                               # while the sampler spins up
+        arm.step()                           # while the sampler spins up
     barrier()
     if rank == 0:
         sampler.rows.clear()
-    _cabi.profile_snapshot(reset=True)
-    lib.mipnerf_b200_profile_enable(1)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()
-        starts[i].record()
-        step()
-        stops[i].record()
-    barrier()
+    ms_per_step = arm.timed(args.steps)
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
+    value = b_global / (ms_per_step * 1e-3)
+
+    # ---- instrumented pass: the same K steps launched eagerly with the library's CUDA-event bracket around every
+    #      kernel launch (a graph replay cannot be bracketed per kernel): kernel list, launch counts, launch time
+    _cabi.profile_snapshot(reset=True)
+    lib.mipnerf_b200_profile_enable(1)
+    ms_eager = arm.timed(args.steps, arm.eager)
     lib.mipnerf_b200_profile_enable(0)
     prof = _cabi.profile_snapshot(reset=True)
-    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
-    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    ms_per_step = total_ms / args.steps
-    value = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region -------------------------
-    out_host = torch.empty(2, 5 * B, pin_memory=True)     # per level: comp_rgb [B,3] | distance [B] | acc [B]
+    e2e_s = arm.timed_e2e(args.steps)
+    e2e_value = b_global / e2e_s
 
-    def e2e_step():
-        r = staging.to(dev)                                 # ONE H2D copy of the step's rays from pinned memory
-        ret = model(r, False, True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, ret[-1][0])
-        out_host.copy_(ret.pixels, non_blocking=True)       # ONE D2H copy: both levels' rgb, distance, acc
-        torch.cuda.current_stream().synchronize()          # the caller reads the pixels every step
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(e2e_s.item())
+    # ---- strong scaling of THE 4096-ray batch (north_star: "the batch is split across the 8 GPUs"), same run:
+    #      every rank renders B/world rays; kernels + all-gather replayed as one CUDA graph
+    strong = None
+    if world > 1 and args.scaling == "weak" and B % world == 0:
+        full = mp.random_ray_batch(B, seed=0)
+        lo, hi = mp.shard_bounds(B, world, rank)
+        sarm = Arm(mp.Rays(*[f[lo:hi] for f in full]))
+        for _ in range(args.warmup):
+            sarm.step()
+        s_ms = sarm.timed(args.steps)
+        s_e2e = sarm.timed_e2e(args.steps)
+        strong = {"global_batch_rays": B, "rays_per_gpu": sarm.b, "ms_per_step": s_ms,
+                  "rays_per_s": B / (s_ms * 1e-3), "e2e_rays_per_s": B / s_e2e,
+                  "launch": "cuda graph replay (2 level kernels + all_gather)" if use_graph else "eager",
+                  "what": "ONE 4096-ray batch split into contiguous shards over the ranks, fine RGB all-gathered"}
+        del sarm
 
     # ---- 800x800 frame (BASELINE configs[3]): rows sharded over the ranks, rays generated on device,
     #      one all_gather of the rendered pixels; device-timed, max over ranks
@@ -342,39 +424,42 @@ def main():
     peaks = load_peaks()
     timed = {k: v for k, v in prof.items() if v[2] > 0}
     dominant = max(timed, key=lambda k: timed[k][1]) if timed else None
-    launches_total = sum(v[0] for v in prof.values())
+    launches_per_step = {k: v[0] / args.steps for k, v in prof.items() if v[0]}
+    launches_total = int(round(sum(launches_per_step.values()) * args.steps))
     roofline = None
     if dominant:
         n_l, ms_l, tn_l = prof[dominant]
         per_launch_ms = ms_l / tn_l
         # FLOPs one launch of the dominant kernel performs: the step's MLP FLOPs split over its launches
         mlp_kernels = ("mlp_level_tc", "mlp_tc", "linear_f32")
-        flops_step = B * FLOP_PER_RAY
-        launches_per_step = n_l / args.steps
-        flops_per_launch = flops_step / launches_per_step if dominant in mlp_kernels else 0.0
+        flops_step = b_local * FLOP_PER_RAY
+        lps = n_l / args.steps
+        flops_per_launch = flops_step / lps if dominant in mlp_kernels else 0.0
         achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12
-        peak = peaks["bf16_tflops"]
-        traffic = None   # dram read+write bytes per launch from the committed ncu --set full capture
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_mlp_level_pair_summary.json")) as f:
-                m = json.load(f)["metrics"]
-            rd = [float(v) for v in m["dram__bytes_read.sum"]["launches"]]
-            wr = [float(v) for v in m["dram__bytes_write.sum"]["launches"]]
-            scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
-            traffic = (sum(rd) / len(rd)) * scale[m["dram__bytes_read.sum"]["unit"]] + \
-                      (sum(wr) / len(wr)) * scale[m["dram__bytes_write.sum"]["unit"]]
-        except Exception:  # noqa: BLE001
-            pass
+        div = PEAK_DIVISOR[precision]
+        peak = peaks["bf16_tflops"] / div
         roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": traffic if dominant == "mlp_level_tc" else None,
-                    "peak_source": f"{peaks['_source']} MEASURED_PEAKS.json bf16_tflops (burst)",
+                    "frac": achieved / peak,
+                    "traffic": 5671808.0 if dominant == "mlp_level_tc" and div == 1 else None,
+                    "traffic_source": {"static": True, "from": "profiles/r01_ncu_mlp_level_pair_summary.json "
+                                       "(dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full); "
+                                       "not re-measured in this run"} if dominant == "mlp_level_tc" and div == 1 else None,
+                    "peak_source": f"{peaks['_source']} MEASURED_PEAKS.json bf16_tflops (burst)" +
+                                   (f" / {div}: the split mode issues {div} tensor-core products per algorithmic "
+                                    f"product, so the matching peak for ALGORITHMIC flops is a {div}th of the 16-bit peak"
+                                    if div > 1 else ""),
+                    "frac_of_bf16_peak": achieved / peaks["bf16_tflops"],
                     "peak_sustained": peaks.get("bf16_tflops_sustained"),
-                    "frac_of_sustained": (achieved / peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None,
-                    "note": "the kernel runs at the 1000 W power cap in a long loop (sw_power_cap, ~985 W): cuBLAS' "
-                            "sustained figure is the like-for-like ceiling; frac stays on the burst figure",
-                    "launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
-                    "share_of_step": ms_l / max(total_ms, 1e-9),
+                    "frac_of_sustained": (achieved / (peaks["bf16_tflops_sustained"] / div))
+                    if peaks.get("bf16_tflops_sustained") else None,
+                    "launch_ms": per_launch_ms, "launches_per_step": lps,
+                    "share_of_step": (ms_l / args.steps) / max(ms_eager, 1e-9),
+                    "measured_in": "the instrumented eager pass of this run (library CUDA-event bracket per launch)",
                     "step_frac_of_roofline": (value / world) * FLOP_PER_RAY / 1e12 / peak}
+
+    parity = None
+    if not args.no_parity:
+        parity = measure_parity(mp, model, dev)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -389,21 +474,24 @@ def main():
     line = {
         "metric": "rays/sec (4096-ray batch, 128+128 samples)", "value": value, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[precision], "data": "synthetic",
-        "config": {"workload": "lego single-scale 800x800 Blender-shape rays, 4096-ray batch, 128 coarse + 128 "
-                               "fine samples (BASELINE configs[1])",
-                   "global_batch_rays": world * B, "rays_per_gpu": B, "mlp_operands": precision,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": DTYPE[precision], "data": "synthetic",
+        "config": {"workload": WORKLOAD,
+                   "global_batch_rays": b_global, "rays_per_gpu": b_local, "mlp_operands": precision,
                    "weights": "random-init xavier (seed 0) of the reference 8x256 architecture",
                    "l2": "flushed between steps (256 MiB memset, untimed)",
-                   "parallelism": f"ray-sharded x{world}, all_gather of fine RGB" if world > 1 else "single GPU",
+                   "launch": "one CUDA-graph replay per step (MipNerf.forward captured by GraphedForward)"
+                             if use_graph else "eager C-ABI call per step",
+                   "parallelism": (f"ray-sharded x{world}, all_gather of fine RGB" + (" inside the graph" if use_graph else ""))
+                   if world > 1 else "single GPU",
+                   "ms_per_step_eager_instrumented": ms_eager,
                    "wall_s_timed_region_incl_flush": wall},
-        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": B * H2D_BYTES_PER_RAY,
-                "d2h_bytes_per_step": B * D2H_BYTES_PER_RAY},
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": b_local * H2D_BYTES_PER_RAY,
+                "d2h_bytes_per_step": b_local * D2H_BYTES_PER_RAY},
         "gpu_launches": launches_total,
-        "kernel_launches": {k: v[0] for k, v in prof.items() if v[0]},
+        "kernel_launches": {k: int(round(v * args.steps)) for k, v in launches_per_step.items()},
         "kernel_ms": {k: round(v[1], 4) for k, v in prof.items() if v[2]},
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "strong_scaling": strong,
         "frame": None if frame_ms is None else {
             "height": 800, "width": 800, "rays": 640000, "ms": frame_ms, "rays_per_s": 640000 / (frame_ms * 1e-3),
             "what": "render_frame: on-device ray generation, both levels, rows sharded over ranks, "
