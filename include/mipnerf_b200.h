@@ -93,6 +93,14 @@ typedef struct mipnerf_b200_level_out {
   int64_t* inds;    /* [B,N+1] nullable; searchsorted indices of the resampler (levels >= 1)       */
 } mipnerf_b200_level_out;
 
+/* In-kernel random numbers for randomized=True: Philox4x32-10 keyed by `seed`; the draw of (ray, index, stream) is a
+ * pure function of (seed, offset, ray's position in the call), so results do not depend on chunking.  Advance `offset`
+ * by one per call for fresh noise (the role of torch's generator offset). */
+typedef struct mipnerf_b200_rng {
+  uint64_t seed;
+  uint64_t offset;
+} mipnerf_b200_rng;
+
 const char* mipnerf_b200_last_error(void);
 int mipnerf_b200_abi_version(void);
 
@@ -112,6 +120,19 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
                          const float* u_jitter, int white_bkgd, int precision,
                          mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes,
                          void* stream);
+
+/* Same, drawing the uniforms of randomized mode INSIDE the kernels that consume them (no torch.rand launch, no
+ * [B,N+1] arrays in HBM): stream 0 = the stratified draws of sample_along_rays (models/mip.py:159), stream 1+l =
+ * the inverse-CDF jitter of level l (models/mip.py:201-202, scaled to [0, 1/(N+1) - eps)). */
+int mipnerf_b200_forward_rng(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                             const mipnerf_b200_rays* rays, const mipnerf_b200_rng* rng, int white_bkgd,
+                             int precision, mipnerf_b200_level_out* outs, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* The uniforms those kernels draw: out[num_rays, ncols] for `stream_id` (0: t_rand in [0,1); >= 1: u_jitter in
+ * [0, 1/ncols - eps)).  forward(t_rand = stream 0, u_jitter = stream 1+level) reproduces forward_rng bit for bit. */
+int mipnerf_b200_philox_uniform(const mipnerf_b200_rng* rng, int stream_id, int64_t num_rays, int ncols, float* out,
+                                void* stream);
 
 /* distloss (models/mip.py:8-20), forward value per ray: weights [B,N], samples [B,N+1] (sorted) ->
  * per_ray_loss [B] = (1/3) sum_i d_i w_i^2 + sum_ij w_i w_j |m_i - m_j|; the reference's scalar is its mean. */
@@ -157,6 +178,12 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
                                   const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
                                   const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
                                   void* workspace, size_t workspace_bytes, void* stream);
+/* randomized=True training step with the in-kernel generator (what a training loop calls every step). */
+int mipnerf_b200_forward_backward_rng(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* weights,
+                                      const mipnerf_b200_rays* rays, const mipnerf_b200_rng* rng, int white_bkgd,
+                                      int precision, const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
+                                      const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stand-alone tensor-core linear layer  y[m,n] = act(x[m,k] . weight[n,k]^T + bias)  (tcgen05, 16-bit operands, fp32
  * accumulate; n in {128,256}, k in {96,128,256}): the GEMM the training step uses for its forward and dgrad passes in

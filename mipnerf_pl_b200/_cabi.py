@@ -53,6 +53,10 @@ class LevelOut(C.Structure):
                 ("weights", C.c_void_p), ("t_samples", C.c_void_p), ("inds", C.c_void_p)]
 
 
+class Rng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64)]
+
+
 class LinearGrad(C.Structure):
     _fields_ = [("weight_grad", C.c_void_p), ("bias_grad", C.c_void_p)]
 
@@ -74,11 +78,17 @@ _SIGNATURES = {
     "mipnerf_b200_pack_weights": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.c_int, _V, C.c_size_t, _V]),
     "mipnerf_b200_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.c_int,
                                        _V, _V, C.c_int, C.c_int, C.POINTER(LevelOut), _V, C.c_size_t, _V]),
+    "mipnerf_b200_forward_rng": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.POINTER(Rng),
+                                           C.c_int, C.c_int, C.POINTER(LevelOut), _V, C.c_size_t, _V]),
+    "mipnerf_b200_philox_uniform": (C.c_int, [C.POINTER(Rng), C.c_int, C.c_int64, C.c_int, _V, _V]),
     "mipnerf_b200_distloss": (C.c_int, [_V, _V, C.c_int64, C.c_int, _V, _V]),
     "mipnerf_b200_train_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int64]),
     "mipnerf_b200_forward_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.c_int,
                                                 _V, _V, C.c_int, C.c_int, C.POINTER(Loss), C.POINTER(LevelOut),
                                                 C.POINTER(LinearGrad), C.c_int, C.c_int, _V, C.c_size_t, _V]),
+    "mipnerf_b200_forward_backward_rng": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct),
+                                                    C.POINTER(Rng), C.c_int, C.c_int, C.POINTER(Loss), C.POINTER(LevelOut),
+                                                    C.POINTER(LinearGrad), C.c_int, C.c_int, _V, C.c_size_t, _V]),
     "mipnerf_b200_linear_tc": (C.c_int, [_V, _V, _V, _V, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _V, C.c_size_t, _V]),
     "mipnerf_b200_adam_step": (C.c_int, [_V, _V, _V, _V, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_int64, C.c_double, _V]),

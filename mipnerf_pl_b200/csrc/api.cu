@@ -243,10 +243,10 @@ int mipnerf_b200_pack_weights(const mipnerf_b200_config* cfg, const mipnerf_b200
   return MIPNERF_B200_OK;
 }
 
-int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
-                         const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
-                         const float* u_jitter, int white_bkgd, int precision, mipnerf_b200_level_out* outs,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+static int forward_impl(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                        const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                        const float* u_jitter, const mipnerf_b200_rng* rng, int white_bkgd, int precision,
+                        mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes, void* stream) {
   Dims d;
   int rc;
   if ((rc = check_config(cfg, &d))) return rc;
@@ -255,8 +255,9 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
   if (!outs) return fail(MIPNERF_B200_EINVAL, "outs is NULL");
   if (cfg->use_viewdirs && rays->num_rays > 0 && !rays->viewdirs)
     return fail(MIPNERF_B200_EINVAL, "use_viewdirs but rays.viewdirs is NULL");
-  if (randomized && (!t_rand || (cfg->num_levels > 1 && !u_jitter)))
-    return fail(MIPNERF_B200_EINVAL, "randomized=1 needs t_rand and u_jitter (the ABI takes the noise as input)");
+  if (randomized && !rng && (!t_rand || (cfg->num_levels > 1 && !u_jitter)))
+    return fail(MIPNERF_B200_EINVAL,
+                "randomized=1 needs t_rand and u_jitter (injected noise) or the _rng entry point (in-kernel Philox)");
   for (int l = 0; l < cfg->num_levels; ++l)
     if (rays->num_rays > 0 && (!outs[l].comp_rgb || !outs[l].distance || !outs[l].acc))
       return fail(MIPNERF_B200_EINVAL, "outs[%d] misses comp_rgb/distance/acc", l);
@@ -275,7 +276,7 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
     if (!w->packed || w->packed_precision != precision ||
         w->packed_bytes < mipnerf::tc_packed_bytes(cfg, precision))
       return fail(MIPNERF_B200_EINVAL, "weights->packed missing or packed for another precision");
-    cudaError_t e = mipnerf::tc_forward(cfg, w, rays, randomized, t_rand, u_jitter, white_bkgd, precision,
+    cudaError_t e = mipnerf::tc_forward(cfg, w, rays, randomized, t_rand, u_jitter, rng, white_bkgd, precision,
                                         outs, workspace, workspace_bytes, st);
     if (e != cudaSuccess) return fail(MIPNERF_B200_ECUDA, "tc_forward: %s", cudaGetErrorString(e));
     return MIPNERF_B200_OK;
@@ -292,11 +293,11 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
       float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (n + 1) : s.t[l & 1];
       float* w_cur = outs[l].weights ? outs[l].weights + off * n : s.w[l & 1];
       if (l == 0) {
-        CUDA_TRY(mipnerf::launch_coarse_t(rc_.near, rc_.far, t_rand ? t_rand + off * (n + 1) : nullptr, t_cur,
-                                          cnt, n, randomized, cfg->disparity, st));
+        CUDA_TRY(mipnerf::launch_coarse_t(rc_.near, rc_.far, mipnerf::level_draws(randomized, t_rand, rng, off, 0, n + 1),
+                                          t_cur, cnt, n, randomized, cfg->disparity, st));
       } else {
-        CUDA_TRY(mipnerf::launch_resample(t_prev, w_prev, u_jitter ? u_jitter + off * (n + 1) : nullptr, t_cur,
-                                          outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr, cnt, n, n + 1,
+        CUDA_TRY(mipnerf::launch_resample(t_prev, w_prev, mipnerf::level_draws(randomized, u_jitter, rng, off, 1 + l, n + 1),
+                                          t_cur, outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr, cnt, n, n + 1,
                                           randomized, 1, cfg->resample_padding, st));
       }
       CUDA_TRY(mipnerf::launch_ipe_from_t(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc, cnt, n,
@@ -313,6 +314,32 @@ int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weig
       w_prev = w_cur;
     }
   }
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                         const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                         const float* u_jitter, int white_bkgd, int precision, mipnerf_b200_level_out* outs,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_impl(cfg, w, rays, randomized, t_rand, u_jitter, nullptr, white_bkgd, precision, outs, workspace,
+                      workspace_bytes, stream);
+}
+
+int mipnerf_b200_forward_rng(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                             const mipnerf_b200_rays* rays, const mipnerf_b200_rng* rng, int white_bkgd,
+                             int precision, mipnerf_b200_level_out* outs, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!rng) return fail(MIPNERF_B200_EINVAL, "rng is NULL");
+  return forward_impl(cfg, w, rays, 1, nullptr, nullptr, rng, white_bkgd, precision, outs, workspace,
+                      workspace_bytes, stream);
+}
+
+int mipnerf_b200_philox_uniform(const mipnerf_b200_rng* rng, int stream_id, int64_t num_rays, int ncols, float* out,
+                                void* stream) {
+  if (!rng || stream_id < 0 || num_rays < 0 || ncols < 1 || (num_rays > 0 && !out))
+    return fail(MIPNERF_B200_EINVAL, "bad argument");
+  const mipnerf::Draws d = mipnerf::level_draws(1, nullptr, rng, 0, stream_id, ncols);
+  CUDA_TRY(mipnerf::launch_philox_uniform(d, out, num_rays, ncols, (cudaStream_t)stream));
   return MIPNERF_B200_OK;
 }
 
@@ -395,12 +422,12 @@ size_t mipnerf_b200_train_workspace_bytes(const mipnerf_b200_config* cfg, int64_
   return carve_train(cfg, d, r > 0 ? r : 1, nullptr).bytes;
 }
 
-int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
-                                  const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
-                                  const float* u_jitter, int white_bkgd, int precision,
-                                  const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
-                                  const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+static int forward_backward_impl(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                                 const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                                 const float* u_jitter, const mipnerf_b200_rng* rng, int white_bkgd, int precision,
+                                 const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
+                                 const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
   Dims d;
   int rc;
   if ((rc = check_config(cfg, &d))) return rc;
@@ -423,8 +450,9 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
     return fail(MIPNERF_B200_EINVAL, "loss multipliers are NULL");
   if (rays->num_rays > 0 && (!loss->target_rgb || !loss->mask_sum || !rays->viewdirs))
     return fail(MIPNERF_B200_EINVAL, "target_rgb / mask_sum / viewdirs is NULL");
-  if (randomized && (!t_rand || (cfg->num_levels > 1 && !u_jitter)))
-    return fail(MIPNERF_B200_EINVAL, "randomized=1 needs t_rand and u_jitter (the ABI takes the noise as input)");
+  if (randomized && !rng && (!t_rand || (cfg->num_levels > 1 && !u_jitter)))
+    return fail(MIPNERF_B200_EINVAL,
+                "randomized=1 needs t_rand and u_jitter (injected noise) or the _rng entry point (in-kernel Philox)");
   for (int l = 0; l < cfg->num_levels; ++l)
     if (rays->num_rays > 0 && (!outs[l].comp_rgb || !outs[l].distance || !outs[l].acc))
       return fail(MIPNERF_B200_EINVAL, "outs[%d] misses comp_rgb/distance/acc", l);
@@ -507,11 +535,11 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
       float* w_cur = outs[l].weights ? outs[l].weights + off * n : s.w[l & 1];
       // ---- forward of this level, every activation kept (models/mip_nerf.py:203-240)
       if (l == 0) {
-        CUDA_TRY(mipnerf::launch_coarse_t(rc_.near, rc_.far, t_rand ? t_rand + off * (n + 1) : nullptr, t_cur,
-                                          cnt, n, randomized, cfg->disparity, st));
+        CUDA_TRY(mipnerf::launch_coarse_t(rc_.near, rc_.far, mipnerf::level_draws(randomized, t_rand, rng, off, 0, n + 1),
+                                          t_cur, cnt, n, randomized, cfg->disparity, st));
       } else {
-        CUDA_TRY(mipnerf::launch_resample(t_prev, w_prev, u_jitter ? u_jitter + off * (n + 1) : nullptr, t_cur,
-                                          outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr, cnt, n, n + 1,
+        CUDA_TRY(mipnerf::launch_resample(t_prev, w_prev, mipnerf::level_draws(randomized, u_jitter, rng, off, 1 + l, n + 1),
+                                          t_cur, outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr, cnt, n, n + 1,
                                           randomized, 1, cfg->resample_padding, st));
       }
       CUDA_TRY(mipnerf::launch_ipe_from_t(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc, cnt, n,
@@ -608,6 +636,26 @@ int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_
   return MIPNERF_B200_OK;
 }
 
+int mipnerf_b200_forward_backward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                                  const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                                  const float* u_jitter, int white_bkgd, int precision,
+                                  const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
+                                  const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  return forward_backward_impl(cfg, w, rays, randomized, t_rand, u_jitter, nullptr, white_bkgd, precision, loss, outs,
+                               grads, num_grads, accumulate, workspace, workspace_bytes, stream);
+}
+
+int mipnerf_b200_forward_backward_rng(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
+                                      const mipnerf_b200_rays* rays, const mipnerf_b200_rng* rng, int white_bkgd,
+                                      int precision, const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
+                                      const mipnerf_b200_linear_grad* grads, int num_grads, int accumulate,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!rng) return fail(MIPNERF_B200_EINVAL, "rng is NULL");
+  return forward_backward_impl(cfg, w, rays, 1, nullptr, nullptr, rng, white_bkgd, precision, loss, outs, grads, num_grads,
+                               accumulate, workspace, workspace_bytes, stream);
+}
+
 int mipnerf_b200_linear_tc(const float* x, const float* weight, const float* bias, float* y, int64_t m, int n,
                            int k, int relu, int precision, void* scratch, size_t scratch_bytes, void* stream) {
   if (m < 0 || !mipnerf::linear_tc_shape_ok(n, k))
@@ -678,8 +726,8 @@ int mipnerf_b200_sample_along_rays(const mipnerf_b200_rays* rays, int num_sample
   if (num_samples < 1 || !t_samples) return fail(MIPNERF_B200_EINVAL, "bad num_samples / t_samples");
   if (randomized && !t_rand) return fail(MIPNERF_B200_EINVAL, "randomized=1 needs t_rand");
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(mipnerf::launch_coarse_t(rays->near, rays->far, t_rand, t_samples, rays->num_rays, num_samples,
-                                    randomized, disparity, st));
+  CUDA_TRY(mipnerf::launch_coarse_t(rays->near, rays->far, mipnerf::draws_from_array(randomized ? t_rand : nullptr),
+                                    t_samples, rays->num_rays, num_samples, randomized, disparity, st));
   if (means && covs)
     CUDA_TRY(mipnerf::launch_cast_rays(rays->origins, rays->directions, rays->radii, t_samples, means, covs,
                                        rays->num_rays, num_samples, st));
@@ -802,8 +850,8 @@ int mipnerf_b200_sorted_piecewise_constant_pdf(const float* bins, const float* w
     return fail(MIPNERF_B200_EUNSUPPORTED, "num_bins=%d: need a multiple of 32, <= 1024", num_bins);
   if (num_rays == 0) return MIPNERF_B200_OK;
   if (!bins || !weights || !samples || (randomized && !u_jitter)) return fail(MIPNERF_B200_EINVAL, "NULL tensor");
-  CUDA_TRY(mipnerf::launch_resample(bins, weights, u_jitter, samples, inds, num_rays, num_bins, num_samples,
-                                    randomized, 0, 0.f, (cudaStream_t)stream));
+  CUDA_TRY(mipnerf::launch_resample(bins, weights, mipnerf::draws_from_array(randomized ? u_jitter : nullptr), samples,
+                                    inds, num_rays, num_bins, num_samples, randomized, 0, 0.f, (cudaStream_t)stream));
   return MIPNERF_B200_OK;
 }
 
@@ -819,8 +867,9 @@ int mipnerf_b200_resample_along_rays(const mipnerf_b200_rays* rays, const float*
   if (!t_samples || !weights || !new_t_samples || (randomized && !u_jitter))
     return fail(MIPNERF_B200_EINVAL, "NULL tensor");
   cudaStream_t st = (cudaStream_t)stream;
-  CUDA_TRY(mipnerf::launch_resample(t_samples, weights, u_jitter, new_t_samples, inds, rays->num_rays,
-                                    num_samples, num_samples + 1, randomized, 1, resample_padding, st));
+  CUDA_TRY(mipnerf::launch_resample(t_samples, weights, mipnerf::draws_from_array(randomized ? u_jitter : nullptr),
+                                    new_t_samples, inds, rays->num_rays, num_samples, num_samples + 1, randomized, 1,
+                                    resample_padding, st));
   if (means && covs)
     CUDA_TRY(mipnerf::launch_cast_rays(rays->origins, rays->directions, rays->radii, new_t_samples, means,
                                        covs, rays->num_rays, num_samples, st));

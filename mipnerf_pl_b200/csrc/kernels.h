@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "draws.h"
+
 namespace mipnerf {
 
 // ---- ray_kernels.cu ----
@@ -17,8 +19,9 @@ cudaError_t launch_rays_from_pixels(const float* cam_table, const int64_t* offse
                                     int num_images, const int64_t* pixel_ids, int64_t count, const float* atlas,
                                     float* origins, float* directions, float* viewdirs, float* radii,
                                     float* lossmult, float* near_o, float* far_o, float* rgb, cudaStream_t st);
-cudaError_t launch_coarse_t(const float* near, const float* far, const float* t_rand, float* t_out,
+cudaError_t launch_coarse_t(const float* near, const float* far, const Draws& t_rand, float* t_out,
                             int64_t num_rays, int n, int randomized, int disparity, cudaStream_t st);
+cudaError_t launch_philox_uniform(const Draws& d, float* out, int64_t num_rays, int ncols, cudaStream_t st);
 cudaError_t launch_cast_rays(const float* origins, const float* directions, const float* radii,
                              const float* t, float* means, float* covs, int64_t num_rays, int n,
                              cudaStream_t st);
@@ -33,7 +36,7 @@ cudaError_t launch_composite(const float* rgb, const float* dens, const float* t
                              float* comp_rgb, float* distance, float* acc, float* weights,
                              int64_t num_rays, int n, int white_bkgd, int activate,
                              float density_bias, float rgb_scale, float rgb_padding, cudaStream_t st);
-cudaError_t launch_resample(const float* bins, const float* weights, const float* jitter, float* out,
+cudaError_t launch_resample(const float* bins, const float* weights, const Draws& jitter, float* out,
                             int64_t* inds, int64_t num_rays, int nb, int ns, int randomized, int blur,
                             float padding, cudaStream_t st);
 

@@ -109,6 +109,8 @@ constexpr size_t kImageBytes = kViewDirOffset + ((kViewDirBytes + 255) / 256 * 2
 // same 16-bit format), same internal layout as the stage part of the first image, appended after it.
 constexpr size_t kLoOffset = kImageBytes;
 constexpr size_t kLoBytes = ((size_t)kViewPairOffset + 2 * 8 * kViewPairStage + 255) / 256 * 256;
+// third region: the "v3" kernel's weight blocks (mlp_tc_v3.cuh), [32 rows x 64 K] per CTA in issue order
+constexpr size_t kV3Offset = kLoOffset + kLoBytes;
 
 #ifdef MIPNERF_TC_TRACE
 // debug build only: (clock64, event) pairs of CTA 0.  Each traced thread (one per role) owns a
@@ -157,11 +159,11 @@ struct LevelParams {
   int vb_mode;             // 0: read p.view_bias; 1: compute it from viewdirs and the fp32 view-layer weights
   const float* near;       // t_mode 1
   const float* far;
-  const float* t_rand;     // t_mode 1, randomized: [B,129] uniforms, else nullptr
+  Draws t_rand;            // t_mode 1, randomized: the [B,129] stratified uniforms (array or in-kernel Philox)
   int disparity;
   const float* t_prev;     // t_mode 2: previous level's fenceposts [B,129] and weights [B,128]
   const float* w_prev;
-  const float* u_jitter;   // t_mode 2, randomized: [B,129], else nullptr
+  Draws u_jitter;          // t_mode 2, randomized: the [B,129] inverse-CDF jitter (array or in-kernel Philox)
   int64_t* inds;           // t_mode 2: optional searchsorted indices [B,129]
   int randomized;
   float resample_padding;
@@ -253,6 +255,69 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
     dens = ((dpart[0] + dpart[1]) + (dpart[2] + dpart[3])) + ((dpart[4] + dpart[5]) + (dpart[6] + dpart[7]));
 }
 
+// Rolled form of the same epilogue with the layer index at RUN time: one copy of the code for all nine layers, a loop
+// over 64-column steps (two pipelined 32-column TMEM loads each).  The ncu source page of the unrolled, per-layer
+// instantiated version shows its arithmetic stalled on instruction fetch (stall_no_inst: ~45 % of the epilogue samples
+// of the bf16 kernel, ~80 % in the split modes, whose nine instantiations are 190 KB of straight-line code that every
+// worker warp streams through once per ray): the rolled body is ~2-5 KB and stays in the instruction caches.
+#ifndef MIPNERF_TC_ROLLED_EPILOGUE
+#define MIPNERF_TC_ROLLED_EPILOGUE 0
+#endif
+template <int kFmt, bool kX3, bool kRelu, bool kDens>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int layer, int c0, uint8_t* myA, uint32_t rowoff,
+                                               uint32_t rx, float (&dpart)[8]) {
+  const float* __restrict__ bias = c_small.bias[layer] + c0;
+  uint8_t* slab = myA + (c0 >> 6) * kStageBytes + rowoff;
+  const uint32_t ci0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t w[4], wl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = j * 8 + 2 * e;
+      float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
+      fadd2(a, b, bias[c], bias[c + 1]);
+      if (kDens)  // density_layer on the fp32 (un-rounded) h7        (models/mip_nerf.py:98)
+        ffma2(dpart[2 * e], dpart[2 * e + 1], fmaxf(a, 0.f), fmaxf(b, 0.f), c_small.w_density[c0 + c],
+              c_small.w_density[c0 + c + 1]);
+      if (kX3) {
+        if (kRelu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+        w[e] = pack2<kFmt>(a, b);
+        const float2 h = unpack2<kFmt>(w[e]);
+        wl[e] = pack2<kFmt>(a - h.x, b - h.y);
+      } else {
+        w[e] = kRelu ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
+      }
+    }
+    const uint32_t off = ((ci0 + j) ^ rx) << 4;  // sw128_offset(row, .) with the row part hoisted
+    *reinterpret_cast<uint4*>(slab + off) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (kX3) *reinterpret_cast<uint4*>(slab + kABytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+  }
+}
+
+template <int kFmt, bool kX3>
+__device__ __noinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* myA, int row, float& dens, int layer) {
+  float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)row & 7u;
+  uint32_t v0[32], v1[32];
+  tmem_ld32(t_acc, v0);
+#pragma unroll 1
+  for (int kk = 0; kk < 4; ++kk) {
+    tmem_ld_wait();
+    tmem_ld32(t_acc + 64 * kk + 32, v1);
+    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v0, layer, 64 * kk, myA, rowoff, rx, dpart);
+    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart);
+    else epilogue_chunk<kFmt, kX3, false, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart);
+    tmem_ld_wait();
+    if (kk < 3) tmem_ld32(t_acc + 64 * kk + 64, v0);
+    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart);
+    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart);
+    else epilogue_chunk<kFmt, kX3, false, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart);
+  }
+  if (layer == 7)
+    dens = ((dpart[0] + dpart[1]) + (dpart[2] + dpart[3])) + ((dpart[4] + dpart[5]) + (dpart[6] + dpart[7]));
+}
+
 // view layer epilogue + colour head (models/mip_nerf.py:108-110); vb = per-ray view-direction bias
 template <int kFmt>
 __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __restrict__ vb, float& rgb0,
@@ -313,6 +378,8 @@ __device__ __forceinline__ void ipe_row_group(const LevelParams& p, const RayGeo
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int f = gi * 8 + e;  // feature index = degree*3 + coord   (models/mip.py:335-341)
+        // (measured: the accurate sinf / expf in place of the MUFU pair changes the split modes' error against the
+        //  reference goldens by < 3 % — 1.06e-4 vs 1.08e-4 on the worst one — and costs 7x the IPE time: not used)
         ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fsin[e], fcos[e]);
       }
     }
@@ -582,13 +649,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       if (p.t_mode == 1) {
         // coarse fenceposts (bit-identical to coarse_t_kernel)
         const float nr = __ldg(p.near + ray), fr = __ldg(p.far + ray);
+        const bool jit = draws_active(p.t_rand);
         for (int j = lane; j <= kN; j += 32)
-          __stcg(t_ray + j, coarse_fencepost(nr, fr, j, kN, p.disparity,
-                                             p.t_rand ? p.t_rand + ray * (kN + 1) + j : nullptr));
+          __stcg(t_ray + j, coarse_fencepost(nr, fr, j, kN, p.disparity, jit,
+                                             jit ? draw_uniform(p.t_rand, ray, j, kN + 1) : 0.f));
       } else if (p.t_mode == 2 && early_scratch) {
-        resample_warp_lean<true>(p.t_prev + ray * (kN + 1), p.w_prev + ray * kN, kN, kN + 1, p.randomized,
-                                 p.u_jitter ? p.u_jitter + ray * (kN + 1) : nullptr, p.resample_padding, early_scratch,
-                                 t_ray, p.inds ? p.inds + ray * (kN + 1) : nullptr, lane);
+        resample_warp_lean<true>(p.t_prev + ray * (kN + 1), p.w_prev + ray * kN, kN, kN + 1, p.randomized, p.u_jitter,
+                                 ray, p.resample_padding, early_scratch, t_ray,
+                                 p.inds ? p.inds + ray * (kN + 1) : nullptr, lane);
       }
       if (p.vb_mode == 1) {
         // per-ray view-layer bias  b[n] + W[n, 256:283] . pos_enc(viewdir)   (models/mip.py:353-363,
@@ -633,9 +701,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       TRACE(EV(3, 0, 0, slot));
       if (p.t_mode == 2 && !early_scratch) {
         // no spare shared memory: the feature tile this warp is about to fill doubles as the scratch
-        resample_warp_lean<true>(p.t_prev + ray * (kN + 1), p.w_prev + ray * kN, kN, kN + 1, p.randomized,
-                                 p.u_jitter ? p.u_jitter + ray * (kN + 1) : nullptr, p.resample_padding,
-                                 reinterpret_cast<float*>(myF), t_ray, p.inds ? p.inds + ray * (kN + 1) : nullptr, lane);
+        resample_warp_lean<true>(p.t_prev + ray * (kN + 1), p.w_prev + ray * kN, kN, kN + 1, p.randomized, p.u_jitter,
+                                 ray, p.resample_padding, reinterpret_cast<float*>(myF), t_ray,
+                                 p.inds ? p.inds + ray * (kN + 1) : nullptr, lane);
         __threadfence_block();
         __syncwarp();
 #pragma unroll
@@ -709,16 +777,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           }
         }
         if (l < 9) {
-          switch (l) {
-            case 0: epilogue_trunk<kFmt, 0, kX3>(t_acc, myA, row, dens); break;
-            case 1: epilogue_trunk<kFmt, 1, kX3>(t_acc, myA, row, dens); break;
-            case 2: epilogue_trunk<kFmt, 2, kX3>(t_acc, myA, row, dens); break;
-            case 3: epilogue_trunk<kFmt, 3, kX3>(t_acc, myA, row, dens); break;
-            case 4: epilogue_trunk<kFmt, 4, kX3>(t_acc, myA, row, dens); break;
-            case 5: epilogue_trunk<kFmt, 5, kX3>(t_acc, myA, row, dens); break;
-            case 6: epilogue_trunk<kFmt, 6, kX3>(t_acc, myA, row, dens); break;
-            case 7: epilogue_trunk<kFmt, 7, kX3>(t_acc, myA, row, dens); break;
-            default: epilogue_trunk<kFmt, 8, kX3>(t_acc, myA, row, dens); break;
+          if (kX3 || MIPNERF_TC_ROLLED_EPILOGUE) {
+            epilogue_trunk_rolled<kFmt, kX3>(t_acc, myA, row, dens, l);
+          } else {
+            switch (l) {
+              case 0: epilogue_trunk<kFmt, 0, kX3>(t_acc, myA, row, dens); break;
+              case 1: epilogue_trunk<kFmt, 1, kX3>(t_acc, myA, row, dens); break;
+              case 2: epilogue_trunk<kFmt, 2, kX3>(t_acc, myA, row, dens); break;
+              case 3: epilogue_trunk<kFmt, 3, kX3>(t_acc, myA, row, dens); break;
+              case 4: epilogue_trunk<kFmt, 4, kX3>(t_acc, myA, row, dens); break;
+              case 5: epilogue_trunk<kFmt, 5, kX3>(t_acc, myA, row, dens); break;
+              case 6: epilogue_trunk<kFmt, 6, kX3>(t_acc, myA, row, dens); break;
+              case 7: epilogue_trunk<kFmt, 7, kX3>(t_acc, myA, row, dens); break;
+              default: epilogue_trunk<kFmt, 8, kX3>(t_acc, myA, row, dens); break;
+            }
           }
           TRACE(EV(2, 3, l, slot));
           fence_proxy_async_smem();
@@ -1177,6 +1249,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v2(const LevelPa
   if (warp == 0) tmem_dealloc_pair(tmem_base, 512);
 }
 
+#include "mlp_tc_v3.cuh"
+
 // view-direction term of the view layer as a per-ray bias: vb[r][n] = b[n] + W[n][256:283] . pos_enc(viewdir[r])
 // (models/mip.py:353-363 + the `cat([bottleneck, viewenc])` half of view_layers.0, models/mip_nerf.py:106-108).
 // Block = 128 threads (thread n = output n keeps its 27 weights in registers) x 16 rays whose 27-wide
@@ -1191,9 +1265,8 @@ __global__ void __launch_bounds__(kCond) ray_prologue_kernel(const float* __rest
                                                              const float* __restrict__ w, const float* __restrict__ b,
                                                              float* __restrict__ out, int64_t num_rays,
                                                              unsigned vb_blocks, const float* __restrict__ near,
-                                                             const float* __restrict__ far,
-                                                             const float* __restrict__ t_rand, float* __restrict__ t_out,
-                                                             int disparity) {
+                                                             const float* __restrict__ far, const Draws t_rand,
+                                                             float* __restrict__ t_out, int disparity) {
   __shared__ float venc[kVbRays][kViewDim + 1];
   const int n = threadIdx.x;
   if (blockIdx.x >= vb_blocks) {
@@ -1204,8 +1277,9 @@ __global__ void __launch_bounds__(kCond) ray_prologue_kernel(const float* __rest
       if (idx >= total) return;
       const int64_t ray = idx / (kN + 1);
       const int j = (int)(idx % (kN + 1));
-      t_out[idx] = coarse_fencepost(__ldg(near + ray), __ldg(far + ray), j, kN, disparity,
-                                    t_rand ? t_rand + idx : nullptr);
+      const bool jit = draws_active(t_rand);
+      t_out[idx] = coarse_fencepost(__ldg(near + ray), __ldg(far + ray), j, kN, disparity, jit,
+                                    jit ? draw_uniform(t_rand, ray, j, kN + 1) : 0.f);
     }
     return;
   }
@@ -1457,10 +1531,46 @@ cudaError_t launch_level_v2(const LevelParams& p, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, kern, q);
 }
 
-// MIPNERF_B200_TC_VARIANT: "shared" = CTA pair + shared weight stream (v2), "pair" = CTA pair (v1),
-// "single" = 1-CTA kernel (cta_group::1).
+bool g_attr_set3[2] = {false, false};
+
+template <int kFmt>
+cudaError_t launch_level_v3(const LevelParams& p, cudaStream_t st) {
+  auto kern = mlp_level_kernel_v3<kFmt>;
+  if (!g_attr_set3[kFmt]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal3);
+    if (e != cudaSuccess) return e;
+    g_attr_set3[kFmt] = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  LevelParams q = p;
+  LaunchScope scope(p.feat_in ? kKernMlpTc : kKernMlpLevelTc, st);
+  const int64_t duos = (p.num_rays + 1) / 2;  // a CTA pair holds 2 rays at a time
+  const int pairs = (int)(duos < g_num_sms / 2 ? duos : g_num_sms / 2);
+  q.rounds = (int)((p.num_rays + 2 * (int64_t)pairs - 1) / (2 * (int64_t)pairs));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemTotal3;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, q);
+}
+
+// MIPNERF_B200_TC_VARIANT: "v3" = activations in tensor memory, one ray per CTA (mlp_tc_v3.cuh), "shared" = CTA pair +
+// shared weight stream (v2), "pair" = CTA pair (v1), "single" = 1-CTA kernel (cta_group::1).
 int tc_variant() {
   const char* v = getenv("MIPNERF_B200_TC_VARIANT");
+  if (v && v[0] == 'v' && v[1] == '3') return 3;
   if (v && v[0] == 's' && v[1] == 'i') return 0;
   if (v && v[0] == 's' && v[1] == 'h') return 2;
   if (v && v[0] == 'p') return 1;
@@ -1471,12 +1581,14 @@ bool use_pair_variant() { return tc_variant() != 0; }
 // default: produced inside the v1 level kernels.
 bool fused_prologue_enabled(int precision) {
   const char* v = getenv("MIPNERF_B200_TC_PROLOGUE");
-  return (is_x3(precision) || tc_variant() != 2) && !(v && v[0] == 's');
+  return (is_x3(precision) || tc_variant() < 2) && !(v && v[0] == 's');
 }
 
 cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
   if (is_x3(precision))  // split-operand parity modes: the CTA-pair kernel, whatever variant is selected
     return fmt_of(precision) ? launch_level_t<1, true, true>(p, st) : launch_level_t<0, true, true>(p, st);
+  if (tc_variant() == 3)
+    return precision == MIPNERF_B200_BF16 ? launch_level_v3<1>(p, st) : launch_level_v3<0>(p, st);
   if (tc_variant() == 2)
     return precision == MIPNERF_B200_BF16 ? launch_level_v2<1>(p, st) : launch_level_v2<0>(p, st);
   const bool pair = use_pair_variant();
@@ -1515,7 +1627,7 @@ bool tc_mlp_supported(const mipnerf_b200_config* c, int samples_per_ray, int pre
 }
 
 size_t tc_packed_bytes(const mipnerf_b200_config* c, int precision) {
-  return tc_supported(c, precision) ? kImageBytes + (is_x3(precision) ? kLoBytes : 0) : 0;
+  return tc_supported(c, precision) ? kV3Offset + kV3Bytes : 0;
 }
 
 size_t tc_workspace_bytes(const mipnerf_b200_config* c, int64_t num_rays, int precision) {
@@ -1530,7 +1642,7 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
   uint8_t* img = static_cast<uint8_t*>(packed_out);
   const bool bf = fmt_of(precision) == 1;
   const int parts = is_x3(precision) ? 2 : 1;  // hi image, then (split modes) the lo stage image
-  cudaError_t e = cudaMemsetAsync(img, 0, kImageBytes + (parts == 2 ? kLoBytes : 0), st);
+  cudaError_t e = cudaMemsetAsync(img, 0, kV3Offset + kV3Bytes, st);
   if (e != cudaSuccess) return e;
   LaunchScope scope(kKernPackWeights, st);
   for (int part = 0; part < parts; ++part) {
@@ -1566,6 +1678,28 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
         }
     }
   }
+  // v3 blocks: per layer, per CTA rank, in the kernel's issue order (mlp_tc_v3.cuh: Sched3)
+  for (int l = 0; l < kNumLayers; ++l) {
+    const int li = l < 8 ? l : (l == 8 ? 9 : 10);
+    const mipnerf_b200_linear& lin = w->linears[li];
+    const int type = layer_type3(l), nb = sched_count3(type);
+    const int fbase = l == 5 ? kWidth : 0;  // K offset of the feature columns: layer 5 is [h (256) | x (96)]
+    for (int r = 0; r < 2; ++r) {
+      uint8_t* dst = img + kV3Offset + layer_offset3(l) + (size_t)r * (layer_bytes3(l) / 2);
+      for (int b = 0; b < nb; ++b, dst += kBlk3) {
+        const Blk3 blk = kSched3Host.blk[type][b];
+        const int row0 = 64 * blk.nq + 32 * r;
+        const int kbase = blk.kind < 4 ? 64 * blk.kind : (blk.kind == 4 ? fbase : fbase + 64);
+        const int kcount = blk.kind == 5 ? 32 : 64;
+        if (bf)
+          pack_stage_kernel<1><<<(32 * kcount + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, row0, kbase, kcount,
+                                                                         dst, 32, 0);
+        else
+          pack_stage_kernel<0><<<(32 * kcount + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, row0, kbase, kcount,
+                                                                         dst, 32, 0);
+      }
+    }
+  }
   SmallSrc src;
   for (int l = 0; l < 8; ++l) src.bias[l] = w->linears[l].bias;
   src.bias[8] = w->linears[9].bias;  // extra_layer
@@ -1580,9 +1714,20 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
   return cudaGetLastError();
 }
 
+// The uniforms of one launch: rows `off..` of the caller's array, or the in-kernel generator (stream 0 = t_rand,
+// 1 + level = that level's u_jitter, scaled like uniform_(to = 1/ncols - eps), models/mip.py:201-202).
+Draws level_draws(int randomized, const float* array, const mipnerf_b200_rng* rng, int64_t off, int stream, int ncols) {
+  if (!randomized) return draws_from_array(nullptr);
+  if (array) return draws_from_array(array + off * ncols);
+  if (!rng) return draws_from_array(nullptr);
+  const float scale = stream == 0 ? 1.0f : (float)(1.0 / (double)ncols) - MIPNERF_F32_EPS;
+  return draws_philox(rng->seed, rng->offset, off, stream, scale);
+}
+
 cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights* w, const mipnerf_b200_rays* rays,
-                       int randomized, const float* t_rand, const float* u_jitter, int white_bkgd, int precision,
-                       mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                       int randomized, const float* t_rand, const float* u_jitter, const mipnerf_b200_rng* rng,
+                       int white_bkgd, int precision, mipnerf_b200_level_out* outs, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
   const uint8_t* img = static_cast<const uint8_t*>(w->packed);
   SmallUpload small(img, st);  // biases / heads -> constant bank, ordered against other streams' forwards
   cudaError_t e = small.error();
@@ -1606,14 +1751,14 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
       const unsigned ct_blocks = (unsigned)((cnt * (kN + 1) + kCoarsePerBlock - 1) / kCoarsePerBlock);
       ray_prologue_kernel<<<vb_blocks + ct_blocks, kCond, 0, st>>>(
           rays->viewdirs + off * 3, view.weight, view.bias, s.vbias, cnt, vb_blocks, rays->near + off, rays->far + off,
-          (randomized && t_rand) ? t_rand + off * (kN + 1) : nullptr, t0, c->disparity);
+          level_draws(randomized, t_rand, rng, off, 0, kN + 1), t0, c->disparity);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     const float *t_prev = nullptr, *w_prev = nullptr;
     for (int l = 0; l < c->num_levels; ++l) {
       float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (kN + 1) : s.t[l & 1];
       float* w_cur = outs[l].weights ? outs[l].weights + off * kN : s.w[l & 1];
-      const float* jit = (randomized && u_jitter) ? u_jitter + off * (kN + 1) : nullptr;
+      const Draws jit = level_draws(randomized, u_jitter, rng, off, 1 + l, kN + 1);  // one stream per level
       int64_t* inds = outs[l].inds ? outs[l].inds + off * (kN + 1) : nullptr;
       if (l > 0 && !fused_prologue) {
         e = launch_resample(t_prev, w_prev, jit, t_cur, inds, cnt, kN, kN + 1, randomized, 1, c->resample_padding, st);
@@ -1628,7 +1773,7 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
         p.t_mode = l == 0 ? 1 : 2;
         p.vb_mode = l == 0 ? 1 : 0;  // level 0 leaves the per-ray bias in s.vbias for the later levels
         p.near = rays->near + off, p.far = rays->far + off;
-        p.t_rand = (randomized && t_rand) ? t_rand + off * (kN + 1) : nullptr;
+        p.t_rand = level_draws(randomized, t_rand, rng, off, 0, kN + 1);
         p.disparity = c->disparity;
         p.t_prev = t_prev, p.w_prev = w_prev;
         p.u_jitter = jit;
@@ -1681,6 +1826,7 @@ cudaError_t tc_mlp_forward(const mipnerf_b200_config* c, const mipnerf_b200_weig
   // MLP-only mode lives in the v1 kernels (CTA pair unless MIPNERF_B200_TC_VARIANT=single)
   if (is_x3(precision))
     return fmt_of(precision) ? launch_level_t<1, true, true>(p, st) : launch_level_t<0, true, true>(p, st);
+  if (tc_variant() == 3) return precision == MIPNERF_B200_BF16 ? launch_level_v3<1>(p, st) : launch_level_v3<0>(p, st);
   const bool pair = tc_variant() != 0;
   if (precision == MIPNERF_B200_BF16) return pair ? launch_level_t<1, true>(p, st) : launch_level_t<1, false>(p, st);
   return pair ? launch_level_t<0, true>(p, st) : launch_level_t<0, false>(p, st);

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/mipnerf_b200.h"
+#include "draws.h"
 
 namespace mipnerf {
 
@@ -17,8 +18,10 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* cfg, const mipnerf_b200_w
                             void* packed_out, cudaStream_t st);
 cudaError_t tc_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
                        const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
-                       const float* u_jitter, int white_bkgd, int precision, mipnerf_b200_level_out* outs,
-                       void* workspace, size_t workspace_bytes, cudaStream_t st);
+                       const float* u_jitter, const mipnerf_b200_rng* rng, int white_bkgd, int precision,
+                       mipnerf_b200_level_out* outs, void* workspace, size_t workspace_bytes, cudaStream_t st);
+// the uniforms of one launch (see mlp_tc.cu)
+Draws level_draws(int randomized, const float* array, const mipnerf_b200_rng* rng, int64_t off, int stream, int ncols);
 cudaError_t tc_mlp_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w, const float* x,
                            const float* view_enc, int64_t num_rays, int precision, float* raw_rgb,
                            float* raw_density, void* workspace, cudaStream_t st);

@@ -1,0 +1,576 @@
+// mlp_tc_v3.cuh — "v3": the level kernel with the ACTIVATIONS IN TENSOR MEMORY (included into mlp_tc.cu's namespace).
+//
+// Why: in v1 every layer-slot moves 256 KB through the 128 B/clk shared-memory port (A reads 64 + B reads 64 + weight
+// stage writes 64 + epilogue stores 64) in the 2048 cycles its MMAs need, i.e. the port is saturated exactly when the
+// tensor pipe is, and the clock64 trace shows both effects: MMA phases 30 % longer than their ideal and epilogues 2.3x
+// longer when they overlap the other slot's MMAs.  Here the A operand never touches shared memory:
+//   * tile = ONE ray per CTA (M = 128 rows; CTA pair M = 256), accumulator 256 fp32 TMEM columns, and TWO 16-bit
+//     activation buffers of 128 TMEM columns each (2 elements per column): layer l reads A[(l-1)&1] with the TS form of
+//     tcgen05.mma (A from TMEM, B from shared memory) and its epilogue writes A[l&1] with tcgen05.st — no in-place
+//     hazard, no st.shared, no fence.proxy.async; shared memory carries only the weight stream (B reads 64 KB + stage
+//     writes 64 KB per layer: half the port) and the 24 KB feature tile of layers 0 / 5 (SS form).
+//   * a layer is cut into 4 x 4 blocks (N quarter nq x K quarter kq; one block = 4 MMAs of M256 N64 K16 = 128 cycles)
+//     issued in SHELL order (max(nq,kq) = 0,1,2,3): block (nq,kq) needs only the previous layer's epilogue of quarters
+//     kq (its A columns) and nq (its accumulator columns drained), so the next layer's first 9 blocks run while the
+//     last quarter of the previous epilogue is still converting, and the epilogue of quarter q starts as soon as the
+//     blocks (q, 0..3) are done.  One ray per CTA keeps the tensor pipe busy by itself; no second slot is needed.
+//   * the weight ring is 32 stages x 4 KB (one block per stage; two layers of look-ahead), packed in issue order.
+//   * worker warps: two groups of four (thread = sample row = TMEM lane); group 0 converts quarters 0 / 2, group 1
+//     quarters 1 / 3; group 1 composites the finished ray while group 0 alone converts the next ray's layer 0.
+// Fenceposts and the per-ray view bias come from the separate prologue / resample launches (t_mode = vb_mode = 0).
+#pragma once
+
+constexpr int kStages3 = 32;
+constexpr uint32_t kBlk3 = 4096;                             // one stage: [32 rows x 64 K] SW128, or [32 x 32] SW64 (2 KB used)
+constexpr uint32_t kSmemF3 = 0;                              // 2 feature tiles (ray parity)
+constexpr uint32_t kSmemW3 = 2 * kFBytes;
+constexpr uint32_t kSmemMisc3 = kSmemW3 + kStages3 * kBlk3;
+constexpr int kNumBars3 = 2 * kStages3 + 4 + 4 + 2 + 2;      // w_full, w_empty, acc_full[4], epi_done[4], f_ready[2], f_free[2]
+constexpr uint32_t kBarBytes3 = (kNumBars3 * 8 + 127) / 128 * 128;
+//   misc: barriers | tmem slot (16) | vb_s[128] | dens_part[4][128] | rgb_part[2][3][128] | cs[4] | ps[4][8]
+constexpr uint32_t kMisc3Bytes = kBarBytes3 + 16 + 128 * 4 + 4 * 128 * 4 + 6 * 128 * 4 + 4 * 4 + 4 * 8 * 4;
+constexpr uint32_t kSmemTotal3 = kSmemMisc3 + kMisc3Bytes + 1024;
+static_assert(kSmemTotal3 <= 232448, "exceeds 227 KB of shared memory per CTA");
+constexpr uint32_t kAccCols3 = 0, kACols3 = 256;             // TMEM columns: accumulator | A[0] (128) | A[1] (128)
+
+// ---- static block schedule -------------------------------------------------------------------------------------------
+// kind 0..3: TS block, K quarter `kind` of the TMEM activations; 4: feature K 0..63 (SS, SW128); 5: feature K 64..95 (SS, SW64)
+struct Blk3 {
+  uint8_t nq, kind, wait_q, flags;
+};
+constexpr uint8_t kB3First = 1, kB3AccFull = 2, kB3FFree = 4, kB3FReady = 8, kNoWait = 0xFF;
+// layer types: 0 = layer 0 (features only), 1 = 256-wide TS layer, 2 = layer 5 (TS + features), 3 = view layer (N = 128)
+constexpr int kSchedMax = 24;
+struct Sched3 {
+  Blk3 blk[4][kSchedMax];
+  int count[4];
+};
+constexpr Sched3 make_sched3() {
+  Sched3 s{};
+  {  // layer 0: accumulator quarters in the order they are known to be drained (2, 3 by the bottleneck epilogue, 0, 1 by the
+     // previous ray's view epilogue)
+    int n = 0;
+    const uint8_t order[4] = {2, 3, 0, 1};
+    for (int i = 0; i < 4; ++i) {
+      const uint8_t q = order[i];
+      s.blk[0][n++] = Blk3{q, 4, (uint8_t)(q < 2 ? q : kNoWait), (uint8_t)(kB3First | (i == 0 ? kB3FReady : 0))};
+      s.blk[0][n++] = Blk3{q, 5, kNoWait, kB3AccFull};
+    }
+    s.count[0] = n;
+  }
+  for (int type = 1; type <= 2; ++type) {  // shells
+    int n = 0;
+    for (int sh = 0; sh < 4; ++sh) {
+      bool waited = false;
+      auto wq = [&]() -> uint8_t {
+        if (waited) return kNoWait;
+        waited = true;
+        return (uint8_t)sh;
+      };
+      if (type == 2) {  // layer 5: the feature part of accumulator quarter `sh` opens the shell
+        s.blk[type][n++] = Blk3{(uint8_t)sh, 4, wq(), kB3First};
+        s.blk[type][n++] = Blk3{(uint8_t)sh, 5, kNoWait, (uint8_t)(sh == 3 ? kB3FFree : 0)};
+      }
+      for (int nq = 0; nq < sh; ++nq)  // (nq, sh): completes accumulator quarter nq when sh == 3
+        s.blk[type][n++] = Blk3{(uint8_t)nq, (uint8_t)sh, wq(), (uint8_t)(sh == 3 ? kB3AccFull : 0)};
+      for (int kq = 0; kq <= sh; ++kq)  // (sh, kq)
+        s.blk[type][n++] = Blk3{(uint8_t)sh, (uint8_t)kq, wq(),
+                                (uint8_t)(((type == 1 && kq == 0) ? kB3First : 0) | ((sh == 3 && kq == 3) ? kB3AccFull : 0))};
+    }
+    s.count[type] = n;
+  }
+  {  // view layer: N = 128 -> accumulator quarters 0, 1
+    int n = 0;
+    for (int sh = 0; sh < 4; ++sh) {
+      bool waited = false;
+      auto wq = [&]() -> uint8_t {
+        if (waited) return kNoWait;
+        waited = true;
+        return (uint8_t)sh;
+      };
+      for (int nq = 0; nq < 2 && nq < sh; ++nq)
+        s.blk[3][n++] = Blk3{(uint8_t)nq, (uint8_t)sh, wq(), (uint8_t)(sh == 3 ? kB3AccFull : 0)};
+      if (sh < 2)
+        for (int kq = 0; kq <= sh; ++kq)
+          s.blk[3][n++] = Blk3{(uint8_t)sh, (uint8_t)kq, wq(), (uint8_t)(kq == 0 ? kB3First : 0)};
+    }
+    s.count[3] = n;
+  }
+  return s;
+}
+__constant__ Sched3 c_sched3 = make_sched3();
+constexpr Sched3 kSched3Host = make_sched3();
+static_assert(kSched3Host.count[0] == 8 && kSched3Host.count[1] == 16 && kSched3Host.count[2] == 24 &&
+                  kSched3Host.count[3] == 8,
+              "block schedule");
+__host__ __device__ constexpr int layer_type3(int l) { return l == 0 ? 0 : (l == 5 ? 2 : (l == 9 ? 3 : 1)); }
+__host__ __device__ constexpr int sched_count3(int type) { return type == 0 ? 8 : (type == 1 ? 16 : (type == 2 ? 24 : 8)); }
+// v3 weight image: per layer, per CTA rank, the layer's blocks in schedule order, 4 KB slots
+__host__ __device__ constexpr uint32_t layer_bytes3(int l) { return 2u * sched_count3(layer_type3(l)) * kBlk3; }
+__host__ __device__ constexpr uint32_t layer_offset3(int l) {
+  uint32_t o = 0;
+  for (int i = 0; i < l; ++i) o += layer_bytes3(i);
+  return o;
+}
+constexpr size_t kV3Bytes = layer_offset3(kNumLayers);
+
+// D[tmem] (+)= A[tmem] * B[smem]^T over the CTA pair; descriptors as {lo, hi} halves
+__device__ __forceinline__ void umma_ts_pair_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// quarter epilogue of a 256-wide layer L: 64 accumulator columns -> +bias -> ReLU (L < 8) -> 16 bit -> 32 TMEM columns of
+// the next layer's A operand.  L == 7 also returns this quarter's share of the density head (fp32, un-rounded h7).
+template <int kFmt, int L>
+__device__ __forceinline__ float epilogue_quarter3(uint32_t t_acc_q, uint32_t t_a_q, int q) {
+  float dpart[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t v[2][32];
+  tmem_ld32(t_acc_q, v[0]);
+  tmem_ld32(t_acc_q + 32, v[1]);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (k == 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    uint32_t w[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int c = 64 * q + 32 * k + 2 * e;  // bias index: runtime q -> constant bank with a register offset
+      float a = __uint_as_float(v[k][2 * e]), b = __uint_as_float(v[k][2 * e + 1]);
+      fadd2(a, b, c_small.bias[L][c], c_small.bias[L][c + 1]);
+      if (L == 7)
+        ffma2(dpart[e & 1 ? 2 : 0], dpart[e & 1 ? 3 : 1], fmaxf(a, 0.f), fmaxf(b, 0.f), c_small.w_density[c],
+              c_small.w_density[c + 1]);
+      w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
+    }
+    tmem_st16(t_a_q + 16 * k, w);
+  }
+  tmem_st_wait();
+  return (dpart[0] + dpart[1]) + (dpart[2] + dpart[3]);
+}
+
+// view-layer quarter (64 of its 128 outputs): +per-ray view bias -> ReLU -> this quarter's share of the colour head
+template <int kFmt>
+__device__ __forceinline__ void epilogue_view_quarter3(uint32_t t_acc_q, const float* __restrict__ vb, int q, float& r0,
+                                                       float& r1, float& r2) {
+  float acc[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  uint32_t v[2][32];
+  tmem_ld32(t_acc_q, v[0]);
+  tmem_ld32(t_acc_q + 32, v[1]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 2) {
+      const int c = 64 * q + 32 * k + e;
+      float y0 = __uint_as_float(v[k][e]), y1 = __uint_as_float(v[k][e + 1]);
+      fadd2(y0, y1, vb[c], vb[c + 1]);
+      y0 = fmaxf(y0, 0.f), y1 = fmaxf(y1, 0.f);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) ffma2(acc[ch][0], acc[ch][1], y0, y1, c_small.w_color[ch][c], c_small.w_color[ch][c + 1]);
+    }
+  }
+  r0 = acc[0][0] + acc[0][1];
+  r1 = acc[1][0] + acc[1][1];
+  r2 = acc[2][0] + acc[2][1];
+}
+
+// trace build: cumulative clock64 counters of CTA 0 (g_trace[16 + i]); see tools/v3_counters.py
+#ifdef MIPNERF_TC_TRACE
+#define V3_CLK() clock64()
+#define V3_ADD(slot, t0) v3c[slot] += clock64() - (t0)
+#define V3_DECL long long v3c[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define V3_FLUSH(base)                                                       \
+  if (blockIdx.x == 0 && g_trace) {                                          \
+    for (int i_ = 0; i_ < 8; ++i_) g_trace[16 + (base) + i_] = (unsigned long long)v3c[i_]; \
+  }
+#else
+#define V3_CLK() 0
+#define V3_ADD(slot, t0) ((void)(t0))
+#define V3_DECL ((void)0)
+#define V3_FLUSH(base) ((void)0)
+#endif
+
+template <int kFmt>
+__global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel_v3(const LevelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sF = smem + kSmemF3;
+  uint8_t* sW = smem + kSmemW3;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemMisc3);
+  uint64_t* w_full = bars;                          // [32] producer (+ peer relay) -> MMA            (tx bytes)
+  uint64_t* w_empty = bars + kStages3;              // [32] MMA -> producers of both CTAs             (tcgen05.commit)
+  uint64_t* acc_full = bars + 2 * kStages3;         // [4]  MMA -> workers: accumulator quarter complete
+  uint64_t* epi_done = bars + 2 * kStages3 + 4;     // [4]  workers (both CTAs) -> MMA: quarter drained, A quarter written
+  uint64_t* f_ready = bars + 2 * kStages3 + 8;      // [2]  IPE warps (both CTAs) -> MMA: feature tile of parity written
+  uint64_t* f_free = bars + 2 * kStages3 + 10;      // [2]  MMA -> IPE warps: layer 5 has read the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc3 + kBarBytes3);
+  float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc3 + kBarBytes3 + 16);  // [128] view bias of the ray
+  float* dens_part = vb_s + 128;                                                // [4][128]
+  float* rgb_part = dens_part + 4 * 128;                                        // [2][3][128]
+  float* cs = rgb_part + 6 * 128;                                               // [4] scan carries
+  float* ps = cs + 4;                                                           // [4][8] partial sums
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (tid == 0) {
+    for (int i = 0; i < kStages3; ++i) {
+      mbar_init(&w_full[i], leader ? 2 : 1);  // leader: own producer + the peer's relay
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int q = 0; q < 4; ++q) {
+      mbar_init(&acc_full[q], 1);
+      mbar_init(&epi_done[q], 8);  // 4 worker warps of the owning group, in both CTAs
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&f_ready[s], 4);  // 2 IPE warps x 2 CTAs
+      mbar_init(&f_free[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int rounds = p.rounds;
+  auto tile_of = [&](int round) -> int64_t {
+    return ((int64_t)round * (gridDim.x >> 1) + (blockIdx.x >> 1)) * 2 + rank;
+  };
+
+  if (warp == 0) {
+    // ============================ weight producer: this CTA's half of every block, in issue order ============
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int round = 0; round < rounds; ++round)
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int type = layer_type3(l), nb = sched_count3(type);
+          const uint8_t* src = p.wimage + kV3Offset + layer_offset3(l) + rank * (layer_bytes3(l) / 2);
+          for (int b = 0; b < nb; ++b) {
+            const uint32_t bytes = c_sched3.blk[type][b].kind == 5 ? kBlk3 / 2 : kBlk3;
+            mbar_wait(&w_empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&w_full[st], bytes);
+            bulk_g2s(sW + st * kBlk3, src + (uint32_t)b * kBlk3, bytes, &w_full[st]);
+            if (++st == kStages3) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader) / stage relay (peer) ============================
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sF_u = __shfl_sync(0xffffffffu, smem_u32(sF), 0);
+    const uint32_t sW_u = __shfl_sync(0xffffffffu, smem_u32(sW), 0);
+    const uint32_t bars_u = __shfl_sync(0xffffffffu, smem_u32(bars), 0);
+    const uint32_t rank_u = __shfl_sync(0xffffffffu, rank, 0);
+    if (elect_one_sync()) {
+      if (rank_u == 0) {
+        const uint32_t idesc = make_idesc_f16(256, 64, kFmt);
+        const uint32_t acc_full_u = bars_u + (2 * kStages3) * 8, epi_done_u = bars_u + (2 * kStages3 + 4) * 8,
+                       f_ready_u = bars_u + (2 * kStages3 + 8) * 8, f_free_u = bars_u + (2 * kStages3 + 10) * 8;
+        uint32_t st = 0, wph = 0;
+        uint32_t ph_epi = 0;  // bit q: parity of the next epi_done[q] completion to consume
+        V3_DECL;
+        const long long v3_start = V3_CLK();
+        for (int round = 0; round < rounds; ++round) {
+          const uint32_t par = round & 1, ph_f = (round >> 1) & 1;
+          const uint32_t f_base = sF_u + par * kFBytes;
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int type = layer_type3(l), nb = sched_count3(type);
+            const uint32_t a_cols = tm_u + kACols3 + (((l - 1) & 1) ? 128u : 0u);  // layer l reads A[(l-1)&1]
+            for (int b = 0; b < nb; ++b) {
+              const Blk3 blk = c_sched3.blk[type][b];
+              if (blk.flags & kB3FReady) {
+                const long long t_ = V3_CLK();
+                mbar_wait_fast(f_ready_u + par * 8, ph_f);
+                V3_ADD(0, t_);
+              }
+              if (blk.wait_q != kNoWait) {
+                const long long t_ = V3_CLK();
+                mbar_wait_fast(epi_done_u + blk.wait_q * 8, (ph_epi >> blk.wait_q) & 1u);
+                ph_epi ^= 1u << blk.wait_q;
+                V3_ADD(1 + (l == 0 ? 0 : (blk.wait_q == 3 ? 2 : 1)), t_);  // 1: layer-0 waits, 2: q0-2, 3: q3
+              }
+              {
+                const long long t_ = V3_CLK();
+                mbar_wait_fast(bars_u + st * 8, wph);  // w_full[st]: both CTAs' halves landed
+                V3_ADD(4, t_);
+              }
+              tc_fence_after();
+              const uint32_t d_tmem = tm_u + kAccCols3 + 64u * blk.nq;
+              const uint32_t b_lo = desc_lo(sW_u + st * kBlk3);
+              uint32_t accumulate = (blk.flags & kB3First) ? 0u : 1u;
+              if (blk.kind < 4) {
+                const uint32_t a0 = a_cols + 32u * blk.kind;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  umma_ts_pair_lohi(d_tmem, a0 + 8u * j, b_lo + 2u * j, kDescHiSw128, idesc, accumulate);
+                  accumulate = 1u;
+                }
+              } else if (blk.kind == 4) {
+                const uint32_t a_lo = desc_lo(f_base);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  umma_ss_pair_lohi(d_tmem, a_lo + 2u * j, kDescHiSw128, b_lo + 2u * j, kDescHiSw128, idesc, accumulate);
+                  accumulate = 1u;
+                }
+              } else {
+                const uint32_t a_lo = desc_lo(f_base + kStageBytes);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  umma_ss_pair_lohi(d_tmem, a_lo + 2u * j, kDescHiSw64, b_lo + 2u * j, kDescHiSw64, idesc, 1u);
+              }
+              umma_commit_pair_addr(bars_u + (kStages3 + st) * 8);  // stage free in both CTAs once these MMAs are done
+              if (blk.flags & kB3AccFull) umma_commit_pair_addr(acc_full_u + blk.nq * 8);
+              if (blk.flags & kB3FFree) umma_commit_pair_addr(f_free_u + par * 8);
+              if (++st == (uint32_t)kStages3) {
+                st = 0;
+                wph ^= 1;
+              }
+            }
+          }
+        }
+        V3_ADD(5, v3_start);  // total
+        V3_FLUSH(0);
+      } else {
+        // peer CTA: relay "my half of stage st has landed" to the leader's w_full[st], in fill order
+        uint32_t st = 0, wph = 0;
+        const uint32_t leader_w_full = mapa_u32(bars_u, 0);
+        for (int round = 0; round < rounds; ++round)
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int nb = sched_count3(layer_type3(l));
+            for (int b = 0; b < nb; ++b) {
+              mbar_wait_fast(bars_u + st * 8, wph);
+              mbar_arrive_remote(leader_w_full + st * 8);
+              if (++st == (uint32_t)kStages3) {
+                st = 0;
+                wph ^= 1;
+              }
+            }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 10) {
+    // ============================ IPE warps: 64 rows each of the ray's feature tile, one ray ahead ============
+    const int half = warp - 10;
+    const uint32_t f_ready_leader = mapa_u32(smem_u32(f_ready), 0);
+    V3_DECL;
+    for (int round = 0; round < rounds; ++round) {
+      const int par = round & 1;
+      uint8_t* myF = sF + par * kFBytes;
+      const int64_t tile = tile_of(round);
+      const int64_t ray = tile < p.num_rays ? tile : p.num_rays - 1;
+      RayGeom g{};
+      if (!p.feat_in) g = load_ray_geom(p.origins, p.directions, p.radii, ray);
+      const float* t_ray = p.t + ray * (kN + 1);
+      float tq[2][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = (2 * half + i) * 32 + lane;
+        tq[i][0] = p.feat_in ? 0.f : __ldg(t_ray + row);
+        tq[i][1] = p.feat_in ? 0.f : __ldg(t_ray + row + 1);
+      }
+      // the tile of this parity was last read by layer 5 of ray (round - 2): f_free completion number (round>>1) - 1
+      const long long t_w_ = V3_CLK();
+      mbar_wait(&f_free[par], ((uint32_t)(round >> 1) & 1u) ^ 1u);  // first use of each tile falls through
+      V3_ADD(0, t_w_);
+      const long long t_c_ = V3_CLK();
+      ipe_row_group<kFmt, false>(p, g, ray, (2 * half) * 32 + lane, tq[0][0], tq[0][1], myF);
+      ipe_row_group<kFmt, false>(p, g, ray, (2 * half + 1) * 32 + lane, tq[1][0], tq[1][1], myF);
+      V3_ADD(1, t_c_);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(f_ready_leader + par * 8);
+    }
+    if (lane == 0 && half == 0) { V3_FLUSH(24); }
+  } else {
+    // ============================ workers: group 0 = warps 2-5, group 1 = warps 6-9 ============================
+    // Every worker follows EVERY accumulator completion in commit order (that keeps the mbarrier parities honest:
+    // nobody can fall two phases behind) and converts the quarters it owns: group 0 quarters 0 / 2, group 1 quarters
+    // 1 / 3.  Group 1 also composites: the heads of ray r are final after its view epilogue, but the outputs are
+    // needed by nobody inside the kernel, so group 1 first serves layer 0 of ray r+1 (whose accumulators complete
+    // right behind the view layer) and composites ray r while layer 1 of ray r+1 runs.
+    const int grp = (warp - 2) >> 2;
+    const int lq = warp & 3;  // TMEM lane quarter this warp may access == sample quarter
+    const int row = lq * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    const uint32_t epi_done_leader = mapa_u32(smem_u32(epi_done), 0);
+    uint32_t ph_acc = 0;  // bit q: parity of the next acc_full[q] completion
+    auto arrive_epi = [&](int q) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(epi_done_leader + q * 8);
+    };
+    V3_DECL;
+    auto wait_acc = [&](int q) {
+      const long long t_ = V3_CLK();
+      mbar_wait(&acc_full[q], (ph_acc >> q) & 1u);
+      ph_acc ^= 1u << q;
+      tc_fence_after();
+      V3_ADD(0, t_);
+    };
+    // pending composite of group 1: the previous ray's per-row operands
+    bool pend = false, pend_valid = false;
+    int64_t pend_ray = 0;
+    float t0 = 0.f, t1 = 0.f, dnorm = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+    auto composite = [&]() {
+      named_bar_sync(4, 256);  // group 0's colour partials of that ray are in shared memory
+      const int64_t ray = pend_ray;
+      const bool valid = pend_valid;
+      const float c0 = rgb0 + rgb_part[0 * 128 + row], c1 = rgb1 + rgb_part[1 * 128 + row],
+                  c2 = rgb2 + rgb_part[2 * 128 + row];
+      const float dens = (dens_part[row] + dens_part[128 + row]) + (dens_part[256 + row] + dens_part[384 + row]);
+      pend = false;
+      if (p.raw_rgb_out) {  // MLP-only mode: hand back the raw heads (models/mip_nerf.py:98,110)
+        if (valid) {
+          const int64_t sidx = ray * kN + row;
+          p.raw_rgb_out[sidx * 3 + 0] = c0 + c_small.b_color[0];
+          p.raw_rgb_out[sidx * 3 + 1] = c1 + c_small.b_color[1];
+          p.raw_rgb_out[sidx * 3 + 2] = c2 + c_small.b_color[2];
+          p.raw_density_out[sidx] = dens + c_small.b_density;
+        }
+        return;
+      }
+      // ---- activations + compositing over the ray's 128 samples (the four warps of group 1)
+      const float density = density_activation(dens + c_small.b_density, p.density_bias);
+      const float cr = rgb_activation(c0 + c_small.b_color[0], p.rgb_scale, p.rgb_padding);
+      const float cg = rgb_activation(c1 + c_small.b_color[1], p.rgb_scale, p.rgb_padding);
+      const float cb = rgb_activation(c2 + c_small.b_color[2], p.rgb_scale, p.rgb_padding);
+      const float dd = density * ((t1 - t0) * dnorm);
+      float incl = dd;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 0.f;
+      if (lane == 31) cs[lq] = incl;
+      named_bar_sync(2, 128);
+      float before = 0.f;
+      for (int qq = 0; qq < lq; ++qq) before += cs[qq];
+      const float w = -expm1f(-dd) * expf(-(before + excl));
+      if (valid) p.weights[ray * kN + row] = w;
+      float pr = warp_sum(w * cr), pg = warp_sum(w * cg), pb = warp_sum(w * cb), pw = warp_sum(w),
+            pd = warp_sum(w * (0.5f * (t0 + t1)));
+      if (lane == 0) {
+        float* dst = ps + lq * 8;
+        dst[0] = pr, dst[1] = pg, dst[2] = pb, dst[3] = pw, dst[4] = pd;
+      }
+      named_bar_sync(2, 128);
+      if (row == 0 && valid) {
+        float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int qq = 0; qq < 4; ++qq)
+          for (int k = 0; k < 5; ++k) s[k] += ps[qq * 8 + k];
+        const float t_first = __ldg(p.t + ray * (kN + 1)), t_last = __ldg(p.t + ray * (kN + 1) + kN);
+        float d = s[4];
+        if (isnan(d)) d = 0.f;
+        else if (isinf(d)) d = d > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+        d = fminf(fmaxf(d, t_first), t_last);
+        const float bg = p.white_bkgd ? 1.0f - s[3] : 0.f;
+        p.comp_rgb[ray * 3 + 0] = s[0] + bg;
+        p.comp_rgb[ray * 3 + 1] = s[1] + bg;
+        p.comp_rgb[ray * 3 + 2] = s[2] + bg;
+        p.distance[ray] = d;
+        p.acc[ray] = s[3];
+      }
+      named_bar_sync(2, 128);  // row 0 has consumed ps / everyone cs before the next ray reuses them
+    };
+    // stand-in for "the previous ray's view epilogue has drained accumulator quarters 0 / 1"
+    arrive_epi(grp);
+    for (int round = 0; round < rounds; ++round) {
+      const int64_t tile = tile_of(round);
+      const bool valid = tile < p.num_rays;
+      const int64_t ray = valid ? tile : p.num_rays - 1;
+      float n_t0 = 0.f, n_t1 = 0.f, n_dnorm = 0.f;
+      for (int l = 0; l < kNumLayers; ++l) {
+        const int nquarters = l == 9 ? 2 : 4;
+        if (l == 1 && grp == 1 && pend) {  // previous ray, while this ray's layer 1 runs
+          const long long t_ = V3_CLK();
+          composite();
+          V3_ADD(2, t_);
+        }
+        if (l == 8 && grp == 1) {  // per-ray operands of the view epilogue / compositing, one layer early
+          vb_s[row] = __ldg(p.view_bias + ray * kCond + row);
+          if (!p.raw_rgb_out) {
+            n_t0 = __ldg(p.t + ray * (kN + 1) + row), n_t1 = __ldg(p.t + ray * (kN + 1) + row + 1);
+            const float dx = __ldg(p.directions + ray * 3), dy = __ldg(p.directions + ray * 3 + 1),
+                        dz = __ldg(p.directions + ray * 3 + 2);
+            n_dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+          }
+          named_bar_sync(2, 128);  // vb_s complete within group 1 ...
+        }
+        if (l == 9) {  // ... and visible to group 0 before anybody's view epilogue
+          if (grp == 1) {
+            __threadfence_block();
+            named_bar_arrive(3, 256);
+          } else {
+            named_bar_sync(3, 256);
+          }
+        }
+        for (int i = 0; i < nquarters; ++i) {
+          const int q = l == 0 ? ((i + 2) & 3) : i;  // layer 0 completes its quarters in the order 2, 3, 0, 1
+          wait_acc(q);
+          if ((q & 1) != grp) continue;
+          const long long t_epi_ = V3_CLK();
+          const uint32_t t_acc_q = t_lane + kAccCols3 + 64u * q;
+          if (l < 9) {
+            const uint32_t t_a_q = t_lane + kACols3 + ((l & 1) ? 128u : 0u) + 32u * q;  // epilogue l writes A[l&1]
+            float d = 0.f;
+            switch (l) {
+              case 0: d = epilogue_quarter3<kFmt, 0>(t_acc_q, t_a_q, q); break;
+              case 1: d = epilogue_quarter3<kFmt, 1>(t_acc_q, t_a_q, q); break;
+              case 2: d = epilogue_quarter3<kFmt, 2>(t_acc_q, t_a_q, q); break;
+              case 3: d = epilogue_quarter3<kFmt, 3>(t_acc_q, t_a_q, q); break;
+              case 4: d = epilogue_quarter3<kFmt, 4>(t_acc_q, t_a_q, q); break;
+              case 5: d = epilogue_quarter3<kFmt, 5>(t_acc_q, t_a_q, q); break;
+              case 6: d = epilogue_quarter3<kFmt, 6>(t_acc_q, t_a_q, q); break;
+              case 7: d = epilogue_quarter3<kFmt, 7>(t_acc_q, t_a_q, q); break;
+              default: d = epilogue_quarter3<kFmt, 8>(t_acc_q, t_a_q, q); break;
+            }
+            if (l == 7) dens_part[q * 128 + row] = d;
+            tc_fence_before();
+            arrive_epi(q);
+            V3_ADD(1, t_epi_);
+          } else {
+            float r0, r1, r2;
+            epilogue_view_quarter3<kFmt>(t_acc_q, vb_s, q, r0, r1, r2);
+            tc_fence_before();
+            arrive_epi(q);  // accumulator quarter drained: the next ray's layer 0 may overwrite it
+            if (grp == 0) {
+              rgb_part[0 * 128 + row] = r0;
+              rgb_part[1 * 128 + row] = r1;
+              rgb_part[2 * 128 + row] = r2;
+              __threadfence_block();
+              named_bar_arrive(4, 256);  // hand-over to group 1's composite of this ray
+            } else {
+              rgb0 = r0, rgb1 = r1, rgb2 = r2;
+              t0 = n_t0, t1 = n_t1, dnorm = n_dnorm;
+              pend = true, pend_valid = valid, pend_ray = ray;
+            }
+          }
+        }
+      }
+    }
+    if (grp == 1 && pend) composite();  // the last ray
+    if (lane == 0 && lq == 2) { V3_FLUSH(8 + 8 * grp); }  // warps 2 / 6
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tmem_base, 512);
+}

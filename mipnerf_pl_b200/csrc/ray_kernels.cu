@@ -21,15 +21,22 @@ static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)(
 // coarse fenceposts: one thread per (ray, j)
 // ---------------------------------------------------------------------------------------------
 __global__ void coarse_t_kernel(const float* __restrict__ near, const float* __restrict__ far,
-                                const float* __restrict__ t_rand, float* __restrict__ t_out,
+                                const Draws t_rand, float* __restrict__ t_out,
                                 int64_t num_rays, int n, int randomized, int disparity) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = num_rays * (n + 1);
   if (idx >= total) return;
   const int64_t ray = idx / (n + 1);
   const int j = (int)(idx % (n + 1));
-  t_out[idx] = coarse_fencepost(__ldg(near + ray), __ldg(far + ray), j, n, disparity,
-                                randomized ? t_rand + idx : nullptr);
+  t_out[idx] = coarse_fencepost(__ldg(near + ray), __ldg(far + ray), j, n, disparity, randomized != 0,
+                                randomized ? draw_uniform(t_rand, ray, j, n + 1) : 0.f);
+}
+
+// the uniforms the kernels draw for (seed, offset, stream): test / reproduction helper
+__global__ void philox_uniform_kernel(const Draws d, float* __restrict__ out, int64_t num_rays, int ncols) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * ncols) return;
+  out[idx] = draw_uniform(d, idx / ncols, (int)(idx % ncols), ncols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -198,7 +205,7 @@ __global__ void composite_kernel(const float* __restrict__ rgb_in, const float* 
 
 template <bool kBlur>
 __global__ void resample_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
-                                const float* __restrict__ jitter, float* __restrict__ out,
+                                const Draws jitter, float* __restrict__ out,
                                 int64_t* __restrict__ inds, int64_t num_rays, int nb, int ns,
                                 int randomized, float padding) {
   extern __shared__ float smem[];
@@ -208,9 +215,8 @@ __global__ void resample_kernel(const float* __restrict__ bins, const float* __r
   float* s_w = smem + (size_t)warp * (3 * nb + 2);
   float* s_cdf = s_w + nb;
   float* s_bins = s_cdf + nb + 1;
-  resample_warp<kBlur>(bins + ray * (nb + 1), weights + ray * nb, nb, ns, randomized,
-                       jitter ? jitter + ray * ns : nullptr, padding, s_w, s_cdf, s_bins,
-                       out + ray * ns, inds ? inds + ray * ns : nullptr, lane);
+  resample_warp<kBlur>(bins + ray * (nb + 1), weights + ray * nb, nb, ns, randomized, jitter, ray, padding, s_w,
+                       s_cdf, s_bins, out + ray * ns, inds ? inds + ray * ns : nullptr, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -396,7 +402,13 @@ cudaError_t launch_distloss(const float* weights, const float* t, float* out, in
   return cudaGetLastError();
 }
 
-cudaError_t launch_coarse_t(const float* near, const float* far, const float* t_rand, float* t_out,
+cudaError_t launch_philox_uniform(const Draws& d, float* out, int64_t num_rays, int ncols, cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  philox_uniform_kernel<<<blocks_for(num_rays * ncols, 256), 256, 0, st>>>(d, out, num_rays, ncols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_coarse_t(const float* near, const float* far, const Draws& t_rand, float* t_out,
                             int64_t num_rays, int n, int randomized, int disparity, cudaStream_t st) {
   if (num_rays == 0) return cudaSuccess;
   LaunchScope scope(kKernCoarseT, st);
@@ -486,7 +498,7 @@ cudaError_t launch_composite(const float* rgb, const float* dens, const float* t
                                    white_bkgd, density_bias, rgb_scale, rgb_padding, st);
 }
 
-cudaError_t launch_resample(const float* bins, const float* weights, const float* jitter, float* out,
+cudaError_t launch_resample(const float* bins, const float* weights, const Draws& jitter, float* out,
                             int64_t* inds, int64_t num_rays, int nb, int ns, int randomized, int blur,
                             float padding, cudaStream_t st) {
   if (num_rays == 0) return cudaSuccess;

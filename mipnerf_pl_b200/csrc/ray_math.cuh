@@ -9,6 +9,8 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include "draws.h"
+
 namespace mipnerf {
 
 #define MIPNERF_HALF_PI_F32 1.57079637050628662109375f  // fl32(0.5*pi) = 0x3FC90FDB (models/mip.py:350)
@@ -33,17 +35,48 @@ __device__ __forceinline__ float linspace_f32(float start, float end, int steps,
   return j < steps / 2 ? __fmaf_rn(step, (float)j, start) : __fmaf_rn(-step, (float)(steps - 1 - j), end);
 }
 
-// fencepost j of n+1; `jitter` = &t_rand[ray][j] for the stratified draw, nullptr when deterministic
-__device__ __forceinline__ float coarse_fencepost(float nr, float fr, int j, int n, int disparity,
-                                                  const float* __restrict__ jitter) {
+// ---- uniforms of randomized=True --------------------------------------------------------------------
+// The reference draws them with torch.rand / uniform_ (models/mip.py:159, :201-202).  Here they come either from an
+// explicit array (caller-injected noise: what the parity tests use to feed the reference's own draws) or from a
+// counter-based generator evaluated inside the kernels that consume them: Philox4x32-10 keyed by `seed`, counter =
+// (global ray index, draw index, stream, offset).  No state, no extra launch, no [B, N+1] array in HBM; draws do not
+// depend on how the batch is chunked or sharded (ray_base) and are reproduced by mipnerf_b200_philox_uniform.
+__device__ __forceinline__ uint32_t philox4x32_10_first(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                        uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+// draw j of `ray` (row-local index): explicit array element, or scale * U[0,1) with 24 random bits
+__device__ __forceinline__ float draw_uniform(const Draws& d, int64_t ray, int j, int ncols) {
+  if (d.ptr) return __ldg(d.ptr + ray * ncols + j);
+  const uint64_t g = (uint64_t)(d.ray_base + ray);
+  const uint32_t x = philox4x32_10_first((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)j | ((uint32_t)d.stream << 24),
+                                         (uint32_t)d.offset, (uint32_t)d.seed,
+                                         (uint32_t)(d.seed >> 32) ^ (uint32_t)(d.offset >> 32));
+  return __fmul_rn((float)(x >> 8) * 5.9604644775390625e-08f, d.scale);  // 2^-24
+}
+
+// fencepost j of n+1; `jit` = t_rand[ray][j] for the stratified draw when has_jitter, ignored otherwise
+__device__ __forceinline__ float coarse_fencepost(float nr, float fr, int j, int n, int disparity, bool has_jitter,
+                                                  float jit) {
   float t = coarse_t(nr, fr, linspace_f32(0.0f, 1.0f, n + 1, j), disparity);  // models/mip.py:143
-  if (jitter) {
+  if (has_jitter) {
     // mids / upper / lower (models/mip.py:156-160)
     const float lower =
         j == 0 ? t : __fmul_rn(0.5f, __fadd_rn(t, coarse_t(nr, fr, linspace_f32(0.0f, 1.0f, n + 1, j - 1), disparity)));
     const float upper =
         j == n ? t : __fmul_rn(0.5f, __fadd_rn(coarse_t(nr, fr, linspace_f32(0.0f, 1.0f, n + 1, j + 1), disparity), t));
-    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), __ldg(jitter)));
+    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), jit));
   }
   return t;
 }

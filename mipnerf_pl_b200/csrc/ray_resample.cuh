@@ -17,7 +17,7 @@ namespace mipnerf {
 template <bool kBlur>
 __device__ __forceinline__ void resample_warp(const float* __restrict__ bins_g,
                                               const float* __restrict__ w_g, int nb, int ns,
-                                              int randomized, const float* __restrict__ jitter_g,
+                                              int randomized, const Draws& jitter, int64_t ray,
                                               float padding, float* s_w, float* s_cdf,
                                               float* s_bins, float* __restrict__ out_g,
                                               int64_t* __restrict__ inds_g, int lane) {
@@ -101,7 +101,7 @@ __device__ __forceinline__ void resample_warp(const float* __restrict__ bins_g,
   for (int j = lane; j < ns; j += 32) {
     // deterministic: torch.linspace(0, 1-eps, ns)   (models/mip.py:206-207)
     float u = randomized ? __fmul_rn((float)j, step) : linspace_f32(0.0f, one_m_eps, ns, j);
-    if (randomized) u = fminf(__fadd_rn(u, __ldg(jitter_g + j)), one_m_eps);
+    if (randomized) u = fminf(__fadd_rn(u, draw_uniform(jitter, ray, j, ns)), one_m_eps);
     int lo = 0, hi = nb + 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -126,8 +126,8 @@ __device__ __forceinline__ void resample_warp(const float* __restrict__ bins_g,
 // neighbours), the pdf in 32-strided order, and finally the cdf.  Results are bit-identical to resample_warp.
 template <bool kBlur>
 __device__ __forceinline__ void resample_warp_lean(const float* __restrict__ bins_g, const float* __restrict__ w_g,
-                                                   int nb, int ns, int randomized,
-                                                   const float* __restrict__ jitter_g, float padding, float* s_a,
+                                                   int nb, int ns, int randomized, const Draws& jitter,
+                                                   int64_t ray, float padding, float* s_a,
                                                    float* __restrict__ out_g, int64_t* __restrict__ inds_g, int lane) {
   constexpr int kMaxChunks = 8;  // nb <= 256
   const int chunks = nb >> 5;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void resample_warp_lean(const float* __restrict__ bin
   for (int j = lane; j < ns; j += 32) {
     // deterministic: torch.linspace(0, 1-eps, ns)   (models/mip.py:206-207)
     float u = randomized ? __fmul_rn((float)j, step) : linspace_f32(0.0f, one_m_eps, ns, j);
-    if (randomized) u = fminf(__fadd_rn(u, __ldg(jitter_g + j)), one_m_eps);
+    if (randomized) u = fminf(__fadd_rn(u, draw_uniform(jitter, ray, j, ns)), one_m_eps);
     int lo = 0, hi = nb + 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;

@@ -227,8 +227,20 @@ class MipNerf(torch.nn.Module):
         # forward() always encodes viewdirs with append_identity=True (models/mip_nerf.py:221-226);
         # a model built with append_identity=False has a 24-wide view input and fails in the reference.
         self._append_identity = bool(append_identity)
-        # 'fp32' | 'bf16' | 'fp16'; None -> $MIPNERF_B200_PRECISION or 'fp32'
+        # 'fp32' | 'bf16' | 'fp16' | 'fp16x3' | 'bf16x3'; None -> $MIPNERF_B200_PRECISION or 'fp32'
         self.precision = precision or os.environ.get("MIPNERF_B200_PRECISION", "fp32")
+        # randomized=True without injected noise draws its uniforms inside the kernels (Philox4x32-10, counter-based):
+        # seed from torch's global generator at first use, offset advanced by one per call.
+        self.rng_seed: Optional[int] = None
+        self.rng_offset = 0
+
+    def next_rng(self) -> "_cabi.Rng":
+        """(seed, offset) of the next randomized call; advances the offset (the role of torch's generator offset)."""
+        if self.rng_seed is None:
+            self.rng_seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        rng = _cabi.Rng(self.rng_seed, self.rng_offset)
+        self.rng_offset += 1
+        return rng
 
     def _config(self) -> "_cabi.Config":
         return self.mlp._config(
@@ -261,7 +273,10 @@ class MipNerf(torch.nn.Module):
                 _f32(rays.near).reshape(-1), _f32(rays.far).reshape(-1)]
         rs = _cabi.RaysStruct(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(),
                               keep[4].data_ptr(), keep[5].data_ptr(), b)
-        if randomized:
+        rng = None
+        if randomized and t_rand is None and u_jitter is None:
+            rng = self.next_rng()                       # in-kernel Philox: no torch.rand launch, no [B,N+1] arrays
+        elif randomized:
             t_rand = _f32(t_rand) if t_rand is not None else draw_t_rand(b, n, dev)
             u_jitter = _f32(u_jitter) if u_jitter is not None else draw_u_jitter(b, n + 1, dev)
         else:
@@ -294,11 +309,17 @@ class MipNerf(torch.nn.Module):
             _cabi.check(lib.mipnerf_b200_forward(C.byref(cfg), C.byref(ws), C.byref(rs), 0, None, None, 0, prec,
                                                  outs, None, 0, None), "MipNerf.forward")
         scratch = _Workspace.get(dev, nbytes)
-        args = (C.byref(cfg), C.byref(ws), C.byref(rs), int(bool(randomized)), _ptr(t_rand), _ptr(u_jitter),
-                int(bool(white_bkgd)), prec, outs, scratch.data_ptr(), scratch.numel(), _stream(dev))
+        if rng is not None:
+            fn = lib.mipnerf_b200_forward_rng
+            args = (C.byref(cfg), C.byref(ws), C.byref(rs), C.byref(rng), int(bool(white_bkgd)), prec, outs,
+                    scratch.data_ptr(), scratch.numel(), _stream(dev))
+        else:
+            fn = lib.mipnerf_b200_forward
+            args = (C.byref(cfg), C.byref(ws), C.byref(rs), int(bool(randomized)), _ptr(t_rand), _ptr(u_jitter),
+                    int(bool(white_bkgd)), prec, outs, scratch.data_ptr(), scratch.numel(), _stream(dev))
         if dev.index is None or dev.index == torch.cuda.current_device():
-            _cabi.check(lib.mipnerf_b200_forward(*args), "MipNerf.forward")
+            _cabi.check(fn(*args), "MipNerf.forward")
         else:
             with torch.cuda.device(dev):
-                _cabi.check(lib.mipnerf_b200_forward(*args), "MipNerf.forward")
+                _cabi.check(fn(*args), "MipNerf.forward")
         return ret

@@ -64,6 +64,19 @@ def draw_u_jitter(batch: int, num_draws: int, device) -> torch.Tensor:
         0.0, 1.0 / num_draws - F32_EPS)
 
 
+def philox_uniform(seed: int, offset: int, stream_id: int, batch: int, num_draws: int, device) -> torch.Tensor:
+    """The uniforms the kernels draw in-kernel for (seed, offset): stream 0 = t_rand in [0,1) (models/mip.py:159),
+    stream 1 + level = that level's u_jitter in [0, 1/num_draws - eps) (models/mip.py:201-202).  Passing them as
+    `t_rand` / `u_jitter` reproduces the in-kernel randomized forward bit for bit."""
+    dev = torch.device(device)
+    out = torch.empty(batch, num_draws, device=dev)
+    rng = _cabi.Rng(seed & 0xFFFFFFFFFFFFFFFF, offset)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().mipnerf_b200_philox_uniform(C.byref(rng), stream_id, batch, num_draws, out.data_ptr(),
+                                                            _stream(dev)), "philox_uniform")
+    return out
+
+
 def cast_rays(t_samples, origins, directions, radii, ray_shape, diagonal=True):
     """models/mip.py:81-103."""
     if ray_shape == "cylinder":

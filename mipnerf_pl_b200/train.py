@@ -144,7 +144,10 @@ def _run(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white
     keep = [_f32(rays.origins), _f32(rays.directions), _f32(rays.viewdirs), _f32(rays.radii).reshape(-1),
             _f32(rays.near).reshape(-1), _f32(rays.far).reshape(-1)]
     rs = _cabi.RaysStruct(*[k.data_ptr() for k in keep], b)
-    if randomized:
+    rng = None
+    if randomized and t_rand is None and u_jitter is None:
+        rng = model.next_rng()          # uniforms drawn inside the kernels (Philox), as every training step does
+    elif randomized:
         t_rand = _f32(t_rand) if t_rand is not None else draw_t_rand(b, n, dev)
         u_jitter = _f32(u_jitter) if u_jitter is not None else draw_u_jitter(b, n + 1, dev)
     else:
@@ -177,12 +180,15 @@ def _run(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white
     lib = _cabi.lib()
     nbytes = lib.mipnerf_b200_train_workspace_bytes(C.byref(cfg), b)
     scratch = _Workspace.get(dev, nbytes)
+    tail = (int(bool(white_bkgd)), prec, C.byref(loss), outs, garr, len(lins), int(bool(accumulate)),
+            scratch.data_ptr() if nbytes else None, scratch.numel() if nbytes else 0, _stream(dev))
     with torch.cuda.device(dev):
-        _cabi.check(lib.mipnerf_b200_forward_backward(
-            C.byref(cfg), C.byref(ws), C.byref(rs), int(bool(randomized)), _ptr(t_rand), _ptr(u_jitter),
-            int(bool(white_bkgd)), prec, C.byref(loss), outs, garr, len(lins), int(bool(accumulate)),
-            scratch.data_ptr() if nbytes else None, scratch.numel() if nbytes else 0, _stream(dev)),
-            "forward_backward")
+        if rng is not None:
+            rc = lib.mipnerf_b200_forward_backward_rng(C.byref(cfg), C.byref(ws), C.byref(rs), C.byref(rng), *tail)
+        else:
+            rc = lib.mipnerf_b200_forward_backward(C.byref(cfg), C.byref(ws), C.byref(rs), int(bool(randomized)),
+                                                   _ptr(t_rand), _ptr(u_jitter), *tail)
+        _cabi.check(rc, "forward_backward")
     mse = sqerr.sum(dim=1) / mask_sum                      # [levels]   (models/nerf_system.py:104-105)
     distl = dl.sum(dim=1) / max(global_rays, 1)            # [levels]   (:106)
     total = (mse * torch.tensor(mse_m, device=dev) + distl * torch.tensor(dist_m, device=dev)).sum()

@@ -167,7 +167,8 @@ def test_fused_adam_resumes_from_torch_adam_state():
         ref.step()
     b_ = torch.nn.Parameter(a.detach().clone())
     fused = mp.FusedAdam([b_], lr=1e-3)
-    fused.load_state_dict(ref.state_dict())
+    import copy
+    fused.load_state_dict(copy.deepcopy(ref.state_dict()))   # (load_state_dict aliases the float32 `step` tensor)
     for _ in range(5):
         gr = torch.randn(4097, device=DEV, generator=gen)
         a.grad, b_.grad = gr.clone(), gr.clone()

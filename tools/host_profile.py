@@ -13,7 +13,7 @@ import torch  # noqa: E402
 import mipnerf_pl_b200 as mp  # noqa: E402
 
 dev = torch.device("cuda", 0)
-model = mp.MipNerf(precision="bf16")
+model = mp.MipNerf(precision=os.environ.get("TRACE_PRECISION", "bf16"))
 model.load_state_dict(mp.make_state_dict(seed=0))
 model = model.to(dev).eval()
 staging = mp.RayStaging(mp.random_ray_batch(256, seed=0))

@@ -20,7 +20,7 @@ from mipnerf_pl_b200 import _cabi  # noqa: E402
 
 lib = _cabi.lib()
 dev = "cuda:0"
-model = mp.MipNerf(precision="bf16")
+model = mp.MipNerf(precision=os.environ.get("TRACE_PRECISION", "bf16"))
 model.load_state_dict(mp.make_state_dict(0))
 model = model.to(dev).eval()
 rays = mp.namedtuple_map(lambda t: t.to(dev), mp.random_ray_batch(4096, seed=0))
