@@ -296,7 +296,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int laye
 }
 
 template <int kFmt, bool kX3>
-__device__ __noinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* myA, int row, float& dens, int layer) {
+__device__ __forceinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* myA, int row, float& dens, int layer) {
   float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)row & 7u;
   uint32_t v0[32], v1[32];

@@ -41,6 +41,7 @@ print(f"MMA thread: total {mma[5]} cycles = {mma[5] / rounds:.0f} per ray | wait
       f"wait w_full {mma[4] / rounds:.0f} | rest (issue) {(mma[5] - sum(mma[0:5])) / rounds:.0f}")
 for g in range(2):
     w = c[8 + 8 * g: 16 + 8 * g]
-    print(f"worker group {g}: wait acc_full {w[0] / rounds:.0f} per ray | epilogues {w[1] / rounds:.0f} | composite {w[2] / rounds:.0f}")
+    print(f"worker group {g}: wait acc_full {w[0] / rounds:.0f} per ray | epilogues {w[1] / rounds:.0f} | composite {w[2] / rounds:.0f}"
+          f" | of the epilogues: tmem ld+wait {w[3] / rounds:.0f}, convert+st issue {w[4] / rounds:.0f}, wait::st {w[5] / rounds:.0f}")
 i = c[24:32]
 print(f"IPE warp: wait f_free {i[0] / rounds:.0f} per ray | features {i[1] / rounds:.0f}")
