@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import FLOORS, assert_close, make_state_dict, oracle, oracle_rays, rel_err
+from helpers import (FLOORS, FINE_WEIGHTS_FLOOR, assert_close, exceed_stats, golden, golden_levels, golden_rays,
+                     make_state_dict, oracle, oracle_rays, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -42,10 +43,13 @@ def test_tc_forward_vs_emulated_oracle(precision):
     params = make_state_dict(seed=4, kind="xavier")
     want = oracle.forward(params, oracle_rays(rays), False, True, operand_dtype=DT[precision])
     got = run(precision, "xavier", rays)
+    # same floors as the fp32 parity tests (helpers.FLOORS); bounds = 2x the errors measured on B200 (round 2):
+    # the kernel and the emulation round the same operands but sum in different orders
     tol = 2e-3 if precision == "bf16" else 4e-4
     for lvl in range(2):
         for k, name in enumerate(("comp_rgb", "distance", "acc", "weights", "t_samples")):
-            e = rel_err(got[lvl][k].cpu().numpy(), want[lvl][k].numpy(), FLOORS[name] * 10)
+            floor = FINE_WEIGHTS_FLOOR if (name == "weights" and lvl > 0) else FLOORS[name]
+            e = rel_err(got[lvl][k].cpu().numpy(), want[lvl][k].numpy(), floor)
             print(f"{precision} level {lvl} {name}: rel err vs emulated oracle {e:.3e}")
             assert e <= tol, (precision, lvl, name, e)
 
@@ -69,10 +73,33 @@ def test_tc_trained_like_and_black_background():
     want = oracle.forward(params, oracle_rays(rays), False, False, operand_dtype=torch.bfloat16)
     got = run("bf16", "trained_like", rays, seed=5, white=False)
     for lvl in range(2):
-        e = rel_err(got[lvl][0].cpu().numpy(), want[lvl][0].numpy(), 0.2)
-        print(f"trained_like level {lvl}: comp_rgb rel err vs emulated oracle {e:.3e}")
-        assert e <= 2e-2
+        # x40 density head: the coarse level is well conditioned; at the fine level a bf16-sized change of one coarse
+        # weight moves fine fenceposts across density edges, so kernel and emulation (same roundings, other summation
+        # order) agree on almost every ray and differ by up to a few 1e-2 on the few that graze an edge
+        frac, mx = exceed_stats(got[lvl][0], want[lvl][0], 0.2, rtol=4e-3)
+        print(f"trained_like level {lvl}: comp_rgb vs emulated oracle: max rel err {mx:.3e}, {frac:.3%} of elements > 4e-3")
+        assert mx <= (4e-3 if lvl == 0 else 5e-2) and frac <= 0.02
         assert torch.all(got[lvl][3] >= 0) and torch.all(got[lvl][2] <= 1 + 1e-4)
+
+
+@pytest.mark.parametrize("precision,bound", [("bf16", 2e-2), ("fp16", 4e-3)])
+@pytest.mark.parametrize("name,kind", [("forward_xavier.npz", "xavier"), ("forward_trained_like.npz", "trained_like")])
+def test_tc_16bit_modes_vs_reference_goldens(precision, bound, name, kind):
+    """The plain 16-bit modes against the COMMITTED outputs of the reference (the same files the fp32 and fp16x3 paths
+    are held to at 1e-4): measured error printed, asserted at ~3x the round-2 measurement (bf16 6.1e-3, fp16 1.2e-3
+    relative on the stress golden's RGB).  These modes do not claim the 1e-4 contract; fp16x3 does (test_gpu_x3.py)."""
+    g = golden(name)
+    seed, randomized, white = (int(v) for v in g["meta"])
+    model = mp.MipNerf(precision=precision)
+    model.load_state_dict(make_state_dict(seed=seed, kind=kind))
+    model = model.to(DEV).eval()
+    ret = model(golden_rays(g, device=DEV), bool(randomized), bool(white))
+    want = golden_levels(g)
+    for lvl in range(2):
+        e = rel_err(ret[lvl][0].cpu().numpy(), want[lvl][0], FLOORS["comp_rgb"])
+        a = float(np.abs(ret[lvl][0].cpu().numpy() - want[lvl][0]).max())
+        print(f"{precision} {name} level {lvl}: comp_rgb max rel err {e:.3e} (max abs {a:.3e}) vs the reference golden")
+        assert e <= bound, (precision, name, lvl, e)
 
 
 def test_tc_batch_split_invariance_and_sizes():
