@@ -206,6 +206,14 @@ int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, flo
                                float* viewdirs, float* radii, float* near_out, float* far_out,
                                void* stream);
 
+/* eval_errors (utils/metrics.py:190-197) of one rendered frame: pred / target [H, W, C] fp32 row-major (the layout
+ * render_image produces) -> out[0] = PSNR = -10 log10(mean squared error) (utils/metrics.py:182-188), out[1] = mean
+ * SSIM with the reference's 11x11 Gaussian window (sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2; :44-126),
+ * out[2] = the mean squared error.  `scratch`: mipnerf_b200_image_metrics_scratch_bytes() bytes. */
+size_t mipnerf_b200_image_metrics_scratch_bytes(int height, int width, int channels);
+int mipnerf_b200_image_metrics(const float* pred, const float* target, int height, int width, int channels,
+                               void* scratch, size_t scratch_bytes, float* out, void* stream);
+
 /* Training rays from pixel ids, scene resident in HBM (replaces the per-pixel host arrays of
  * datasets/datasets.py:116-168, 216-263 and the DataLoader's H2D copies):
  *   cam_table [num_images, 24] = pix2cam (3x3 row-major, maps (x+.5, y+.5, 1) to a camera direction) |

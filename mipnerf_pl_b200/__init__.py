@@ -16,6 +16,7 @@ from .datasets import (Blender, Multicam, DeviceRayBank, Scene, dataset_dict, lo
                        image_rays, convert_blender_to_multiscale, write_synthetic_blender_scene)
 from .render import generate_rays, render_frame, render_sharded, shard_bounds, shard_rows, gather_rows
 from .graph import GraphedForward
+from .metrics import eval_errors, ssim, evaluate, render_path, spheric_path, save_images
 
 __all__ = [
     "Rays", "Rays_keys", "namedtuple_map", "rearrange_render_image", "blender_rays", "spheric_pose",
@@ -25,5 +26,6 @@ __all__ = [
     "render_sharded", "shard_bounds", "shard_rows", "gather_rows", "FusedAdam", "MipLRDecay", "allreduce_grads",
     "forward_backward", "fused_loss", "mip_lr", "Blender", "Multicam", "DeviceRayBank", "Scene", "dataset_dict",
     "load_blender_scene", "load_multicam_scene", "image_rays", "convert_blender_to_multiscale",
-    "write_synthetic_blender_scene", "GraphedForward", "philox_uniform",
+    "write_synthetic_blender_scene", "GraphedForward", "philox_uniform", "eval_errors", "ssim", "evaluate",
+    "render_path", "spheric_path", "save_images",
 ]

@@ -94,6 +94,8 @@ _SIGNATURES = {
                                          C.c_int64, C.c_double, _V]),
     "mipnerf_b200_generate_rays": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                              _V, _V, _V, _V, _V, _V, _V]),
+    "mipnerf_b200_image_metrics_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "mipnerf_b200_image_metrics": (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, _V, C.c_size_t, _V, _V]),
     "mipnerf_b200_rays_from_pixels": (C.c_int, [_V, _V, _V, C.c_int, _V, C.c_int64, _V, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "mipnerf_b200_sample_along_rays": (C.c_int, [C.POINTER(RaysStruct), C.c_int, C.c_int, C.c_int, _V, _V, _V, _V, _V]),
     "mipnerf_b200_cast_rays": (C.c_int, [C.POINTER(RaysStruct), _V, C.c_int, _V, _V, _V]),

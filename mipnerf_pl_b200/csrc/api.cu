@@ -691,6 +691,22 @@ int mipnerf_b200_distloss(const float* weights, const float* samples, int64_t nu
   return MIPNERF_B200_OK;
 }
 
+size_t mipnerf_b200_image_metrics_scratch_bytes(int height, int width, int channels) {
+  if (height < 1 || width < 1 || channels < 1) return 0;
+  return mipnerf::image_metrics_scratch_bytes(height, width, channels);
+}
+
+int mipnerf_b200_image_metrics(const float* pred, const float* target, int height, int width, int channels,
+                               void* scratch, size_t scratch_bytes, float* out, void* stream) {
+  if (height < 1 || width < 1 || channels < 1) return fail(MIPNERF_B200_EINVAL, "bad image shape");
+  if (!pred || !target || !out) return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  const size_t need = mipnerf::image_metrics_scratch_bytes(height, width, channels);
+  if (!scratch || scratch_bytes < need) return fail(MIPNERF_B200_EWORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, need);
+  CUDA_TRY(mipnerf::launch_image_metrics(pred, target, height, width, channels, 11, 1.5f, 1.0f, scratch, out,
+                                         (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
 int mipnerf_b200_generate_rays(const float* c2w_host, int height, int width, float focal, float near, float far,
                                int row0, int rows, float* origins, float* directions, float* viewdirs,
                                float* radii, float* near_out, float* far_out, void* stream) {

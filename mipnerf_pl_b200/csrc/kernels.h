@@ -40,6 +40,11 @@ cudaError_t launch_resample(const float* bins, const float* weights, const Draws
                             int64_t* inds, int64_t num_rays, int nb, int ns, int randomized, int blur,
                             float padding, cudaStream_t st);
 
+// ---- metrics.cu ----
+size_t image_metrics_scratch_bytes(int height, int width, int channels);
+cudaError_t launch_image_metrics(const float* pred, const float* target, int height, int width, int channels,
+                                 int window, float sigma, float max_val, void* scratch, float* out, cudaStream_t st);
+
 // ---- linear_f32.cu ----
 // Y[M,N] = act( [X1 | X2[row / x2_row_div]] @ W[N, K1+K2]^T + bias ),  fp32 FFMA.
 cudaError_t launch_linear_f32(const float* x1, int ld1, int k1, const float* x2, int ld2, int k2,

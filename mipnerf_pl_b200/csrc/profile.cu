@@ -28,7 +28,8 @@ State& state() {
 const char* const kNames[kKernCount] = {"coarse_t",  "cast_rays", "ipe",          "pos_enc",      "linear_f32",
                                         "composite", "resample",  "pack_weights", "mlp_level_tc", "mlp_tc",
                                         "generate_rays", "distloss", "ray_prologue",
-                                        "render_backward", "dgrad_f32", "wgrad_f32", "adam", "linear_tc", "wgrad_tc"};
+                                        "render_backward", "dgrad_f32", "wgrad_f32", "adam", "linear_tc", "wgrad_tc",
+                                        "image_metrics"};
 
 }  // namespace
 

@@ -27,6 +27,7 @@ enum KernelId : int {
   kKernAdam,
   kKernLinearTc,     // stand-alone tcgen05 linear layer (training forward / dgrad)
   kKernWgradTc,      // tcgen05 wgrad partials
+  kKernImageMetrics, // PSNR + SSIM of a rendered frame
   kKernCount
 };
 

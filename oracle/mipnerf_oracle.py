@@ -385,6 +385,30 @@ def training_loss(params: Dict[str, torch.Tensor], rays: Rays, rgbs, randomized:
     return loss, losses, dls, ret
 
 
+def gaussian_window(window_size=11, sigma=1.5):
+    """utils/metrics.py:10-17."""
+    g = torch.stack([torch.exp(torch.tensor(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)))
+                     for x in range(window_size)])
+    return g / g.sum()
+
+
+def eval_errors(pred_color, batch_pixels, window_size=11, max_val=1.0):
+    """(psnr, ssim) of [1,H,W,3] images: utils/metrics.py:190-197 (calc_psnr :182-188; SSIM :44-126 with the Gaussian
+    window, zero padding and reduction='mean')."""
+    psnr = -10.0 * torch.log10(torch.mean((pred_color - batch_pixels) ** 2))
+    a, b = pred_color.permute(0, 3, 1, 2), batch_pixels.permute(0, 3, 1, 2)
+    c = a.shape[1]
+    g = gaussian_window(window_size, 1.5)
+    kernel = torch.matmul(g.unsqueeze(-1), g.unsqueeze(-1).t()).repeat(c, 1, 1, 1)
+    pad = (window_size - 1) // 2
+    f = lambda x: F.conv2d(x, kernel, padding=pad, groups=c)  # noqa: E731
+    mu1, mu2 = f(a), f(b)
+    s1, s2, s12 = f(a * a) - mu1.pow(2), f(b * b) - mu2.pow(2), f(a * b) - mu1 * mu2
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    ssim_map = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1.pow(2) + mu2.pow(2) + c1) * (s1 + s2 + c2))
+    return psnr, ssim_map.mean()
+
+
 def mip_lr(step, lr_init, lr_final, max_steps, lr_delay_steps=0, lr_delay_mult=1.0):
     """MipLRDecay.get_lr (utils/lr_schedule.py:51-60) at `last_epoch == step`."""
     import numpy as np

@@ -316,7 +316,31 @@ def datasets_case():
     save("datasets.npz", **out)
 
 
+def metrics_case():
+    """eval_errors / calc_psnr / ssim of the reference (utils/metrics.py:44-126, 182-197) on small synthetic frames:
+    a smooth image against a noisy copy (high SSIM), against an unrelated one (low SSIM), odd sizes (tile edges of the
+    CUDA kernel), plus the 1-D window itself."""
+    from utils import metrics as ref_metrics  # reference
+    rng = np.random.RandomState(11)
+    out = {}
+    for tag, (h, w) in (("a", (37, 29)), ("b", (16, 48)), ("c", (50, 50))):
+        yy, xx = np.meshgrid(np.linspace(0, 3, h), np.linspace(0, 2, w), indexing="ij")
+        base = np.stack([0.5 + 0.4 * np.sin(3 * xx + c) * np.cos(2 * yy) for c in range(3)], -1).astype(np.float32)
+        noisy = np.clip(base + rng.normal(0, 0.03, base.shape), 0, 1).astype(np.float32)
+        other = rng.uniform(0, 1, base.shape).astype(np.float32)
+        for name, (p_, t_) in (("near", (noisy, base)), ("far", (other, base))):
+            pred, tgt = torch.from_numpy(p_)[None], torch.from_numpy(t_)[None]
+            psnr, ssim = ref_metrics.eval_errors(pred, tgt)
+            out[f"{tag}_{name}_pred"], out[f"{tag}_{name}_target"] = p_, t_
+            out[f"{tag}_{name}_psnr"], out[f"{tag}_{name}_ssim"] = np.float32(psnr.item()), np.float32(ssim.item())
+    out["window"] = ref_metrics.get_gaussian_kernel(11, 1.5).numpy()
+    save("metrics.npz", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":    # regenerate only metrics.npz
+        metrics_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "training":   # regenerate only training.npz
         training_case()
         sys.exit(0)
@@ -334,6 +358,7 @@ if __name__ == "__main__":
     stages_case()
     training_case()
     datasets_case()
+    metrics_case()
     with open(os.path.join(HERE, "VERSIONS.txt"), "w") as f:
         f.write(f"torch {torch.__version__}\nnumpy {np.__version__}\nreference {REF} (hjxwhy/mipnerf_pl @ 6c07452)\n"
                 f"cpu_capability {torch.backends.cpu.get_cpu_capability()}\n")
