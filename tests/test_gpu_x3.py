@@ -48,7 +48,7 @@ def test_fp16x3_forward_vs_reference_golden(name, kind):
     for lvl, (got, ref) in enumerate(zip(ret, want)):
         if lvl > 0 and kind == "trained_like":   # see helpers.assert_fine_level_close: per-element statement
             st = assert_fine_level_close(got[:5], ref, what=f"{name} level {lvl} ")
-            print(f"fp16x3 {name} level {lvl}: " + ", ".join(f"{k} max {v[1]:.2e} ({v[0]:.4%} > 1e-4)" for k, v in st.items()))
+            print(f"fp16x3 {name} level {lvl}: " + ", ".join(f"{k} max {v[1]:.2e} ({v[0]} rays > 1e-4)" for k, v in st.items()))
         else:
             errs = assert_level_close(got[:5], ref, rtol=RTOL, what=f"{name} level {lvl} ", level=lvl)
             print(f"fp16x3 {name} level {lvl}: " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
@@ -71,7 +71,7 @@ def test_fp16x3_forward_vs_oracle(kind):
     for lvl in range(2):
         if lvl > 0 and kind == "trained_like":
             st = assert_fine_level_close(got[lvl], want[lvl], what=f"{kind} level {lvl} ")
-            print(f"fp16x3 {kind} level {lvl} vs fp32 oracle: " + ", ".join(f"{k} max {v[1]:.2e} ({v[0]:.4%} > 1e-4)" for k, v in st.items()))
+            print(f"fp16x3 {kind} level {lvl} vs fp32 oracle: " + ", ".join(f"{k} max {v[1]:.2e} ({v[0]} rays > 1e-4)" for k, v in st.items()))
             st = assert_fine_level_close(got[lvl], emu[lvl], what=f"{kind} level {lvl} (emulated) ")
             print(f"fp16x3 {kind} level {lvl} vs emulated split oracle: " + ", ".join(f"{k} max {v[1]:.2e}" for k, v in st.items()))
             continue
