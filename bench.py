@@ -415,9 +415,19 @@ def main():
             dist.all_reduce(frame_ms, op=dist.ReduceOp.MAX)
         frame_ms = float(frame_ms.item())
 
-    if rank != 0:
+    def shutdown():
+        """Tear down in an order that cannot hang: the captured graphs hold NCCL kernels, so they go first."""
+        nonlocal arm
         if world > 1:
+            import gc
+            barrier()
+            arm = None
+            gc.collect()
+            torch.cuda.synchronize()
             dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
@@ -497,9 +507,8 @@ def main():
             "what": "render_frame: on-device ray generation, both levels, rows sharded over ranks, "
                     "all_gather of coarse+fine RGB and distance"},
     }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown()
 
 
 if __name__ == "__main__":
