@@ -416,15 +416,14 @@ def main():
         frame_ms = float(frame_ms.item())
 
     def shutdown():
-        """Tear down in an order that cannot hang: the captured graphs hold NCCL kernels, so they go first."""
-        nonlocal arm
+        """Leave without tearing NCCL down: the captured graphs hold NCCL kernels and `destroy_process_group` was seen
+        to hang behind them (round 2, N = 2).  Every rank waits for the others (so nobody's peer disappears under a
+        collective), flushes its output and exits the process; torchrun sees exit code 0."""
         if world > 1:
-            import gc
             barrier()
-            arm = None
-            gc.collect()
-            torch.cuda.synchronize()
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
     if rank != 0:
         shutdown()

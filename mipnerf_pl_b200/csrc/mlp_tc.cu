@@ -265,8 +265,20 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
 #endif
 template <int kFmt, bool kX3, bool kRelu, bool kDens>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int layer, int c0, uint8_t* myA, uint32_t rowoff,
-                                               uint32_t rx, float (&dpart)[8]) {
-  const float* __restrict__ bias = c_small.bias[layer] + c0;
+                                               uint32_t rx, float (&dpart)[8], const SmallParams* __restrict__ gsp) {
+  // A runtime layer index turns c_small.bias[layer][c] into indexed constant-bank loads (LDC c[3][R+imm], ~30 cycles
+  // each and not pipelined); the same words read from the packed image in global memory are warp-uniform LDG.128s
+  // that pipeline, so the rolled epilogue takes its biases from there.
+  float bias[32], wden[kDens ? 32 : 1];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(gsp->bias[layer] + c0) + q);
+    bias[4 * q] = t.x, bias[4 * q + 1] = t.y, bias[4 * q + 2] = t.z, bias[4 * q + 3] = t.w;
+    if (kDens) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(gsp->w_density + c0) + q);
+      wden[4 * q] = u.x, wden[4 * q + 1] = u.y, wden[4 * q + 2] = u.z, wden[4 * q + 3] = u.w;
+    }
+  }
   uint8_t* slab = myA + (c0 >> 6) * kStageBytes + rowoff;
   const uint32_t ci0 = (uint32_t)(c0 & 63) >> 3;
 #pragma unroll
@@ -278,8 +290,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int laye
       float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
       fadd2(a, b, bias[c], bias[c + 1]);
       if (kDens)  // density_layer on the fp32 (un-rounded) h7        (models/mip_nerf.py:98)
-        ffma2(dpart[2 * e], dpart[2 * e + 1], fmaxf(a, 0.f), fmaxf(b, 0.f), c_small.w_density[c0 + c],
-              c_small.w_density[c0 + c + 1]);
+        ffma2(dpart[2 * e], dpart[2 * e + 1], fmaxf(a, 0.f), fmaxf(b, 0.f), wden[kDens ? c : 0],
+              wden[kDens ? c + 1 : 0]);
       if (kX3) {
         if (kRelu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
         w[e] = pack2<kFmt>(a, b);
@@ -296,7 +308,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int laye
 }
 
 template <int kFmt, bool kX3>
-__device__ __forceinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* myA, int row, float& dens, int layer) {
+__device__ __forceinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* myA, int row, float& dens, int layer,
+                                                      const SmallParams* __restrict__ gsp) {
   float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)row & 7u;
   uint32_t v0[32], v1[32];
@@ -305,14 +318,14 @@ __device__ __forceinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* m
   for (int kk = 0; kk < 4; ++kk) {
     tmem_ld_wait();
     tmem_ld32(t_acc + 64 * kk + 32, v1);
-    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v0, layer, 64 * kk, myA, rowoff, rx, dpart);
-    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart);
-    else epilogue_chunk<kFmt, kX3, false, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart);
+    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
+    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
+    else epilogue_chunk<kFmt, kX3, false, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
     tmem_ld_wait();
     if (kk < 3) tmem_ld32(t_acc + 64 * kk + 64, v0);
-    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart);
-    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart);
-    else epilogue_chunk<kFmt, kX3, false, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart);
+    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
+    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
+    else epilogue_chunk<kFmt, kX3, false, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
   }
   if (layer == 7)
     dens = ((dpart[0] + dpart[1]) + (dpart[2] + dpart[3])) + ((dpart[4] + dpart[5]) + (dpart[6] + dpart[7]));
@@ -778,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         }
         if (l < 9) {
           if (kX3 || MIPNERF_TC_ROLLED_EPILOGUE) {
-            epilogue_trunk_rolled<kFmt, kX3>(t_acc, myA, row, dens, l);
+            epilogue_trunk_rolled<kFmt, kX3>(t_acc, myA, row, dens, l, gsp);
           } else {
             switch (l) {
               case 0: epilogue_trunk<kFmt, 0, kX3>(t_acc, myA, row, dens); break;
