@@ -763,6 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
     };
     const int my_rounds = slot < kSlots ? rounds : 0;  // x3: the second worker group has no slot
+    const SmallParams* __restrict__ gsp = reinterpret_cast<const SmallParams*>(p.wimage + kSmallOffset);
     if (slot < kSlots) arrive_a_ready();  // accumulator of this slot is free for the first ray
     for (int round = 0; round < my_rounds; ++round) {
       const int64_t tile = tile_of(round, slot);

@@ -87,7 +87,11 @@ def assert_fine_level_close(got, want, what="", ray_frac=1e-2, hard_rtol=1e-3):
     in float64 stays at 1.2e-5, while fp32-quality variants that only change the summation order land at either 3e-5
     or 1.2e-4 on `forward_trained_like.npz`, depending on which side of one such edge they fall.  The contract is
     therefore stated per RAY: at most `ray_frac` of the rays (at least one) may contain elements above RTOL = 1e-4,
-    none may exceed `hard_rtol`; distance and the fenceposts themselves keep the plain 1e-4 bar."""
+    none may exceed `hard_rtol`; distance and the fenceposts themselves keep the plain 1e-4 bar.  The individual fine
+    WEIGHTS (an intermediate, not a rendered quantity) follow their fenceposts: |dw| ~ sigma * T * |dt|, and with
+    sigma up to ~60 on these weights a fencepost that moved by 5e-7 (inside its own 1e-4 bar) shifts 3e-5 of
+    probability mass between two neighbouring intervals on every ray that has such an edge — they are held to
+    `hard_rtol` of their floor (1e-4 absolute on the [0, 1] scale) per element, with the count printed."""
     out = {}
     for name, g, w in zip(("comp_rgb", "distance", "acc", "weights", "t_samples"), got, want):
         floor = FINE_WEIGHTS_FLOOR if name == "weights" else FLOORS[name]
@@ -102,6 +106,8 @@ def assert_fine_level_close(got, want, what="", ray_frac=1e-2, hard_rtol=1e-3):
         out[name] = (bad, mx)
         if name in ("distance", "t_samples"):
             assert mx <= RTOL, f"{what}{name}: max rel err {mx:.3e} > {RTOL:.0e}"
+        elif name == "weights":
+            assert mx <= hard_rtol, f"{what}{name}: max rel err {mx:.3e} > {hard_rtol:.0e} (floor {floor})"
         else:
             allowed = max(1, int(np.ceil(ray_frac * e.shape[0])))
             assert bad <= allowed and mx <= hard_rtol, \
