@@ -191,6 +191,15 @@ int mipnerf_b200_forward_backward_rng(const mipnerf_b200_config* cfg, const mipn
 int mipnerf_b200_linear_tc(const float* x, const float* weight, const float* bias, float* y, int64_t m, int n,
                            int k, int relu, int precision, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Stand-alone tensor-core weight gradient of one nn.Linear (what loss.backward() accumulates into layer.weight.grad /
+ * layer.bias.grad, models/nerf_system.py:108-111):  dw[n, k1+k2] = dy[m,n]^T . [x1[m,k1] | x2[m / x2_row_div, k2]],
+ * db[n] = column sums of dy; n in {128,256}, 16-bit operands rounded while staging, fp32 accumulation, per-slice
+ * partials reduced in a fixed order (bit-reproducible).  x2 may be NULL (k2 = 0). */
+size_t mipnerf_b200_wgrad_tc_scratch_bytes(int n, int k);
+int mipnerf_b200_wgrad_tc(const float* dy, int n, const float* x1, int k1, const float* x2, int k2, int x2_row_div,
+                          int64_t m, float* dw, float* db, int precision, void* scratch, size_t scratch_bytes,
+                          void* stream);
+
 /* torch.optim.Adam.step() for one flat fp32 tensor (models/nerf_system.py:70-72; amsgrad off, no weight
  * decay): `step` is the 1-based step count after this update; the gradient is read as grad * grad_scale
  * (1/world_size after a sum all-reduce). */

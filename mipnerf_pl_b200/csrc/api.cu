@@ -672,6 +672,30 @@ int mipnerf_b200_linear_tc(const float* x, const float* weight, const float* bia
   return MIPNERF_B200_OK;
 }
 
+size_t mipnerf_b200_wgrad_tc_scratch_bytes(int n, int k) {
+  if (n < 1 || k < 1) return 0;
+  return sizeof(float) * (size_t)mipnerf::kWgradMaxSlices * n * (k + 1);
+}
+
+int mipnerf_b200_wgrad_tc(const float* dy, int n, const float* x1, int k1, const float* x2, int k2, int x2_row_div,
+                          int64_t m, float* dw, float* db, int precision, void* scratch, size_t scratch_bytes,
+                          void* stream) {
+  if (m < 0 || k1 < 1 || k2 < 0 || !mipnerf::wgrad_tc_shape_ok(n))
+    return fail(MIPNERF_B200_EUNSUPPORTED, "wgrad_tc: n in {128,256} (got n=%d)", n);
+  if (precision != MIPNERF_B200_BF16 && precision != MIPNERF_B200_FP16)
+    return fail(MIPNERF_B200_EINVAL, "wgrad_tc: precision must be BF16 or FP16");
+  if (!dw || !db || (m > 0 && (!dy || !x1 || (k2 > 0 && !x2)))) return fail(MIPNERF_B200_EINVAL, "NULL tensor");
+  const size_t need = mipnerf_b200_wgrad_tc_scratch_bytes(n, k1 + k2);
+  if (!scratch || scratch_bytes < need) return fail(MIPNERF_B200_EWORKSPACE, "scratch %zu < %zu bytes", scratch_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  int slices = 0;
+  CUDA_TRY(mipnerf::launch_wgrad_tc_partials(dy, n, x1, k1, k1, k2 > 0 ? x2 : nullptr, k2, k2, x2_row_div,
+                                             static_cast<float*>(scratch), m, mipnerf::kWgradMaxSlices, precision,
+                                             &slices, st));
+  CUDA_TRY(mipnerf::launch_wgrad_reduce(static_cast<float*>(scratch), slices, n, k1 + k2, dw, db, 0, st));
+  return MIPNERF_B200_OK;
+}
+
 int mipnerf_b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                            double lr, double beta1, double beta2, double eps, int64_t step, double grad_scale,
                            void* stream) {

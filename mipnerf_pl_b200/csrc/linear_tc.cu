@@ -13,6 +13,8 @@
 //     ReLU, ReLU-mask by another activation (dgrad);
 //   * staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap (warp-specialised, two TMEM
 //     accumulators): the pass is bound by its 1 GB of HBM traffic, not by its 69 GFLOP.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "profile.h"
 #include "tc_common.cuh"
@@ -354,6 +356,205 @@ __global__ void __launch_bounds__(128, 2) wgrad_tc_kernel(const WgradTcParams p)
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad, second generation: NO transposition.  The reduction index of dW = dY^T . X is the row m, and a row-major
+// [m][col] tile IS the canonical "MN-major" UMMA operand (instruction-descriptor bits 15 / 16): 64 consecutive
+// columns (128 B) x 8 rows form one 128-byte-swizzle atom, column blocks LBO apart, 8-row groups SBO apart.  Staging
+// is therefore a straight copy: a warp reads one whole row (1 KB, coalesced), rounds to 16 bit and stores one 16-byte
+// chunk per lane at the swizzled position of the same row — no per-thread column walks, no 32-row register tiles.
+//   grid (slices, k tiles); one CTA per SM covers ALL n_dim <= 256 output rows (two M = 128 accumulators, 2 x 256
+//   TMEM columns), so dY and X are each read once per k tile;
+//   warps 0-7 stage 64-row slabs into a 3-deep ring (64 KB per stage), warp 8 issues 4 K-steps x n_dim/128 MMAs per
+//   slab and frees the stage with tcgen05.commit; after the last slab warps 0-7 drain the accumulators through a
+//   shared-memory transpose (coalesced partial rows) and add up the bias gradient (column sums of dY, kept in fp32
+//   by the thread that staged the column) in a fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWgStages = 3;
+constexpr int kWgSlab = 64;                    // rows (reduction steps) per stage
+constexpr uint32_t kWgOperand = kWgSlab * 512; // 64 rows x 256 cols x 2 B
+constexpr uint32_t kWgStage = 2 * kWgOperand;
+constexpr uint32_t kWgBlock = kWgSlab * 128;   // one 64-column block of a slab
+
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;  // stride between 64-element blocks along M / N
+  d |= (uint64_t)(sbo >> 4) << 32;  // stride between 8-row groups along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+  return d;
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p, int swap_strides) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* ring = smem;
+  float* bias_s = reinterpret_cast<float*>(ring + kWgStages * kWgStage);  // [8 warps][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 8 * 256);
+  uint64_t* full = bars;                  // [stages], 8 arrivals (one per stager warp)
+  uint64_t* empty = bars + kWgStages;     // [stages], tcgen05.commit
+  uint64_t* done = bars + 2 * kWgStages;  // all MMAs of the slice have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.k1 + p.k2;
+  const int kg0 = blockIdx.y * 256;
+  const int nk = K - kg0 < 256 ? K - kg0 : 256;  // valid output columns of this k tile
+  const int nk_mma = (nk + 63) & ~63;            // whole 64-column blocks (padding staged as zeros)
+  const int n_halves = p.n_dim >> 7;
+  const int64_t m_begin = (int64_t)blockIdx.x * p.slice_rows;
+  const int64_t m_end = (m_begin + p.slice_rows) < p.m ? (m_begin + p.slice_rows) : p.m;
+  const bool has_rows = m_begin < m_end;
+  const int slabs = has_rows ? (int)((m_end - m_begin + kWgSlab - 1) / kWgSlab) : 0;
+  // the k tile lies in X1 or in X2 (the launcher guarantees it never straddles)
+  const bool in_x1 = kg0 < p.k1;
+  const float* xs = in_x1 ? p.x1 : p.x2;
+  const int ldx = in_x1 ? p.ld1 : p.ld2, xdiv = in_x1 ? 1 : p.x2_row_div, xc0 = in_x1 ? kg0 : kg0 - p.k1;
+  const bool xvec = (ldx & 3) == 0 && xdiv == 1 && (xc0 & 3) == 0 && (nk & 7) == 0 &&
+                    (reinterpret_cast<uintptr_t>(xs) & 15) == 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full[s], 8);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ================================================ MMA issue ================================================
+    if (lane == 0 && has_rows) {
+      const uint32_t idesc = make_idesc_f16(128, nk_mma, kFmt) | (1u << 15) | (1u << 16);  // A and B MN-major
+      const uint32_t lbo = swap_strides ? 1024u : kWgBlock, sbo = swap_strides ? kWgBlock : 1024u;
+      for (int it = 0; it < slabs; ++it) {
+        const int s = it % kWgStages;
+        mbar_wait(&full[s], (uint32_t)(it / kWgStages) & 1u);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + (size_t)s * kWgStage), sb = sa + kWgOperand;
+#pragma unroll
+        for (int j = 0; j < kWgSlab / 16; ++j) {  // 16 rows = two 8-row groups = 2 KB further into every block
+          for (int h = 0; h < n_halves; ++h)
+            umma_ss(tmem_base + h * 256, make_sw128_mn_desc(sa + h * 2 * kWgBlock + j * 2048, lbo, sbo),
+                    make_sw128_mn_desc(sb + j * 2048, lbo, sbo), idesc, (it | j) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ================================================= stagers =================================================
+    float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // column sums of dY, columns lane*8 .. +7, this warp's rows
+    const int c8 = lane * 8;
+    const bool a_on = c8 < p.n_dim, b_on = c8 < nk_mma;
+    const uint32_t blk = (uint32_t)(lane >> 3) * kWgBlock, chunk = (uint32_t)(lane & 7);
+    for (int it = 0; it < slabs; ++it) {
+      const int s = it % kWgStages;
+      if (it >= kWgStages) mbar_wait(&empty[s], (uint32_t)(it / kWgStages - 1) & 1u);
+      uint8_t* sa = ring + (size_t)s * kWgStage;
+      uint8_t* sb = sa + kWgOperand;
+      const int64_t m0 = m_begin + (int64_t)it * kWgSlab;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 fa[4][2], fb[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + 8 * (half * 4 + i);
+          const int64_t row = m0 + r;
+          const bool ok = row < m_end;
+          fa[i][0] = fa[i][1] = fb[i][0] = fb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && a_on) {
+            const float4* src = reinterpret_cast<const float4*>(p.dy + row * (int64_t)p.n_dim + c8);
+            fa[i][0] = __ldg(src), fa[i][1] = __ldg(src + 1);
+          }
+          if (ok && c8 < nk) {
+            if (xvec) {
+              const float4* src = reinterpret_cast<const float4*>(xs + row * (int64_t)ldx + xc0 + c8);
+              fb[i][0] = __ldg(src), fb[i][1] = __ldg(src + 1);
+            } else {
+              const float* src = xs + (row / xdiv) * (int64_t)ldx + xc0 + c8;
+              float t[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = (c8 + e < nk) ? __ldg(src + e) : 0.f;
+              fb[i][0] = make_float4(t[0], t[1], t[2], t[3]), fb[i][1] = make_float4(t[4], t[5], t[6], t[7]);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = warp + 8 * (half * 4 + i);
+          const uint32_t off = blk + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4);
+          if (a_on) {
+            bs[0] += fa[i][0].x, bs[1] += fa[i][0].y, bs[2] += fa[i][0].z, bs[3] += fa[i][0].w;
+            bs[4] += fa[i][1].x, bs[5] += fa[i][1].y, bs[6] += fa[i][1].z, bs[7] += fa[i][1].w;
+            *reinterpret_cast<uint4*>(sa + off) =
+                make_uint4(pack2<kFmt>(fa[i][0].x, fa[i][0].y), pack2<kFmt>(fa[i][0].z, fa[i][0].w),
+                           pack2<kFmt>(fa[i][1].x, fa[i][1].y), pack2<kFmt>(fa[i][1].z, fa[i][1].w));
+          }
+          if (b_on)
+            *reinterpret_cast<uint4*>(sb + off) =
+                make_uint4(pack2<kFmt>(fb[i][0].x, fb[i][0].y), pack2<kFmt>(fb[i][0].z, fb[i][0].w),
+                           pack2<kFmt>(fb[i][1].x, fb[i][1].y), pack2<kFmt>(fb[i][1].z, fb[i][1].w));
+        }
+      }
+      fence_proxy_async_smem();  // this thread's st.shared -> visible to the tensor core's (async-proxy) reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    // ---- bias gradient: per-warp column sums -> fixed-order sum over the 8 warps
+    if (a_on) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bias_s[warp * 256 + c8 + e] = bs[e];
+    }
+    if (has_rows) {
+      mbar_wait(done, 0);  // every MMA has completed: accumulators final, the ring is free
+      tc_fence_after();
+    }
+    named_bar(1, 256);
+    float* out = p.part + (size_t)blockIdx.x * p.n_dim * (K + 1);
+    if (blockIdx.y == 0 && tid < p.n_dim) {
+      float t = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += bias_s[w8 * 256 + tid];
+      out[(size_t)tid * (K + 1) + K] = t;
+    }
+    // ---- accumulators: warp -> (half = warp / 4, TMEM lane quarter = warp % 4), 32 columns at a time through a
+    //      padded shared-memory tile so that the global stores run along k (coalesced)
+    const int h = warp >> 2, q = warp & 3;
+    if (h < n_halves) {
+      float* tile = reinterpret_cast<float*>(ring) + warp * (32 * 33);
+      const int n_base = h * 128 + q * 32;
+      for (int c = 0; c < nk_mma; c += 32) {
+        uint32_t v[32];
+        if (has_rows) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) tile[lane * 33 + e] = __uint_as_float(v[e]);
+        __syncwarp();
+        if (c + lane < nk) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) out[(size_t)(n_base + r) * (K + 1) + kg0 + c + lane] = tile[r * 33 + lane];
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 int g_sms = 0;
 bool g_attr[2] = {false, false};
 
@@ -412,6 +613,7 @@ cudaError_t launch_linear_tc(const float* x, int ldx, const void* image, float* 
 bool wgrad_tc_shape_ok(int n_dim) { return n_dim == 128 || n_dim == 256; }
 
 // Partials only; the caller runs the fixed-order reduction (train_kernels.cu) afterwards.  Returns the slice count.
+// MIPNERF_B200_WGRAD_TC=1 selects the first-generation (transposing) kernel for A/B runs.
 cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
                                      int ld2, int k2, int x2_row_div, float* part, int64_t m, int max_slices,
                                      int precision, int* slices_out, cudaStream_t st) {
@@ -423,6 +625,39 @@ cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  const int fmt = precision == 1 ? 1 : 0;
+  const char* gen_env = getenv("MIPNERF_B200_WGRAD_TC");  // read per call: the tests flip it inside one process
+  const int generation = (gen_env && gen_env[0] == '1') ? 1 : 2;
+  const char* swap_env = getenv("MIPNERF_B200_WGRAD_SWAP");
+  const int swap_strides = (swap_env && swap_env[0] == '1') ? 1 : 0;
+  const bool mn_ok = (k2 == 0 || k1 % 256 == 0) && (n_dim & 7) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
+  if (generation == 2 && mn_ok) {
+    const int k_tiles = (K + 255) / 256;
+    int64_t slices = g_sms / k_tiles;  // one CTA per SM, one wave
+    const int64_t by_rows = (m + kWgSlab - 1) / kWgSlab;
+    if (slices > by_rows) slices = by_rows;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    int64_t slice_rows = (m + slices - 1) / slices;
+    slice_rows = (slice_rows + kWgSlab - 1) / kWgSlab * kWgSlab;
+    static bool attr2[2] = {false, false};
+    const size_t smem = 1024 + (size_t)kWgStages * kWgStage + 8 * 256 * sizeof(float) + 128;
+    if (!attr2[fmt]) {
+      cudaError_t e = fmt ? cudaFuncSetAttribute(wgrad_mn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(wgrad_mn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr2[fmt] = true;
+    }
+    WgradTcParams p{};
+    p.dy = dy, p.n_dim = n_dim, p.x1 = x1, p.ld1 = ld1, p.k1 = k1, p.x2 = x2, p.ld2 = ld2, p.k2 = k2;
+    p.x2_row_div = x2_row_div, p.part = part, p.m = m, p.slice_rows = slice_rows;
+    dim3 grid((unsigned)slices, (unsigned)k_tiles);
+    LaunchScope scope(kKernWgradTc, st);
+    if (fmt) wgrad_mn_kernel<1><<<grid, 288, smem, st>>>(p, swap_strides);
+    else wgrad_mn_kernel<0><<<grid, 288, smem, st>>>(p, swap_strides);
+    *slices_out = (int)slices;
+    return cudaGetLastError();
+  }
   const int n_tiles = (n_dim + 127) / 128, k_tiles = (K + 255) / 256;
   int64_t slices = (2 * (int64_t)g_sms + n_tiles * k_tiles - 1) / (n_tiles * k_tiles);  // one wave of 2 CTAs per SM
   const int64_t by_rows = (m + 63) / 64;
@@ -431,7 +666,6 @@ cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1
   if (slices < 1) slices = 1;
   int64_t slice_rows = (m + slices - 1) / slices;
   slice_rows = (slice_rows + 63) / 64 * 64;
-  const int fmt = precision == 1 ? 1 : 0;
   static bool attr[2] = {false, false};
   const size_t smem = 1024 + 16384 + 32768 + 64;
   if (!attr[fmt]) {

@@ -242,7 +242,42 @@ def test_linear_tc_matches_fp32_linear(precision, tol, n, k):
     assert float((y.double() - exact).abs().max()) <= tol * scale
 
 
-@pytest.mark.parametrize("wgrad_tc", ["0", "1"])
+@pytest.mark.parametrize("generation", ["1", "2"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n,k1,k2,div,m", [(256, 256, 0, 1, 128 * 173 + 37), (256, 96, 0, 1, 9000), (256, 256, 96, 1, 20000),
+                                           (128, 256, 27, 128, 128 * 100), (256, 256, 0, 1, 40)])
+def test_wgrad_tc_matches_rounded_operands(precision, n, k1, k2, div, m, generation, monkeypatch):
+    """dW = dY^T [X1 | X2[row / div]] and db = colsum(dY) on tcgen05: against the exact product of the SAME 16-bit
+    operands (isolates layout / descriptor bugs from rounding: only the fp32 accumulation order differs), ragged row
+    counts, the skip concat (K = 352 -> two k tiles), the per-ray view-direction operand, fewer rows than one slab.
+    generation 2 = both operands MN-major straight from their row-major tiles, 1 = the transposing kernel."""
+    from mipnerf_pl_b200 import _cabi
+    monkeypatch.setenv("MIPNERF_B200_WGRAD_TC", generation)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    dy = torch.randn(m, n, generator=gen).to(DEV)
+    x1 = torch.randn(m, k1, generator=gen).to(DEV)
+    x2 = torch.randn((m + div - 1) // div, k2, generator=gen).to(DEV) if k2 else None
+    K = k1 + k2
+    dw = torch.full((n, K), float("nan"), device=DEV)
+    db = torch.full((n,), float("nan"), device=DEV)
+    lib = _cabi.lib()
+    scratch = torch.empty(lib.mipnerf_b200_wgrad_tc_scratch_bytes(n, K), dtype=torch.uint8, device=DEV)
+    prec = _cabi.BF16 if precision == "bf16" else _cabi.FP16
+    _cabi.check(lib.mipnerf_b200_wgrad_tc(dy.data_ptr(), n, x1.data_ptr(), k1, x2.data_ptr() if k2 else None, k2, div, m,
+                                          dw.data_ptr(), db.data_ptr(), prec, scratch.data_ptr(), scratch.numel(),
+                                          torch.cuda.current_stream().cuda_stream), "wgrad_tc")
+    torch.cuda.synchronize()
+    dt = torch.bfloat16 if precision == "bf16" else torch.float16
+    xc = x1 if not k2 else torch.cat([x1, x2.repeat_interleave(div, dim=0)[:m]], dim=1)
+    want = dy.to(dt).double().T @ xc.to(dt).double()
+    scale = float(want.abs().max())
+    err = float((dw.double() - want).abs().max())
+    assert err <= 3e-6 * scale * max(1.0, (m / 64) ** 0.5), (err, scale)
+    want_b = dy.double().sum(dim=0)
+    assert float((db.double() - want_b).abs().max()) <= 1e-5 * float(dy.abs().sum(dim=0).max())
+
+
+@pytest.mark.parametrize("wgrad_tc", ["0", "1", "2"])
 @pytest.mark.parametrize("precision,loss_tol,grad_tol", [("bf16", 5e-3, 1.5e-1), ("fp16", 1e-3, 1.5e-1)])
 def test_tensor_core_training_mode_tracks_fp32(precision, loss_tol, grad_tol, wgrad_tc, monkeypatch):
     """precision='bf16'|'fp16': forward and dgrad GEMMs on tcgen05.  Loss and every gradient tensor stay within
@@ -250,7 +285,7 @@ def test_tensor_core_training_mode_tracks_fp32(precision, loss_tol, grad_tol, wg
     NOT the operand epsilon for the trunk: an activation perturbed by eps flips the ReLU masks of a fraction ~eps of
     the units, each flip adds/removes a full-size term, so the gradient moves by ~sqrt(eps) (observed: 5e-2 for fp16
     on layers.0, 6e-2 for bf16) — the same mechanism that limits the fp32 trunk bar to 2e-3."""
-    monkeypatch.setenv("MIPNERF_B200_WGRAD_TC", wgrad_tc)   # "1" (default): tcgen05 wgrad partials; "0": fp32 FFMA wgrad
+    monkeypatch.setenv("MIPNERF_B200_WGRAD_TC", wgrad_tc)   # "2" (default): MN-major tcgen05 wgrad, "1": transposing tcgen05 wgrad, "0": fp32 FFMA wgrad
     b = 200
     rays = to_dev(mp.random_ray_batch(b, seed=41, multiscale=True))
     rgbs = torch.rand(b, 3, device=DEV)
