@@ -390,6 +390,60 @@ TrainScratch carve_train(const mipnerf_b200_config* c, const Dims& d, int64_t ra
   return s;
 }
 
+// Scratch of the fused tensor-core training step (forward = the level kernels with the activation dump, backward on
+// 16-bit tile images, train_t16.cu).  Overlays the same workspace as TrainScratch.
+struct FusedScratch {
+  uint8_t *act[2], *v[2];                // forward dump per level: [9][rays][64 KB], [rays][32 KB]
+  float *raw_rgb[2], *raw_density[2];    // raw heads per level
+  float *enc, *venc, *d_raw_rgb, *d_raw_density, *part, *t[2], *w[2];
+  uint8_t *d_v, *d_a, *d_b;              // gradient tile images: [rays][32 KB], [rays][64 KB] x 2
+  uint8_t *images, *packed, *tcws;
+  size_t tcws_bytes, bytes;
+};
+
+FusedScratch carve_fused(const mipnerf_b200_config* c, const Dims& d, int64_t rays, int precision, void* base) {
+  FusedScratch s{};
+  const size_t m = (size_t)rays * c->num_samples;
+  size_t off = 0;
+  auto take_bytes = [&](size_t bytes) {
+    uint8_t* p = base ? static_cast<uint8_t*>(base) + off : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  auto take = [&](size_t elems) { return reinterpret_cast<float*>(take_bytes(elems * sizeof(float))); };
+  for (int l = 0; l < 2; ++l) {
+    s.act[l] = take_bytes((size_t)9 * rays * 65536);
+    s.v[l] = take_bytes((size_t)rays * 32768);
+    s.raw_rgb[l] = take(m * 3);
+    s.raw_density[l] = take(m);
+    s.t[l] = take((size_t)rays * (c->num_samples + 1));
+    s.w[l] = take(m);
+  }
+  s.enc = take(m * d.xyz_dim);
+  s.venc = take((size_t)rays * d.view_dim);
+  s.d_raw_rgb = take(m * 3);
+  s.d_raw_density = take(m);
+  s.d_v = take_bytes((size_t)rays * 32768);
+  s.d_a = take_bytes((size_t)rays * 65536);
+  s.d_b = take_bytes((size_t)rays * 65536);
+  const size_t max_n = c->net_width > c->net_width_condition ? c->net_width : c->net_width_condition;
+  const size_t max_k = (size_t)c->net_width + (d.xyz_dim > d.view_dim ? d.xyz_dim : d.view_dim) + 1;
+  s.part = take((size_t)mipnerf::kWgradMaxSlices * max_n * max_k);
+  s.images = take_bytes((size_t)kTrainImages * kTrainImageBytes);
+  s.packed = take_bytes(mipnerf::tc_packed_bytes(c, precision));
+  s.tcws_bytes = mipnerf::tc_workspace_bytes(c, rays, precision);
+  s.tcws = take_bytes(s.tcws_bytes);
+  s.bytes = off;
+  return s;
+}
+
+// The fused step needs the level kernels' architecture (8 x 256 trunk, 128 samples, ...) and at most two levels.
+// MIPNERF_B200_TRAIN_FUSED=0 keeps the per-layer tensor-core path (A/B runs).
+bool train_fused_supported(const mipnerf_b200_config* c, int precision) {
+  return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16) && mipnerf::tc_supported(c, precision) &&
+         c->num_levels <= 2 && c->net_depth == 8;
+}
+
 // Tensor-core GEMMs of the training step exist for the default widths only (linear_tc.cu).
 bool train_tc_supported(const mipnerf_b200_config* c, const Dims& d) {
   if (!(c->net_width == 256 && c->net_width_condition == 128 && d.xyz_dim == 96 && c->net_depth <= kMaxTrainDepth))
@@ -419,7 +473,128 @@ size_t mipnerf_b200_train_workspace_bytes(const mipnerf_b200_config* cfg, int64_
   if (check_config(cfg, &d) != MIPNERF_B200_OK || check_train_config(cfg) != MIPNERF_B200_OK || num_rays < 0)
     return 0;
   const int64_t r = num_rays < kChunkRaysFp32 ? num_rays : kChunkRaysFp32;
-  return carve_train(cfg, d, r > 0 ? r : 1, nullptr).bytes;
+  size_t bytes = carve_train(cfg, d, r > 0 ? r : 1, nullptr).bytes;
+  for (int precision : {MIPNERF_B200_BF16, MIPNERF_B200_FP16})  // the fused tensor-core step overlays the same buffer
+    if (train_fused_supported(cfg, precision)) {
+      const size_t f = carve_fused(cfg, d, r > 0 ? r : 1, precision, nullptr).bytes;
+      if (f > bytes) bytes = f;
+    }
+  return bytes;
+}
+
+static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d, const mipnerf_b200_weights* w,
+                                  const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
+                                  const float* u_jitter, const mipnerf_b200_rng* rng, int white_bkgd, int precision,
+                                  const mipnerf_b200_loss* loss, mipnerf_b200_level_out* outs,
+                                  const mipnerf_b200_linear_grad* grads, bool* touched, void* workspace,
+                                  cudaStream_t st) {
+  const int n = cfg->num_samples, depth = cfg->net_depth, W = cfg->net_width, Wc = cfg->net_width_condition;
+  const float rgb_scale = (float)(1.0 + 2.0 * (double)cfg->rgb_padding);
+  const int64_t B = rays->num_rays;
+  const FusedScratch s0 = carve_fused(cfg, d, B < kChunkRaysFp32 ? B : kChunkRaysFp32, precision, workspace);
+  // ---- once per call (the weights change every optimiser step): the level kernels' packed image, and the
+  //      transposed B operands of the dgrad chain  bwd[i] = W_i[:, :256]^T  (slots depth / depth+1: bottleneck, view)
+  mipnerf_b200_weights wl = *w;
+  wl.packed = s0.packed;
+  CUDA_TRY(mipnerf::tc_pack_weights(cfg, w, precision, s0.packed, st, /*with_v3=*/false));
+  const uint8_t* img_bwd[kMaxTrainDepth + 2] = {nullptr};
+  {
+    int slot = 0;
+    auto pack = [&](const mipnerf_b200_linear& l, int nn, int kk, const uint8_t** out) {
+      uint8_t* dst = s0.images + (size_t)(slot++) * kTrainImageBytes;
+      *out = dst;
+      return mipnerf::launch_pack_linear_image(l.weight, l.in_features, 0, 1, dst, nn, kk, precision, st);
+    };
+    for (int i = 1; i < depth; ++i) CUDA_TRY(pack(w->linears[i], W, W, &img_bwd[i]));
+    CUDA_TRY(pack(w->linears[depth + 1], W, W, &img_bwd[depth]));
+    CUDA_TRY(pack(w->linears[depth + 2], W, Wc, &img_bwd[depth + 1]));
+  }
+  const mipnerf_b200_linear& dl = w->linears[depth];
+  const mipnerf_b200_linear& cl = w->linears[d.n_lin - 1];
+  // fp16 gradients underflow: d loss / d activation is ~1e-7 .. 1e-4 per sample (the loss is a mean over the batch),
+  // below fp16's 6e-5 normal range.  The backward pass is linear in d loss / d raw, so render_backward emits it
+  // scaled by 2^10 (it is bounded by 2/3 per sample: no overflow), every gradient tile image carries that factor, and
+  // the fixed-order reduction of the wgrad partials takes it out again.  bf16 has fp32's range: scale 1.
+  const float gscale = precision == MIPNERF_B200_FP16 ? 1024.f : 1.f, inv_gscale = 1.f / gscale;
+  for (int64_t off = 0; off < B; off += kChunkRaysFp32) {
+    const int64_t cnt = (B - off) < kChunkRaysFp32 ? (B - off) : kChunkRaysFp32;
+    const int64_t m = cnt * n;
+    const mipnerf_b200_rays rc_ = offset_rays(*rays, off, cnt);
+    const FusedScratch s = carve_fused(cfg, d, cnt, precision, workspace);
+    CUDA_TRY(mipnerf::launch_pos_enc(rc_.viewdirs, s.venc, cnt, 0, cfg->deg_view, 1, st));
+    // ---- forward of all levels: two launches, everything the backward needs is left behind as tile images
+    mipnerf_b200_level_out lo[2];
+    mipnerf::TcTrainDump dump{};
+    for (int l = 0; l < cfg->num_levels; ++l) {
+      lo[l] = outs[l];
+      lo[l].comp_rgb = outs[l].comp_rgb + off * 3, lo[l].distance = outs[l].distance + off, lo[l].acc = outs[l].acc + off;
+      lo[l].t_samples = outs[l].t_samples ? outs[l].t_samples + off * (n + 1) : s.t[l];
+      lo[l].weights = outs[l].weights ? outs[l].weights + off * n : s.w[l];
+      lo[l].inds = outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr;
+      dump.act[l] = s.act[l], dump.v[l] = s.v[l], dump.raw_rgb[l] = s.raw_rgb[l], dump.raw_density[l] = s.raw_density[l];
+    }
+    CUDA_TRY(mipnerf::tc_forward(cfg, &wl, &rc_, randomized, t_rand ? t_rand + off * (n + 1) : nullptr,
+                                 u_jitter ? u_jitter + off * (n + 1) : nullptr, rng, white_bkgd, precision, lo, s.tcws,
+                                 s.tcws_bytes, st, &dump, off));
+    auto wgrad = [&](int idx, const void* dy16, const void* x1, int x1_t16, int k1, const float* x2, int k2, int div) {
+      const mipnerf_b200_linear& l = w->linears[idx];
+      int slices = 0;
+      cudaError_t e2 = mipnerf::launch_wgrad_mn_partials(dy16, 1, l.out_features, x1, x1_t16, k1, k1, x2, k2, k2, div,
+                                                         s.part, m, mipnerf::kWgradMaxSlices, precision, &slices, st);
+      if (e2 != cudaSuccess) return e2;
+      e2 = mipnerf::launch_wgrad_reduce(s.part, slices, l.out_features, k1 + k2, grads[idx].weight_grad,
+                                        grads[idx].bias_grad, touched[idx] ? 1 : 0, st, inv_gscale);
+      touched[idx] = true;
+      return e2;
+    };
+    for (int l = 0; l < cfg->num_levels; ++l) {
+      const float* t_cur = lo[l].t_samples;
+      const uint8_t* act = s.act[l];
+      auto h16 = [&](int i) { return act + (size_t)i * cnt * 65536; };  // h_0..h_7, 8 = bottleneck
+      // the IPE features again, in fp32 (operand of two wgrads; the level kernel keeps its own 16-bit copy on chip)
+      CUDA_TRY(mipnerf::launch_ipe_from_t(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc, cnt, n,
+                                          cfg->min_deg_point, cfg->max_deg_point, cfg->disable_integration, st));
+      CUDA_TRY(mipnerf::launch_render_backward(
+          s.raw_rgb[l], s.raw_density[l], t_cur, rc_.directions, loss->target_rgb + off * 3,
+          loss->lossmult ? loss->lossmult + off : nullptr, loss->mask_sum, loss->level_mse_mult[l] * gscale,
+          loss->level_dist_mult[l] * loss->dist_scale * gscale, white_bkgd, cfg->density_bias, rgb_scale,
+          cfg->rgb_padding, s.d_raw_rgb, s.d_raw_density,
+          loss->per_ray_sqerr ? loss->per_ray_sqerr + (int64_t)l * B + off : nullptr,
+          loss->per_ray_distloss ? loss->per_ray_distloss + (int64_t)l * B + off : nullptr, cnt, n, st));
+      // colour head, view layer                                          (models/mip_nerf.py:106-110)
+      CUDA_TRY(mipnerf::launch_wgrad_small_n_t16(s.d_raw_rgb, 3, s.v[l], Wc, s.part, grads[d.n_lin - 1].weight_grad,
+                                                 grads[d.n_lin - 1].bias_grad, touched[d.n_lin - 1] ? 1 : 0, m,
+                                                 precision, st, inv_gscale));
+      touched[d.n_lin - 1] = true;
+      CUDA_TRY(mipnerf::launch_color_dgrad_t16(s.d_raw_rgb, cl.weight, s.v[l], s.d_v, m, Wc, precision, st));
+      CUDA_TRY(wgrad(depth + 2, s.d_v, h16(8), 1, W, s.venc, d.view_dim, n));
+      CUDA_TRY(mipnerf::launch_linear_t16(s.d_v, img_bwd[depth + 1], s.d_a, m, W, Wc, nullptr, nullptr, nullptr,
+                                          precision, st));
+      // bottleneck + density head share h_7                              (models/mip_nerf.py:98-101)
+      CUDA_TRY(wgrad(depth + 1, s.d_a, h16(depth - 1), 1, W, nullptr, 0, 1));
+      CUDA_TRY(mipnerf::launch_wgrad_small_n_t16(s.d_raw_density, 1, h16(depth - 1), W, s.part,
+                                                 grads[depth].weight_grad, grads[depth].bias_grad,
+                                                 touched[depth] ? 1 : 0, m, precision, st, inv_gscale));
+      touched[depth] = true;
+      CUDA_TRY(mipnerf::launch_linear_t16(s.d_a, img_bwd[depth], s.d_b, m, W, W, s.d_raw_density, dl.weight,
+                                          h16(depth - 1), precision, st));
+      // trunk                                                            (models/mip_nerf.py:93-97)
+      uint8_t *cur = s.d_b, *other = s.d_a;
+      for (int i = depth - 1; i >= 0; --i) {
+        const bool skip = takes_skip(cfg, i);
+        if (i == 0) CUDA_TRY(wgrad(0, cur, s.enc, 0, d.xyz_dim, nullptr, 0, 1));
+        else CUDA_TRY(wgrad(i, cur, h16(i - 1), 1, W, skip ? s.enc : nullptr, skip ? d.xyz_dim : 0, 1));
+        if (i > 0) {
+          CUDA_TRY(mipnerf::launch_linear_t16(cur, img_bwd[i], other, m, W, W, nullptr, nullptr, h16(i - 1), precision,
+                                              st));
+          uint8_t* tmp = cur;
+          cur = other;
+          other = tmp;
+        }
+      }
+    }
+  }
+  return MIPNERF_B200_OK;
 }
 
 static int forward_backward_impl(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
@@ -472,6 +647,12 @@ static int forward_backward_impl(const mipnerf_b200_config* cfg, const mipnerf_b
       CUDA_TRY(cudaMemsetAsync(grads[i].bias_grad, 0, sizeof(float) * l.out_features, st));
     }
 
+  {
+    const char* fused_env = getenv("MIPNERF_B200_TRAIN_FUSED");
+    if (tc && B > 0 && train_fused_supported(cfg, precision) && !(fused_env && fused_env[0] == '0'))
+      return forward_backward_fused(cfg, d, w, rays, randomized, t_rand, u_jitter, rng, white_bkgd, precision, loss, outs,
+                                    grads, touched, workspace, st);
+  }
   // ---- tensor-core mode: B operands of every forward / dgrad GEMM, packed once per call (the weights change every
   //      optimiser step).  fwd[i] = W_i[:, :k_main], fwd_skip[i] = W_i[:, 256:352], bwd[i] = W_i[:, :256]^T;
   //      slots depth / depth+1 hold the bottleneck and the view layer.

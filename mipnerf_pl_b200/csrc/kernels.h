@@ -89,9 +89,25 @@ bool wgrad_tc_shape_ok(int n_dim);
 cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
                                      int ld2, int k2, int x2_row_div, float* part, int64_t m, int max_slices,
                                      int precision, int* slices_out, cudaStream_t st);
+cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, const void* x1, int x1_t16, int ld1, int k1,
+                                     const float* x2, int ld2, int k2, int x2_row_div, float* part, int64_t m,
+                                     int max_slices, int precision, int* slices_out, cudaStream_t st);
 // fixed-order reduction of [slices, n_dim, k_dim + 1] partials into dW / db (train_kernels.cu)
 cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_dim, float* dw, float* db,
-                                int accumulate, cudaStream_t st);
+                                int accumulate, cudaStream_t st, float scale = 1.f);
+
+// ---- train_t16.cu (backward pass on 16-bit tile images: [tile = 128 rows][64-column slab][128 rows x 128 B, SW128]) ----
+size_t t16_image_bytes(int64_t rows, int cols);
+cudaError_t launch_t16_pack(const float* src, int ld, int cols, int64_t m, void* image, int precision, cudaStream_t st);
+cudaError_t launch_t16_unpack(const void* image, int cols, float* dst, int ld, int64_t m, int precision,
+                              cudaStream_t st);
+cudaError_t launch_linear_t16(const void* x, const void* image, void* y, int64_t m, int n, int k, const float* r1,
+                              const float* r1w, const void* mask, int precision, cudaStream_t st);
+cudaError_t launch_color_dgrad_t16(const float* d_rgb, const float* wc, const void* v, void* d_v, int64_t m, int k_dim,
+                                   int precision, cudaStream_t st);
+cudaError_t launch_wgrad_small_n_t16(const float* dy, int n_dim, const void* x, int k_dim, float* part, float* dw,
+                                     float* db, int accumulate, int64_t m, int precision, cudaStream_t st,
+                                     float scale = 1.f);
 
 // ---- mlp_tc.cu ----
 // out[ray][n] = b[n] + W[n, in_main : in_main + view_dim] . venc[ray]   (view-direction part of the view layer)

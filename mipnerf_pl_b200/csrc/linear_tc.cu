@@ -248,6 +248,9 @@ struct WgradTcParams {
   int ld2, k2, x2_row_div;
   float* part;      // [slices, n_dim, K + 1]
   int64_t m, slice_rows;
+  // second-generation kernel only: dy / x1 are 16-bit tile images (train_t16.cu) instead of fp32 row-major matrices;
+  // x1's image has k1 / 64 slabs per tile.  x2 is always fp32.
+  int dy_t16, x1_t16;
 };
 
 template <int kFmt>
@@ -386,7 +389,13 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t saddr, uint32_t 
 }
 
 template <int kFmt>
-__global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p, int swap_strides) {
+__device__ __forceinline__ float2 unpack16x2(uint32_t v) {
+  if (kFmt == 1) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+
+template <int kFmt>
+__global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p, int swap_strides) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -396,7 +405,8 @@ __global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p,
   uint64_t* full = bars;                  // [stages], 8 arrivals (one per stager warp)
   uint64_t* empty = bars + kWgStages;     // [stages], tcgen05.commit
   uint64_t* done = bars + 2 * kWgStages;  // all MMAs of the slice have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  uint64_t* rdone = bars + 2 * kWgStages + 1;  // [stages] tile-image dY: the bias-gradient readers are done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kWgStages + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.k1 + p.k2;
   const int kg0 = blockIdx.y * 256;
@@ -413,11 +423,16 @@ __global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p,
   const int ldx = in_x1 ? p.ld1 : p.ld2, xdiv = in_x1 ? 1 : p.x2_row_div, xc0 = in_x1 ? kg0 : kg0 - p.k1;
   const bool xvec = (ldx & 3) == 0 && xdiv == 1 && (xc0 & 3) == 0 && (nk & 7) == 0 &&
                     (reinterpret_cast<uintptr_t>(xs) & 15) == 0;
+  // tile-image operands arrive by bulk copy (warp 9), fp32 operands through the stager warps' registers
+  const bool a16 = p.dy_t16 != 0, b16 = in_x1 && p.x1_t16 != 0;
+  const bool bias_read = a16 && blockIdx.y == 0;  // column sums of dY are then taken from the staged tile
+  const int a_blocks = p.n_dim >> 6, b_blocks = nk_mma >> 6;
 
   if (tid == 0) {
     for (int s = 0; s < kWgStages; ++s) {
-      mbar_init(&full[s], 8);
+      mbar_init(&full[s], ((a16 && b16) ? 0 : 8) + ((a16 || b16) ? 1 : 0));
       mbar_init(&empty[s], 1);
+      mbar_init(&rdone[s], 8);
     }
     mbar_init(done, 1);
     fence_mbar_init();
@@ -448,6 +463,34 @@ __global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p,
       }
       umma_commit(done);
     }
+  } else if (warp == 9) {
+    // ============================== bulk producer (tile-image operands) ==============================
+    if (lane == 0 && (a16 || b16)) {
+      const uint8_t* dy16 = reinterpret_cast<const uint8_t*>(p.dy);
+      const uint8_t* x16 = reinterpret_cast<const uint8_t*>(p.x1);
+      const int x_slabs = p.k1 >> 6;
+      const uint32_t bytes = (uint32_t)((a16 ? a_blocks : 0) + (b16 ? b_blocks : 0)) * kWgBlock;
+      for (int it = 0; it < slabs; ++it) {
+        const int s = it % kWgStages;
+        if (it >= kWgStages) {
+          const uint32_t par = (uint32_t)(it / kWgStages - 1) & 1u;
+          mbar_wait(&empty[s], par);
+          if (bias_read) mbar_wait(&rdone[s], par);
+        }
+        uint8_t* sa = ring + (size_t)s * kWgStage;
+        uint8_t* sb = sa + kWgOperand;
+        const int64_t row0 = m_begin + (int64_t)it * kWgSlab;  // a multiple of 64: one half of a 128-row tile
+        const size_t tile = (size_t)(row0 >> 7), half = (size_t)((row0 >> 6) & 1) * kWgBlock;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        if (a16)
+          for (int b = 0; b < a_blocks; ++b)
+            bulk_g2s(sa + (size_t)b * kWgBlock, dy16 + (tile * a_blocks + b) * 16384 + half, kWgBlock, &full[s]);
+        if (b16)
+          for (int b = 0; b < b_blocks; ++b)
+            bulk_g2s(sb + (size_t)b * kWgBlock, x16 + (tile * x_slabs + (xc0 >> 6) + b) * 16384 + half, kWgBlock,
+                     &full[s]);
+      }
+    }
   } else {
     // ================================================= stagers =================================================
     float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // column sums of dY, columns lane*8 .. +7, this warp's rows
@@ -456,9 +499,12 @@ __global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p,
     const uint32_t blk = (uint32_t)(lane >> 3) * kWgBlock, chunk = (uint32_t)(lane & 7);
     for (int it = 0; it < slabs; ++it) {
       const int s = it % kWgStages;
-      if (it >= kWgStages) mbar_wait(&empty[s], (uint32_t)(it / kWgStages - 1) & 1u);
       uint8_t* sa = ring + (size_t)s * kWgStage;
       uint8_t* sb = sa + kWgOperand;
+      if (a16 && b16) {
+        if (!bias_read) break;  // nothing for the stager warps to do in this CTA
+      } else {
+      if (it >= kWgStages) mbar_wait(&empty[s], (uint32_t)(it / kWgStages - 1) & 1u);
       const int64_t m0 = m_begin + (int64_t)it * kWgSlab;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -469,11 +515,11 @@ __global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p,
           const int64_t row = m0 + r;
           const bool ok = row < m_end;
           fa[i][0] = fa[i][1] = fb[i][0] = fb[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok && a_on) {
+          if (ok && a_on && !a16) {
             const float4* src = reinterpret_cast<const float4*>(p.dy + row * (int64_t)p.n_dim + c8);
             fa[i][0] = __ldg(src), fa[i][1] = __ldg(src + 1);
           }
-          if (ok && c8 < nk) {
+          if (ok && c8 < nk && !b16) {
             if (xvec) {
               const float4* src = reinterpret_cast<const float4*>(xs + row * (int64_t)ldx + xc0 + c8);
               fb[i][0] = __ldg(src), fb[i][1] = __ldg(src + 1);
@@ -490,14 +536,14 @@ __global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p,
         for (int i = 0; i < 4; ++i) {
           const int r = warp + 8 * (half * 4 + i);
           const uint32_t off = blk + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4);
-          if (a_on) {
+          if (a_on && !a16) {
             bs[0] += fa[i][0].x, bs[1] += fa[i][0].y, bs[2] += fa[i][0].z, bs[3] += fa[i][0].w;
             bs[4] += fa[i][1].x, bs[5] += fa[i][1].y, bs[6] += fa[i][1].z, bs[7] += fa[i][1].w;
             *reinterpret_cast<uint4*>(sa + off) =
                 make_uint4(pack2<kFmt>(fa[i][0].x, fa[i][0].y), pack2<kFmt>(fa[i][0].z, fa[i][0].w),
                            pack2<kFmt>(fa[i][1].x, fa[i][1].y), pack2<kFmt>(fa[i][1].z, fa[i][1].w));
           }
-          if (b_on)
+          if (b_on && !b16)
             *reinterpret_cast<uint4*>(sb + off) =
                 make_uint4(pack2<kFmt>(fb[i][0].x, fb[i][0].y), pack2<kFmt>(fb[i][0].z, fb[i][0].w),
                            pack2<kFmt>(fb[i][1].x, fb[i][1].y), pack2<kFmt>(fb[i][1].z, fb[i][1].w));
@@ -506,6 +552,23 @@ __global__ void __launch_bounds__(288, 1) wgrad_mn_kernel(const WgradTcParams p,
       fence_proxy_async_smem();  // this thread's st.shared -> visible to the tensor core's (async-proxy) reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      }
+      if (bias_read) {  // dY arrived as a tile image: take its column sums from shared memory
+        mbar_wait(&full[s], (uint32_t)(it / kWgStages) & 1u);
+        if (a_on) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = warp + 8 * i;
+            const uint4 w = *reinterpret_cast<const uint4*>(sa + blk + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4));
+            const float2 f0 = unpack16x2<kFmt>(w.x), f1 = unpack16x2<kFmt>(w.y), f2 = unpack16x2<kFmt>(w.z),
+                         f3 = unpack16x2<kFmt>(w.w);
+            bs[0] += f0.x, bs[1] += f0.y, bs[2] += f1.x, bs[3] += f1.y;
+            bs[4] += f2.x, bs[5] += f2.y, bs[6] += f3.x, bs[7] += f3.y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rdone[s]);
+      }
     }
     // ---- bias gradient: per-warp column sums -> fixed-order sum over the 8 warps
     if (a_on) {
@@ -612,6 +675,53 @@ cudaError_t launch_linear_tc(const float* x, int ldx, const void* image, float* 
 
 bool wgrad_tc_shape_ok(int n_dim) { return n_dim == 128 || n_dim == 256; }
 
+// Second-generation wgrad partials.  dy / x1 are fp32 row-major matrices, or (dy_t16 / x1_t16 != 0) 16-bit tile images
+// (then m must be a multiple of 128 and x1 has k1 / 64 slabs per tile); x2 is fp32 row-major.
+cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, const void* x1, int x1_t16, int ld1, int k1,
+                                     const float* x2, int ld2, int k2, int x2_row_div, float* part, int64_t m,
+                                     int max_slices, int precision, int* slices_out, cudaStream_t st) {
+  if (!x2) x2 = static_cast<const float*>(x1), ld2 = ld1, k2 = 0;
+  if (x2_row_div < 1) x2_row_div = 1;
+  const int K = k1 + k2;
+  if (!(k2 == 0 || k1 % 256 == 0) || !(n_dim == 128 || n_dim == 256)) return cudaErrorInvalidValue;
+  if ((dy_t16 || x1_t16) && m % 128 != 0) return cudaErrorInvalidValue;
+  if (x1_t16 && k1 % 64 != 0) return cudaErrorInvalidValue;
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int fmt = precision == 1 ? 1 : 0;
+  const char* swap_env = getenv("MIPNERF_B200_WGRAD_SWAP");
+  const int swap_strides = (swap_env && swap_env[0] == '1') ? 1 : 0;
+  const int k_tiles = (K + 255) / 256;
+  int64_t slices = g_sms / k_tiles;  // one CTA per SM, one wave
+  const int64_t by_rows = (m + kWgSlab - 1) / kWgSlab;
+  if (slices > by_rows) slices = by_rows;
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  int64_t slice_rows = (m + slices - 1) / slices;
+  slice_rows = (slice_rows + kWgSlab - 1) / kWgSlab * kWgSlab;
+  static bool attr2[2] = {false, false};
+  const size_t smem = 1024 + (size_t)kWgStages * kWgStage + 8 * 256 * sizeof(float) + 128;
+  if (!attr2[fmt]) {
+    cudaError_t e = fmt ? cudaFuncSetAttribute(wgrad_mn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(wgrad_mn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr2[fmt] = true;
+  }
+  WgradTcParams p{};
+  p.dy = static_cast<const float*>(dy), p.n_dim = n_dim, p.x1 = static_cast<const float*>(x1), p.ld1 = ld1, p.k1 = k1;
+  p.x2 = x2, p.ld2 = ld2, p.k2 = k2, p.x2_row_div = x2_row_div, p.part = part, p.m = m, p.slice_rows = slice_rows;
+  p.dy_t16 = dy_t16, p.x1_t16 = x1_t16;
+  dim3 grid((unsigned)slices, (unsigned)k_tiles);
+  LaunchScope scope(kKernWgradTc, st);
+  if (fmt) wgrad_mn_kernel<1><<<grid, 320, smem, st>>>(p, swap_strides);
+  else wgrad_mn_kernel<0><<<grid, 320, smem, st>>>(p, swap_strides);
+  *slices_out = (int)slices;
+  return cudaGetLastError();
+}
+
 // Partials only; the caller runs the fixed-order reduction (train_kernels.cu) afterwards.  Returns the slice count.
 // MIPNERF_B200_WGRAD_TC=1 selects the first-generation (transposing) kernel for A/B runs.
 cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1, int ld1, int k1, const float* x2,
@@ -628,36 +738,10 @@ cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1
   const int fmt = precision == 1 ? 1 : 0;
   const char* gen_env = getenv("MIPNERF_B200_WGRAD_TC");  // read per call: the tests flip it inside one process
   const int generation = (gen_env && gen_env[0] == '1') ? 1 : 2;
-  const char* swap_env = getenv("MIPNERF_B200_WGRAD_SWAP");
-  const int swap_strides = (swap_env && swap_env[0] == '1') ? 1 : 0;
   const bool mn_ok = (k2 == 0 || k1 % 256 == 0) && (n_dim & 7) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
-  if (generation == 2 && mn_ok) {
-    const int k_tiles = (K + 255) / 256;
-    int64_t slices = g_sms / k_tiles;  // one CTA per SM, one wave
-    const int64_t by_rows = (m + kWgSlab - 1) / kWgSlab;
-    if (slices > by_rows) slices = by_rows;
-    if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
-    int64_t slice_rows = (m + slices - 1) / slices;
-    slice_rows = (slice_rows + kWgSlab - 1) / kWgSlab * kWgSlab;
-    static bool attr2[2] = {false, false};
-    const size_t smem = 1024 + (size_t)kWgStages * kWgStage + 8 * 256 * sizeof(float) + 128;
-    if (!attr2[fmt]) {
-      cudaError_t e = fmt ? cudaFuncSetAttribute(wgrad_mn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(wgrad_mn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr2[fmt] = true;
-    }
-    WgradTcParams p{};
-    p.dy = dy, p.n_dim = n_dim, p.x1 = x1, p.ld1 = ld1, p.k1 = k1, p.x2 = x2, p.ld2 = ld2, p.k2 = k2;
-    p.x2_row_div = x2_row_div, p.part = part, p.m = m, p.slice_rows = slice_rows;
-    dim3 grid((unsigned)slices, (unsigned)k_tiles);
-    LaunchScope scope(kKernWgradTc, st);
-    if (fmt) wgrad_mn_kernel<1><<<grid, 288, smem, st>>>(p, swap_strides);
-    else wgrad_mn_kernel<0><<<grid, 288, smem, st>>>(p, swap_strides);
-    *slices_out = (int)slices;
-    return cudaGetLastError();
-  }
+  if (generation == 2 && mn_ok)
+    return launch_wgrad_mn_partials(dy, 0, n_dim, x1, 0, ld1, k1, x2, ld2, k2, x2_row_div, part, m, max_slices, precision,
+                                    slices_out, st);
   const int n_tiles = (n_dim + 127) / 128, k_tiles = (K + 255) / 256;
   int64_t slices = (2 * (int64_t)g_sms + n_tiles * k_tiles - 1) / (n_tiles * k_tiles);  // one wave of 2 CTAs per SM
   const int64_t by_rows = (m + 63) / 64;

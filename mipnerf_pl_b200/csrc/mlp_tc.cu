@@ -172,6 +172,14 @@ struct LevelParams {
   float* raw_rgb_out;      // MLP-only mode: [B,128,3] / [B,128] raw heads instead of compositing
   float* raw_density_out;
   uint8_t* feat_scratch;   // v2 kernel: per-CTA pre-swizzled feature slabs in global memory (L2 resident)
+  // Training forward (v1 kernels): every activation the backward pass needs leaves the SM exactly as the tensor core
+  // saw it — the 16-bit SW128 activation tile of each trunk layer / the bottleneck is copied out by ONE bulk store
+  // (64 KB, shared -> global) after its epilogue; the view layer's output and the raw heads go out from registers.
+  uint8_t* act_dump;       // [9][dump_tiles][64 KB]: h_0..h_7 (post-ReLU), bottleneck; tile = ray
+  uint8_t* v_dump;         // [dump_tiles][32 KB]: view-layer output (post-ReLU), two SW128 slabs
+  float* raw_rgb_keep;     // [B,128,3] / [B,128]: raw heads (before the activations) for render_backward
+  float* raw_density_keep;
+  int64_t dump_tiles;
   float* comp_rgb;
   float* distance;
   float* acc;
@@ -334,7 +342,8 @@ __device__ __forceinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* m
 // view layer epilogue + colour head (models/mip_nerf.py:108-110); vb = per-ray view-direction bias
 template <int kFmt>
 __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __restrict__ vb, float& rgb0,
-                                              float& rgb1, float& rgb2) {
+                                              float& rgb1, float& rgb2, uint8_t* __restrict__ vdump = nullptr,
+                                              int row = 0) {
   float acc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // independent chains
   uint32_t v[2][32];
   tmem_ld32(t_acc, v[0]);
@@ -352,9 +361,23 @@ __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __res
         float y0 = __uint_as_float(v[k & 1][e + i]), y1 = __uint_as_float(v[k & 1][e + i + 1]);
         fadd2(y0, y1, bb[i], bb[i + 1]);
         y0 = fmaxf(y0, 0.f), y1 = fmaxf(y1, 0.f);
+        v[k & 1][e + i] = __float_as_uint(y0), v[k & 1][e + i + 1] = __float_as_uint(y1);  // kept for the dump
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch)
           ffma2(acc[ch][i], acc[ch][i + 1], y0, y1, c_small.w_color[ch][c], c_small.w_color[ch][c + 1]);
+      }
+    }
+    if (vdump) {  // training: the 16-bit view-layer output, same tile layout as the trunk's activation slabs
+      uint8_t* slab = vdump + (k >> 1) * kStageBytes + (uint32_t)row * 128u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t* y = v[k & 1] + 8 * j;
+        const uint32_t ci = (uint32_t)((k & 1) * 4 + j);
+        *reinterpret_cast<uint4*>(slab + ((ci ^ ((uint32_t)row & 7u)) << 4)) =
+            make_uint4(pack2<kFmt>(__uint_as_float(y[0]), __uint_as_float(y[1])),
+                       pack2<kFmt>(__uint_as_float(y[2]), __uint_as_float(y[3])),
+                       pack2<kFmt>(__uint_as_float(y[4]), __uint_as_float(y[5])),
+                       pack2<kFmt>(__uint_as_float(y[6]), __uint_as_float(y[7])));
       }
     }
   }
@@ -413,9 +436,10 @@ __device__ __forceinline__ void ipe_row_group(const LevelParams& p, const RayGeo
 // carried as hi + lo 16-bit halves (A_lo and F_lo live where slot 1's tiles would be, W_lo stages alternate with W_hi
 // in the ring) and every K step issues  A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  into the same fp32 accumulator: 3x the MMAs,
 // ~2^-22 (fp16 halves) / 2^-16 (bf16 halves) relative operand error instead of 2^-11 / 2^-8.
-template <int kFmt, bool kPair, bool kX3>
+template <int kFmt, bool kPair, bool kX3, bool kTrain = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
   static_assert(!kX3 || kPair, "split-operand modes exist for the CTA-pair kernel only");
+  static_assert(!kTrain || (kPair && !kX3), "the training forward (activation dump) is the plain CTA-pair kernel");
   constexpr int kSlots = kX3 ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -764,6 +788,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     };
     const int my_rounds = slot < kSlots ? rounds : 0;  // x3: the second worker group has no slot
     const SmallParams* __restrict__ gsp = reinterpret_cast<const SmallParams*>(p.wimage + kSmallOffset);
+    constexpr bool dumping = kTrain;  // a separate instantiation: the inference kernel carries none of this
+    bool dump_pending = false;
     if (slot < kSlots) arrive_a_ready();  // accumulator of this slot is free for the first ray
     for (int round = 0; round < my_rounds; ++round) {
       const int64_t tile = tile_of(round, slot);
@@ -791,6 +817,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           }
         }
         if (l < 9) {
+          if (dumping) {  // the previous layer's bulk store must have READ the tile before anyone overwrites it
+            if (row == 0 && dump_pending) {
+              bulk_store_wait_read();
+              dump_pending = false;
+            }
+            named_bar_sync(1 + slot, 128);
+          }
           if (kX3 || MIPNERF_TC_ROLLED_EPILOGUE) {
             epilogue_trunk_rolled<kFmt, kX3>(t_acc, myA, row, dens, l, gsp);
           } else {
@@ -811,10 +844,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           tc_fence_before();
           arrive_a_ready();
           TRACE(EV(2, 4, l, slot));
+          if (dumping) {
+            named_bar_sync(1 + slot, 128);  // the whole tile is written (and fenced towards the async proxy)
+            if (row == 0 && valid) {
+              bulk_s2g(p.act_dump + ((size_t)l * p.dump_tiles + ray) * kABytes, myA, kABytes);
+              dump_pending = true;
+            }
+          }
         } else {
           vb_s[slot * 128 + row] = vb;
           named_bar_sync(1 + slot, 128);  // vb_s of this ray visible to the whole slot
-          epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2);
+          epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2,
+                              (dumping && valid) ? p.v_dump + (size_t)ray * (2 * kStageBytes) : nullptr, row);
           tc_fence_before();
           arrive_a_ready();  // accumulator drained: the next ray's layer 0 may start while we composite
           TRACE(EV(2, 3, l, slot));
@@ -830,6 +871,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         }
         named_bar_sync(1 + slot, 128);  // vb_s is rewritten before the next ray's view epilogue
         continue;
+      }
+      if (kTrain && valid) {  // training: the raw heads as well (render_backward recomputes the rest)
+        const int64_t sidx = ray * kN + row;
+        p.raw_rgb_keep[sidx * 3 + 0] = rgb0 + c_small.b_color[0];
+        p.raw_rgb_keep[sidx * 3 + 1] = rgb1 + c_small.b_color[1];
+        p.raw_rgb_keep[sidx * 3 + 2] = rgb2 + c_small.b_color[2];
+        p.raw_density_keep[sidx] = dens + c_small.b_density;
       }
       // ---- activations + compositing over the ray's 128 samples (4 warps of this slot)
       const float density = density_activation(dens + c_small.b_density, p.density_bias);
@@ -877,6 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
       named_bar_sync(1 + slot, 128);  // row 0 has consumed ps / everyone cs before the next ray reuses them
     }
+    if (dump_pending) bulk_store_wait_all();  // the last tile's store has left shared memory and reached global
 #ifdef MIPNERF_TC_TRACE
     if (q == 0 && lane == 0) tracer.finish(2 + slot);
 #endif
@@ -1341,11 +1390,6 @@ __global__ void view_bias_from_enc_kernel(const float* __restrict__ venc, const 
 }
 
 // ---- weight packing ---------------------------------------------------------------------------
-template <int kFmt>
-__device__ __forceinline__ float from16(uint16_t h) {
-  if (kFmt == 1) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&h));
-  return __half2float(*reinterpret_cast<__half*>(&h));
-}
 // lo != 0: the low half  fl16(w - fl16(w))  of the split-operand modes instead of fl16(w)
 template <int kFmt>
 __global__ void pack_stage_kernel(const float* __restrict__ w, int in_features, int row0, int kbase, int kcount,
@@ -1357,6 +1401,46 @@ __global__ void pack_stage_kernel(const float* __restrict__ w, int in_features, 
   if (lo) v = v - from16<kFmt>(to16<kFmt>(v));
   const uint32_t off = kcount == 64 ? sw128_offset(i, j) : sw64_offset(i, j);
   *reinterpret_cast<uint16_t*>(dst + off) = to16<kFmt>(v);
+}
+
+// All stages of one (hi or lo) v1 image in ONE launch: block = stage.  Main stages: layer l, N-half h, K-slab s of 32
+// (K order of layer 5 is the reference's concat [h (256) | x (96)], mip_nerf.py:96-97) -> [128 x 64 B] SW64; then the
+// 16 stages of the pair-mode view layer (two 64-row halves x 8 slabs).
+struct PackV1Src {
+  const float* weight[kNumLayers];
+  int in_features[kNumLayers];
+};
+__host__ __device__ constexpr int v1_stage_begin(int l) {
+  int n = 0;
+  for (int i = 0; i < l; ++i) n += num_halves(i) * num_k32(i);
+  return n;
+}
+constexpr int kV1MainStages = v1_stage_begin(kNumLayers);
+template <int kFmt>
+__global__ void __launch_bounds__(256) pack_v1_image_kernel(const PackV1Src src, uint8_t* __restrict__ base, int lo) {
+  const int stage = blockIdx.x;
+  const float* w;
+  int in_features, row0, kbase, nrows;
+  uint8_t* dst;
+  if (stage < kV1MainStages) {
+    int l = 0;
+    while (l + 1 < kNumLayers && stage >= v1_stage_begin(l + 1)) ++l;
+    const int local = stage - v1_stage_begin(l);
+    const int h = local / num_k32(l), sl = local % num_k32(l);
+    w = src.weight[l], in_features = src.in_features[l], row0 = h * 128, kbase = sl * 32, nrows = 128;
+    dst = base + layer_offset(l) + (size_t)local * kWStage;
+  } else {
+    const int local = stage - kV1MainStages;
+    w = src.weight[kNumLayers - 1], in_features = src.in_features[kNumLayers - 1];
+    row0 = (local >> 3) * 64, kbase = (local & 7) * 32, nrows = 64;
+    dst = base + kViewPairOffset + (size_t)local * kViewPairStage;
+  }
+  for (int idx = threadIdx.x; idx < nrows * 32; idx += 256) {
+    const int i = idx >> 5, j = idx & 31;
+    float v = w[(size_t)(row0 + i) * in_features + kbase + j];
+    if (lo) v = v - from16<kFmt>(to16<kFmt>(v));
+    *reinterpret_cast<uint16_t*>(dst + sw64_offset(i, j)) = to16<kFmt>(v);
+  }
 }
 
 struct SmallSrc {
@@ -1467,13 +1551,14 @@ bool g_attr_set[2][2][2] = {};
 inline int fmt_of(int precision) { return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_BF16X3) ? 1 : 0; }
 inline bool is_x3(int precision) { return precision == MIPNERF_B200_FP16X3 || precision == MIPNERF_B200_BF16X3; }
 
-template <int kFmt, bool kPair, bool kX3 = false>
+template <int kFmt, bool kPair, bool kX3 = false, bool kTrain = false>
 cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
-  auto kern = mlp_level_kernel<kFmt, kPair, kX3>;
-  if (!g_attr_set[kFmt][kPair][kX3]) {
+  auto kern = mlp_level_kernel<kFmt, kPair, kX3, kTrain>;
+  static bool attr_set = false;  // one flag per instantiation
+  if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
     if (e != cudaSuccess) return e;
-    g_attr_set[kFmt][kPair][kX3] = true;
+    attr_set = true;
   }
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1599,6 +1684,9 @@ bool fused_prologue_enabled(int precision) {
 }
 
 cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
+  if (p.act_dump)  // training forward: the CTA-pair kernel with the activation dump
+    return precision == MIPNERF_B200_BF16 ? launch_level_t<1, true, false, true>(p, st)
+                                          : launch_level_t<0, true, false, true>(p, st);
   if (is_x3(precision))  // split-operand parity modes: the CTA-pair kernel, whatever variant is selected
     return fmt_of(precision) ? launch_level_t<1, true, true>(p, st) : launch_level_t<0, true, true>(p, st);
   if (tc_variant() == 3)
@@ -1651,49 +1739,27 @@ size_t tc_workspace_bytes(const mipnerf_b200_config* c, int64_t num_rays, int pr
 }
 
 cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_weights* w, int precision,
-                            void* packed_out, cudaStream_t st) {
+                            void* packed_out, cudaStream_t st, bool with_v3) {
   if (!tc_supported(c, precision)) return cudaErrorNotSupported;
   uint8_t* img = static_cast<uint8_t*>(packed_out);
   const bool bf = fmt_of(precision) == 1;
   const int parts = is_x3(precision) ? 2 : 1;  // hi image, then (split modes) the lo stage image
-  cudaError_t e = cudaMemsetAsync(img, 0, kV3Offset + kV3Bytes, st);
+  cudaError_t e = cudaMemsetAsync(img, 0, with_v3 ? kV3Offset + kV3Bytes : kV3Offset, st);
   if (e != cudaSuccess) return e;
   LaunchScope scope(kKernPackWeights, st);
+  PackV1Src v1{};
+  for (int l = 0; l < kNumLayers; ++l) {
+    const int li = l < 8 ? l : (l == 8 ? 9 : 10);  // layers.l | extra_layer | view_layers.0
+    v1.weight[l] = w->linears[li].weight, v1.in_features[l] = w->linears[li].in_features;
+  }
   for (int part = 0; part < parts; ++part) {
     uint8_t* base = img + (part ? kLoOffset : 0);
-    for (int l = 0; l < kNumLayers; ++l) {
-      const int li = l < 8 ? l : (l == 8 ? 9 : 10);  // layers.l | extra_layer | view_layers.0
-      const mipnerf_b200_linear& lin = w->linears[li];
-      uint8_t* dst = base + layer_offset(l);
-      for (int h = 0; h < num_halves(l); ++h)
-        for (int s = 0; s < num_k32(l); ++s) {
-          // K order of layer 5 is the reference's concat [h (256) | x (96)]   (mip_nerf.py:96-97)
-          if (bf)
-            pack_stage_kernel<1><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32,
-                                                                        32, dst, 128, part);
-          else
-            pack_stage_kernel<0><<<(128 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, h * 128, s * 32,
-                                                                        32, dst, 128, part);
-          dst += kWStage;
-        }
-    }
-    {  // pair-mode view layer: two 64-row halves
-      const mipnerf_b200_linear& lin = w->linears[10];
-      uint8_t* dst = base + kViewPairOffset;
-      for (int r = 0; r < 2; ++r)
-        for (int s = 0; s < 8; ++s) {
-          if (bf)
-            pack_stage_kernel<1><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
-                                                                       dst, 64, part);
-          else
-            pack_stage_kernel<0><<<(64 * 32 + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, r * 64, s * 32, 32,
-                                                                       dst, 64, part);
-          dst += kViewPairStage;
-        }
-    }
+    if (bf) pack_v1_image_kernel<1><<<kV1MainStages + 16, 256, 0, st>>>(v1, base, part);
+    else pack_v1_image_kernel<0><<<kV1MainStages + 16, 256, 0, st>>>(v1, base, part);
   }
-  // v3 blocks: per layer, per CTA rank, in the kernel's issue order (mlp_tc_v3.cuh: Sched3)
-  for (int l = 0; l < kNumLayers; ++l) {
+  // v3 blocks: per layer, per CTA rank, in the kernel's issue order (mlp_tc_v3.cuh: Sched3); the training step
+  // repacks every optimiser step and runs the v1 pair kernel only, so it skips them
+  for (int l = 0; with_v3 && l < kNumLayers; ++l) {
     const int li = l < 8 ? l : (l == 8 ? 9 : 10);
     const mipnerf_b200_linear& lin = w->linears[li];
     const int type = layer_type3(l), nb = sched_count3(type);
@@ -1741,7 +1807,7 @@ Draws level_draws(int randomized, const float* array, const mipnerf_b200_rng* rn
 cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights* w, const mipnerf_b200_rays* rays,
                        int randomized, const float* t_rand, const float* u_jitter, const mipnerf_b200_rng* rng,
                        int white_bkgd, int precision, mipnerf_b200_level_out* outs, void* workspace,
-                       size_t workspace_bytes, cudaStream_t st) {
+                       size_t workspace_bytes, cudaStream_t st, const TcTrainDump* dump, int64_t ray_base) {
   const uint8_t* img = static_cast<const uint8_t*>(w->packed);
   SmallUpload small(img, st);  // biases / heads -> constant bank, ordered against other streams' forwards
   cudaError_t e = small.error();
@@ -1757,7 +1823,13 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
     const float* radii = rays->radii + off;
     // v1 kernels produce fenceposts and the view bias inside the level kernels (IPE warps); the shared-stream
     // variant keeps the separate prologue / resample launches.
-    const bool fused_prologue = fused_prologue_enabled(precision);
+    const bool fused_prologue = dump != nullptr || fused_prologue_enabled(precision);  // training: always the v1 pair kernel
+    // in-kernel Philox: the counter is the ray index of the caller's whole batch (ray_base = offset of `rays` in it)
+    auto draws = [&](const float* array, int stream) {
+      Draws d = level_draws(randomized, array, rng, off, stream, kN + 1);
+      if (!array) d.ray_base += ray_base;
+      return d;
+    };
     if (!fused_prologue) {
       LaunchScope scope(kKernRayPrologue, st);
       float* t0 = outs[0].t_samples ? outs[0].t_samples + off * (kN + 1) : s.t[0];
@@ -1765,14 +1837,14 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
       const unsigned ct_blocks = (unsigned)((cnt * (kN + 1) + kCoarsePerBlock - 1) / kCoarsePerBlock);
       ray_prologue_kernel<<<vb_blocks + ct_blocks, kCond, 0, st>>>(
           rays->viewdirs + off * 3, view.weight, view.bias, s.vbias, cnt, vb_blocks, rays->near + off, rays->far + off,
-          level_draws(randomized, t_rand, rng, off, 0, kN + 1), t0, c->disparity);
+          draws(t_rand, 0), t0, c->disparity);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     const float *t_prev = nullptr, *w_prev = nullptr;
     for (int l = 0; l < c->num_levels; ++l) {
       float* t_cur = outs[l].t_samples ? outs[l].t_samples + off * (kN + 1) : s.t[l & 1];
       float* w_cur = outs[l].weights ? outs[l].weights + off * kN : s.w[l & 1];
-      const Draws jit = level_draws(randomized, u_jitter, rng, off, 1 + l, kN + 1);  // one stream per level
+      const Draws jit = draws(u_jitter, 1 + l);  // one stream per level
       int64_t* inds = outs[l].inds ? outs[l].inds + off * (kN + 1) : nullptr;
       if (l > 0 && !fused_prologue) {
         e = launch_resample(t_prev, w_prev, jit, t_cur, inds, cnt, kN, kN + 1, randomized, 1, c->resample_padding, st);
@@ -1787,7 +1859,7 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
         p.t_mode = l == 0 ? 1 : 2;
         p.vb_mode = l == 0 ? 1 : 0;  // level 0 leaves the per-ray bias in s.vbias for the later levels
         p.near = rays->near + off, p.far = rays->far + off;
-        p.t_rand = level_draws(randomized, t_rand, rng, off, 0, kN + 1);
+        p.t_rand = draws(t_rand, 0);
         p.disparity = c->disparity;
         p.t_prev = t_prev, p.w_prev = w_prev;
         p.u_jitter = jit;
@@ -1797,6 +1869,11 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
         p.viewdirs = rays->viewdirs + off * 3;
       }
       p.feat_scratch = s.feat;
+      if (dump) {  // training forward: one chunk only (the caller chunks), tile index = ray index
+        p.act_dump = dump->act[l], p.v_dump = dump->v[l];
+        p.raw_rgb_keep = dump->raw_rgb[l], p.raw_density_keep = dump->raw_density[l];
+        p.dump_tiles = cnt;
+      }
       p.comp_rgb = outs[l].comp_rgb + off * 3;
       p.distance = outs[l].distance + off;
       p.acc = outs[l].acc + off;

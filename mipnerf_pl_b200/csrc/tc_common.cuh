@@ -119,6 +119,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// shared -> global 1-D bulk copy (one bulk async-group per call); the issuing thread waits with the two helpers below
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {  // the source may be overwritten
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_all() {  // the writes are complete
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 // global -> shared 1-D bulk copy on the TMA engine, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -365,6 +377,11 @@ __host__ __device__ __forceinline__ uint16_t to16(float x) {
     __half h = __float2half_rn(x);
     return *reinterpret_cast<uint16_t*>(&h);
   }
+}
+template <int kFmt>
+__device__ __forceinline__ float from16(uint16_t h) {
+  if (kFmt == 1) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&h));
+  return __half2float(*reinterpret_cast<__half*>(&h));
 }
 
 }  // namespace tc

@@ -371,6 +371,7 @@ wgrad_small_n_kernel(const float* __restrict__ dy, int n_dim, const float* __res
   const int64_t m_end = (m_begin + slice_rows) < m ? (m_begin + slice_rows) : m;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
   if (grp < groups) {
+#pragma unroll 8  // independent loads: eight rows in flight per thread (the loop is latency-bound otherwise)
     for (int64_t row = m_begin + grp; row < m_end; row += groups) {
       const float xv = __ldg(x + row * k_dim + k);
 #pragma unroll
@@ -407,7 +408,7 @@ wgrad_small_n_kernel(const float* __restrict__ dy, int n_dim, const float* __res
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, int n_dim, int k_dim,
-                                    float* __restrict__ dw, float* __restrict__ db, int accumulate) {
+                                    float* __restrict__ dw, float* __restrict__ db, int accumulate, float scale = 1.f) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = k_dim + 1;
   if (idx >= n_dim * per) return;
@@ -415,6 +416,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, 
   float acc = 0.f;
   for (int s = 0; s < slices; ++s) acc += __ldg(part + (size_t)s * n_dim * per + idx);
   float* dst = kg < k_dim ? dw + (size_t)n * k_dim + kg : db + n;
+  acc *= scale;  // 1 / (the fp16 step's gradient scale); exactly 1 otherwise
   *dst = accumulate ? *dst + acc : acc;
 }
 
@@ -443,10 +445,10 @@ int wgrad_num_slices(int64_t m, int tiles) {
 }
 
 cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_dim, float* dw, float* db,
-                                int accumulate, cudaStream_t st) {
+                                int accumulate, cudaStream_t st, float scale) {
   LaunchScope scope(kKernWgrad, st);
   wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (k_dim + 1), 256), 256, 0, st>>>(part, slices, n_dim, k_dim, dw, db,
-                                                                                     accumulate);
+                                                                                     accumulate, scale);
   return cudaGetLastError();
 }
 

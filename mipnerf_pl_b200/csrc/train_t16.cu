@@ -1,0 +1,378 @@
+// train_t16.cu — the backward pass of the tensor-core training step on 16-bit "tile images".
+//
+// The training forward (mlp_tc.cu, mlp_level_kernel<.., kTrain>) leaves every activation in HBM exactly as the tensor
+// core consumed it: per 128-row tile (= one ray's samples) and 64-column slab a [128 x 128 B] block in the
+// 128-byte-swizzle layout (tc::sw128_offset), the slabs of a tile contiguous.  Everything here reads and writes that
+// format, so operand staging is one cp.async.bulk per slab — no conversion, no register staging:
+//   linear_t16_kernel     dX = [mask > 0] * (dY . B^T + r1[row] * r1w[col])        the dgrad chain, tcgen05
+//   color_dgrad_t16       d v = [v > 0] * (d raw_rgb @ Wc)                           colour head -> view layer
+//   wgrad_small_n_t16     partials of dY^T X for the two narrow heads (n = 1, 3)     X = tile image, dY fp32
+//   t16_pack / t16_unpack fp32 row-major <-> tile image (tests, stand-alone entry points)
+// The wgrad GEMMs on tile images are in linear_tc.cu (wgrad_mn_kernel: a row-major tile IS an MN-major operand).
+#include "kernels.h"
+#include "profile.h"
+#include "tc_common.cuh"
+
+namespace mipnerf {
+namespace {
+
+using namespace tc;
+
+constexpr uint32_t kSlab = 16384;  // [128 rows x 64 cols] 16-bit
+
+struct LinearT16Params {
+  const uint8_t* x;      // [tiles][k / 64][16 KB]
+  const uint8_t* image;  // packed B: [k / 64][n x 128 B]   (pack_linear_image_kernel)
+  uint8_t* y;            // [tiles][n / 64][16 KB]
+  const uint8_t* mask;   // like y, or null: output zeroed where mask <= 0 (ReLU backward)
+  const float* r1;       // [tiles * 128] or null, with r1w [n]: + r1[row] * r1w[col]  (density head)
+  const float* r1w;
+  int64_t tiles;
+  int n, k;
+};
+
+// 384 threads: warps 0-3 and 8-11 epilogue (thread = accumulator row, the two groups split the columns), warp 4 lane 0 =
+// bulk producer, warp 5 lane 0 = MMA issue.
+//   a_full[s] / a_free[s]  per 64-column slab of the A tile: the next tile's slab s streams in as soon as the MMAs of
+//                          this tile's slab s have completed (a 4-deep ring at slab granularity, one A buffer);
+//   acc_full[b] / acc_free[b]  two TMEM accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
+template <int kFmt>
+__global__ void __launch_bounds__(384, 1) linear_t16_kernel(const LinearT16Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  const int slabs = p.k >> 6;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)slabs * kSlab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)slabs * p.n * 128);
+  uint64_t* bar_b = bars;
+  uint64_t* a_full = bars + 1;     // [4]
+  uint64_t* a_free = bars + 5;     // [4]
+  uint64_t* acc_full = bars + 9;   // [2]
+  uint64_t* acc_free = bars + 11;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(bar_b, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_free[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_free[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int y_slabs = p.n >> 6;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_b, (uint32_t)(slabs * p.n * 128));
+      for (int s = 0; s < slabs; ++s)
+        bulk_g2s(sB + (size_t)s * p.n * 128, p.image + (size_t)s * p.n * 128, (uint32_t)(p.n * 128), bar_b);
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        for (int s = 0; s < slabs; ++s) {
+          if (it > 0) mbar_wait(&a_free[s], (uint32_t)(it - 1) & 1u);
+          mbar_arrive_expect_tx(&a_full[s], kSlab);
+          bulk_g2s(sA + (size_t)s * kSlab, p.x + ((size_t)tile * slabs + s) * kSlab, kSlab, &a_full[s]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, p.n, kFmt);
+      mbar_wait(bar_b, 0);
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(&acc_free[buf], (uint32_t)((it >> 1) - 1) & 1u);
+        for (int s = 0; s < slabs; ++s) {
+          mbar_wait(&a_full[s], (uint32_t)it & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            umma_ss(tmem_base + buf * 256, make_sw128_desc(smem_u32(sA + (size_t)s * kSlab) + j * 32),
+                    make_sw128_desc(smem_u32(sB + (size_t)s * p.n * 128) + j * 32), idesc, (s | j) ? 1u : 0u);
+          umma_commit(&a_free[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp < 4 || warp >= 8) {
+    // ============================================== epilogue warps ==============================================
+    int it = 0;
+    const int row = (warp & 3) * 32 + lane;          // TMEM lane quarter = warp % 4
+    const int c_begin = warp < 4 ? 0 : (p.n >> 1), c_end = warp < 4 ? (p.n >> 1) : p.n;
+    const uint32_t rx = (uint32_t)row & 7u;
+    for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const float rv = p.r1 ? __ldg(p.r1 + tile * 128 + row) : 0.f;
+      uint8_t* yrow = p.y + (size_t)tile * y_slabs * kSlab + (uint32_t)row * 128u;
+      const uint8_t* mrow = p.mask ? p.mask + (size_t)tile * y_slabs * kSlab + (uint32_t)row * 128u : nullptr;
+      mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256 + c, v);
+        uint4 mk[4];
+        if (mrow) {  // issued before the TMEM wait so both latencies overlap
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t ci = (uint32_t)(((c & 63) >> 3) + j);
+            mk[j] = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(c >> 6) * kSlab + ((ci ^ rx) << 4)));
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
+          if (p.r1) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.r1w + c + 8 * j));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.r1w + c + 8 * j + 4));
+            o[0] = fmaf(rv, w0.x, o[0]), o[1] = fmaf(rv, w0.y, o[1]), o[2] = fmaf(rv, w0.z, o[2]);
+            o[3] = fmaf(rv, w0.w, o[3]), o[4] = fmaf(rv, w1.x, o[4]), o[5] = fmaf(rv, w1.y, o[5]);
+            o[6] = fmaf(rv, w1.z, o[6]), o[7] = fmaf(rv, w1.w, o[7]);
+          }
+          if (mrow) {  // a 16-bit float is > 0 iff its bits, read as a signed integer, are > 0
+            const uint32_t mw[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (!((int16_t)(mw[e] & 0xffffu) > 0)) o[2 * e] = 0.f;
+              if (!((int32_t)mw[e] >= 0x00010000)) o[2 * e + 1] = 0.f;
+            }
+          }
+          const uint32_t ci = (uint32_t)(((c & 63) >> 3) + j);
+          *reinterpret_cast<uint4*>(yrow + (size_t)(c >> 6) * kSlab + ((ci ^ rx) << 4)) =
+              make_uint4(pack2<kFmt>(o[0], o[1]), pack2<kFmt>(o[2], o[3]), pack2<kFmt>(o[4], o[5]),
+                         pack2<kFmt>(o[6], o[7]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// d v[row][c] = [v[row][c] > 0] * sum_j d_rgb[row][j] * wc[j][c]      thread = (row, 8-column chunk), k_dim = 128
+template <int kFmt>
+__global__ void color_dgrad_t16_kernel(const float* __restrict__ d_rgb, const float* __restrict__ wc,
+                                       const uint8_t* __restrict__ v, uint8_t* __restrict__ d_v, int64_t m,
+                                       int k_dim) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks = k_dim >> 3;
+  if (idx >= m * chunks) return;
+  const int64_t row = idx / chunks;
+  const int ch = (int)(idx % chunks);
+  const int r = (int)(row & 127);
+  const size_t off = ((size_t)(row >> 7) * (k_dim >> 6) + (ch >> 3)) * kSlab + (uint32_t)r * 128u +
+                     ((((uint32_t)ch & 7u) ^ ((uint32_t)r & 7u)) << 4);
+  const float g0 = __ldg(d_rgb + row * 3), g1 = __ldg(d_rgb + row * 3 + 1), g2 = __ldg(d_rgb + row * 3 + 2);
+  const uint4 mk = __ldg(reinterpret_cast<const uint4*>(v + off));
+  const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = ch * 8 + e;
+    o[e] = fmaf(g2, __ldg(wc + 2 * k_dim + c), fmaf(g1, __ldg(wc + k_dim + c), g0 * __ldg(wc + c)));
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (!((int16_t)(mw[e] & 0xffffu) > 0)) o[2 * e] = 0.f;
+    if (!((int32_t)mw[e] >= 0x00010000)) o[2 * e + 1] = 0.f;
+  }
+  *reinterpret_cast<uint4*>(d_v + off) =
+      make_uint4(pack2<kFmt>(o[0], o[1]), pack2<kFmt>(o[2], o[3]), pack2<kFmt>(o[4], o[5]), pack2<kFmt>(o[6], o[7]));
+}
+
+template <int kFmt>
+__device__ __forceinline__ float t16_load(const uint8_t* base, int64_t row, int col, int cols) {
+  const uint16_t bits = __ldg(reinterpret_cast<const uint16_t*>(
+      base + ((size_t)(row >> 7) * (cols >> 6) + (col >> 6)) * kSlab + sw128_offset((int)(row & 127), col & 63)));
+  return from16<kFmt>(bits);
+}
+
+// The two narrow heads' weight gradients (train_kernels.cu: wgrad_small_n_kernel) with X read from a tile image:
+// thread = input column k, dY values are warp-uniform fp32 loads.  Same partial layout.
+template <int kFmt>
+__global__ void __launch_bounds__(256)
+wgrad_small_n_t16_kernel(const float* __restrict__ dy, int n_dim, const uint8_t* __restrict__ x, int k_dim,
+                         float* __restrict__ part, int64_t m, int64_t slice_rows) {
+  __shared__ float red[256][5];
+  const int tid = threadIdx.x;
+  const int groups = 256 / k_dim;  // k_dim in {128, 256}
+  const int grp = tid / k_dim, k = tid % k_dim;
+  const int64_t m_begin = (int64_t)blockIdx.x * slice_rows;
+  const int64_t m_end = (m_begin + slice_rows) < m ? (m_begin + slice_rows) : m;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  if (grp < groups) {
+#pragma unroll 8  // independent loads: eight rows in flight per thread (the loop is latency-bound otherwise)
+    for (int64_t row = m_begin + grp; row < m_end; row += groups) {
+      const float xv = t16_load<kFmt>(x, row, k, k_dim);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < n_dim) {
+          const float d = __ldg(dy + row * n_dim + j);
+          acc[j] = fmaf(d, xv, acc[j]);
+          bsum[j] += d;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[tid][j] = acc[j];
+  __syncthreads();
+  float* out = part + (size_t)blockIdx.x * n_dim * (k_dim + 1);
+  if (tid < k_dim) {
+    for (int j = 0; j < n_dim; ++j) {
+      float v = 0.f;
+      for (int g2 = 0; g2 < groups; ++g2) v += red[g2 * k_dim + tid][j];
+      out[(size_t)j * (k_dim + 1) + tid] = v;
+    }
+  }
+  __syncthreads();
+  if (k == 0)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[grp][j] = bsum[j];
+  __syncthreads();
+  if (tid < n_dim) {
+    float v = 0.f;
+    for (int g2 = 0; g2 < groups; ++g2) v += red[g2][tid];
+    out[(size_t)tid * (k_dim + 1) + k_dim] = v;
+  }
+}
+
+// fp32 row-major [m, cols] (ld) <-> tile image; rows beyond m / columns beyond cols are zero in the image
+template <int kFmt>
+__global__ void t16_pack_kernel(const float* __restrict__ src, int ld, int cols, int64_t m, uint8_t* __restrict__ dst,
+                                int img_cols, int64_t padded_rows) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= padded_rows * img_cols) return;
+  const int64_t row = idx / img_cols;
+  const int col = (int)(idx % img_cols);
+  const float v = (row < m && col < cols) ? __ldg(src + row * ld + col) : 0.f;
+  *reinterpret_cast<uint16_t*>(dst + ((size_t)(row >> 7) * (img_cols >> 6) + (col >> 6)) * kSlab +
+                               sw128_offset((int)(row & 127), col & 63)) = to16<kFmt>(v);
+}
+template <int kFmt>
+__global__ void t16_unpack_kernel(const uint8_t* __restrict__ src, int img_cols, float* __restrict__ dst, int ld,
+                                  int cols, int64_t m) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * cols) return;
+  const int64_t row = idx / cols;
+  const int col = (int)(idx % cols);
+  dst[row * ld + col] = t16_load<kFmt>(src, row, col, img_cols);
+}
+
+int g_sms_t16 = 0;
+inline unsigned blocks_of(int64_t n, int per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+}  // namespace
+
+size_t t16_image_bytes(int64_t rows, int cols) {
+  return (size_t)((rows + 127) / 128) * (size_t)((cols + 63) / 64) * kSlab;
+}
+
+cudaError_t launch_t16_pack(const float* src, int ld, int cols, int64_t m, void* image, int precision,
+                            cudaStream_t st) {
+  const int img_cols = (cols + 63) / 64 * 64;
+  const int64_t padded = (m + 127) / 128 * 128;
+  if (padded == 0) return cudaSuccess;
+  if (precision == 1)
+    t16_pack_kernel<1><<<blocks_of(padded * img_cols, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded);
+  else
+    t16_pack_kernel<0><<<blocks_of(padded * img_cols, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_t16_unpack(const void* image, int cols, float* dst, int ld, int64_t m, int precision,
+                              cudaStream_t st) {
+  const int img_cols = (cols + 63) / 64 * 64;
+  if (m == 0) return cudaSuccess;
+  if (precision == 1)
+    t16_unpack_kernel<1><<<blocks_of(m * cols, 256), 256, 0, st>>>((const uint8_t*)image, img_cols, dst, ld, cols, m);
+  else
+    t16_unpack_kernel<0><<<blocks_of(m * cols, 256), 256, 0, st>>>((const uint8_t*)image, img_cols, dst, ld, cols, m);
+  return cudaGetLastError();
+}
+
+// y = [mask > 0] * (x . B^T + r1 * r1w) on tile images; m rows (a multiple of 128), n in {128, 256}, k in {128, 256}
+cudaError_t launch_linear_t16(const void* x, const void* image, void* y, int64_t m, int n, int k, const float* r1,
+                              const float* r1w, const void* mask, int precision, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  if (m % 128 != 0 || !(n == 128 || n == 256) || !(k == 128 || k == 256)) return cudaErrorInvalidValue;
+  const int slabs = k / 64;
+  const size_t smem = 1024 + (size_t)slabs * kSlab + linear_tc_image_bytes(n, k) + 128;
+  const int fmt = precision == 1 ? 1 : 0;
+  static bool attr[2] = {false, false};
+  if (!attr[fmt]) {
+    cudaError_t e = fmt ? cudaFuncSetAttribute(linear_t16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                        : cudaFuncSetAttribute(linear_t16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr[fmt] = true;
+  }
+  if (g_sms_t16 == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms_t16, cudaDevAttrMultiProcessorCount, dev);
+  }
+  LinearT16Params p{};
+  p.x = static_cast<const uint8_t*>(x), p.image = static_cast<const uint8_t*>(image), p.y = static_cast<uint8_t*>(y);
+  p.mask = static_cast<const uint8_t*>(mask), p.r1 = r1, p.r1w = r1w, p.tiles = m / 128, p.n = n, p.k = k;
+  const int grid = (int)(p.tiles < g_sms_t16 ? p.tiles : g_sms_t16);
+  LaunchScope scope(kKernLinearTc, st);
+  if (fmt) linear_t16_kernel<1><<<grid, 384, smem, st>>>(p);
+  else linear_t16_kernel<0><<<grid, 384, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_color_dgrad_t16(const float* d_rgb, const float* wc, const void* v, void* d_v, int64_t m, int k_dim,
+                                   int precision, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  if (k_dim % 64 != 0) return cudaErrorInvalidValue;
+  LaunchScope scope(kKernDgrad, st);
+  const int64_t total = m * (k_dim / 8);
+  if (precision == 1)
+    color_dgrad_t16_kernel<1><<<blocks_of(total, 256), 256, 0, st>>>(d_rgb, wc, (const uint8_t*)v, (uint8_t*)d_v, m, k_dim);
+  else
+    color_dgrad_t16_kernel<0><<<blocks_of(total, 256), 256, 0, st>>>(d_rgb, wc, (const uint8_t*)v, (uint8_t*)d_v, m, k_dim);
+  return cudaGetLastError();
+}
+
+// narrow heads: dW[n_dim <= 4, k_dim] and db from dy (fp32 [m, n_dim]) and a tile-image X; partials + fixed-order sum
+cudaError_t launch_wgrad_small_n_t16(const float* dy, int n_dim, const void* x, int k_dim, float* part, float* dw,
+                                     float* db, int accumulate, int64_t m, int precision, cudaStream_t st,
+                                     float scale) {
+  if (m == 0 || n_dim == 0) return cudaSuccess;
+  if (n_dim > 4 || !(k_dim == 128 || k_dim == 256)) return cudaErrorInvalidValue;
+  int64_t want = m / 512;
+  if (want < 1) want = 1;
+  if (want > 1184) want = 1184;
+  const int slices = (int)want;
+  const int64_t rows = (m + slices - 1) / slices;
+  {
+    LaunchScope scope(kKernWgrad, st);
+    if (precision == 1)
+      wgrad_small_n_t16_kernel<1><<<slices, 256, 0, st>>>(dy, n_dim, (const uint8_t*)x, k_dim, part, m, rows);
+    else
+      wgrad_small_n_t16_kernel<0><<<slices, 256, 0, st>>>(dy, n_dim, (const uint8_t*)x, k_dim, part, m, rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return launch_wgrad_reduce(part, slices, n_dim, k_dim, dw, db, accumulate, st, scale);
+}
+
+}  // namespace mipnerf

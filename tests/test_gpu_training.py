@@ -277,7 +277,24 @@ def test_wgrad_tc_matches_rounded_operands(precision, n, k1, k2, div, m, generat
     assert float((db.double() - want_b).abs().max()) <= 1e-5 * float(dy.abs().sum(dim=0).max())
 
 
-@pytest.mark.parametrize("wgrad_tc", ["0", "1", "2"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_fused_training_forward_is_the_inference_forward(precision):
+    """The fused step's forward is the inference level kernel plus the activation dump: every level output is
+    bit-identical to MipNerf.forward in the same precision (ragged ray count: not a multiple of a CTA pair's four)."""
+    b = 203
+    rays = to_dev(mp.random_ray_batch(b, seed=8, multiscale=True))
+    rgbs = torch.rand(b, 3, device=DEV)
+    model = gpu_model(3, "trained_like", precision=precision)
+    out = mp.forward_backward(model, rays, rgbs, False, True)
+    with torch.no_grad():
+        want = model(rays, False, True)
+    torch.cuda.synchronize()
+    for lvl, (got, ref) in enumerate(zip(out["ret"], want)):
+        for name, g, r in zip(("comp_rgb", "distance", "acc", "weights", "t_samples"), got, ref):
+            assert torch.equal(g, r), f"level {lvl} {name}: max diff {float((g - r).abs().max()):.3e}"
+
+
+@pytest.mark.parametrize("wgrad_tc", ["0", "1", "2", "fused"])
 @pytest.mark.parametrize("precision,loss_tol,grad_tol", [("bf16", 5e-3, 1.5e-1), ("fp16", 1e-3, 1.5e-1)])
 def test_tensor_core_training_mode_tracks_fp32(precision, loss_tol, grad_tol, wgrad_tc, monkeypatch):
     """precision='bf16'|'fp16': forward and dgrad GEMMs on tcgen05.  Loss and every gradient tensor stay within
@@ -285,7 +302,12 @@ def test_tensor_core_training_mode_tracks_fp32(precision, loss_tol, grad_tol, wg
     NOT the operand epsilon for the trunk: an activation perturbed by eps flips the ReLU masks of a fraction ~eps of
     the units, each flip adds/removes a full-size term, so the gradient moves by ~sqrt(eps) (observed: 5e-2 for fp16
     on layers.0, 6e-2 for bf16) — the same mechanism that limits the fp32 trunk bar to 2e-3."""
-    monkeypatch.setenv("MIPNERF_B200_WGRAD_TC", wgrad_tc)   # "2" (default): MN-major tcgen05 wgrad, "1": transposing tcgen05 wgrad, "0": fp32 FFMA wgrad
+    # "fused" (default): forward = the level kernels with the activation dump, backward on 16-bit tile images;
+    # otherwise the per-layer tensor-core path with "2": MN-major tcgen05 wgrad, "1": transposing tcgen05 wgrad,
+    # "0": fp32 FFMA wgrad
+    monkeypatch.setenv("MIPNERF_B200_TRAIN_FUSED", "1" if wgrad_tc == "fused" else "0")
+    if wgrad_tc != "fused":
+        monkeypatch.setenv("MIPNERF_B200_WGRAD_TC", wgrad_tc)
     b = 200
     rays = to_dev(mp.random_ray_batch(b, seed=41, multiscale=True))
     rgbs = torch.rand(b, 3, device=DEV)
@@ -297,8 +319,8 @@ def test_tensor_core_training_mode_tracks_fp32(precision, loss_tol, grad_tol, wg
     torch.cuda.synchronize()
     assert float(out["loss"]) == pytest.approx(float(ref["loss"]), rel=loss_tol)
     errs = {k: float((p.grad - g_ref[k]).norm() / g_ref[k].norm()) for k, p in model.named_parameters()}
-    print(f"{precision}: per-tensor gradient distance to the fp32 step "
-          f"{ {k.replace('mlp.', ''): float(f'{v:.1e}') for k, v in errs.items() if k.endswith('weight')} }")
+    print(f"{precision} [{wgrad_tc}]: per-tensor gradient distance to the fp32 step "
+          f"{ {k.replace('mlp.', ''): float(f'{v:.1e}') for k, v in errs.items()} }")
     assert max(errs.values()) <= grad_tol, errs
     # and it trains
     opt = mp.FusedAdam(model.parameters(), lr=5e-4)
