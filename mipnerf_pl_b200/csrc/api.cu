@@ -396,6 +396,7 @@ struct FusedScratch {
   uint8_t *act[2], *v[2];                // forward dump per level: [9][rays][64 KB], [rays][32 KB]
   float *raw_rgb[2], *raw_density[2];    // raw heads per level
   float *enc, *venc, *d_raw_rgb, *d_raw_density, *part, *t[2], *w[2];
+  uint8_t *enc16;                        // the IPE features as a tile image [rays][2 slabs] (96 columns + zero padding)
   uint8_t *d_v, *d_a, *d_b;              // gradient tile images: [rays][32 KB], [rays][64 KB] x 2
   uint8_t *images, *packed, *tcws;
   size_t tcws_bytes, bytes;
@@ -423,6 +424,7 @@ FusedScratch carve_fused(const mipnerf_b200_config* c, const Dims& d, int64_t ra
   s.venc = take((size_t)rays * d.view_dim);
   s.d_raw_rgb = take(m * 3);
   s.d_raw_density = take(m);
+  s.enc16 = take_bytes((size_t)rays * 32768);
   s.d_v = take_bytes((size_t)rays * 32768);
   s.d_a = take_bytes((size_t)rays * 65536);
   s.d_b = take_bytes((size_t)rays * 65536);
@@ -536,10 +538,10 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
     CUDA_TRY(mipnerf::tc_forward(cfg, &wl, &rc_, randomized, t_rand ? t_rand + off * (n + 1) : nullptr,
                                  u_jitter ? u_jitter + off * (n + 1) : nullptr, rng, white_bkgd, precision, lo, s.tcws,
                                  s.tcws_bytes, st, &dump, off));
-    auto wgrad = [&](int idx, const void* dy16, const void* x1, int x1_t16, int k1, const float* x2, int k2, int div) {
+    auto wgrad = [&](int idx, const void* dy16, const void* x1, int k1, const void* x2, int x2_t16, int k2, int div) {
       const mipnerf_b200_linear& l = w->linears[idx];
       int slices = 0;
-      cudaError_t e2 = mipnerf::launch_wgrad_mn_partials(dy16, 1, l.out_features, x1, x1_t16, k1, k1, x2, k2, k2, div,
+      cudaError_t e2 = mipnerf::launch_wgrad_mn_partials(dy16, 1, l.out_features, x1, 1, k1, k1, x2, x2_t16, k2, k2, div,
                                                          s.part, m, mipnerf::kWgradMaxSlices, precision, &slices, st);
       if (e2 != cudaSuccess) return e2;
       e2 = mipnerf::launch_wgrad_reduce(s.part, slices, l.out_features, k1 + k2, grads[idx].weight_grad,
@@ -551,9 +553,11 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
       const float* t_cur = lo[l].t_samples;
       const uint8_t* act = s.act[l];
       auto h16 = [&](int i) { return act + (size_t)i * cnt * 65536; };  // h_0..h_7, 8 = bottleneck
-      // the IPE features again, in fp32 (operand of two wgrads; the level kernel keeps its own 16-bit copy on chip)
+      // the IPE features again (operand of two wgrads; the level kernel keeps its own 16-bit copy on chip), as a
+      // tile image so that those wgrads stage them by bulk copy like every other operand
       CUDA_TRY(mipnerf::launch_ipe_from_t(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc, cnt, n,
                                           cfg->min_deg_point, cfg->max_deg_point, cfg->disable_integration, st));
+      CUDA_TRY(mipnerf::launch_t16_pack(s.enc, d.xyz_dim, d.xyz_dim, m, s.enc16, precision, st));
       CUDA_TRY(mipnerf::launch_render_backward(
           s.raw_rgb[l], s.raw_density[l], t_cur, rc_.directions, loss->target_rgb + off * 3,
           loss->lossmult ? loss->lossmult + off : nullptr, loss->mask_sum, loss->level_mse_mult[l] * gscale,
@@ -567,11 +571,11 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
                                                  precision, st, inv_gscale));
       touched[d.n_lin - 1] = true;
       CUDA_TRY(mipnerf::launch_color_dgrad_t16(s.d_raw_rgb, cl.weight, s.v[l], s.d_v, m, Wc, precision, st));
-      CUDA_TRY(wgrad(depth + 2, s.d_v, h16(8), 1, W, s.venc, d.view_dim, n));
+      CUDA_TRY(wgrad(depth + 2, s.d_v, h16(8), W, s.venc, 0, d.view_dim, n));
       CUDA_TRY(mipnerf::launch_linear_t16(s.d_v, img_bwd[depth + 1], s.d_a, m, W, Wc, nullptr, nullptr, nullptr,
                                           precision, st));
       // bottleneck + density head share h_7                              (models/mip_nerf.py:98-101)
-      CUDA_TRY(wgrad(depth + 1, s.d_a, h16(depth - 1), 1, W, nullptr, 0, 1));
+      CUDA_TRY(wgrad(depth + 1, s.d_a, h16(depth - 1), W, nullptr, 0, 0, 1));
       CUDA_TRY(mipnerf::launch_wgrad_small_n_t16(s.d_raw_density, 1, h16(depth - 1), W, s.part,
                                                  grads[depth].weight_grad, grads[depth].bias_grad,
                                                  touched[depth] ? 1 : 0, m, precision, st, inv_gscale));
@@ -582,8 +586,8 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
       uint8_t *cur = s.d_b, *other = s.d_a;
       for (int i = depth - 1; i >= 0; --i) {
         const bool skip = takes_skip(cfg, i);
-        if (i == 0) CUDA_TRY(wgrad(0, cur, s.enc, 0, d.xyz_dim, nullptr, 0, 1));
-        else CUDA_TRY(wgrad(i, cur, h16(i - 1), 1, W, skip ? s.enc : nullptr, skip ? d.xyz_dim : 0, 1));
+        if (i == 0) CUDA_TRY(wgrad(0, cur, s.enc16, d.xyz_dim, nullptr, 0, 0, 1));
+        else CUDA_TRY(wgrad(i, cur, h16(i - 1), W, skip ? s.enc16 : nullptr, 1, skip ? d.xyz_dim : 0, 1));
         if (i > 0) {
           CUDA_TRY(mipnerf::launch_linear_t16(cur, img_bwd[i], other, m, W, W, nullptr, nullptr, h16(i - 1), precision,
                                               st));

@@ -90,8 +90,8 @@ cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1
                                      int ld2, int k2, int x2_row_div, float* part, int64_t m, int max_slices,
                                      int precision, int* slices_out, cudaStream_t st);
 cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, const void* x1, int x1_t16, int ld1, int k1,
-                                     const float* x2, int ld2, int k2, int x2_row_div, float* part, int64_t m,
-                                     int max_slices, int precision, int* slices_out, cudaStream_t st);
+                                     const void* x2, int x2_t16, int ld2, int k2, int x2_row_div, float* part,
+                                     int64_t m, int max_slices, int precision, int* slices_out, cudaStream_t st);
 // fixed-order reduction of [slices, n_dim, k_dim + 1] partials into dW / db (train_kernels.cu)
 cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_dim, float* dw, float* db,
                                 int accumulate, cudaStream_t st, float scale = 1.f);

@@ -249,8 +249,8 @@ struct WgradTcParams {
   float* part;      // [slices, n_dim, K + 1]
   int64_t m, slice_rows;
   // second-generation kernel only: dy / x1 are 16-bit tile images (train_t16.cu) instead of fp32 row-major matrices;
-  // x1's image has k1 / 64 slabs per tile.  x2 is always fp32.
-  int dy_t16, x1_t16;
+  // x1's / x2's image has ceil(k / 64) slabs per tile (x2 as an image: x2_row_div == 1).
+  int dy_t16, x1_t16, x2_t16;
 };
 
 template <int kFmt>
@@ -424,7 +424,10 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
   const bool xvec = (ldx & 3) == 0 && xdiv == 1 && (xc0 & 3) == 0 && (nk & 7) == 0 &&
                     (reinterpret_cast<uintptr_t>(xs) & 15) == 0;
   // tile-image operands arrive by bulk copy (warp 9), fp32 operands through the stager warps' registers
-  const bool a16 = p.dy_t16 != 0, b16 = in_x1 && p.x1_t16 != 0;
+  const bool a16 = p.dy_t16 != 0, b16 = in_x1 ? p.x1_t16 != 0 : p.x2_t16 != 0;
+  // fp32 operand whose row index is the same for a whole 64-row slab (the per-ray view encodings, one ray = 128 rows):
+  // fetched once per slab instead of once per row
+  const bool x_per_slab = !b16 && !xvec && (xdiv & 63) == 0;
   const bool bias_read = a16 && blockIdx.y == 0;  // column sums of dY are then taken from the staged tile
   const int a_blocks = p.n_dim >> 6, b_blocks = nk_mma >> 6;
 
@@ -467,8 +470,8 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
     // ============================== bulk producer (tile-image operands) ==============================
     if (lane == 0 && (a16 || b16)) {
       const uint8_t* dy16 = reinterpret_cast<const uint8_t*>(p.dy);
-      const uint8_t* x16 = reinterpret_cast<const uint8_t*>(p.x1);
-      const int x_slabs = p.k1 >> 6;
+      const uint8_t* x16 = reinterpret_cast<const uint8_t*>(in_x1 ? p.x1 : p.x2);
+      const int x_slabs = ((in_x1 ? p.k1 : p.k2) + 63) >> 6;
       const uint32_t bytes = (uint32_t)((a16 ? a_blocks : 0) + (b16 ? b_blocks : 0)) * kWgBlock;
       for (int it = 0; it < slabs; ++it) {
         const int s = it % kWgStages;
@@ -506,6 +509,14 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
       } else {
       if (it >= kWgStages) mbar_wait(&empty[s], (uint32_t)(it / kWgStages - 1) & 1u);
       const int64_t m0 = m_begin + (int64_t)it * kWgSlab;
+      float4 xs0 = make_float4(0.f, 0.f, 0.f, 0.f), xs1 = xs0;
+      if (x_per_slab && c8 < nk) {
+        const float* src = xs + (m0 / xdiv) * (int64_t)ldx + xc0 + c8;
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = (c8 + e < nk) ? __ldg(src + e) : 0.f;
+        xs0 = make_float4(t[0], t[1], t[2], t[3]), xs1 = make_float4(t[4], t[5], t[6], t[7]);
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float4 fa[4][2], fb[4][2];
@@ -520,7 +531,9 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
             fa[i][0] = __ldg(src), fa[i][1] = __ldg(src + 1);
           }
           if (ok && c8 < nk && !b16) {
-            if (xvec) {
+            if (x_per_slab) {
+              fb[i][0] = xs0, fb[i][1] = xs1;
+            } else if (xvec) {
               const float4* src = reinterpret_cast<const float4*>(xs + row * (int64_t)ldx + xc0 + c8);
               fb[i][0] = __ldg(src), fb[i][1] = __ldg(src + 1);
             } else {
@@ -678,14 +691,14 @@ bool wgrad_tc_shape_ok(int n_dim) { return n_dim == 128 || n_dim == 256; }
 // Second-generation wgrad partials.  dy / x1 are fp32 row-major matrices, or (dy_t16 / x1_t16 != 0) 16-bit tile images
 // (then m must be a multiple of 128 and x1 has k1 / 64 slabs per tile); x2 is fp32 row-major.
 cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, const void* x1, int x1_t16, int ld1, int k1,
-                                     const float* x2, int ld2, int k2, int x2_row_div, float* part, int64_t m,
-                                     int max_slices, int precision, int* slices_out, cudaStream_t st) {
-  if (!x2) x2 = static_cast<const float*>(x1), ld2 = ld1, k2 = 0;
+                                     const void* x2, int x2_t16, int ld2, int k2, int x2_row_div, float* part,
+                                     int64_t m, int max_slices, int precision, int* slices_out, cudaStream_t st) {
+  if (!x2) x2 = x1, x2_t16 = x1_t16, ld2 = ld1, k2 = 0;
   if (x2_row_div < 1) x2_row_div = 1;
   const int K = k1 + k2;
   if (!(k2 == 0 || k1 % 256 == 0) || !(n_dim == 128 || n_dim == 256)) return cudaErrorInvalidValue;
-  if ((dy_t16 || x1_t16) && m % 128 != 0) return cudaErrorInvalidValue;
-  if (x1_t16 && k1 % 64 != 0) return cudaErrorInvalidValue;
+  if ((dy_t16 || x1_t16 || x2_t16) && m % 128 != 0) return cudaErrorInvalidValue;
+  if (x2_t16 && k2 > 0 && x2_row_div != 1) return cudaErrorInvalidValue;
   if (g_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -712,8 +725,8 @@ cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, cons
   }
   WgradTcParams p{};
   p.dy = static_cast<const float*>(dy), p.n_dim = n_dim, p.x1 = static_cast<const float*>(x1), p.ld1 = ld1, p.k1 = k1;
-  p.x2 = x2, p.ld2 = ld2, p.k2 = k2, p.x2_row_div = x2_row_div, p.part = part, p.m = m, p.slice_rows = slice_rows;
-  p.dy_t16 = dy_t16, p.x1_t16 = x1_t16;
+  p.x2 = static_cast<const float*>(x2), p.ld2 = ld2, p.k2 = k2, p.x2_row_div = x2_row_div, p.part = part, p.m = m;
+  p.slice_rows = slice_rows, p.dy_t16 = dy_t16, p.x1_t16 = x1_t16, p.x2_t16 = x2_t16;
   dim3 grid((unsigned)slices, (unsigned)k_tiles);
   LaunchScope scope(kKernWgradTc, st);
   if (fmt) wgrad_mn_kernel<1><<<grid, 320, smem, st>>>(p, swap_strides);
@@ -740,8 +753,8 @@ cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1
   const int generation = (gen_env && gen_env[0] == '1') ? 1 : 2;
   const bool mn_ok = (k2 == 0 || k1 % 256 == 0) && (n_dim & 7) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0;
   if (generation == 2 && mn_ok)
-    return launch_wgrad_mn_partials(dy, 0, n_dim, x1, 0, ld1, k1, x2, ld2, k2, x2_row_div, part, m, max_slices, precision,
-                                    slices_out, st);
+    return launch_wgrad_mn_partials(dy, 0, n_dim, x1, 0, ld1, k1, x2, 0, ld2, k2, x2_row_div, part, m, max_slices,
+                                    precision, slices_out, st);
   const int n_tiles = (n_dim + 127) / 128, k_tiles = (K + 255) / 256;
   int64_t slices = (2 * (int64_t)g_sms + n_tiles * k_tiles - 1) / (n_tiles * k_tiles);  // one wave of 2 CTAs per SM
   const int64_t by_rows = (m + 63) / 64;

@@ -846,16 +846,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           TRACE(EV(2, 4, l, slot));
           if (dumping) {
             named_bar_sync(1 + slot, 128);  // the whole tile is written (and fenced towards the async proxy)
+#ifndef MIPNERF_TRAIN_EXPERIMENT_NO_STORE  // timing experiments only (the dump is then incomplete)
             if (row == 0 && valid) {
               bulk_s2g(p.act_dump + ((size_t)l * p.dump_tiles + ray) * kABytes, myA, kABytes);
               dump_pending = true;
             }
+#endif
           }
         } else {
           vb_s[slot * 128 + row] = vb;
           named_bar_sync(1 + slot, 128);  // vb_s of this ray visible to the whole slot
           epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2,
+#ifdef MIPNERF_TRAIN_EXPERIMENT_NO_VDUMP
+                              nullptr, row);
+#else
                               (dumping && valid) ? p.v_dump + (size_t)ray * (2 * kStageBytes) : nullptr, row);
+#endif
           tc_fence_before();
           arrive_a_ready();  // accumulator drained: the next ray's layer 0 may start while we composite
           TRACE(EV(2, 3, l, slot));

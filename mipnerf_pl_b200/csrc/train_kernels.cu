@@ -413,8 +413,19 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, 
   const int per = k_dim + 1;
   if (idx >= n_dim * per) return;
   const int n = idx / per, kg = idx % per;
+  // fixed order s = 0, 1, ..; the loads do not depend on the sum, so eight of them are kept in flight (one DRAM
+  // round trip per slice otherwise: 148 slices x ~0.6 us made this kernel 60 us per layer)
   float acc = 0.f;
-  for (int s = 0; s < slices; ++s) acc += __ldg(part + (size_t)s * n_dim * per + idx);
+  const size_t stride = (size_t)n_dim * per;
+  int s = 0;
+  for (; s + 8 <= slices; s += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (size_t)(s + u) * stride + idx);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += v[u];
+  }
+  for (; s < slices; ++s) acc += __ldg(part + (size_t)s * stride + idx);
   float* dst = kg < k_dim ? dw + (size_t)n * k_dim + kg : db + n;
   acc *= scale;  // 1 / (the fp16 step's gradient scale); exactly 1 otherwise
   *dst = accumulate ? *dst + acc : acc;

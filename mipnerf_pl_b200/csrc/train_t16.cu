@@ -185,9 +185,15 @@ __global__ void color_dgrad_t16_kernel(const float* __restrict__ d_rgb, const fl
   const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
   float o[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = ch * 8 + e;
-    o[e] = fmaf(g2, __ldg(wc + 2 * k_dim + c), fmaf(g1, __ldg(wc + k_dim + c), g0 * __ldg(wc + c)));
+  for (int h = 0; h < 2; ++h) {  // Wc rows as float4 (six 16-byte loads instead of 24 scalar ones)
+    const int c = ch * 8 + 4 * h;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + c));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + k_dim + c));
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(wc + 2 * k_dim + c));
+    o[4 * h + 0] = fmaf(g2, w2.x, fmaf(g1, w1.x, g0 * w0.x));
+    o[4 * h + 1] = fmaf(g2, w2.y, fmaf(g1, w1.y, g0 * w0.y));
+    o[4 * h + 2] = fmaf(g2, w2.z, fmaf(g1, w1.z, g0 * w0.z));
+    o[4 * h + 3] = fmaf(g2, w2.w, fmaf(g1, w1.w, g0 * w0.w));
   }
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -205,67 +211,115 @@ __device__ __forceinline__ float t16_load(const uint8_t* base, int64_t row, int 
   return from16<kFmt>(bits);
 }
 
-// The two narrow heads' weight gradients (train_kernels.cu: wgrad_small_n_kernel) with X read from a tile image:
-// thread = input column k, dY values are warp-uniform fp32 loads.  Same partial layout.
-template <int kFmt>
+// The two narrow heads' weight gradients (density n = 1, colour n = 3) with X read from a tile image: an HBM-bound
+// streaming pass.  A warp (k_dim = 256) or half-warp (128) owns a row at a time, each lane one 16-byte chunk (8 columns,
+// coalesced 512 / 256 B per row), eight rows in flight per lane; the dY values of the row are warp-uniform fp32 loads.
+// Lane partials are combined through shared memory in a fixed order; same partial layout as wgrad_small_n_kernel.
+template <int kFmt, int kN>
 __global__ void __launch_bounds__(256)
-wgrad_small_n_t16_kernel(const float* __restrict__ dy, int n_dim, const uint8_t* __restrict__ x, int k_dim,
+wgrad_small_n_t16_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ x, int k_dim,
                          float* __restrict__ part, int64_t m, int64_t slice_rows) {
-  __shared__ float red[256][5];
-  const int tid = threadIdx.x;
-  const int groups = 256 / k_dim;  // k_dim in {128, 256}
-  const int grp = tid / k_dim, k = tid % k_dim;
+  __shared__ float red[8][32][kN * 8 + 1];
+  __shared__ float bred[16][kN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cpr = k_dim >> 3;        // 16-byte chunks per row: 32 or 16
+  const int rpw = 32 / cpr;          // rows a warp covers per step: 1 or 2
+  const int sub = lane / cpr, chunk = lane % cpr;
   const int64_t m_begin = (int64_t)blockIdx.x * slice_rows;
   const int64_t m_end = (m_begin + slice_rows) < m ? (m_begin + slice_rows) : m;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
-  if (grp < groups) {
-#pragma unroll 8  // independent loads: eight rows in flight per thread (the loop is latency-bound otherwise)
-    for (int64_t row = m_begin + grp; row < m_end; row += groups) {
-      const float xv = t16_load<kFmt>(x, row, k, k_dim);
+  float acc[kN][8], bsum[kN];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < n_dim) {
-          const float d = __ldg(dy + row * n_dim + j);
-          acc[j] = fmaf(d, xv, acc[j]);
-          bsum[j] += d;
+  for (int j = 0; j < kN; ++j) {
+    bsum[j] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+  }
+  const size_t slab_off = (size_t)(chunk >> 3) * kSlab;
+  const uint32_t ci = (uint32_t)chunk & 7u;
+  const int step = 8 * rpw;
+  for (int64_t row0 = m_begin + warp * rpw + sub; row0 < m_end; row0 += (int64_t)step * 8) {
+    uint4 xv[8];
+    float d[8][kN];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {  // eight independent rows in flight
+      const int64_t row = row0 + (int64_t)u * step;
+      const bool ok = row < m_end;
+      const int r = (int)(row & 127);
+      xv[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + (size_t)(row >> 7) * (cpr >> 3) * kSlab + slab_off +
+                                                        (uint32_t)r * 128u + ((ci ^ ((uint32_t)r & 7u)) << 4)))
+                 : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int j = 0; j < kN; ++j) d[u][j] = ok ? __ldg(dy + row * kN + j) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t w[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = from16<kFmt>((uint16_t)(w[e] & 0xffffu)), x1 = from16<kFmt>((uint16_t)(w[e] >> 16));
+#pragma unroll
+        for (int j = 0; j < kN; ++j) {
+          acc[j][2 * e] = fmaf(d[u][j], x0, acc[j][2 * e]);
+          acc[j][2 * e + 1] = fmaf(d[u][j], x1, acc[j][2 * e + 1]);
         }
       }
+#pragma unroll
+      for (int j = 0; j < kN; ++j) bsum[j] += d[u][j];
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) red[tid][j] = acc[j];
+  for (int j = 0; j < kN; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[warp][lane][j * 8 + e] = acc[j][e];
+  if (chunk == 0)
+#pragma unroll
+    for (int j = 0; j < kN; ++j) bred[warp * 2 + sub][j] = bsum[j];
   __syncthreads();
-  float* out = part + (size_t)blockIdx.x * n_dim * (k_dim + 1);
-  if (tid < k_dim) {
-    for (int j = 0; j < n_dim; ++j) {
+  float* out = part + (size_t)blockIdx.x * kN * (k_dim + 1);
+  if (tid < k_dim) {  // column tid = chunk tid / 8, element tid % 8: fixed-order sum over warps and sub-rows
+    const int c = tid >> 3, e = tid & 7;
+#pragma unroll
+    for (int j = 0; j < kN; ++j) {
       float v = 0.f;
-      for (int g2 = 0; g2 < groups; ++g2) v += red[g2 * k_dim + tid][j];
+      for (int w8 = 0; w8 < 8; ++w8)
+        for (int sb = 0; sb < rpw; ++sb) v += red[w8][sb * cpr + c][j * 8 + e];
       out[(size_t)j * (k_dim + 1) + tid] = v;
     }
   }
-  __syncthreads();
-  if (k == 0)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) red[grp][j] = bsum[j];
-  __syncthreads();
-  if (tid < n_dim) {
+  if (tid < kN) {
     float v = 0.f;
-    for (int g2 = 0; g2 < groups; ++g2) v += red[g2][tid];
+    for (int w8 = 0; w8 < 8; ++w8)
+      for (int sb = 0; sb < rpw; ++sb) v += bred[w8 * 2 + sb][tid];
     out[(size_t)tid * (k_dim + 1) + k_dim] = v;
   }
 }
 
-// fp32 row-major [m, cols] (ld) <-> tile image; rows beyond m / columns beyond cols are zero in the image
+// fp32 row-major [m, cols] (ld) <-> tile image; rows beyond m / columns beyond cols are zero in the image.
+// thread = (row, 16-byte chunk of 8 columns): two float4 loads when the source allows it, one 16-byte store
 template <int kFmt>
 __global__ void t16_pack_kernel(const float* __restrict__ src, int ld, int cols, int64_t m, uint8_t* __restrict__ dst,
-                                int img_cols, int64_t padded_rows) {
+                                int img_cols, int64_t padded_rows, int vec) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= padded_rows * img_cols) return;
-  const int64_t row = idx / img_cols;
-  const int col = (int)(idx % img_cols);
-  const float v = (row < m && col < cols) ? __ldg(src + row * ld + col) : 0.f;
-  *reinterpret_cast<uint16_t*>(dst + ((size_t)(row >> 7) * (img_cols >> 6) + (col >> 6)) * kSlab +
-                               sw128_offset((int)(row & 127), col & 63)) = to16<kFmt>(v);
+  const int chunks = img_cols >> 3;
+  if (idx >= padded_rows * chunks) return;
+  const int64_t row = idx / chunks;
+  const int ch = (int)(idx % chunks), c0 = ch * 8;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (row < m) {
+    if (vec && c0 + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + row * ld + c0));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + row * ld + c0 + 4));
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < cols) v[e] = __ldg(src + row * ld + c0 + e);
+    }
+  }
+  const int r = (int)(row & 127);
+  *reinterpret_cast<uint4*>(dst + ((size_t)(row >> 7) * (img_cols >> 6) + (ch >> 3)) * kSlab + (uint32_t)r * 128u +
+                            ((((uint32_t)ch & 7u) ^ ((uint32_t)r & 7u)) << 4)) =
+      make_uint4(pack2<kFmt>(v[0], v[1]), pack2<kFmt>(v[2], v[3]), pack2<kFmt>(v[4], v[5]), pack2<kFmt>(v[6], v[7]));
 }
 template <int kFmt>
 __global__ void t16_unpack_kernel(const uint8_t* __restrict__ src, int img_cols, float* __restrict__ dst, int ld,
@@ -291,10 +345,13 @@ cudaError_t launch_t16_pack(const float* src, int ld, int cols, int64_t m, void*
   const int img_cols = (cols + 63) / 64 * 64;
   const int64_t padded = (m + 127) / 128 * 128;
   if (padded == 0) return cudaSuccess;
+  LaunchScope scope(kKernIpe, st);  // accounted with the feature kernels (its use in the training step)
+  const int vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  const int64_t total = padded * (img_cols / 8);
   if (precision == 1)
-    t16_pack_kernel<1><<<blocks_of(padded * img_cols, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded);
+    t16_pack_kernel<1><<<blocks_of(total, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded, vec);
   else
-    t16_pack_kernel<0><<<blocks_of(padded * img_cols, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded);
+    t16_pack_kernel<0><<<blocks_of(total, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded, vec);
   return cudaGetLastError();
 }
 
@@ -352,23 +409,31 @@ cudaError_t launch_color_dgrad_t16(const float* d_rgb, const float* wc, const vo
   return cudaGetLastError();
 }
 
-// narrow heads: dW[n_dim <= 4, k_dim] and db from dy (fp32 [m, n_dim]) and a tile-image X; partials + fixed-order sum
+// narrow heads: dW[n_dim, k_dim] and db from dy (fp32 [m, n_dim], n_dim = 1 or 3) and a tile-image X; partials +
+// fixed-order sum
 cudaError_t launch_wgrad_small_n_t16(const float* dy, int n_dim, const void* x, int k_dim, float* part, float* dw,
                                      float* db, int accumulate, int64_t m, int precision, cudaStream_t st,
                                      float scale) {
   if (m == 0 || n_dim == 0) return cudaSuccess;
-  if (n_dim > 4 || !(k_dim == 128 || k_dim == 256)) return cudaErrorInvalidValue;
-  int64_t want = m / 512;
+  if (!(n_dim == 1 || n_dim == 3) || !(k_dim == 128 || k_dim == 256)) return cudaErrorInvalidValue;
+  if (g_sms_t16 == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms_t16, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int64_t want = 4 * (int64_t)g_sms_t16;  // four resident blocks per SM, one wave
+  if (want > (m + 63) / 64) want = (m + 63) / 64;
   if (want < 1) want = 1;
-  if (want > 1184) want = 1184;
   const int slices = (int)want;
   const int64_t rows = (m + slices - 1) / slices;
+  const uint8_t* x8 = static_cast<const uint8_t*>(x);
   {
     LaunchScope scope(kKernWgrad, st);
-    if (precision == 1)
-      wgrad_small_n_t16_kernel<1><<<slices, 256, 0, st>>>(dy, n_dim, (const uint8_t*)x, k_dim, part, m, rows);
-    else
-      wgrad_small_n_t16_kernel<0><<<slices, 256, 0, st>>>(dy, n_dim, (const uint8_t*)x, k_dim, part, m, rows);
+    const int fmt = precision == 1 ? 1 : 0;
+    if (fmt && n_dim == 1) wgrad_small_n_t16_kernel<1, 1><<<slices, 256, 0, st>>>(dy, x8, k_dim, part, m, rows);
+    else if (fmt) wgrad_small_n_t16_kernel<1, 3><<<slices, 256, 0, st>>>(dy, x8, k_dim, part, m, rows);
+    else if (n_dim == 1) wgrad_small_n_t16_kernel<0, 1><<<slices, 256, 0, st>>>(dy, x8, k_dim, part, m, rows);
+    else wgrad_small_n_t16_kernel<0, 3><<<slices, 256, 0, st>>>(dy, x8, k_dim, part, m, rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }

@@ -16,3 +16,5 @@ try:
     print('strong', d['strong_scaling'])
 except Exception as e: print(n,'failed',e); print(open(f'gpurun_out/r2_scale_n{n}.err').read()[-2500:])
 PY
+echo "== data-parallel training step N=$N"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 tools/train_bench_multi.py > gpurun_out/r2_train_multi_n$N.json 2> gpurun_out/r2_train_multi_n$N.err; tail -1 gpurun_out/r2_train_multi_n$N.json; tail -2 gpurun_out/r2_train_multi_n$N.err | cut -c1-300

@@ -21,7 +21,7 @@ FLOP_PER_RAY_FWD = 312_475_648
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=4096)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "fp16"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -41,17 +41,23 @@ def main():
         step()
     torch.cuda.synchronize()
     lib = _cabi.lib()
-    _cabi.profile_snapshot(reset=True)
-    lib.mipnerf_b200_profile_enable(1)
+    # the step time: CUDA events around `steps` un-instrumented steps ...
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    # ... and the per-kernel breakdown from a second pass with an event pair around every launch (which itself
+    # costs a few microseconds per launch, so its sum is not the step time)
+    _cabi.profile_snapshot(reset=True)
+    lib.mipnerf_b200_profile_enable(1)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
     lib.mipnerf_b200_profile_enable(0)
     prof = _cabi.profile_snapshot(reset=True)
-    ms = e0.elapsed_time(e1) / args.steps
     flops = 3 * args.rays * FLOP_PER_RAY_FWD          # forward + dgrad + wgrad (dgrad of layer 0 is not needed)
     print(json.dumps({"what": f"{args.precision} training step (forward + backward + Adam), randomized, 128+128 samples",
                       "rays": args.rays, "ms_per_step": ms, "rays_per_s": args.rays / (ms * 1e-3),
