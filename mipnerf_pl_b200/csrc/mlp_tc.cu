@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       TRACER_DECL(0);
       int st = 0;
       uint32_t ph = 0;
+      const uint64_t w_policy = kTrain ? l2_policy_evict_last() : 0ull;
       for (int round = 0; round < rounds; ++round)
         for (int l = 0; l < kNumLayers; ++l) {
           const int ns = num_k32(l);
@@ -513,7 +514,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                 for (int part = 0; part < (kX3 ? 2 : 1); ++part) {  // x3: W_hi stage, then the W_lo stage of the slab
                   mbar_wait(&w_empty[st], ph ^ 1);
                   mbar_arrive_expect_tx(&w_full[st], bytes);
-                  bulk_g2s(sW + st * kWStage, src + (part ? kLoOffset : 0), bytes, &w_full[st]);
+                  if (kTrain) bulk_g2s_hint(sW + st * kWStage, src, bytes, &w_full[st], w_policy);  // keep the image in L2
+                  else bulk_g2s(sW + st * kWStage, src + (part ? kLoOffset : 0), bytes, &w_full[st]);
                   TRACE(EV(0, 0, l, st));
                   if (++st == kStages) {
                     st = 0;
@@ -789,6 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
     const int my_rounds = slot < kSlots ? rounds : 0;  // x3: the second worker group has no slot
     const SmallParams* __restrict__ gsp = reinterpret_cast<const SmallParams*>(p.wimage + kSmallOffset);
     constexpr bool dumping = kTrain;  // a separate instantiation: the inference kernel carries none of this
+    const uint64_t dump_policy = kTrain ? l2_policy_evict_first() : 0ull;
     bool dump_pending = false;
     if (slot < kSlots) arrive_a_ready();  // accumulator of this slot is free for the first ray
     for (int round = 0; round < my_rounds; ++round) {
@@ -847,8 +850,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
           if (dumping) {
             named_bar_sync(1 + slot, 128);  // the whole tile is written (and fenced towards the async proxy)
 #ifndef MIPNERF_TRAIN_EXPERIMENT_NO_STORE  // timing experiments only (the dump is then incomplete)
-            if (row == 0 && valid) {
-              bulk_s2g(p.act_dump + ((size_t)l * p.dump_tiles + ray) * kABytes, myA, kABytes);
+            if (row == 0 && valid) {  // evict-first: the dump must not push the weight image out of L2
+              bulk_s2g_hint(p.act_dump + ((size_t)l * p.dump_tiles + ray) * kABytes, myA, kABytes, dump_policy);
               dump_pending = true;
             }
 #endif

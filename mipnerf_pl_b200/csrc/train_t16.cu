@@ -20,6 +20,18 @@ using namespace tc;
 
 constexpr uint32_t kSlab = 16384;  // [128 rows x 64 cols] 16-bit
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one whole 32-byte sector per thread
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 struct LinearT16Params {
   const uint8_t* x;      // [tiles][k / 64][16 KB]
   const uint8_t* image;  // packed B: [k / 64][n x 128 B]   (pack_linear_image_kernel)
@@ -122,39 +134,51 @@ __global__ void __launch_bounds__(384, 1) linear_t16_kernel(const LinearT16Param
       for (int c = c_begin; c < c_end; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 256 + c, v);
-        uint4 mk[4];
+        // Two adjacent 16-byte chunks of a row share a 32-byte sector of the swizzled tile (positions p and p ^ 1), so
+        // the row is read and written one whole sector at a time (256-bit LDG / STG): half the L2 requests of
+        // per-chunk accesses.  Which chunk comes first in the sector depends on the row's swizzle bit 0.
+        const uint32_t ce0 = (uint32_t)((c & 63) >> 3);  // first (even) chunk of this 32-column group: 0 or 4
+        uint32_t mk[2][8];
         if (mrow) {  // issued before the TMEM wait so both latencies overlap
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t ci = (uint32_t)(((c & 63) >> 3) + j);
-            mk[j] = __ldg(reinterpret_cast<const uint4*>(mrow + (size_t)(c >> 6) * kSlab + ((ci ^ rx) << 4)));
-          }
+          for (int pr = 0; pr < 2; ++pr)
+            ldg256(mrow + (size_t)(c >> 6) * kSlab + ((((ce0 + 2 * pr) ^ rx) & ~1u) << 4), mk[pr]);
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float o[8];
+        for (int pr = 0; pr < 2; ++pr) {
+          uint32_t out[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
-          if (p.r1) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.r1w + c + 8 * j));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.r1w + c + 8 * j + 4));
-            o[0] = fmaf(rv, w0.x, o[0]), o[1] = fmaf(rv, w0.y, o[1]), o[2] = fmaf(rv, w0.z, o[2]);
-            o[3] = fmaf(rv, w0.w, o[3]), o[4] = fmaf(rv, w1.x, o[4]), o[5] = fmaf(rv, w1.y, o[5]);
-            o[6] = fmaf(rv, w1.z, o[6]), o[7] = fmaf(rv, w1.w, o[7]);
-          }
-          if (mrow) {  // a 16-bit float is > 0 iff its bits, read as a signed integer, are > 0
-            const uint32_t mw[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+          for (int hf = 0; hf < 2; ++hf) {  // chunk ce0 + 2 pr + hf sits in half (hf ^ (rx & 1)) of the sector
+            const int j = 2 * pr + hf;
+            const uint32_t side = (uint32_t)hf ^ (rx & 1u);
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
+            if (p.r1) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.r1w + c + 8 * j));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.r1w + c + 8 * j + 4));
+              o[0] = fmaf(rv, w0.x, o[0]), o[1] = fmaf(rv, w0.y, o[1]), o[2] = fmaf(rv, w0.z, o[2]);
+              o[3] = fmaf(rv, w0.w, o[3]), o[4] = fmaf(rv, w1.x, o[4]), o[5] = fmaf(rv, w1.y, o[5]);
+              o[6] = fmaf(rv, w1.z, o[6]), o[7] = fmaf(rv, w1.w, o[7]);
+            }
+            if (mrow) {  // a 16-bit float is > 0 iff its bits, read as a signed integer, are > 0
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t mw = side ? mk[pr][4 + e] : mk[pr][e];
+                if (!((int16_t)(mw & 0xffffu) > 0)) o[2 * e] = 0.f;
+                if (!((int32_t)mw >= 0x00010000)) o[2 * e + 1] = 0.f;
+              }
+            }
+            const uint32_t w4[4] = {pack2<kFmt>(o[0], o[1]), pack2<kFmt>(o[2], o[3]), pack2<kFmt>(o[4], o[5]),
+                                    pack2<kFmt>(o[6], o[7])};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (!((int16_t)(mw[e] & 0xffffu) > 0)) o[2 * e] = 0.f;
-              if (!((int32_t)mw[e] >= 0x00010000)) o[2 * e + 1] = 0.f;
+              if (side) out[4 + e] = w4[e];
+              else out[e] = w4[e];
             }
           }
-          const uint32_t ci = (uint32_t)(((c & 63) >> 3) + j);
-          *reinterpret_cast<uint4*>(yrow + (size_t)(c >> 6) * kSlab + ((ci ^ rx) << 4)) =
-              make_uint4(pack2<kFmt>(o[0], o[1]), pack2<kFmt>(o[2], o[3]), pack2<kFmt>(o[4], o[5]),
-                         pack2<kFmt>(o[6], o[7]));
+          stg256(yrow + (size_t)(c >> 6) * kSlab + ((((ce0 + 2 * pr) ^ rx) & ~1u) << 4), out);
         }
       }
       tc_fence_before();

@@ -57,6 +57,35 @@ def test_forward_backward_matches_reference_autograd(tag):
     assert_grad_errors(errs, f"case {tag}")
 
 
+# per-tensor bars of the fused tensor-core step against the REFERENCE's autograd (golden training.npz: reference
+# MipNerf + distloss + torch autograd on the x40-density stress weights), measured on B200 and granted ~2x:
+#   (loss rel, trunk weights, heads)
+TC_GOLDEN_BARS = {"bf16": (2e-2, 4e-1, 5e-2), "fp16": (4e-3, 2e-1, 1e-2)}
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_tensor_core_step_vs_reference_autograd_golden(tag, precision):
+    """The 16-bit-operand step against the committed outputs of the reference itself, with the per-tensor bar stated
+    (the fp32 step is held to 2e-6 / 2e-3 by test_forward_backward_matches_reference_autograd)."""
+    g = golden("training.npz")
+    rays, rgbs, randomized, white, disable_ms, t_rand, u_jit, seed = training_golden_case(g, tag)
+    model = gpu_model(seed, "trained_like", precision=precision)
+    out = mp.forward_backward(model, to_dev(rays), rgbs.to(DEV), randomized, white, coarse_loss_mult=0.1,
+                              disable_multiscale_loss=disable_ms,
+                              t_rand=None if t_rand is None else t_rand.to(DEV),
+                              u_jitter=None if u_jit is None else u_jit.to(DEV))
+    torch.cuda.synchronize()
+    loss_bar, trunk_bar, head_bar = TC_GOLDEN_BARS[precision]
+    loss_err = abs(float(out["loss"]) - float(g[f"{tag}_loss"][0])) / abs(float(g[f"{tag}_loss"][0]))
+    errs = grad_errors_vs_golden(named_grads(model), g, tag)
+    trunk = max(v for k, v in errs.items() if ".layers." in k or "extra_layer" in k)
+    heads = max(v for k, v in errs.items() if not (".layers." in k or "extra_layer" in k))
+    print(f"{precision} case {tag}: loss rel err {loss_err:.2e}, worst trunk tensor {trunk:.2e}, worst head tensor {heads:.2e}; "
+          f"{ {k.replace('mlp.', ''): float(f'{v:.1e}') for k, v in errs.items() if k.endswith('weight')} }")
+    assert loss_err <= loss_bar and trunk <= trunk_bar and heads <= head_bar
+
+
 @pytest.mark.parametrize("kind,white", [("xavier", True), ("trained_like", False)])
 def test_forward_backward_vs_oracle_autograd_full_tensors(kind, white):
     b = 70                                                           # ragged vs the 128-row tiles
