@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame", action="store_true", help="skip the 800x800 frame metric (profiling runs)")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step metric (N = 1 only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity measurement")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -480,6 +481,38 @@ def main():
                "sample": f"{sample} of {B} rays (same rays/weights), 2 timed runs of {CPU_ARM_WHAT[kind]} on "
                          f"{cores} torch threads (fastest of a sweep up to {os.cpu_count()} host threads)"}
 
+    # SURVEY §8f N2, reported next to the headline (not part of it): one data-parallel training step of the same batch
+    # shape — forward with the activation dump, backward on tile images, Adam — timed with CUDA events on rank 0, N = 1.
+    train = None
+    if not args.no_train and world == 1 and precision in ("bf16", "fp16"):
+        tmodel = mp.MipNerf(precision=precision)
+        tmodel.load_state_dict(mp.make_state_dict(seed=0, kind="xavier"))
+        tmodel = tmodel.to(dev)
+        opt = mp.FusedAdam(tmodel.parameters(), lr=5e-4)
+        trays = mp.namedtuple_map(lambda t: t.to(dev), mp.random_ray_batch(b_local, seed=1, multiscale=True))
+        trgb = torch.rand(b_local, 3, device=dev)
+
+        def tstep():
+            out = mp.forward_backward(tmodel, trays, trgb, True, True)   # randomized: in-kernel Philox draws
+            opt.step()
+            return out
+        for _ in range(3):
+            tstep()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(10):
+            tout = tstep()
+        t1.record()
+        torch.cuda.synchronize()
+        tms = t0.elapsed_time(t1) / 10
+        train = {"ms_per_step": tms, "rays_per_s": b_local / (tms * 1e-3), "rays": b_local, "steps": 10,
+                 "loss": float(tout["loss"]), "precision": precision,
+                 "what": "MipNeRFSystem.training_step equivalent: forward (both levels, randomized) + backward + Adam "
+                         "on the fused tensor-core path (DESIGN.md §8); not part of `value`"}
+        del tmodel, opt, trays, trgb
+        torch.cuda.empty_cache()
+
     line = {
         "metric": "rays/sec (4096-ray batch, 128+128 samples)", "value": value, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -501,6 +534,7 @@ def main():
         "kernel_launches": {k: int(round(v * args.steps)) for k, v in launches_per_step.items()},
         "kernel_ms": {k: round(v[1], 4) for k, v in prof.items() if v[2]},
         "clocks": clocks, "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "strong_scaling": strong,
+        "train_step": train,
         "frame": None if frame_ms is None else {
             "height": 800, "width": 800, "rays": 640000, "ms": frame_ms, "rays_per_s": 640000 / (frame_ms * 1e-3),
             "what": "render_frame: on-device ray generation, both levels, rows sharded over ranks, "

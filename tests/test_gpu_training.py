@@ -60,7 +60,8 @@ def test_forward_backward_matches_reference_autograd(tag):
 # per-tensor bars of the fused tensor-core step against the REFERENCE's autograd (golden training.npz: reference
 # MipNerf + distloss + torch autograd on the x40-density stress weights), measured on B200 and granted ~2x:
 #   (loss rel, trunk weights, heads)
-TC_GOLDEN_BARS = {"bf16": (2e-2, 4e-1, 5e-2), "fp16": (4e-3, 2e-1, 1e-2)}
+# measured: bf16 loss 2.7e-4, trunk 9.4e-2 (layers.0), heads 1.1e-2; fp16 4.9e-5, 8.2e-2, 1.5e-3
+TC_GOLDEN_BARS = {"bf16": (1e-3, 2e-1, 2.5e-2), "fp16": (2e-4, 1.6e-1, 4e-3)}
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])

@@ -8,5 +8,11 @@ python - <<'PY'
 import json
 d=json.load(open("gpurun_out/r2_bench_bf16.json"))
 print({k:d[k] for k in ("value","ms_per_step","e2e","kernel_ms","gpu_launches","clocks","parity","cpu_baseline")})
-print(d["roofline"]); print(d["frame"])
+print(d["roofline"]); print(d["frame"]); print(d.get("train_step"))
 PY
+echo "== bench fp16x3"; timeout 900 python bench.py --precision fp16x3 --no-frame > gpurun_out/r2_bench_fp16x3.json 2> gpurun_out/r2_bench_fp16x3.err; python - <<'PY'
+import json
+d=json.load(open("gpurun_out/r2_bench_fp16x3.json"))
+print({k:d[k] for k in ("value","ms_per_step","e2e","parity")}); print(d["roofline"]["frac"])
+PY
+echo "== reference arm"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-600

@@ -4,6 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 if [ "$N" = "2-tests" ]; then
   echo "== multi-GPU tests"; timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q 2>&1 | tail -3
+  exit 0
 fi
 echo "== bench N=$N"
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 10 > gpurun_out/r2_scale_n$N.json 2> gpurun_out/r2_scale_n$N.err
