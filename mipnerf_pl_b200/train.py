@@ -101,6 +101,20 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
 
+def _flat_view(grads) -> Optional[torch.Tensor]:
+    """The one contiguous tensor the gradients are consecutive views of, or None."""
+    g0 = grads[0]
+    if not all(g.is_contiguous() and g.dtype == g0.dtype and g.device == g0.device for g in grads):
+        return None
+    store = g0.untyped_storage()
+    off = g0.storage_offset()
+    for g in grads:
+        if g.untyped_storage().data_ptr() != store.data_ptr() or g.storage_offset() != off:
+            return None
+        off += g.numel()
+    return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(store, g0.storage_offset(), (off - g0.storage_offset(),))
+
+
 def allreduce_grads(params: Iterable[torch.Tensor], group=None, average: bool = True) -> None:
     """DDP semantics (train.py:60 of the reference) for the ray-sharded step: one all-reduce of all
     gradients as a flat buffer, then scattered back into `p.grad`."""
@@ -109,6 +123,12 @@ def allreduce_grads(params: Iterable[torch.Tensor], group=None, average: bool = 
         return
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
+        return
+    flat = _flat_view(grads)
+    if flat is not None:                    # gradients already live back to back in one buffer (forward_backward)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= dist.get_world_size(group)
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
@@ -207,6 +227,14 @@ def forward_backward(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized:
     into `param.grad`.  For a ray shard of a larger batch pass the GLOBAL `mask_sum` / `global_rays`;
     shard gradients then sum to the full-batch gradient."""
     params = _param_list(model)
+    if all(p.grad is None for p in params) and len({(p.device, p.dtype) for p in params}) == 1:
+        # first step: carve every .grad out of ONE flat buffer, so that the data-parallel all-reduce
+        # (`allreduce_grads`) is a single NCCL call on it with no concatenate / scatter copies
+        flat = torch.zeros(sum(p.numel() for p in params), device=params[0].device, dtype=params[0].dtype)
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)

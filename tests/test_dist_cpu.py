@@ -75,6 +75,19 @@ def _grad_worker(rank, world, port, out_dir):
         ok = all(torch.allclose(p.grad, w, rtol=0, atol=1e-6) for p, w in zip(params, want)) and params[-1].grad is None
         allreduce_grads(params, average=False)
         ok = ok and all(torch.allclose(p.grad, w * world, rtol=0, atol=1e-5) for p, w in zip(params, want))
+        # gradients that are consecutive views of one buffer (what forward_backward sets up): reduced in place,
+        # no concatenate / scatter — same values, and the views still alias the buffer afterwards
+        flat = torch.cat([t.reshape(-1) for t in per_rank[rank]])
+        off = 0
+        for p, sh in zip(params, shapes):
+            n = int(torch.tensor(sh).prod())
+            p.grad = flat[off:off + n].view(*sh)
+            off += n
+        from mipnerf_pl_b200.train import _flat_view
+        ok = ok and _flat_view([p.grad for p in params[:-1]]) is not None
+        allreduce_grads(params)
+        ok = ok and all(torch.allclose(p.grad, w, rtol=0, atol=1e-6) for p, w in zip(params, want))
+        ok = ok and params[0].grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
         torch.save(ok, os.path.join(out_dir, f"gok{rank}.pt"))
     finally:
         dist.destroy_process_group()
