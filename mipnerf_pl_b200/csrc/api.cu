@@ -397,6 +397,7 @@ struct FusedScratch {
   float *raw_rgb[2], *raw_density[2];    // raw heads per level
   float *enc, *venc, *d_raw_rgb, *d_raw_density, *part, *t[2], *w[2];
   uint8_t *enc16;                        // the IPE features as a tile image [rays][2 slabs] (96 columns + zero padding)
+  uint8_t *relu_bits;                    // [m][32 B]: sign mask of the layer input the current wgrad streams
   uint8_t *d_v, *d_a, *d_b;              // gradient tile images: [rays][32 KB], [rays][64 KB] x 2
   uint8_t *images, *packed, *tcws;
   size_t tcws_bytes, bytes;
@@ -425,6 +426,7 @@ FusedScratch carve_fused(const mipnerf_b200_config* c, const Dims& d, int64_t ra
   s.d_raw_rgb = take(m * 3);
   s.d_raw_density = take(m);
   s.enc16 = take_bytes((size_t)rays * 32768);
+  s.relu_bits = take_bytes(m * 32);
   s.d_v = take_bytes((size_t)rays * 32768);
   s.d_a = take_bytes((size_t)rays * 65536);
   s.d_b = take_bytes((size_t)rays * 65536);
@@ -538,11 +540,16 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
     CUDA_TRY(mipnerf::tc_forward(cfg, &wl, &rc_, randomized, t_rand ? t_rand + off * (n + 1) : nullptr,
                                  u_jitter ? u_jitter + off * (n + 1) : nullptr, rng, white_bkgd, precision, lo, s.tcws,
                                  s.tcws_bytes, st, &dump, off));
-    auto wgrad = [&](int idx, const void* dy16, const void* x1, int k1, const void* x2, int x2_t16, int k2, int div) {
+    // MIPNERF_B200_TRAIN_MASKBITS=0: the dgrad GEMMs read the ReLU mask from the activation tile images again (A/B)
+    const char* bits_env = getenv("MIPNERF_B200_TRAIN_MASKBITS");
+    const bool use_bits = !(bits_env && bits_env[0] == '0');
+    auto wgrad = [&](int idx, const void* dy16, const void* x1, int k1, const void* x2, int x2_t16, int k2, int div,
+                     bool emit_mask = false) {
       const mipnerf_b200_linear& l = w->linears[idx];
       int slices = 0;
       cudaError_t e2 = mipnerf::launch_wgrad_mn_partials(dy16, 1, l.out_features, x1, 1, k1, k1, x2, x2_t16, k2, k2, div,
-                                                         s.part, m, mipnerf::kWgradMaxSlices, precision, &slices, st);
+                                                         s.part, m, mipnerf::kWgradMaxSlices, precision, &slices, st,
+                                                         emit_mask && use_bits ? s.relu_bits : nullptr);
       if (e2 != cudaSuccess) return e2;
       e2 = mipnerf::launch_wgrad_reduce(s.part, slices, l.out_features, k1 + k2, grads[idx].weight_grad,
                                         grads[idx].bias_grad, touched[idx] ? 1 : 0, st, inv_gscale);
@@ -575,22 +582,24 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
       CUDA_TRY(mipnerf::launch_linear_t16(s.d_v, img_bwd[depth + 1], s.d_a, m, W, Wc, nullptr, nullptr, nullptr,
                                           precision, st));
       // bottleneck + density head share h_7                              (models/mip_nerf.py:98-101)
-      CUDA_TRY(wgrad(depth + 1, s.d_a, h16(depth - 1), W, nullptr, 0, 0, 1));
+      CUDA_TRY(wgrad(depth + 1, s.d_a, h16(depth - 1), W, nullptr, 0, 0, 1, /*emit_mask=*/true));  // sign mask of h_7
       CUDA_TRY(mipnerf::launch_wgrad_small_n_t16(s.d_raw_density, 1, h16(depth - 1), W, s.part,
                                                  grads[depth].weight_grad, grads[depth].bias_grad,
                                                  touched[depth] ? 1 : 0, m, precision, st, inv_gscale));
       touched[depth] = true;
       CUDA_TRY(mipnerf::launch_linear_t16(s.d_a, img_bwd[depth], s.d_b, m, W, W, s.d_raw_density, dl.weight,
-                                          h16(depth - 1), precision, st));
+                                          use_bits ? nullptr : h16(depth - 1), precision, st,
+                                          use_bits ? s.relu_bits : nullptr));
       // trunk                                                            (models/mip_nerf.py:93-97)
       uint8_t *cur = s.d_b, *other = s.d_a;
       for (int i = depth - 1; i >= 0; --i) {
         const bool skip = takes_skip(cfg, i);
         if (i == 0) CUDA_TRY(wgrad(0, cur, s.enc16, d.xyz_dim, nullptr, 0, 0, 1));
-        else CUDA_TRY(wgrad(i, cur, h16(i - 1), W, skip ? s.enc16 : nullptr, 1, skip ? d.xyz_dim : 0, 1));
-        if (i > 0) {
-          CUDA_TRY(mipnerf::launch_linear_t16(cur, img_bwd[i], other, m, W, W, nullptr, nullptr, h16(i - 1), precision,
-                                              st));
+        else CUDA_TRY(wgrad(i, cur, h16(i - 1), W, skip ? s.enc16 : nullptr, 1, skip ? d.xyz_dim : 0, 1, true));
+        if (i > 0) {  // the wgrad just streamed h_{i-1} and left its sign mask behind: 32 B per row instead of 512
+          CUDA_TRY(mipnerf::launch_linear_t16(cur, img_bwd[i], other, m, W, W, nullptr, nullptr,
+                                              use_bits ? nullptr : h16(i - 1), precision, st,
+                                              use_bits ? s.relu_bits : nullptr));
           uint8_t* tmp = cur;
           cur = other;
           other = tmp;

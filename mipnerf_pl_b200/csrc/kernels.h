@@ -91,7 +91,8 @@ cudaError_t launch_wgrad_tc_partials(const float* dy, int n_dim, const float* x1
                                      int precision, int* slices_out, cudaStream_t st);
 cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, const void* x1, int x1_t16, int ld1, int k1,
                                      const void* x2, int x2_t16, int ld2, int k2, int x2_row_div, float* part,
-                                     int64_t m, int max_slices, int precision, int* slices_out, cudaStream_t st);
+                                     int64_t m, int max_slices, int precision, int* slices_out, cudaStream_t st,
+                                     void* mask_out = nullptr);
 // fixed-order reduction of [slices, n_dim, k_dim + 1] partials into dW / db (train_kernels.cu)
 cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_dim, float* dw, float* db,
                                 int accumulate, cudaStream_t st, float scale = 1.f);
@@ -101,8 +102,11 @@ size_t t16_image_bytes(int64_t rows, int cols);
 cudaError_t launch_t16_pack(const float* src, int ld, int cols, int64_t m, void* image, int precision, cudaStream_t st);
 cudaError_t launch_t16_unpack(const void* image, int cols, float* dst, int ld, int64_t m, int precision,
                               cudaStream_t st);
+// mask: a tile image like y (zero where mask <= 0), or mask_bits: [m][32 B] sign bits of a 256-column image
+// (wgrad_mn_kernel's by-product); at most one of them
 cudaError_t launch_linear_t16(const void* x, const void* image, void* y, int64_t m, int n, int k, const float* r1,
-                              const float* r1w, const void* mask, int precision, cudaStream_t st);
+                              const float* r1w, const void* mask, int precision, cudaStream_t st,
+                              const void* mask_bits = nullptr);
 cudaError_t launch_color_dgrad_t16(const float* d_rgb, const float* wc, const void* v, void* d_v, int64_t m, int k_dim,
                                    int precision, cudaStream_t st);
 cudaError_t launch_wgrad_small_n_t16(const float* dy, int n_dim, const void* x, int k_dim, float* part, float* dw,

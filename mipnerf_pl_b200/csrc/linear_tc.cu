@@ -251,6 +251,10 @@ struct WgradTcParams {
   // second-generation kernel only: dy / x1 are 16-bit tile images (train_t16.cu) instead of fp32 row-major matrices;
   // x1's / x2's image has ceil(k / 64) slabs per tile (x2 as an image: x2_row_div == 1).
   int dy_t16, x1_t16, x2_t16;
+  // optional by-product when x1 is a 256-column tile image: its sign mask, [m][32 bytes], bit c of a row = x1[row][c] > 0.
+  // The dgrad GEMM that follows needs exactly this (the ReLU mask of the layer input) and then reads 32 bytes per row
+  // instead of the 512-byte activation row again.
+  uint8_t* mask_out;
 };
 
 template <int kFmt>
@@ -429,6 +433,8 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
   // fetched once per slab instead of once per row
   const bool x_per_slab = !b16 && !xvec && (xdiv & 63) == 0;
   const bool bias_read = a16 && blockIdx.y == 0;  // column sums of dY are then taken from the staged tile
+  const bool mask_write = p.mask_out != nullptr && b16 && in_x1 && blockIdx.y == 0 && nk == 256;
+  const bool reader = bias_read || mask_write;    // the stager warps read staged tile images out of shared memory
   const int a_blocks = p.n_dim >> 6, b_blocks = nk_mma >> 6;
 
   if (tid == 0) {
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
         if (it >= kWgStages) {
           const uint32_t par = (uint32_t)(it / kWgStages - 1) & 1u;
           mbar_wait(&empty[s], par);
-          if (bias_read) mbar_wait(&rdone[s], par);
+          if (reader) mbar_wait(&rdone[s], par);
         }
         uint8_t* sa = ring + (size_t)s * kWgStage;
         uint8_t* sb = sa + kWgOperand;
@@ -505,7 +511,7 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
       uint8_t* sa = ring + (size_t)s * kWgStage;
       uint8_t* sb = sa + kWgOperand;
       if (a16 && b16) {
-        if (!bias_read) break;  // nothing for the stager warps to do in this CTA
+        if (!reader) break;  // nothing for the stager warps to do in this CTA
       } else {
       if (it >= kWgStages) mbar_wait(&empty[s], (uint32_t)(it / kWgStages - 1) & 1u);
       const int64_t m0 = m_begin + (int64_t)it * kWgSlab;
@@ -566,9 +572,25 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
       }
-      if (bias_read) {  // dY arrived as a tile image: take its column sums from shared memory
+      if (reader) {  // operands that arrived as tile images: column sums of dY, sign mask of X, from shared memory
         mbar_wait(&full[s], (uint32_t)(it / kWgStages) & 1u);
-        if (a_on) {
+        if (mask_write) {
+          const int64_t m0r = m_begin + (int64_t)it * kWgSlab;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = warp + 8 * i;
+            const uint4 w = *reinterpret_cast<const uint4*>(sb + blk + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4));
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            uint32_t bits = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {  // a 16-bit float is > 0 iff its bits, read as a signed integer, are > 0
+              bits |= ((int16_t)(ww[e] & 0xffffu) > 0 ? 1u : 0u) << (2 * e);
+              bits |= ((int32_t)ww[e] >= 0x00010000 ? 1u : 0u) << (2 * e + 1);
+            }
+            p.mask_out[(m0r + r) * 32 + lane] = (uint8_t)bits;  // byte = columns lane*8 .. +7: 32 B per row, coalesced
+          }
+        }
+        if (bias_read && a_on) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = warp + 8 * i;
@@ -692,7 +714,8 @@ bool wgrad_tc_shape_ok(int n_dim) { return n_dim == 128 || n_dim == 256; }
 // (then m must be a multiple of 128 and x1 has k1 / 64 slabs per tile); x2 is fp32 row-major.
 cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, const void* x1, int x1_t16, int ld1, int k1,
                                      const void* x2, int x2_t16, int ld2, int k2, int x2_row_div, float* part,
-                                     int64_t m, int max_slices, int precision, int* slices_out, cudaStream_t st) {
+                                     int64_t m, int max_slices, int precision, int* slices_out, cudaStream_t st,
+                                     void* mask_out) {
   if (!x2) x2 = x1, x2_t16 = x1_t16, ld2 = ld1, k2 = 0;
   if (x2_row_div < 1) x2_row_div = 1;
   const int K = k1 + k2;
@@ -727,6 +750,7 @@ cudaError_t launch_wgrad_mn_partials(const void* dy, int dy_t16, int n_dim, cons
   p.dy = static_cast<const float*>(dy), p.n_dim = n_dim, p.x1 = static_cast<const float*>(x1), p.ld1 = ld1, p.k1 = k1;
   p.x2 = static_cast<const float*>(x2), p.ld2 = ld2, p.k2 = k2, p.x2_row_div = x2_row_div, p.part = part, p.m = m;
   p.slice_rows = slice_rows, p.dy_t16 = dy_t16, p.x1_t16 = x1_t16, p.x2_t16 = x2_t16;
+  p.mask_out = (x1_t16 && k1 == 256) ? static_cast<uint8_t*>(mask_out) : nullptr;
   dim3 grid((unsigned)slices, (unsigned)k_tiles);
   LaunchScope scope(kKernWgradTc, st);
   if (fmt) wgrad_mn_kernel<1><<<grid, 320, smem, st>>>(p, swap_strides);

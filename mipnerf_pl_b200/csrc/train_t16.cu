@@ -37,6 +37,7 @@ struct LinearT16Params {
   const uint8_t* image;  // packed B: [k / 64][n x 128 B]   (pack_linear_image_kernel)
   uint8_t* y;            // [tiles][n / 64][16 KB]
   const uint8_t* mask;   // like y, or null: output zeroed where mask <= 0 (ReLU backward)
+  const uint8_t* mask_bits;  // or the same mask as sign bits, [tiles * 128][32 B] (n = 256)
   const float* r1;       // [tiles * 128] or null, with r1w [n]: + r1[row] * r1w[col]  (density head)
   const float* r1w;
   int64_t tiles;
@@ -129,6 +130,8 @@ __global__ void __launch_bounds__(384, 1) linear_t16_kernel(const LinearT16Param
       const float rv = p.r1 ? __ldg(p.r1 + tile * 128 + row) : 0.f;
       uint8_t* yrow = p.y + (size_t)tile * y_slabs * kSlab + (uint32_t)row * 128u;
       const uint8_t* mrow = p.mask ? p.mask + (size_t)tile * y_slabs * kSlab + (uint32_t)row * 128u : nullptr;
+      uint32_t mb[8] = {~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u, ~0u};
+      if (p.mask_bits) ldg256(p.mask_bits + ((size_t)tile * 128 + row) * 32, mb);  // one sector per row per tile
       mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       for (int c = c_begin; c < c_end; c += 32) {
@@ -169,6 +172,11 @@ __global__ void __launch_bounds__(384, 1) linear_t16_kernel(const LinearT16Param
                 if (!((int16_t)(mw & 0xffffu) > 0)) o[2 * e] = 0.f;
                 if (!((int32_t)mw >= 0x00010000)) o[2 * e + 1] = 0.f;
               }
+            } else if (p.mask_bits) {  // bit (column % 32) of word (column / 32)
+              const uint32_t word = mb[c >> 5] >> (8 * j);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (!((word >> e) & 1u)) o[e] = 0.f;
             }
             const uint32_t w4[4] = {pack2<kFmt>(o[0], o[1]), pack2<kFmt>(o[2], o[3]), pack2<kFmt>(o[4], o[5]),
                                     pack2<kFmt>(o[6], o[7])};
@@ -392,9 +400,11 @@ cudaError_t launch_t16_unpack(const void* image, int cols, float* dst, int ld, i
 
 // y = [mask > 0] * (x . B^T + r1 * r1w) on tile images; m rows (a multiple of 128), n in {128, 256}, k in {128, 256}
 cudaError_t launch_linear_t16(const void* x, const void* image, void* y, int64_t m, int n, int k, const float* r1,
-                              const float* r1w, const void* mask, int precision, cudaStream_t st) {
+                              const float* r1w, const void* mask, int precision, cudaStream_t st,
+                              const void* mask_bits) {
   if (m == 0) return cudaSuccess;
   if (m % 128 != 0 || !(n == 128 || n == 256) || !(k == 128 || k == 256)) return cudaErrorInvalidValue;
+  if (mask_bits && (mask || n != 256)) return cudaErrorInvalidValue;
   const int slabs = k / 64;
   const size_t smem = 1024 + (size_t)slabs * kSlab + linear_tc_image_bytes(n, k) + 128;
   const int fmt = precision == 1 ? 1 : 0;
@@ -412,6 +422,7 @@ cudaError_t launch_linear_t16(const void* x, const void* image, void* y, int64_t
   }
   LinearT16Params p{};
   p.x = static_cast<const uint8_t*>(x), p.image = static_cast<const uint8_t*>(image), p.y = static_cast<uint8_t*>(y);
+  p.mask_bits = static_cast<const uint8_t*>(mask_bits);
   p.mask = static_cast<const uint8_t*>(mask), p.r1 = r1, p.r1w = r1w, p.tiles = m / 128, p.n = n, p.k = k;
   const int grid = (int)(p.tiles < g_sms_t16 ? p.tiles : g_sms_t16);
   LaunchScope scope(kKernLinearTc, st);

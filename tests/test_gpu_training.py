@@ -324,6 +324,25 @@ def test_fused_training_forward_is_the_inference_forward(precision):
             assert torch.equal(g, r), f"level {lvl} {name}: max diff {float((g - r).abs().max()):.3e}"
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_fused_step_relu_bitmask_is_exact(precision, monkeypatch):
+    """The dgrad GEMMs take the ReLU mask either from the forward's activation tile images (512 B per row) or from the
+    32-byte-per-row sign mask the preceding wgrad leaves behind while it streams the same tile: identical gradients,
+    bit for bit."""
+    b = 77
+    rays = to_dev(mp.random_ray_batch(b, seed=19, multiscale=True))
+    rgbs = torch.rand(b, 3, device=DEV)
+    grads = {}
+    for bits in ("0", "1"):
+        monkeypatch.setenv("MIPNERF_B200_TRAIN_MASKBITS", bits)
+        model = gpu_model(2, "trained_like", precision=precision)
+        mp.forward_backward(model, rays, rgbs, False, True)
+        torch.cuda.synchronize()
+        grads[bits] = {k: p.grad.clone() for k, p in model.named_parameters()}
+    for k in grads["0"]:
+        assert torch.equal(grads["0"][k], grads["1"][k]), k
+
+
 @pytest.mark.parametrize("wgrad_tc", ["0", "1", "2", "fused"])
 @pytest.mark.parametrize("precision,loss_tol,grad_tol", [("bf16", 5e-3, 1.5e-1), ("fp16", 1e-3, 1.5e-1)])
 def test_tensor_core_training_mode_tracks_fp32(precision, loss_tol, grad_tol, wgrad_tc, monkeypatch):
