@@ -206,6 +206,11 @@ int mipnerf_b200_wgrad_tc(const float* dy, int n, const float* x1, int k1, const
 int mipnerf_b200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                            double lr, double beta1, double beta2, double eps, int64_t step, double grad_scale,
                            void* stream);
+/* The same update for `count` tensors that share lr / betas / eps / step (one optimiser group) in ONE launch; the
+ * arrays are host arrays of device pointers / element counts. */
+int mipnerf_b200_adam_step_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                                 float* const* exp_avg_sq, const int64_t* sizes, double lr, double beta1, double beta2,
+                                 double eps, int64_t step, double grad_scale, void* stream);
 
 /* Pinhole rays of rows [row0,row0+rows) of an H x W frame generated on the device, replacing the
  * host NumPy loaders (datasets/datasets.py:214-263, render_video.py:29-105).  `c2w_host` is a HOST

@@ -95,6 +95,8 @@ _SIGNATURES = {
                                         C.c_size_t, _V]),
     "mipnerf_b200_adam_step": (C.c_int, [_V, _V, _V, _V, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_int64, C.c_double, _V]),
+    "mipnerf_b200_adam_step_multi": (C.c_int, [C.c_int, _V, _V, _V, _V, _V, C.c_double, C.c_double, C.c_double,
+                                               C.c_double, C.c_int64, C.c_double, _V]),
     "mipnerf_b200_generate_rays": (C.c_int, [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                              _V, _V, _V, _V, _V, _V, _V]),
     "mipnerf_b200_image_metrics_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

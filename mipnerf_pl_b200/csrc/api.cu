@@ -560,11 +560,10 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
       const float* t_cur = lo[l].t_samples;
       const uint8_t* act = s.act[l];
       auto h16 = [&](int i) { return act + (size_t)i * cnt * 65536; };  // h_0..h_7, 8 = bottleneck
-      // the IPE features again (operand of two wgrads; the level kernel keeps its own 16-bit copy on chip), as a
-      // tile image so that those wgrads stage them by bulk copy like every other operand
-      CUDA_TRY(mipnerf::launch_ipe_from_t(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc, cnt, n,
-                                          cfg->min_deg_point, cfg->max_deg_point, cfg->disable_integration, st));
-      CUDA_TRY(mipnerf::launch_t16_pack(s.enc, d.xyz_dim, d.xyz_dim, m, s.enc16, precision, st));
+      // the IPE features again (operand of two wgrads; the level kernel keeps its own 16-bit copy on chip), written
+      // straight into a tile image so that those wgrads stage them by bulk copy like every other operand
+      CUDA_TRY(mipnerf::launch_ipe_t16(rc_.origins, rc_.directions, rc_.radii, t_cur, s.enc16, cnt, n,
+                                       cfg->disable_integration, precision, st));
       CUDA_TRY(mipnerf::launch_render_backward(
           s.raw_rgb[l], s.raw_density[l], t_cur, rc_.directions, loss->target_rgb + off * 3,
           loss->lossmult ? loss->lossmult + off : nullptr, loss->mask_sum, loss->level_mse_mult[l] * gscale,
@@ -898,6 +897,28 @@ int mipnerf_b200_adam_step(float* param, const float* grad, float* exp_avg, floa
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   CUDA_TRY(mipnerf::launch_adam(param, grad, exp_avg, exp_avg_sq, n, (float)beta1, (float)beta2, (float)eps,
                                 (float)(lr / bc1), (float)sqrt(bc2), (float)grad_scale, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
+}
+
+int mipnerf_b200_adam_step_multi(int count, float* const* params, const float* const* grads, float* const* exp_avg,
+                                 float* const* exp_avg_sq, const int64_t* sizes, double lr, double beta1, double beta2,
+                                 double eps, int64_t step, double grad_scale, void* stream) {
+  if (count < 0 || step < 1) return fail(MIPNERF_B200_EINVAL, "bad count / step");
+  if (count > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes)) return fail(MIPNERF_B200_EINVAL, "NULL array");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  for (int base = 0; base < count; base += mipnerf::kAdamMaxTensors) {
+    mipnerf::AdamMulti t{};
+    t.count = (count - base) < mipnerf::kAdamMaxTensors ? (count - base) : mipnerf::kAdamMaxTensors;
+    for (int k = 0; k < t.count; ++k) {
+      const int i = base + k;
+      if (sizes[i] < 0 || (sizes[i] > 0 && (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i])))
+        return fail(MIPNERF_B200_EINVAL, "tensor %d: NULL pointer or negative size", i);
+      t.p[k] = params[i], t.g[k] = grads[i], t.m[k] = exp_avg[i], t.v[k] = exp_avg_sq[i], t.n[k] = sizes[i];
+      t.blocks[k] = (int)((sizes[i] + 255) / 256);
+    }
+    CUDA_TRY(mipnerf::launch_adam_multi(t, (float)beta1, (float)beta2, (float)eps, (float)(lr / bc1), (float)sqrt(bc2),
+                                        (float)grad_scale, (cudaStream_t)stream));
+  }
   return MIPNERF_B200_OK;
 }
 

@@ -72,6 +72,18 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
                              int accumulate, int64_t m, cudaStream_t st);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,
                         float eps, float step_size, float bc2_sqrt, float grad_scale, cudaStream_t st);
+constexpr int kAdamMaxTensors = 32;
+struct AdamMulti {  // passed by value in the kernel parameters
+  float* p[kAdamMaxTensors];
+  const float* g[kAdamMaxTensors];
+  float* m[kAdamMaxTensors];
+  float* v[kAdamMaxTensors];
+  int64_t n[kAdamMaxTensors];
+  int blocks[kAdamMaxTensors];  // ceil(n / 256)
+  int count;
+};
+cudaError_t launch_adam_multi(const AdamMulti& t, float beta1, float beta2, float eps, float step_size, float bc2_sqrt,
+                              float grad_scale, cudaStream_t st);
 
 // ---- linear_tc.cu (tcgen05 linear layer for the training step's forward / dgrad GEMMs) ----
 size_t linear_tc_image_bytes(int n, int k);
@@ -100,6 +112,8 @@ cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_
 // ---- train_t16.cu (backward pass on 16-bit tile images: [tile = 128 rows][64-column slab][128 rows x 128 B, SW128]) ----
 size_t t16_image_bytes(int64_t rows, int cols);
 cudaError_t launch_t16_pack(const float* src, int ld, int cols, int64_t m, void* image, int precision, cudaStream_t st);
+cudaError_t launch_ipe_t16(const float* origins, const float* directions, const float* radii, const float* t, void* image,
+                           int64_t num_rays, int n, int disable_integration, int precision, cudaStream_t st);
 cudaError_t launch_t16_unpack(const void* image, int cols, float* dst, int ld, int64_t m, int precision,
                               cudaStream_t st);
 // mask: a tile image like y (zero where mask <= 0), or mask_bits: [m][32 B] sign bits of a 256-column image

@@ -407,28 +407,42 @@ wgrad_small_n_kernel(const float* __restrict__ dy, int n_dim, const float* __res
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int slices, int n_dim, int k_dim,
-                                    float* __restrict__ dw, float* __restrict__ db, int accumulate, float scale = 1.f) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// Fixed-order sum of the per-slice partials.  The loads do not depend on the running sum, but one thread walking all
+// 148 slices is a chain of ~19 DRAM / L2 round trips even with eight loads in flight (22 us per layer); so four
+// threads share an output element — thread g sums slices [g * q, (g + 1) * q) in order, eight loads in flight — and
+// the four partial sums are added in the order g = 0..3: still one fixed order, a quarter of the latency chain.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, int slices, int n_dim, int k_dim, float* __restrict__ dw,
+                    float* __restrict__ db, int accumulate, float scale = 1.f) {
+  __shared__ float sm[4][64];
+  const int lane64 = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int idx = blockIdx.x * 64 + lane64;
   const int per = k_dim + 1;
-  if (idx >= n_dim * per) return;
-  const int n = idx / per, kg = idx % per;
-  // fixed order s = 0, 1, ..; the loads do not depend on the sum, so eight of them are kept in flight (one DRAM
-  // round trip per slice otherwise: 148 slices x ~0.6 us made this kernel 60 us per layer)
+  const bool ok = idx < n_dim * per;
+  const int q = (slices + 3) / 4;
+  const int s_begin = g * q, s_end = (g + 1) * q < slices ? (g + 1) * q : slices;
   float acc = 0.f;
-  const size_t stride = (size_t)n_dim * per;
-  int s = 0;
-  for (; s + 8 <= slices; s += 8) {
-    float v[8];
+  if (ok) {
+    const size_t stride = (size_t)n_dim * per;
+    int s = s_begin;
+    for (; s + 8 <= s_end; s += 8) {
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (size_t)(s + u) * stride + idx);
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(part + (size_t)(s + u) * stride + idx);
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc += v[u];
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; s < s_end; ++s) acc += __ldg(part + (size_t)s * stride + idx);
   }
-  for (; s < slices; ++s) acc += __ldg(part + (size_t)s * stride + idx);
-  float* dst = kg < k_dim ? dw + (size_t)n * k_dim + kg : db + n;
-  acc *= scale;  // 1 / (the fp16 step's gradient scale); exactly 1 otherwise
-  *dst = accumulate ? *dst + acc : acc;
+  sm[g][lane64] = acc;
+  __syncthreads();
+  if (g == 0 && ok) {
+    float t = ((sm[0][lane64] + sm[1][lane64]) + sm[2][lane64]) + sm[3][lane64];
+    const int n = idx / per, kg = idx % per;
+    float* dst = kg < k_dim ? dw + (size_t)n * k_dim + kg : db + n;
+    t *= scale;  // 1 / (the fp16 step's gradient scale); exactly 1 otherwise
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
 // Number of M-slices for a wgrad with `tiles` output tiles.  Small problems: one slice per 4096 rows.  Large ones:
@@ -458,8 +472,8 @@ int wgrad_num_slices(int64_t m, int tiles) {
 cudaError_t launch_wgrad_reduce(const float* part, int slices, int n_dim, int k_dim, float* dw, float* db,
                                 int accumulate, cudaStream_t st, float scale) {
   LaunchScope scope(kKernWgrad, st);
-  wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (k_dim + 1), 256), 256, 0, st>>>(part, slices, n_dim, k_dim, dw, db,
-                                                                                     accumulate, scale);
+  wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (k_dim + 1), 64), 256, 0, st>>>(part, slices, n_dim, k_dim, dw, db,
+                                                                                    accumulate, scale);
   return cudaGetLastError();
 }
 
@@ -484,7 +498,7 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
     wgrad_small_n_kernel<<<slices, 256, 0, st>>>(dy, n_dim, x1, k1, part, m, rows);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (K + 1), 256), 256, 0, st>>>(part, slices, n_dim, K, dw, db,
+    wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (K + 1), 64), 256, 0, st>>>(part, slices, n_dim, K, dw, db,
                                                                                  accumulate);
     return cudaGetLastError();
   }
@@ -500,7 +514,7 @@ cudaError_t launch_wgrad_f32(const float* dy, int n_dim, const float* x1, int ld
                                                   vec_a, vec_b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (K + 1), 256), 256, 0, st>>>(part, slices, n_dim, K, dw, db,
+  wgrad_reduce_kernel<<<blocks_of((int64_t)n_dim * (K + 1), 64), 256, 0, st>>>(part, slices, n_dim, K, dw, db,
                                                                                accumulate);
   return cudaGetLastError();
 }
@@ -521,6 +535,36 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   v[i] = vi;
   const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
   p[i] = __fadd_rn(p[i], __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+}
+
+// All tensors of one optimiser group in ONE launch (24 launches of ~7 us otherwise): block -> tensor by a scan of the
+// per-tensor block counts carried in the kernel parameters.
+__global__ void adam_multi_kernel(const AdamMulti t, float beta1, float beta2, float eps, float step_size,
+                                  float bc2_sqrt, float grad_scale) {
+  int b = blockIdx.x, k = 0;
+  while (k + 1 < t.count && b >= t.blocks[k]) b -= t.blocks[k++];
+  const int64_t i = (int64_t)b * blockDim.x + threadIdx.x;
+  if (i >= t.n[k]) return;
+  float* __restrict__ p = t.p[k];
+  float* __restrict__ m = t.m[k];
+  float* __restrict__ v = t.v[k];
+  const float gi = __fmul_rn(t.g[k][i], grad_scale);
+  const float mi = __fadd_rn(m[i], __fmul_rn(__fsub_rn(gi, m[i]), 1.0f - beta1));
+  const float vi = __fadd_rn(__fmul_rn(v[i], beta2), __fmul_rn(__fmul_rn(gi, gi), 1.0f - beta2));
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(vi), bc2_sqrt), eps);
+  p[i] = __fadd_rn(p[i], __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+}
+
+cudaError_t launch_adam_multi(const AdamMulti& t, float beta1, float beta2, float eps, float step_size, float bc2_sqrt,
+                              float grad_scale, cudaStream_t st) {
+  int total = 0;
+  for (int k = 0; k < t.count; ++k) total += t.blocks[k];
+  if (total == 0) return cudaSuccess;
+  LaunchScope scope(kKernAdam, st);
+  adam_multi_kernel<<<total, 256, 0, st>>>(t, beta1, beta2, eps, step_size, bc2_sqrt, grad_scale);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float beta1, float beta2,

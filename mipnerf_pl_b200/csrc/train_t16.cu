@@ -11,6 +11,7 @@
 // The wgrad GEMMs on tile images are in linear_tc.cu (wgrad_mn_kernel: a row-major tile IS an MN-major operand).
 #include "kernels.h"
 #include "profile.h"
+#include "ray_math.cuh"
 #include "tc_common.cuh"
 
 namespace mipnerf {
@@ -326,6 +327,50 @@ wgrad_small_n_t16_kernel(const float* __restrict__ dy, const uint8_t* __restrict
   }
 }
 
+// The 96 IPE features of every sample as a tile image [rays][2 slabs] (columns 96..127 zero): the X operand of the
+// layer-0 / skip-layer wgrads.  Same device functions and the same MUFU fast path as the level kernel's IPE warps
+// (mlp_tc.cu: ipe_row_group), so these are bit for bit the features the forward multiplied with.  Thread = (sample row,
+// k): k < 6 computes the Gaussian once and the eight (degree, coordinate) pairs 8k..8k+7, i.e. sin chunk k and cos
+// chunk 6 + k; k = 6, 7 zero the padding chunks.
+template <int kFmt>
+__global__ void __launch_bounds__(256) ipe_t16_kernel(const float* __restrict__ origins,
+                                                      const float* __restrict__ directions,
+                                                      const float* __restrict__ radii, const float* __restrict__ t,
+                                                      uint8_t* __restrict__ out, int64_t num_rays, int n,
+                                                      int disable_integration) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * n * 8) return;
+  const int64_t p = idx >> 3;  // sample index = ray * n + j   (n = 128: tile = ray, row = j)
+  const int k = (int)(idx & 7);
+  const int r = (int)(p & 127);
+  uint8_t* tile = out + (size_t)(p >> 7) * (2 * kSlab) + (uint32_t)r * 128u;
+  const uint32_t rx = (uint32_t)r & 7u;
+  auto chunk_ptr = [&](int ch) { return tile + (size_t)(ch >> 3) * kSlab + ((((uint32_t)ch & 7u) ^ rx) << 4); };
+  if (k >= 6) {
+    *reinterpret_cast<uint4*>(chunk_ptr(12 + 2 * (k - 6))) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(chunk_ptr(13 + 2 * (k - 6))) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const int64_t ray = p / n;
+  const int j = (int)(p % n);
+  const RayGeom g = load_ray_geom(origins, directions, radii, ray);
+  const float t0 = __ldg(t + ray * (n + 1) + j), t1 = __ldg(t + ray * (n + 1) + j + 1);
+  float tm, tv, rv, mean[3], cov[3];
+  frustum_moments(t0, t1, g.radius_sq, tm, tv, rv);
+  lift_gaussian(g, tm, tv, rv, mean, cov);
+  if (disable_integration) cov[0] = cov[1] = cov[2] = 0.f;
+  float fs[8], fc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int f = k * 8 + e;  // feature index = degree * 3 + coord   (models/mip.py:335-341)
+    ipe_pair<true>(mean[f % 3], cov[f % 3], f / 3, fs[e], fc[e]);
+  }
+  *reinterpret_cast<uint4*>(chunk_ptr(k)) =
+      make_uint4(pack2<kFmt>(fs[0], fs[1]), pack2<kFmt>(fs[2], fs[3]), pack2<kFmt>(fs[4], fs[5]), pack2<kFmt>(fs[6], fs[7]));
+  *reinterpret_cast<uint4*>(chunk_ptr(6 + k)) =
+      make_uint4(pack2<kFmt>(fc[0], fc[1]), pack2<kFmt>(fc[2], fc[3]), pack2<kFmt>(fc[4], fc[5]), pack2<kFmt>(fc[6], fc[7]));
+}
+
 // fp32 row-major [m, cols] (ld) <-> tile image; rows beyond m / columns beyond cols are zero in the image.
 // thread = (row, 16-byte chunk of 8 columns): two float4 loads when the source allows it, one 16-byte store
 template <int kFmt>
@@ -384,6 +429,22 @@ cudaError_t launch_t16_pack(const float* src, int ld, int cols, int64_t m, void*
     t16_pack_kernel<1><<<blocks_of(total, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded, vec);
   else
     t16_pack_kernel<0><<<blocks_of(total, 256), 256, 0, st>>>(src, ld, cols, m, (uint8_t*)image, img_cols, padded, vec);
+  return cudaGetLastError();
+}
+
+// min_deg = 0, max_deg = 16 (96 features), n = 128 samples per ray: the level kernels' shape
+cudaError_t launch_ipe_t16(const float* origins, const float* directions, const float* radii, const float* t, void* image,
+                           int64_t num_rays, int n, int disable_integration, int precision, cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  if (n != 128) return cudaErrorInvalidValue;
+  LaunchScope scope(kKernIpe, st);
+  const int64_t total = num_rays * n * 8;
+  if (precision == 1)
+    ipe_t16_kernel<1><<<blocks_of(total, 256), 256, 0, st>>>(origins, directions, radii, t, (uint8_t*)image, num_rays, n,
+                                                              disable_integration);
+  else
+    ipe_t16_kernel<0><<<blocks_of(total, 256), 256, 0, st>>>(origins, directions, radii, t, (uint8_t*)image, num_rays, n,
+                                                              disable_integration);
   return cudaGetLastError();
 }
 

@@ -69,6 +69,39 @@ class FusedAdam(torch.optim.Optimizer):
         step = st["step"]
         return step if isinstance(step, int) else int(float(step))
 
+    def _step_group(self, lib, group, b1: float, b2: float, grad_scale: float) -> bool:
+        """One launch for the whole group (`mipnerf_b200_adam_step_multi`) when its tensors sit on one CUDA device
+        and share a step count — the normal case; otherwise the caller falls back to one launch per tensor."""
+        ps = [p for p in group["params"] if p.grad is not None]
+        if not ps or any(p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous() or
+                         p.device != ps[0].device or not p.is_cuda for p in ps):
+            return False
+        for p in ps:
+            st = self.state[p]
+            if not st:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+        steps = {self._step_count(self.state[p]) for p in ps}
+        if len(steps) != 1:
+            return False
+        step = steps.pop() + 1
+        n = len(ps)
+        arr = C.c_void_p * n
+        dev = _dev(ps[0])
+        with torch.cuda.device(dev):
+            _cabi.check(lib.mipnerf_b200_adam_step_multi(
+                n, arr(*[p.data_ptr() for p in ps]), arr(*[p.grad.data_ptr() for p in ps]),
+                arr(*[self.state[p]["exp_avg"].data_ptr() for p in ps]),
+                arr(*[self.state[p]["exp_avg_sq"].data_ptr() for p in ps]),
+                (C.c_int64 * n)(*[p.numel() for p in ps]), float(group["lr"]), b1, b2, float(group["eps"]), step,
+                grad_scale, _stream(dev)), "FusedAdam.step")
+        for p in ps:
+            self.state[p]["step"] = step
+            torch.autograd.graph.increment_version(p)  # written in place by the library: keep the packed-weight
+            #                                            caches (keyed on _version) honest
+        return True
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -79,6 +112,8 @@ class FusedAdam(torch.optim.Optimizer):
         for group in self.param_groups:
             b1, b2 = group["betas"]
             grad_scale = float(group.get("grad_scale", 1.0))   # absent after loading a torch.optim.Adam state_dict
+            if self._step_group(lib, group, float(b1), float(b2), grad_scale):
+                continue
             for p in group["params"]:
                 if p.grad is None:
                     continue
