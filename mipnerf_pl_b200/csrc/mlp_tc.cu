@@ -220,10 +220,22 @@ __device__ __forceinline__ void store8_split(uint8_t* dst_hi, uint8_t* dst_lo, c
   *reinterpret_cast<uint4*>(dst_lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// Byte offset of the 16-byte chunk holding columns [col, col + 8) of `row` in a slot's activation tile.
+//   kA32 == false: four 64-column SW128 slabs ([128 x 128 B] each) — the layout the training dump / the backward
+//                  pass use (tile images), and the v2 kernel;
+//   kA32 == true:  sixteen K = 16 blocks ([128 x 32 B] each, 32-byte swizzle): the block one MMA reads is DENSE in
+//                  shared memory (32 lines of 128 B instead of 32 B out of each of 128 lines), which takes the A
+//                  operand's shared-memory port time per MMA from 128 to 32 cycles.
+template <bool kA32>
+__device__ __forceinline__ uint32_t a_chunk_offset(int row, int col) {
+  if (kA32) return (uint32_t)(col >> 4) * 4096u + sw32_offset(row, col & 15);
+  return (uint32_t)(col >> 6) * kStageBytes + sw128_offset(row, col & 63);
+}
+
 // Epilogue of trunk layer / bottleneck L (compile-time so that every bias is an immediate
 // constant-bank operand): TMEM accumulator row -> +bias -> ReLU (L < 8) -> 16-bit -> A operand
 // slabs, software-pipelined over 32-column TMEM loads.  L == 7 also accumulates the density head.
-template <int kFmt, int L, bool kX3>
+template <int kFmt, int L, bool kX3, bool kA32 = false>
 __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int row, float& dens) {
   float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // independent chains for the density head
   uint32_t v[2][32];
@@ -233,7 +245,6 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
     tmem_ld_wait();  // chunk k has landed
     if (k < 7) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) & 1]);  // next chunk in flight while we work
     const int c0 = 32 * k;
-    uint8_t* slab = myA + (c0 >> 6) * kStageBytes;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t w[4], wl[4];
@@ -254,9 +265,9 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
           w[e] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
         }
       }
-      const uint32_t off = sw128_offset(row, (c0 & 63) + j * 8);
-      *reinterpret_cast<uint4*>(slab + off) = make_uint4(w[0], w[1], w[2], w[3]);
-      if (kX3) *reinterpret_cast<uint4*>(slab + kABytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      const uint32_t off = a_chunk_offset<kA32>(row, c0 + j * 8);
+      *reinterpret_cast<uint4*>(myA + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      if (kX3) *reinterpret_cast<uint4*>(myA + kABytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
   }
   if (L == 7)
@@ -271,7 +282,7 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
 #ifndef MIPNERF_TC_ROLLED_EPILOGUE
 #define MIPNERF_TC_ROLLED_EPILOGUE 0
 #endif
-template <int kFmt, bool kX3, bool kRelu, bool kDens>
+template <int kFmt, bool kX3, bool kRelu, bool kDens, bool kA32>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int layer, int c0, uint8_t* myA, uint32_t rowoff,
                                                uint32_t rx, float (&dpart)[8], const SmallParams* __restrict__ gsp) {
   // A runtime layer index turns c_small.bias[layer][c] into indexed constant-bank loads (LDC c[3][R+imm], ~30 cycles
@@ -309,31 +320,39 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int laye
         w[e] = kRelu ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
       }
     }
-    const uint32_t off = ((ci0 + j) ^ rx) << 4;  // sw128_offset(row, .) with the row part hoisted
-    *reinterpret_cast<uint4*>(slab + off) = make_uint4(w[0], w[1], w[2], w[3]);
-    if (kX3) *reinterpret_cast<uint4*>(slab + kABytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    if (kA32) {
+      const uint32_t off = a_chunk_offset<true>((int)(rowoff >> 7), c0 + j * 8);
+      *reinterpret_cast<uint4*>(myA + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      if (kX3) *reinterpret_cast<uint4*>(myA + kABytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    } else {
+      const uint32_t off = ((ci0 + j) ^ rx) << 4;  // sw128_offset(row, .) with the row part hoisted
+      *reinterpret_cast<uint4*>(slab + off) = make_uint4(w[0], w[1], w[2], w[3]);
+      if (kX3) *reinterpret_cast<uint4*>(slab + kABytes + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
   }
 }
 
-template <int kFmt, bool kX3>
+template <int kFmt, bool kX3, bool kA32 = false>
 __device__ __forceinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* myA, int row, float& dens, int layer,
-                                                      const SmallParams* __restrict__ gsp) {
+                                                      const SmallParams* __restrict__ gsp, int kk_begin = 0,
+                                                      int kk_end = 4) {
+  // columns [64 kk_begin, 64 kk_end): the split modes share one ray's epilogue between both worker groups
   float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const uint32_t rowoff = (uint32_t)row * 128u, rx = (uint32_t)row & 7u;
   uint32_t v0[32], v1[32];
-  tmem_ld32(t_acc, v0);
+  tmem_ld32(t_acc + 64 * kk_begin, v0);
 #pragma unroll 1
-  for (int kk = 0; kk < 4; ++kk) {
+  for (int kk = kk_begin; kk < kk_end; ++kk) {
     tmem_ld_wait();
     tmem_ld32(t_acc + 64 * kk + 32, v1);
-    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
-    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
-    else epilogue_chunk<kFmt, kX3, false, false>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
+    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true, kA32>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
+    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false, kA32>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
+    else epilogue_chunk<kFmt, kX3, false, false, kA32>(v0, layer, 64 * kk, myA, rowoff, rx, dpart, gsp);
     tmem_ld_wait();
-    if (kk < 3) tmem_ld32(t_acc + 64 * kk + 64, v0);
-    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
-    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
-    else epilogue_chunk<kFmt, kX3, false, false>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
+    if (kk + 1 < kk_end) tmem_ld32(t_acc + 64 * kk + 64, v0);
+    if (layer == 7) epilogue_chunk<kFmt, kX3, true, true, kA32>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
+    else if (layer < 8) epilogue_chunk<kFmt, kX3, true, false, kA32>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
+    else epilogue_chunk<kFmt, kX3, false, false, kA32>(v1, layer, 64 * kk + 32, myA, rowoff, rx, dpart, gsp);
   }
   if (layer == 7)
     dens = ((dpart[0] + dpart[1]) + (dpart[2] + dpart[3])) + ((dpart[4] + dpart[5]) + (dpart[6] + dpart[7]));
@@ -343,14 +362,16 @@ __device__ __forceinline__ void epilogue_trunk_rolled(uint32_t t_acc, uint8_t* m
 template <int kFmt>
 __device__ __forceinline__ void epilogue_view(uint32_t t_acc, const float* __restrict__ vb, float& rgb0,
                                               float& rgb1, float& rgb2, uint8_t* __restrict__ vdump = nullptr,
-                                              int row = 0) {
+                                              int row = 0, int k_begin = 0, int k_end = 4) {
+  // columns [32 k_begin, 32 k_end) (split modes: half of the 128 per worker group, partial colour dots)
   float acc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};  // independent chains
   uint32_t v[2][32];
-  tmem_ld32(t_acc, v[0]);
+  tmem_ld32(t_acc + 32 * k_begin, v[0]);  // k_begin is even (0 or 2)
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    if (k < k_begin || k >= k_end) continue;
     tmem_ld_wait();
-    if (k < 3) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) & 1]);
+    if (k + 1 < k_end) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) & 1]);
 #pragma unroll
     for (int e = 0; e < 32; e += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(vb + 32 * k + e);
@@ -440,6 +461,15 @@ template <int kFmt, bool kPair, bool kX3, bool kTrain = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
   static_assert(!kX3 || kPair, "split-operand modes exist for the CTA-pair kernel only");
   static_assert(!kTrain || (kPair && !kX3), "the training forward (activation dump) is the plain CTA-pair kernel");
+  // Activation-tile layout (a_chunk_offset).  -DMIPNERF_TC_A_SW32 builds the dense K = 16 block layout (never in the
+  // training forward, whose tiles leave the SM as tile images).  Measured: all parity tests pass with it and the level
+  // kernel takes 0.542 ms against 0.541 ms — the A operand's access pattern is not what holds a weight stage at 331
+  // instead of 256 cycles — so the proven SW128 layout stays the default.
+#ifdef MIPNERF_TC_A_SW32
+  constexpr bool kA32 = !kTrain;
+#else
+  constexpr bool kA32 = false;
+#endif
   constexpr int kSlots = kX3 ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -469,7 +499,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       mbar_init(&w_empty[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&a_ready[s], kPair ? 8 : 4);  // one arrive per worker warp (of both CTAs in pair mode)
+      mbar_init(&a_ready[s], kX3 ? 16 : (kPair ? 8 : 4));  // one arrive per worker warp (of both CTAs in pair mode;
+                                                             // split modes: both worker groups work on the one slot)
       mbar_init(&acc_full[s], 1);
       mbar_init(&f_ready[s], kPair ? 2 : 1);  // one arrive per IPE warp (of both CTAs)
       mbar_init(&f_free[s], 1);
@@ -583,13 +614,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                   // one SW128 slab (K 0..63) + one SW64 slab (K 64..95)
                   const int fs = (l == 0) ? s : (l == 5 ? s - 8 : -1);  // >= 0: K-slab fs of the feature tile
                   const bool a_sw64 = fs == 2;
-                  const uint32_t a_addr = fs < 0 ? a_base + (s >> 1) * kStageBytes + (s & 1) * 64
+                  const bool a_blk = kA32 && fs < 0;  // activation tile as dense K = 16 blocks (2 per K-slab)
+                  const uint32_t a_addr = fs < 0 ? (kA32 ? a_base + s * 8192u : a_base + (s >> 1) * kStageBytes + (s & 1) * 64)
                                                  : (fs < 2 ? f_base + fs * 64 : f_base + kStageBytes);
                   const uint32_t a_lo_addr = a_addr + (fs < 0 ? kABytes : kFBytes);  // x3: low halves of the A operand
+                  const uint32_t a_step = a_blk ? 4096u : 32u;  // second K = 16 half of the slab
+                  auto a_desc = [&](uint32_t addr) {
+                    return a_blk ? make_sw32_desc(addr) : (a_sw64 ? make_sw64_desc(addr) : make_sw128_desc(addr));
+                  };
                   uint32_t b_addr = sW_u + st * kWStage;
 #pragma unroll
                   for (int j = 0; j < 2; ++j) {
-                    const uint64_t ad = a_sw64 ? make_sw64_desc(a_addr + j * 32) : make_sw128_desc(a_addr + j * 32);
+                    const uint64_t ad = a_desc(a_addr + j * a_step);
                     const uint64_t bd = make_sw64_desc(b_addr + j * 32);
                     if (kPair) umma_ss_pair(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
                     else umma_ss(d_tmem, ad, bd, id, (s > 0 || j > 0) ? 1u : 0u);
@@ -597,8 +633,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                   if (kX3) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {  // A_lo . W_hi
-                      const uint64_t ad =
-                          a_sw64 ? make_sw64_desc(a_lo_addr + j * 32) : make_sw128_desc(a_lo_addr + j * 32);
+                      const uint64_t ad = a_desc(a_lo_addr + j * a_step);
                       umma_ss_pair(d_tmem, ad, make_sw64_desc(b_addr + j * 32), id, 1u);
                     }
                     umma_commit_pair(&w_empty[st]);
@@ -611,7 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
                     b_addr = sW_u + st * kWStage;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {  // A_hi . W_lo
-                      const uint64_t ad = a_sw64 ? make_sw64_desc(a_addr + j * 32) : make_sw128_desc(a_addr + j * 32);
+                      const uint64_t ad = a_desc(a_addr + j * a_step);
                       umma_ss_pair(d_tmem, ad, make_sw64_desc(b_addr + j * 32), id, 1u);
                     }
                   }
@@ -770,7 +805,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
 #endif
   } else {
     // ============================ slot workers ============================
-    const int slot = (warp - 2) >> 2;
+    // split modes (one ray in flight per CTA): both worker groups share that ray's epilogues — group g takes columns
+    // [128 g, 128 g + 128) of every trunk layer (64 g .. of the view layer), so the epilogue, which is fully exposed
+    // with a single slot, takes half as long; group 1 hands its partial head sums to group 0 through four spare
+    // TMEM columns, group 0 composites.
+    const int grp = (warp - 2) >> 2;
+    const int slot = kX3 ? 0 : grp;
     const int q = warp & 3;  // TMEM lane quarter this warp may access == sample quarter
     const int row = q * 32 + lane;
     uint8_t* myA = sA + slot * kABytes;
@@ -788,7 +828,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         else mbar_arrive(&a_ready[slot]);
       }
     };
-    const int my_rounds = slot < kSlots ? rounds : 0;  // x3: the second worker group has no slot
+    const int my_rounds = slot < kSlots ? rounds : 0;
+    const int kk0 = kX3 ? 2 * grp : 0, kk1 = kX3 ? 2 * grp + 2 : 4;  // this group's share of an epilogue
+    const uint32_t t_xchg = tmem_base + ((uint32_t)(q * 32) << 16) + 256;  // split modes: slot 1's columns are unused
     const SmallParams* __restrict__ gsp = reinterpret_cast<const SmallParams*>(p.wimage + kSmallOffset);
     constexpr bool dumping = kTrain;  // a separate instantiation: the inference kernel carries none of this
     const uint64_t dump_policy = kTrain ? l2_policy_evict_first() : 0ull;
@@ -828,18 +870,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
             named_bar_sync(1 + slot, 128);
           }
           if (kX3 || MIPNERF_TC_ROLLED_EPILOGUE) {
-            epilogue_trunk_rolled<kFmt, kX3>(t_acc, myA, row, dens, l, gsp);
+            epilogue_trunk_rolled<kFmt, kX3, kA32>(t_acc, myA, row, dens, l, gsp, kk0, kk1);
           } else {
             switch (l) {
-              case 0: epilogue_trunk<kFmt, 0, kX3>(t_acc, myA, row, dens); break;
-              case 1: epilogue_trunk<kFmt, 1, kX3>(t_acc, myA, row, dens); break;
-              case 2: epilogue_trunk<kFmt, 2, kX3>(t_acc, myA, row, dens); break;
-              case 3: epilogue_trunk<kFmt, 3, kX3>(t_acc, myA, row, dens); break;
-              case 4: epilogue_trunk<kFmt, 4, kX3>(t_acc, myA, row, dens); break;
-              case 5: epilogue_trunk<kFmt, 5, kX3>(t_acc, myA, row, dens); break;
-              case 6: epilogue_trunk<kFmt, 6, kX3>(t_acc, myA, row, dens); break;
-              case 7: epilogue_trunk<kFmt, 7, kX3>(t_acc, myA, row, dens); break;
-              default: epilogue_trunk<kFmt, 8, kX3>(t_acc, myA, row, dens); break;
+              case 0: epilogue_trunk<kFmt, 0, kX3, kA32>(t_acc, myA, row, dens); break;
+              case 1: epilogue_trunk<kFmt, 1, kX3, kA32>(t_acc, myA, row, dens); break;
+              case 2: epilogue_trunk<kFmt, 2, kX3, kA32>(t_acc, myA, row, dens); break;
+              case 3: epilogue_trunk<kFmt, 3, kX3, kA32>(t_acc, myA, row, dens); break;
+              case 4: epilogue_trunk<kFmt, 4, kX3, kA32>(t_acc, myA, row, dens); break;
+              case 5: epilogue_trunk<kFmt, 5, kX3, kA32>(t_acc, myA, row, dens); break;
+              case 6: epilogue_trunk<kFmt, 6, kX3, kA32>(t_acc, myA, row, dens); break;
+              case 7: epilogue_trunk<kFmt, 7, kX3, kA32>(t_acc, myA, row, dens); break;
+              default: epilogue_trunk<kFmt, 8, kX3, kA32>(t_acc, myA, row, dens); break;
             }
           }
           TRACE(EV(2, 3, l, slot));
@@ -857,18 +899,33 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
 #endif
           }
         } else {
-          vb_s[slot * 128 + row] = vb;
-          named_bar_sync(1 + slot, 128);  // vb_s of this ray visible to the whole slot
+          if (!kX3 || grp == 0) vb_s[slot * 128 + row] = vb;
+          if (kX3) named_bar_sync(3, 256);       // both groups read it
+          else named_bar_sync(1 + slot, 128);    // vb_s of this ray visible to the whole slot
           epilogue_view<kFmt>(t_acc, vb_s + slot * 128, rgb0, rgb1, rgb2,
 #ifdef MIPNERF_TRAIN_EXPERIMENT_NO_VDUMP
-                              nullptr, row);
+                              nullptr, row, kk0, kk1);
 #else
-                              (dumping && valid) ? p.v_dump + (size_t)ray * (2 * kStageBytes) : nullptr, row);
+                              (dumping && valid) ? p.v_dump + (size_t)ray * (2 * kStageBytes) : nullptr, row, kk0, kk1);
 #endif
           tc_fence_before();
           arrive_a_ready();  // accumulator drained: the next ray's layer 0 may start while we composite
           TRACE(EV(2, 3, l, slot));
         }
+      }
+      if (kX3) {  // partial density / colour dots of group 1 -> group 0 (same TMEM lanes, four spare columns)
+        if (grp == 1) {
+          tmem_st4(t_xchg, __float_as_uint(dens), __float_as_uint(rgb0), __float_as_uint(rgb1), __float_as_uint(rgb2));
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        named_bar_sync(3, 256);
+        tc_fence_after();
+        if (grp == 1) continue;  // next ray
+        uint32_t x0, x1, x2, x3;
+        tmem_ld4(t_xchg, x0, x1, x2, x3);
+        tmem_ld_wait();
+        dens += __uint_as_float(x0), rgb0 += __uint_as_float(x1), rgb1 += __uint_as_float(x2), rgb2 += __uint_as_float(x3);
       }
       if (p.raw_rgb_out) {  // MLP-only mode: hand back the raw heads (models/mip_nerf.py:98,110)
         if (valid) {

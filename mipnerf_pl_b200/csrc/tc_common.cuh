@@ -47,6 +47,23 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// 32-byte swizzle, K-major: a [rows x 16 elements] block with rows of 32 bytes, 8-row atoms of 256 bytes, 16-byte chunk
+// index XOR ((row >> 2) & 1)  (cute Swizzle<1,4,3>).  One K = 16 MMA reads exactly one such block, and the block is DENSE
+// in shared memory (128 rows = 4 KB = 32 lines of 128 B) — with the 128-byte-swizzle layout the same K = 16 slice is 32 B
+// out of every one of 128 lines, i.e. four times the shared-memory port time per MMA.
+__host__ __device__ __forceinline__ uint32_t sw32_offset(int r, int k) {
+  return (uint32_t)(r * 32 + (((((k >> 3) & 1) ^ ((r >> 2) & 1)) << 4) | ((k & 7) << 1)));
+}
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;  // SBO: 8 rows x 32 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;           // SWIZZLE_32B
+  return d;
+}
+
 __device__ __forceinline__ uint64_t make_sw64_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -228,6 +245,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
       "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+// 4 columns x 32 lanes: a per-row scratch exchange between two warps that own the same TMEM lane quarter
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

@@ -193,6 +193,62 @@ umma_selftest_sw64_kernel(const float* __restrict__ a, const float* __restrict__
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// variant bit 3: A as dense K = 16 blocks in the 32-byte-swizzle layout ([k / 16][128 x 32 B]), B as K = 32 slabs in the
+// 64-byte-swizzle layout ([k / 32][n x 64 B]) — the operand layouts of the level kernels' activation tile / weight
+// stages; k a multiple of 32
+template <int kFmt>
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_a32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ d, int n, int k) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;                          // [k / 16][128 x 32 B]
+  uint8_t* sB = sA + (size_t)(k / 16) * 4096;  // [k / 32][n x 64 B]
+  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(sB + (size_t)(k / 32) * n * 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  for (int c = 0; c < k / 8; ++c) {  // 16-byte chunk c of row tid: block c / 2, half c % 2
+    uint32_t w[4];
+    for (int q = 0; q < 4; ++q) w[q] = pack2<kFmt>(a[(size_t)tid * k + c * 8 + q * 2], a[(size_t)tid * k + c * 8 + q * 2 + 1]);
+    *reinterpret_cast<uint4*>(sA + (size_t)(c >> 1) * 4096 + sw32_offset(tid, (c & 1) * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int row = tid; row < n; row += 128)
+    for (int c = 0; c < k / 8; ++c) {
+      uint32_t w[4];
+      for (int q = 0; q < 4; ++q) w[q] = pack2<kFmt>(b[(size_t)row * k + c * 8 + q * 2], b[(size_t)row * k + c * 8 + q * 2 + 1]);
+      *reinterpret_cast<uint4*>(sB + (size_t)(c >> 2) * n * 64 + sw64_offset(row, (c & 3) * 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_f16(128, n, kFmt);
+    for (int j = 0; j < k / 16; ++j)
+      umma_ss(tmem_base, make_sw32_desc(smem_u32(sA) + j * 4096),
+              make_sw64_desc(smem_u32(sB) + (j >> 1) * n * 64 + (j & 1) * 32), idesc, j ? 1u : 0u);
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  for (int c = 0; c < n; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+    for (int q = 0; q < 32; ++q) d[(size_t)tid * n + c + q] = __uint_as_float(v[q]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace
 }  // namespace mipnerf
 
@@ -202,6 +258,22 @@ extern "C" int mipnerf_b200_selftest_umma(const float* a, const float* b, float*
   if (!a || !b || !d || n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || k > 384) return MIPNERF_B200_EINVAL;
   if ((variant & 2) && (k % 32)) return MIPNERF_B200_EINVAL;
   if (precision != MIPNERF_B200_BF16 && precision != MIPNERF_B200_FP16) return MIPNERF_B200_EINVAL;
+  if (variant & 8) {
+    if (k % 32 || n % 32) return MIPNERF_B200_EINVAL;
+    const size_t sm = 1024 + (size_t)(k / 16) * 4096 + (size_t)(k / 32) * n * 64 + 64;
+    if (sm > 227 * 1024) return MIPNERF_B200_EUNSUPPORTED;
+    cudaError_t e2;
+    if (precision == MIPNERF_B200_BF16) {
+      e2 = cudaFuncSetAttribute(umma_selftest_a32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e2 != cudaSuccess) return MIPNERF_B200_ECUDA;
+      umma_selftest_a32_kernel<1><<<1, 128, sm, (cudaStream_t)stream>>>(a, b, d, n, k);
+    } else {
+      e2 = cudaFuncSetAttribute(umma_selftest_a32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e2 != cudaSuccess) return MIPNERF_B200_ECUDA;
+      umma_selftest_a32_kernel<0><<<1, 128, sm, (cudaStream_t)stream>>>(a, b, d, n, k);
+    }
+    return cudaGetLastError() == cudaSuccess ? MIPNERF_B200_OK : MIPNERF_B200_ECUDA;
+  }
   if (variant & 4) {
     if (k != 32 || n % 32) return MIPNERF_B200_EINVAL;
     const size_t sm = 1024 + 8192 + (size_t)n * 64 + 64;

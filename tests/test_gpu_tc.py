@@ -45,3 +45,13 @@ def test_umma_selftest_sw64_tail(n, precision):
     d, ref = run_selftest(n, 32, precision, 4)
     err = float((d.double() - ref).abs().max())
     assert err <= 2e-5 * max(float(ref.abs().max()), 1.0) * (32 ** 0.5), err
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n,k", [(256, 256), (128, 64), (256, 96 + 32), (128, 32)])
+def test_umma_selftest_a_sw32_blocks(n, k, precision):
+    """A as dense K = 16 blocks in the 32-byte-swizzle layout against B as 64-byte-swizzle K = 32 slabs: the operand
+    layouts of the level kernels' activation tile and weight stages."""
+    d, ref = run_selftest(n, k, precision, 8)
+    err = float((d.double() - ref).abs().max())
+    assert err <= 2e-5 * max(float(ref.abs().max()), 1.0) * (k ** 0.5), err
