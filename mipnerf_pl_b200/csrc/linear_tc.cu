@@ -479,6 +479,9 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
       const uint8_t* x16 = reinterpret_cast<const uint8_t*>(in_x1 ? p.x1 : p.x2);
       const int x_slabs = ((in_x1 ? p.k1 : p.k2) + 63) >> 6;
       const uint32_t bytes = (uint32_t)((a16 ? a_blocks : 0) + (b16 ? b_blocks : 0)) * kWgBlock;
+      // the operand tiles stream through once (0.5 GB per launch): evict-first, so that the 39 MB of partial sums this
+      // launch writes are still in L2 when the reduction kernel reads them
+      const uint64_t stream_policy = l2_policy_evict_first();
       for (int it = 0; it < slabs; ++it) {
         const int s = it % kWgStages;
         if (it >= kWgStages) {
@@ -493,11 +496,12 @@ __global__ void __launch_bounds__(320, 1) wgrad_mn_kernel(const WgradTcParams p,
         mbar_arrive_expect_tx(&full[s], bytes);
         if (a16)
           for (int b = 0; b < a_blocks; ++b)
-            bulk_g2s(sa + (size_t)b * kWgBlock, dy16 + (tile * a_blocks + b) * 16384 + half, kWgBlock, &full[s]);
+            bulk_g2s_hint(sa + (size_t)b * kWgBlock, dy16 + (tile * a_blocks + b) * 16384 + half, kWgBlock, &full[s],
+                          stream_policy);
         if (b16)
           for (int b = 0; b < b_blocks; ++b)
-            bulk_g2s(sb + (size_t)b * kWgBlock, x16 + (tile * x_slabs + (xc0 >> 6) + b) * 16384 + half, kWgBlock,
-                     &full[s]);
+            bulk_g2s_hint(sb + (size_t)b * kWgBlock, x16 + (tile * x_slabs + (xc0 >> 6) + b) * 16384 + half, kWgBlock,
+                          &full[s], stream_policy);
       }
     }
   } else {

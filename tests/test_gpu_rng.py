@@ -65,18 +65,21 @@ def test_in_kernel_draws_equal_injected_draws(precision):
     assert torch.all(got[1][4][:, 1:] >= got[1][4][:, :-1])
 
 
-def test_training_step_draws_in_kernel():
-    model = mp.MipNerf(precision="fp32")
+@pytest.mark.parametrize("precision,n", [("fp32", 64), ("bf16", 64), ("bf16", 4096 + 37)])
+def test_training_step_draws_in_kernel(precision, n):
+    """fp32 path and the fused tensor-core step (whose forward is the level kernel with its own in-kernel draws); 4133
+    rays cross the 4096-ray chunk: the Philox counter is the ray index of the whole batch, not of the chunk."""
+    model = mp.MipNerf(precision=precision)
     model.load_state_dict(make_state_dict(seed=1))
     model = model.to(DEV)
-    rays = mp.namedtuple_map(lambda t: t.to(DEV), mp.random_ray_batch(64, seed=2))
-    rgbs = torch.rand(64, 3, device=DEV)
+    rays = mp.namedtuple_map(lambda t: t.to(DEV), mp.random_ray_batch(n, seed=2))
+    rgbs = torch.rand(n, 3, device=DEV)
     model.rng_seed, model.rng_offset = 5, 0
     a = float(mp.forward_backward(model, rays, rgbs, True, True)["loss"])
     g_a = [p.grad.clone() for p in model.parameters()]
     model.rng_offset = 0
     b_ = float(mp.forward_backward(model, rays, rgbs, True, True)["loss"])
     assert a == b_ and all(torch.equal(x, p.grad) for x, p in zip(g_a, model.parameters()))
-    t_rand, u_jit = mp.philox_uniform(5, 0, 0, 64, 129, DEV), mp.philox_uniform(5, 0, 2, 64, 129, DEV)
+    t_rand, u_jit = mp.philox_uniform(5, 0, 0, n, 129, DEV), mp.philox_uniform(5, 0, 2, n, 129, DEV)
     c = float(mp.forward_backward(model, rays, rgbs, True, True, t_rand=t_rand, u_jitter=u_jit)["loss"])
     assert a == c
