@@ -241,6 +241,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frame", action="store_true", help="skip the 800x800 frame metric (profiling runs)")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step metric (N = 1 only)")
+    ap.add_argument("--no-parity-mode", action="store_true",
+                    help="skip the secondary measurement of the 1e-4 contract mode (fp16x3) in a bf16 / fp16 run (N = 1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity measurement")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -513,6 +515,25 @@ def main():
         del tmodel, opt, trays, trgb
         torch.cuda.empty_cache()
 
+    # The headline runs BASELINE configs[1]'s dtype (bf16 operands), which does not meet north_star's 1e-4 on the stress
+    # weights (`parity` says so).  The mode that does — fp16x3, same kernel with split operands — is measured in the same
+    # run on the same resident rays, so that one JSON line carries both: throughput of the headline dtype and
+    # throughput + measured error of the contract mode.  (`--precision fp16x3` makes it the headline instead.)
+    parity_mode = None
+    if not args.no_parity_mode and world == 1 and precision in ("bf16", "fp16"):
+        pmodel = mp.MipNerf(precision="fp16x3")
+        pmodel.load_state_dict(model.state_dict())
+        pmodel = pmodel.to(dev).eval()
+        for _ in range(5):
+            pmodel(arm.rays, False, True)
+        p_ms = arm.timed(min(args.steps, 50), lambda: pmodel(arm.rays, False, True))
+        parity_mode = {"precision": "fp16x3", "rays_per_s": b_local / (p_ms * 1e-3), "ms_per_step": p_ms,
+                       "launch": "eager C-ABI call per step, device-timed, L2 flushed between steps",
+                       "parity": None if args.no_parity else measure_parity(mp, pmodel, dev),
+                       "what": "the same forward with split fp16 operands (3 MMAs per product): the tensor-core mode "
+                               "the 1e-4 contract is claimed on (DESIGN.md §4)"}
+        del pmodel
+
     line = {
         "metric": "rays/sec (4096-ray batch, 128+128 samples)", "value": value, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -534,7 +555,7 @@ def main():
         "kernel_launches": {k: int(round(v * args.steps)) for k, v in launches_per_step.items()},
         "kernel_ms": {k: round(v[1], 4) for k, v in prof.items() if v[2]},
         "clocks": clocks, "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "strong_scaling": strong,
-        "train_step": train,
+        "train_step": train, "parity_mode": parity_mode,
         "frame": None if frame_ms is None else {
             "height": 800, "width": 800, "rays": 640000, "ms": frame_ms, "rays_per_s": 640000 / (frame_ms * 1e-3),
             "what": "render_frame: on-device ray generation, both levels, rows sharded over ranks, "
