@@ -465,7 +465,12 @@ def main():
                     "frac_of_sustained": (achieved / (peaks["bf16_tflops_sustained"] / div))
                     if peaks.get("bf16_tflops_sustained") else None,
                     "launch_ms": per_launch_ms, "launches_per_step": lps,
-                    "share_of_step": (ms_l / args.steps) / max(ms_eager, 1e-9),
+                    # share of the step's GPU time: this kernel's launches over ALL kernels' launches of the instrumented
+                    # pass (what an ncu launch list of the same command shows), and the same time over the headline
+                    # (graph-replayed) step; the eager pass's own wall time also contains host launch gaps
+                    "share_of_step": ms_l / max(sum(v[1] for v in prof.values() if v[2]), 1e-9),
+                    "launch_ms_over_step_ms": (ms_l / args.steps) / max(ms_per_step, 1e-9),
+                    "share_of_eager_instrumented_step": (ms_l / args.steps) / max(ms_eager, 1e-9),
                     "measured_in": "the instrumented eager pass of this run (library CUDA-event bracket per launch)",
                     "step_frac_of_roofline": (value / world) * FLOP_PER_RAY / 1e12 / peak}
 
