@@ -294,6 +294,10 @@ int mipnerf_b200_resample_along_rays(const mipnerf_b200_rays* rays, const float*
  * variant bit 0: B through a pre-swizzled image + cp.async.bulk (needs `scratch`); bit 1: A in TMEM. */
 int mipnerf_b200_selftest_umma(const float* a, const float* b, float* d, int n, int k, int precision,
                                int variant, void* scratch, size_t scratch_bytes, void* stream);
+/* Issue-rate microbenchmark of tcgen05.mma (M = 128, N = n in {128, 256}, K = 16) on resident operands: `ctas` CTAs each
+ * issue iters x 16 MMAs and write their clock64 cycle count to cycles[cta] (device memory).  mode 0: SS form, A as
+ * 128-byte-swizzle slabs; 1: SS form, A as dense 32-byte-swizzle K = 16 blocks; 2: TS form, A in tensor memory. */
+int mipnerf_b200_selftest_umma_rate(int mode, int n, int iters, int precision, int ctas, long long* cycles, void* stream);
 
 /* ---- launch accounting (bench.py: `gpu_launches`, live launch duration of the dominant kernel) ----
  * Every kernel launch of the library is counted per kernel id; with timing enabled each launch is

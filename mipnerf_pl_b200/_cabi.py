@@ -114,6 +114,7 @@ _SIGNATURES = {
     "mipnerf_b200_resample_along_rays": (C.c_int, [C.POINTER(RaysStruct), _V, _V, C.c_int, C.c_int, _V, C.c_float,
                                                    _V, _V, _V, _V, _V]),
     "mipnerf_b200_selftest_umma": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_int, _V, C.c_size_t, _V]),
+    "mipnerf_b200_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V]),
     "mipnerf_b200_profile_enable": (C.c_int, [C.c_int]),
     "mipnerf_b200_profile_num_kernels": (C.c_int, []),
     "mipnerf_b200_profile_kernel_name": (C.c_char_p, [C.c_int]),

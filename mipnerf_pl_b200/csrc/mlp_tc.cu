@@ -137,7 +137,19 @@ struct Tracer {
 #define TRACER_DECL(region) Tracer tracer; tracer.init(region)
 #define TRACE(code) tracer.ev(code)
 #define TRACER_DONE(region) tracer.finish(region)
+// cumulative clock64 counters of CTA 0 (v4 paths): g_trace[16 + base + i], read by tools/v4_counters.py
+#define V4_DECL() long long v4c[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define V4_CLK() clock64()
+#define V4_ADD(i, t0) v4c[i] += clock64() - (t0)
+#define V4_FLUSH(base)                                                                      \
+  if (blockIdx.x == 0 && g_trace) {                                                         \
+    for (int i_ = 0; i_ < 8; ++i_) g_trace[16 + (base) + i_] = (unsigned long long)v4c[i_]; \
+  }
 #else
+#define V4_DECL()
+#define V4_CLK() 0
+#define V4_ADD(i, t0) ((void)(t0))
+#define V4_FLUSH(base)
 #define TRACER_DECL(region) ((void)0)
 #define TRACE(code) ((void)0)
 #define TRACER_DONE(region) ((void)0)
@@ -272,6 +284,65 @@ __device__ __forceinline__ void epilogue_trunk(uint32_t t_acc, uint8_t* myA, int
   }
   if (L == 7)
     dens = ((dpart[0] + dpart[1]) + (dpart[2] + dpart[3])) + ((dpart[4] + dpart[5]) + (dpart[6] + dpart[7]));
+}
+
+// "v4" (kTS): activations live in TENSOR memory and the MMAs take them from there (TS form: 128.6 cycles per
+// M128 x N256 x K16 MMA against 171 for the SS form, tools/umma_rate.py).  A slot owns 256 TMEM columns — 128 for its
+// fp32 accumulator, 128 for its 16-bit activation row (two elements per column) — so a 256-wide layer runs as two
+// N = 128 halves through the same accumulator.  Epilogue of half kHalf of trunk layer / bottleneck L:
+//   kHalf == 0: accumulator -> +bias -> ReLU -> 64 packed words kept in REGISTERS (the activation buffer is still the
+//               A operand of the other half's MMAs); `drained()` runs as soon as the accumulator has been read, so the
+//               second half's MMAs may overwrite it while the arithmetic is still going on;
+//   kHalf == 1: words 64..127 go to the activation buffer as they are produced (every MMA that read it has
+//               completed: that is what this half's acc_full says), then the 64 held words.
+template <int kFmt, int L, int kHalf, class Drained>
+__device__ __forceinline__ void epilogue_half_ts(uint32_t t_acc, uint32_t t_a, uint32_t (&held)[64], float& dens,
+                                                 Drained drained) {
+  float dpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // half 0: all 128 columns are read before any arithmetic (nothing is held yet, the registers are there), so that the
+  // accumulator is handed back to the tensor core at once; half 1: two-chunk pipeline next to the 64 held words
+  constexpr int kBuf = kHalf == 0 ? 4 : 2;
+  uint32_t v[kBuf][32];
+  tmem_ld32(t_acc, v[0]);
+  if (kHalf == 0) {
+    tmem_ld32(t_acc + 32, v[1 % kBuf]);
+    tmem_ld32(t_acc + 64, v[2 % kBuf]);
+    tmem_ld32(t_acc + 96, v[3 % kBuf]);
+    tmem_ld_wait();
+    drained();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (kHalf == 1) {
+      tmem_ld_wait();
+      if (k < 3) tmem_ld32(t_acc + 32 * (k + 1), v[(k + 1) % kBuf]);
+    }
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = 128 * kHalf + 32 * k + 2 * j;
+      float a = __uint_as_float(v[k % kBuf][2 * j]), b = __uint_as_float(v[k % kBuf][2 * j + 1]);
+      fadd2(a, b, c_small.bias[L][c], c_small.bias[L][c + 1]);
+      if (L == 7)  // density_layer on the fp32 (un-rounded) h7        (models/mip_nerf.py:98)
+        ffma2(dpart[(2 * j) & 7], dpart[(2 * j + 1) & 7], fmaxf(a, 0.f), fmaxf(b, 0.f), c_small.w_density[c],
+              c_small.w_density[c + 1]);
+      w[j] = L < 8 ? pack2_relu<kFmt>(a, b) : pack2<kFmt>(a, b);
+    }
+    if (kHalf == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) held[16 * k + j] = w[j];
+    } else {
+      tmem_st16(t_a + 64 + 16 * k, w);
+    }
+  }
+  if (kHalf == 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tmem_st16(t_a + 16 * k, *reinterpret_cast<const uint32_t(*)[16]>(&held[16 * k]));
+  }
+  if (L == 7) {
+    const float d = ((dpart[0] + dpart[1]) + (dpart[2] + dpart[3])) + ((dpart[4] + dpart[5]) + (dpart[6] + dpart[7]));
+    dens = kHalf == 0 ? d : dens + d;
+  }
 }
 
 // Rolled form of the same epilogue with the layer index at RUN time: one copy of the code for all nine layers, a loop
@@ -457,9 +528,50 @@ __device__ __forceinline__ void ipe_row_group(const LevelParams& p, const RayGeo
 // carried as hi + lo 16-bit halves (A_lo and F_lo live where slot 1's tiles would be, W_lo stages alternate with W_hi
 // in the ring) and every K step issues  A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  into the same fp32 accumulator: 3x the MMAs,
 // ~2^-22 (fp16 halves) / 2^-16 (bf16 halves) relative operand error instead of 2^-11 / 2^-8.
-template <int kFmt, bool kPair, bool kX3, bool kTrain = false>
+// v4 (kTS) issue path of one (layer, N half, slot): every K-slab index is a compile-time constant (fully unrolled), so an
+// MMA costs the one issuing thread a handful of uniform-register moves — with run-time slab indices and feature /
+// activation branches it was ~100 cycles per 64-cycle MMA.  kType 0: layer 0 (three feature slabs, SS form);
+// 1: eight activation slabs (TS form); 2: layer 5 = eight activation slabs + three feature slabs.
+constexpr int kTsSlabsPerStage = 4;
+template <int kType>
+__device__ __forceinline__ void ts_issue_half(uint32_t d_tmem, uint32_t a_tmem, uint32_t f_base, uint32_t sW_u,
+                                              uint32_t bars_u, int& st, uint32_t& wph, uint32_t idesc) {
+  constexpr int ns = kType == 0 ? 3 : (kType == 1 ? 8 : 11);
+#pragma unroll
+  for (int s0 = 0; s0 < ns; s0 += kTsSlabsPerStage) {
+    mbar_wait_fast(bars_u + st * 8, wph);  // w_full[st]: both CTAs' rows of up to four slabs landed
+    tc_fence_after();
+    const uint32_t b0 = desc_lo(sW_u + st * (kTsSlabsPerStage * 4096u));
+#pragma unroll
+    for (int i = 0; i < kTsSlabsPerStage; ++i) {
+      const int s2 = s0 + i;
+      if (s2 < ns) {
+        const uint32_t b_lo = b0 + i * (4096u >> 4);
+        const int fs = kType == 0 ? s2 : (kType == 2 ? s2 - 8 : -1);  // >= 0: K-slab fs of the feature tile
+        const uint32_t first = s2 > 0 ? 1u : 0u;
+        if (fs < 0) {  // K-slab s2 of the activations: TMEM columns 16 s2 .. 16 s2 + 15
+          umma_ts_pair_lohi(d_tmem, a_tmem + 16 * s2, b_lo, kDescHiSw64, idesc, first);
+          umma_ts_pair_lohi(d_tmem, a_tmem + 16 * s2 + 8, b_lo + 2, kDescHiSw64, idesc, 1u);
+        } else {  // features: SS form from the slot's feature tile
+          const uint32_t a_lo = desc_lo(fs < 2 ? f_base + fs * 64 : f_base + kStageBytes);
+          const uint32_t a_hi = fs == 2 ? kDescHiSw64 : kDescHiSw128;
+          umma_ss_pair_lohi(d_tmem, a_lo, a_hi, b_lo, kDescHiSw64, idesc, first);
+          umma_ss_pair_lohi(d_tmem, a_lo + 2, a_hi, b_lo + 2, kDescHiSw64, idesc, 1u);
+        }
+      }
+    }
+    umma_commit_pair_addr(bars_u + (kStages + st) * 8);  // w_empty[st]
+    if (++st == kStages) {
+      st = 0;
+      wph ^= 1;
+    }
+  }
+}
+
+template <int kFmt, bool kPair, bool kX3, bool kTrain = false, bool kTS = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
   static_assert(!kX3 || kPair, "split-operand modes exist for the CTA-pair kernel only");
+  static_assert(!kTS || (kPair && !kX3 && !kTrain), "the TS variant is the plain CTA-pair inference kernel");
   static_assert(!kTrain || (kPair && !kX3), "the training forward (activation dump) is the plain CTA-pair kernel");
   // Activation-tile layout (a_chunk_offset).  -DMIPNERF_TC_A_SW32 builds the dense K = 16 block layout (never in the
   // training forward, whose tiles leave the SM as tile images).  Measured: all parity tests pass with it and the level
@@ -476,15 +588,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* sA = smem + kSmemA;
   uint8_t* sF = smem + kSmemF;
-  uint8_t* sW = smem + kSmemW;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemMisc);
-  uint64_t* w_full = bars;                      // [kStages] producer (+ peer relay) -> MMA   (tx bytes)
-  uint64_t* w_empty = bars + kStages;           // [kStages] MMA -> producer                  (tcgen05.commit)
-  uint64_t* a_ready = bars + 2 * kStages;       // [2] worker warps -> MMA: A operand written, accumulator drained
-  uint64_t* acc_full = bars + 2 * kStages + 2;  // [2] MMA -> workers                          (tcgen05.commit)
-  uint64_t* f_ready = bars + 2 * kStages + 4;   // [2] IPE warp -> MMA: feature tile of the next ray written
-  uint64_t* f_free = bars + 2 * kStages + 6;    // [2] MMA -> IPE warp: layer 5 has read the feature tile
-  static_assert((2 * kStages + 8) * 8 <= 256, "barrier block");
+  // kTS: no activation tiles in shared memory; their 128 KB hold the weight ring — 6 stages of 16 KB = up to FOUR K = 32
+  // slabs of this CTA's 64 rows of one N = 128 half (a TS MMA of that shape is 64 cycles: one wait / commit per two
+  // MMAs made the issuing thread the bottleneck, 250 cycles per 128 cycles of tensor work) — and the barrier block
+  constexpr int kNS = kStages;
+  constexpr int kTsSlabs = kTsSlabsPerStage;                   // K slabs per stage
+  constexpr uint32_t kRingStride = kTS ? kTsSlabs * 4096u : kWStage;
+  uint8_t* sW = kTS ? sA : smem + kSmemW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kTS ? sA + kStages * kTsSlabs * 4096 : smem + kSmemMisc);
+  uint64_t* w_full = bars;                  // [kNS] producer (+ peer relay) -> MMA   (tx bytes)
+  uint64_t* w_empty = bars + kNS;           // [kNS] MMA -> producer                  (tcgen05.commit)
+  uint64_t* a_ready = bars + 2 * kNS;       // [2] worker warps -> MMA: A operand written, accumulator drained
+  uint64_t* acc_full = bars + 2 * kNS + 2;  // [2] MMA -> workers                          (tcgen05.commit)
+  uint64_t* f_ready = bars + 2 * kNS + 4;   // [2] IPE warp -> MMA: feature tile of the next ray written
+  uint64_t* f_free = bars + 2 * kNS + 6;    // [2] MMA -> IPE warp: layer 5 has read the feature tile
+  uint64_t* acc_drained = bars + 2 * kNS + 8;  // [2] kTS: worker warps -> MMA: half 0 of the accumulator has been read
+  static_assert(kTS || (2 * kStages + 8) * 8 <= 256, "barrier block");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemMisc + 256);
   float* vb_s = reinterpret_cast<float*>(smem + kSmemMisc + 272);  // [2][128] per-ray view-layer bias
   float* cs = vb_s + 256;                                          // [2][4]   scan carries
@@ -494,11 +613,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = !kPair || rank == 0;
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kNS; ++i) {
       mbar_init(&w_full[i], (kPair && leader) ? 2 : 1);  // leader: own producer + the peer's relay
       mbar_init(&w_empty[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
+      if (kTS) mbar_init(&acc_drained[s], 8);
       mbar_init(&a_ready[s], kX3 ? 16 : (kPair ? 8 : 4));  // one arrive per worker warp (of both CTAs in pair mode;
                                                              // split modes: both worker groups work on the one slot)
       mbar_init(&acc_full[s], 1);
@@ -529,6 +649,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       int st = 0;
       uint32_t ph = 0;
       const uint64_t w_policy = kTrain ? l2_policy_evict_last() : 0ull;
+      if (kTS) {  // per layer: (half 0: slot 0, slot 1), (half 1: slot 0, slot 1) — the MMA issue order
+        for (int round = 0; round < rounds; ++round)
+          for (int l = 0; l < kNumLayers; ++l) {
+            const int ns = num_k32(l), nh = l == 9 ? 1 : 2;
+            for (int h = 0; h < nh; ++h)
+              for (int slot = 0; slot < 2; ++slot) {
+                // rows [64 rank, +64) of the packed image's [128 x 64 B] SW64 stage (layer l, N-half h, K-slab s)
+                const uint8_t* src = p.wimage + layer_offset(l) + (uint32_t)h * (layer_bytes(l) / num_halves(l)) + rank * 4096u;
+                for (int s2 = 0; s2 < ns; s2 += kTsSlabs) {
+                  const int cnt = ns - s2 < kTsSlabs ? ns - s2 : kTsSlabs;
+                  mbar_wait(&w_empty[st], ph ^ 1);
+                  mbar_arrive_expect_tx(&w_full[st], (uint32_t)cnt * 4096u);
+                  for (int i = 0; i < cnt; ++i)
+                    bulk_g2s(sW + st * kRingStride + i * 4096u, src + (size_t)(s2 + i) * kWStage, 4096u, &w_full[st]);
+                  if (++st == kNS) {
+                    st = 0;
+                    ph ^= 1;
+                  }
+                }
+              }
+          }
+      } else
       for (int round = 0; round < rounds; ++round)
         for (int l = 0; l < kNumLayers; ++l) {
           const int ns = num_k32(l);
@@ -578,6 +720,50 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         const uint32_t idesc_view = make_idesc_f16(kM, 128, kFmt);
         int st = 0;
         uint32_t wph = 0, ph_ready0 = 0, ph_ready1 = 0, ph_f0 = 0, ph_f1 = 0;
+        if (kTS) {
+          const uint32_t idesc_t = make_idesc_f16(256, 128, kFmt);
+          uint32_t ph_dr[2] = {0u, 0u}, ph_rd[2] = {0u, 0u}, ph_ff[2] = {0u, 0u};
+          V4_DECL();
+          const long long t_all_ = V4_CLK();
+          for (int round = 0; round < rounds; ++round)
+            for (int l = 0; l < kNumLayers; ++l) {
+              const int ns = num_k32(l), nh = l == 9 ? 1 : 2;
+              for (int h = 0; h < nh; ++h)
+                for (int slot = 0; slot < 2; ++slot) {
+                  if (h == 0) {
+                    if (l == 0) {  // the ray's feature tile (written ahead of time by the IPE warp)
+                      const long long t_ = V4_CLK();
+                      mbar_wait_fast(bars_u + (2 * kNS + 4 + slot) * 8, ph_ff[slot]);
+                      ph_ff[slot] ^= 1;
+                      V4_ADD(0, t_);
+                    }
+                    const long long t_ = V4_CLK();
+                    mbar_wait_fast(bars_u + (2 * kNS + slot) * 8, ph_rd[slot]);  // a_ready: activations written
+                    ph_rd[slot] ^= 1;
+                    V4_ADD(1, t_);
+                  } else {
+                    const long long t_ = V4_CLK();
+                    mbar_wait_fast(bars_u + (2 * kNS + 8 + slot) * 8, ph_dr[slot]);  // acc_drained: half 0 read out
+                    ph_dr[slot] ^= 1;
+                    V4_ADD(2, t_);
+                  }
+                  tc_fence_after();
+                  const uint32_t d_tmem = tm_u + slot * 256, a_tmem = d_tmem + 128;
+                  const uint32_t f_base = sF_u + slot * kFBytes;
+                  {
+                    const long long tw_ = V4_CLK();
+                    if (l == 0) ts_issue_half<0>(d_tmem, a_tmem, f_base, sW_u, bars_u, st, wph, idesc_t);
+                    else if (l == 5) ts_issue_half<2>(d_tmem, a_tmem, f_base, sW_u, bars_u, st, wph, idesc_t);
+                    else ts_issue_half<1>(d_tmem, a_tmem, f_base, sW_u, bars_u, st, wph, idesc_t);
+                    V4_ADD(3, tw_);  // issue + weight waits + tensor back-pressure of this (layer, half, slot)
+                  }
+                  umma_commit_pair(&acc_full[slot]);
+                  if (l == 5 && h == 1) umma_commit_pair(&f_free[slot]);
+                }
+            }
+          V4_ADD(4, t_all_);
+          V4_FLUSH(0);
+        } else
         for (int round = 0; round < rounds; ++round)
           for (int l = 0; l < kNumLayers; ++l) {
             const int ns = num_k32(l);
@@ -677,10 +863,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         for (int round = 0; round < rounds; ++round)
           for (int l = 0; l < kNumLayers; ++l) {
             const int ns = num_k32(l);
-            for (int k = 0; k < 2 * ns; ++k) {
+            // kTS: two N halves per slot, up to four K slabs per stage
+            const int per_layer = kTS ? (l != 9 ? 4 : 2) * ((ns + kTsSlabs - 1) / kTsSlabs) : 2 * ns;
+            for (int k = 0; k < per_layer; ++k) {
               mbar_wait_fast(bars_u + st * 8, wph);
               mbar_arrive_remote(leader_w_full + st * 8);
-              if (++st == kStages) {
+              if (++st == kNS) {
                 st = 0;
                 wph ^= 1;
               }
@@ -828,10 +1016,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         else mbar_arrive(&a_ready[slot]);
       }
     };
+    const uint32_t acc_drained_leader = kTS ? mapa_u32(smem_u32(&acc_drained[slot]), 0) : 0u;
+    auto arrive_acc_drained = [&]() {  // kTS: half 0 of the accumulator is in registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(acc_drained_leader);
+    };
+    const uint32_t t_act = t_acc + 128;  // kTS: the slot's 16-bit activation row (128 TMEM columns)
     const int my_rounds = slot < kSlots ? rounds : 0;
     const int kk0 = kX3 ? 2 * grp : 0, kk1 = kX3 ? 2 * grp + 2 : 4;  // this group's share of an epilogue
     const uint32_t t_xchg = tmem_base + ((uint32_t)(q * 32) << 16) + 256;  // split modes: slot 1's columns are unused
     const SmallParams* __restrict__ gsp = reinterpret_cast<const SmallParams*>(p.wimage + kSmallOffset);
+    V4_DECL();
     constexpr bool dumping = kTrain;  // a separate instantiation: the inference kernel carries none of this
     const uint64_t dump_policy = kTrain ? l2_policy_evict_first() : 0ull;
     bool dump_pending = false;
@@ -845,9 +1041,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
 
       float dens = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
       for (int l = 0; l < kNumLayers; ++l) {
+        const long long tw0_ = V4_CLK();
         mbar_wait(&acc_full[slot], ph_acc);
         ph_acc ^= 1;
         tc_fence_after();
+        V4_ADD(0, tw0_);
         TRACE(EV(2, 2, l, slot));
         if (l == 8) {
           // per-ray operands of the view epilogue / compositing: issued one epilogue early so the latency hides
@@ -861,7 +1059,39 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
             dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
           }
         }
-        if (l < 9) {
+        if (kTS && l < 9) {
+          // two N = 128 halves through the one accumulator; the first half's result waits in registers
+          uint32_t held[64];
+          const long long te0_ = V4_CLK();
+#define MIPNERF_TS_HALF(LL, HH) epilogue_half_ts<kFmt, LL, HH>(t_acc, t_act, held, dens, arrive_acc_drained)
+#define MIPNERF_TS_SWITCH(HH)                 \
+  switch (l) {                                \
+    case 0: MIPNERF_TS_HALF(0, HH); break;    \
+    case 1: MIPNERF_TS_HALF(1, HH); break;    \
+    case 2: MIPNERF_TS_HALF(2, HH); break;    \
+    case 3: MIPNERF_TS_HALF(3, HH); break;    \
+    case 4: MIPNERF_TS_HALF(4, HH); break;    \
+    case 5: MIPNERF_TS_HALF(5, HH); break;    \
+    case 6: MIPNERF_TS_HALF(6, HH); break;    \
+    case 7: MIPNERF_TS_HALF(7, HH); break;    \
+    default: MIPNERF_TS_HALF(8, HH); break;   \
+  }
+          MIPNERF_TS_SWITCH(0)
+          V4_ADD(1, te0_);
+          const long long tw1_ = V4_CLK();
+          mbar_wait(&acc_full[slot], ph_acc);  // second half's accumulator; every MMA that read the activations is done
+          ph_acc ^= 1;
+          tc_fence_after();
+          V4_ADD(2, tw1_);
+          const long long te1_ = V4_CLK();
+          MIPNERF_TS_SWITCH(1)
+#undef MIPNERF_TS_SWITCH
+#undef MIPNERF_TS_HALF
+          tmem_st_wait();
+          tc_fence_before();
+          arrive_a_ready();
+          V4_ADD(3, te1_);
+        } else if (l < 9) {
           if (dumping) {  // the previous layer's bulk store must have READ the tile before anyone overwrites it
             if (row == 0 && dump_pending) {
               bulk_store_wait_read();
@@ -991,6 +1221,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
       }
       named_bar_sync(1 + slot, 128);  // row 0 has consumed ps / everyone cs before the next ray reuses them
     }
+    if (kTS && slot == 0 && q == 0 && lane == 0) { V4_FLUSH(8); }
     if (dump_pending) bulk_store_wait_all();  // the last tile's store has left shared memory and reached global
 #ifdef MIPNERF_TC_TRACE
     if (q == 0 && lane == 0) tracer.finish(2 + slot);
@@ -1617,9 +1848,9 @@ bool g_attr_set[2][2][2] = {};
 inline int fmt_of(int precision) { return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_BF16X3) ? 1 : 0; }
 inline bool is_x3(int precision) { return precision == MIPNERF_B200_FP16X3 || precision == MIPNERF_B200_BF16X3; }
 
-template <int kFmt, bool kPair, bool kX3 = false, bool kTrain = false>
+template <int kFmt, bool kPair, bool kX3 = false, bool kTrain = false, bool kTS = false>
 cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
-  auto kern = mlp_level_kernel<kFmt, kPair, kX3, kTrain>;
+  auto kern = mlp_level_kernel<kFmt, kPair, kX3, kTrain, kTS>;
   static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
@@ -1735,6 +1966,7 @@ cudaError_t launch_level_v3(const LevelParams& p, cudaStream_t st) {
 // shared weight stream (v2), "pair" = CTA pair (v1), "single" = 1-CTA kernel (cta_group::1).
 int tc_variant() {
   const char* v = getenv("MIPNERF_B200_TC_VARIANT");
+  if (v && v[0] == 'v' && v[1] == '4') return 4;
   if (v && v[0] == 'v' && v[1] == '3') return 3;
   if (v && v[0] == 's' && v[1] == 'i') return 0;
   if (v && v[0] == 's' && v[1] == 'h') return 2;
@@ -1746,7 +1978,7 @@ bool use_pair_variant() { return tc_variant() != 0; }
 // default: produced inside the v1 level kernels.
 bool fused_prologue_enabled(int precision) {
   const char* v = getenv("MIPNERF_B200_TC_PROLOGUE");
-  return (is_x3(precision) || tc_variant() < 2) && !(v && v[0] == 's');
+  return (is_x3(precision) || tc_variant() < 2 || tc_variant() == 4) && !(v && v[0] == 's');
 }
 
 cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
@@ -1755,6 +1987,9 @@ cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
                                           : launch_level_t<0, true, false, true>(p, st);
   if (is_x3(precision))  // split-operand parity modes: the CTA-pair kernel, whatever variant is selected
     return fmt_of(precision) ? launch_level_t<1, true, true>(p, st) : launch_level_t<0, true, true>(p, st);
+  if (tc_variant() == 4)  // "v4": the CTA-pair kernel with the activations in tensor memory (TS-form MMAs)
+    return precision == MIPNERF_B200_BF16 ? launch_level_t<1, true, false, false, true>(p, st)
+                                          : launch_level_t<0, true, false, false, true>(p, st);
   if (tc_variant() == 3)
     return precision == MIPNERF_B200_BF16 ? launch_level_v3<1>(p, st) : launch_level_v3<0>(p, st);
   if (tc_variant() == 2)

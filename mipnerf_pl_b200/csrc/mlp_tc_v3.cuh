@@ -121,17 +121,6 @@ __host__ __device__ constexpr uint32_t layer_offset3(int l) {
 }
 constexpr size_t kV3Bytes = layer_offset3(kNumLayers);
 
-// D[tmem] (+)= A[tmem] * B[smem]^T over the CTA pair; descriptors as {lo, hi} halves
-__device__ __forceinline__ void umma_ts_pair_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
-                                                  uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
-      "mov.b64 db, {%2, %3};\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void named_bar_arrive(int id, int count) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }

@@ -365,6 +365,17 @@ __device__ __forceinline__ void umma_ss_pair_lohi(uint32_t d_tmem, uint32_t a_lo
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T over the CTA pair; descriptors as {lo, hi} halves
+__device__ __forceinline__ void umma_ts_pair_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 constexpr uint32_t kDescHiSw128 = 0x40004040u;  // SBO 1024 B, version 1, SWIZZLE_128B
 constexpr uint32_t kDescHiSw64 = 0x80004020u;   // SBO  512 B, version 1, SWIZZLE_64B

@@ -249,8 +249,80 @@ umma_selftest_a32_kernel(const float* __restrict__ a, const float* __restrict__ 
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
+// Issue-rate microbenchmark: one thread per CTA issues `iters` x 16 back-to-back MMAs (M = 128, N = n, K = 16; a
+// 256-deep layer per iteration) on operands that already sit in shared / tensor memory, commits once, and the CTA
+// reports clock64 cycles per MMA.  No loads, no epilogue: the ceiling of the MMA pipe for that operand form.
+//   mode 0: SS, A = 64-column SW128 slabs (the activation tile of the level kernels), B = SW64 K = 32 stages
+//   mode 1: SS, A = dense K = 16 blocks in the 32-byte-swizzle layout, B as above
+//   mode 2: TS, A in tensor memory, B as above
+template <int kFmt>
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int n, int iters, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;            // 64 KB
+  uint8_t* sB = sA + 65536;      // 8 stages x [n x 64 B]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + (size_t)8 * n * 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (uint32_t i = tid * 16; i < 65536u + 8u * n * 64u; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_f16(128, n, kFmt);
+    const uint32_t a_u = smem_u32(sA), b_u = smem_u32(sB);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint64_t bd = make_sw64_desc(b_u + s * n * 64 + j * 32);
+          if (mode == 2) umma_ts(tmem_base, tmem_base + 256 + (s * 32 + j * 16) / 2, bd, idesc, 1u);
+          else if (mode == 1) umma_ss(tmem_base, make_sw32_desc(a_u + (2 * s + j) * 4096), bd, idesc, 1u);
+          else umma_ss(tmem_base, make_sw128_desc(a_u + (s >> 1) * 16384 + (s & 1) * 64 + j * 32), bd, idesc, 1u);
+        }
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace mipnerf
+
+extern "C" int mipnerf_b200_selftest_umma_rate(int mode, int n, int iters, int precision, int ctas, long long* cycles,
+                                               void* stream) {
+  using namespace mipnerf;
+  if (mode < 0 || mode > 2 || !(n == 128 || n == 256) || iters < 1 || ctas < 1 || !cycles) return MIPNERF_B200_EINVAL;
+  if (precision != MIPNERF_B200_BF16 && precision != MIPNERF_B200_FP16) return MIPNERF_B200_EINVAL;
+  const size_t sm = 1024 + 65536 + (size_t)8 * n * 64 + 64;
+  cudaError_t e;
+  if (precision == MIPNERF_B200_BF16) {
+    e = cudaFuncSetAttribute(umma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return MIPNERF_B200_ECUDA;
+    umma_rate_kernel<1><<<ctas, 128, sm, (cudaStream_t)stream>>>(mode, n, iters, cycles);
+  } else {
+    e = cudaFuncSetAttribute(umma_rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return MIPNERF_B200_ECUDA;
+    umma_rate_kernel<0><<<ctas, 128, sm, (cudaStream_t)stream>>>(mode, n, iters, cycles);
+  }
+  return cudaGetLastError() == cudaSuccess ? MIPNERF_B200_OK : MIPNERF_B200_ECUDA;
+}
 
 extern "C" int mipnerf_b200_selftest_umma(const float* a, const float* b, float* d, int n, int k, int precision,
                                           int variant, void* scratch, size_t scratch_bytes, void* stream) {

@@ -21,7 +21,7 @@ DEV = "cuda:0"
 DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
 
-@pytest.fixture(autouse=True, params=["v3", "shared", "pair", "single"])
+@pytest.fixture(autouse=True, params=["v4", "v3", "shared", "pair", "single"])
 def tc_variant(request, monkeypatch):
     """All kernel variants: CTA pair + shared weight stream (v2), CTA pair (v1), 1-CTA kernel."""
     monkeypatch.setenv("MIPNERF_B200_TC_VARIANT", request.param)
