@@ -298,6 +298,10 @@ int mipnerf_b200_selftest_umma(const float* a, const float* b, float* d, int n, 
  * issue iters x 16 MMAs and write their clock64 cycle count to cycles[cta] (device memory).  mode 0: SS form, A as
  * 128-byte-swizzle slabs; 1: SS form, A as dense 32-byte-swizzle K = 16 blocks; 2: TS form, A in tensor memory. */
 int mipnerf_b200_selftest_umma_rate(int mode, int n, int iters, int precision, int ctas, long long* cycles, void* stream);
+/* The same for CTA pairs (cta_group::2, M = 256 over two SMs, n / 2 rows of B per CTA); mode 0 (SS) or 2 (TS);
+ * cycles[pair]. */
+int mipnerf_b200_selftest_umma_rate_pair(int mode, int n, int iters, int precision, int pairs, long long* cycles,
+                                         void* stream);
 
 /* ---- launch accounting (bench.py: `gpu_launches`, live launch duration of the dominant kernel) ----
  * Every kernel launch of the library is counted per kernel id; with timing enabled each launch is

@@ -115,6 +115,7 @@ _SIGNATURES = {
                                                    _V, _V, _V, _V, _V]),
     "mipnerf_b200_selftest_umma": (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_int, _V, C.c_size_t, _V]),
     "mipnerf_b200_selftest_umma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V]),
+    "mipnerf_b200_selftest_umma_rate_pair": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _V, _V]),
     "mipnerf_b200_profile_enable": (C.c_int, [C.c_int]),
     "mipnerf_b200_profile_num_kernels": (C.c_int, []),
     "mipnerf_b200_profile_kernel_name": (C.c_char_p, [C.c_int]),

@@ -302,8 +302,87 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int mode, int n, int 
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// The same for a CTA pair (cta_group::2, M = 256 over two SMs, each CTA holding n / 2 rows of B): the shapes the level
+// kernels issue.  Grid = pairs x 2 with cluster dimension 2; the leader CTA issues and reports.
+template <int kFmt>
+__global__ void __launch_bounds__(128, 1) umma_rate_pair_kernel(int mode, int n, int iters, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* sA = smem;        // 64 KB
+  uint8_t* sB = sA + 65536;  // 8 stages x [n / 2 x 64 B]
+  const uint32_t stage = (uint32_t)(n / 2) * 64u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + (size_t)8 * stage);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_pair(tmem_slot, 512);
+  for (uint32_t i = tid * 16; i < 65536u + 8u * stage; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_f16(256, n, kFmt);
+      const uint32_t a_u = smem_u32(sA), b_u = smem_u32(sB);
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t b_lo = desc_lo(b_u + s * stage + j * 32);
+            if (mode == 2) umma_ts_pair_lohi(tmem_base, tmem_base + 256 + (s * 32 + j * 16) / 2, b_lo, kDescHiSw64, idesc, 1u);
+            else umma_ss_pair_lohi(tmem_base, desc_lo(a_u + (s >> 1) * 16384 + (s & 1) * 64 + j * 32), kDescHiSw128, b_lo,
+                                   kDescHiSw64, idesc, 1u);
+          }
+        }
+      }
+      umma_commit_pair(bar);
+      mbar_wait(bar, 0);
+      cycles[blockIdx.x >> 1] = clock64() - t0;
+    } else {
+      mbar_wait(bar, 0);  // the leader's commit arrives here as well
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace mipnerf
+
+extern "C" int mipnerf_b200_selftest_umma_rate_pair(int mode, int n, int iters, int precision, int pairs, long long* cycles,
+                                                    void* stream) {
+  using namespace mipnerf;
+  if (!(mode == 0 || mode == 2) || !(n == 128 || n == 256) || iters < 1 || pairs < 1 || !cycles) return MIPNERF_B200_EINVAL;
+  if (precision != MIPNERF_B200_BF16 && precision != MIPNERF_B200_FP16) return MIPNERF_B200_EINVAL;
+  const size_t sm = 1024 + 65536 + (size_t)8 * (n / 2) * 64 + 64;
+  auto kern = precision == MIPNERF_B200_BF16 ? umma_rate_pair_kernel<1> : umma_rate_pair_kernel<0>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return MIPNERF_B200_ECUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = sm;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, mode, n, iters, cycles) == cudaSuccess ? MIPNERF_B200_OK : MIPNERF_B200_ECUDA;
+}
 
 extern "C" int mipnerf_b200_selftest_umma_rate(int mode, int n, int iters, int precision, int ctas, long long* cycles,
                                                void* stream) {

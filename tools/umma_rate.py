@@ -25,3 +25,16 @@ for n in (256, 128):
             per = out.double() / (iters * 16)
             print(f"N={n:3d} {names[mode]:45s} {ctas:3d} CTA(s): {float(per.mean()):7.1f} cycles per MMA "
                   f"(min {float(per.min()):.1f}, max {float(per.max()):.1f}; ideal {n // 2})")
+
+print("CTA pairs (cta_group::2, M = 256 over two SMs; ideal N / 2 cycles per MMA):")
+for n in (256, 128):
+    for mode in (0, 2):
+        for pairs in (1, sms // 2):
+            out = torch.zeros(pairs, dtype=torch.int64, device=dev)
+            for _ in range(2):
+                _cabi.check(lib.mipnerf_b200_selftest_umma_rate_pair(mode, n, iters, _cabi.BF16, pairs, out.data_ptr(),
+                                                                     torch.cuda.current_stream().cuda_stream), "umma_rate_pair")
+            torch.cuda.synchronize()
+            per = out.double() / (iters * 16)
+            print(f"N={n:3d} {names[mode]:45s} {pairs:3d} pair(s): {float(per.mean()):7.1f} cycles per MMA "
+                  f"(min {float(per.min()):.1f}, max {float(per.max()):.1f}; ideal {n // 2})")
