@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MIPNERF_B200_ABI_VERSION 3
+#define MIPNERF_B200_ABI_VERSION 4
 
 #define MIPNERF_B200_OK 0
 #define MIPNERF_B200_EINVAL (-1)       /* bad argument (NULL pointer, negative size, ...)            */
@@ -59,6 +59,7 @@ typedef struct mipnerf_b200_config {
   float resample_padding, density_bias, rgb_padding;
   int32_t net_depth, net_width, net_depth_condition, net_width_condition, skip_index;
   int32_t num_rgb_channels, num_density_channels; /* must be 3 and 1                                */
+  float density_noise; /* std of the Gaussian noise added to raw density when randomized (models/mip_nerf.py:232-233) */
 } mipnerf_b200_config;
 
 /* MLP parameters in state_dict order (models/mip_nerf.py:19-73):
@@ -91,6 +92,10 @@ typedef struct mipnerf_b200_level_out {
   float* weights;   /* [B,N]   nullable */
   float* t_samples; /* [B,N+1] nullable */
   int64_t* inds;    /* [B,N+1] nullable; searchsorted indices of the resampler (levels >= 1)       */
+  /* INPUT, nullable: [B,N] standard-normal draws replacing torch.randn of models/mip_nerf.py:233 for this level.
+   * Read only when randomized != 0 and cfg->density_noise > 0; required then by the entry points that take injected
+   * noise (t_rand / u_jitter), ignored by the _rng entry points (in-kernel Philox + Box-Muller, stream 32 + level). */
+  const float* density_normal;
 } mipnerf_b200_level_out;
 
 /* In-kernel random numbers for randomized=True: Philox4x32-10 keyed by `seed`; the draw of (ray, index, stream) is a
@@ -133,6 +138,11 @@ int mipnerf_b200_forward_rng(const mipnerf_b200_config* cfg, const mipnerf_b200_
  * [0, 1/ncols - eps)).  forward(t_rand = stream 0, u_jitter = stream 1+level) reproduces forward_rng bit for bit. */
 int mipnerf_b200_philox_uniform(const mipnerf_b200_rng* rng, int stream_id, int64_t num_rays, int ncols, float* out,
                                 void* stream);
+/* The standard normals the _rng entry points add (times cfg->density_noise) to the raw density of level `level`
+ * (models/mip_nerf.py:232-233): out[num_rays, num_samples].  Passed as outs[level].density_normal to the injected-
+ * noise entry points they reproduce the in-kernel draws bit for bit. */
+int mipnerf_b200_philox_normal(const mipnerf_b200_rng* rng, int level, int64_t num_rays, int num_samples, float* out,
+                               void* stream);
 
 /* distloss (models/mip.py:8-20), forward value per ray: weights [B,N], samples [B,N+1] (sorted) ->
  * per_ray_loss [B] = (1/3) sum_i d_i w_i^2 + sum_ij w_i w_j |m_i - m_j|; the reference's scalar is its mean. */

@@ -9,7 +9,7 @@ from .rays import (Rays, Rays_keys, namedtuple_map, rearrange_render_image, blen
 from .mip_nerf import MLP, MipNerf
 from .nerf_system import MipNeRFSystem, default_hparams, calc_psnr
 from .ops import (sample_along_rays, resample_along_rays, cast_rays, integrated_pos_enc, pos_enc,
-                  sorted_piecewise_constant_pdf, volumetric_rendering, distloss, philox_uniform)
+                  sorted_piecewise_constant_pdf, volumetric_rendering, distloss, philox_uniform, philox_normal)
 from .weights import make_state_dict
 from .train import FusedAdam, MipLRDecay, allreduce_grads, forward_backward, fused_loss, mip_lr
 from .datasets import (Blender, Multicam, DeviceRayBank, Scene, dataset_dict, load_blender_scene, load_multicam_scene,
@@ -26,6 +26,6 @@ __all__ = [
     "render_sharded", "shard_bounds", "shard_rows", "gather_rows", "FusedAdam", "MipLRDecay", "allreduce_grads",
     "forward_backward", "fused_loss", "mip_lr", "Blender", "Multicam", "DeviceRayBank", "Scene", "dataset_dict",
     "load_blender_scene", "load_multicam_scene", "image_rays", "convert_blender_to_multiscale",
-    "write_synthetic_blender_scene", "GraphedForward", "philox_uniform", "eval_errors", "ssim", "evaluate",
+    "write_synthetic_blender_scene", "GraphedForward", "philox_uniform", "philox_normal", "eval_errors", "ssim", "evaluate",
     "render_path", "spheric_path", "save_images",
 ]

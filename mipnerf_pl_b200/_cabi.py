@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "libmipnerf_b200.so"
 LIB_PATH = os.environ.get("MIPNERF_B200_LIB") or os.path.join(_HERE, LIB_NAME)  # env: experiment builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
 FP32, BF16, FP16, FP16X3, BF16X3 = 0, 1, 2, 3, 4
 PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp16": FP16, "fp16x3": FP16X3, "bf16x3": BF16X3}
@@ -35,7 +35,8 @@ class Config(C.Structure):
                 ("resample_padding", C.c_float), ("density_bias", C.c_float), ("rgb_padding", C.c_float),
                 ("net_depth", C.c_int32), ("net_width", C.c_int32), ("net_depth_condition", C.c_int32),
                 ("net_width_condition", C.c_int32), ("skip_index", C.c_int32),
-                ("num_rgb_channels", C.c_int32), ("num_density_channels", C.c_int32)]
+                ("num_rgb_channels", C.c_int32), ("num_density_channels", C.c_int32),
+                ("density_noise", C.c_float)]
 
 
 class Weights(C.Structure):
@@ -50,7 +51,8 @@ class RaysStruct(C.Structure):
 
 class LevelOut(C.Structure):
     _fields_ = [("comp_rgb", C.c_void_p), ("distance", C.c_void_p), ("acc", C.c_void_p),
-                ("weights", C.c_void_p), ("t_samples", C.c_void_p), ("inds", C.c_void_p)]
+                ("weights", C.c_void_p), ("t_samples", C.c_void_p), ("inds", C.c_void_p),
+                ("density_normal", C.c_void_p)]  # INPUT: [B,N] normals of the density noise (models/mip_nerf.py:233)
 
 
 class Rng(C.Structure):
@@ -81,6 +83,7 @@ _SIGNATURES = {
     "mipnerf_b200_forward_rng": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.POINTER(Rng),
                                            C.c_int, C.c_int, C.POINTER(LevelOut), _V, C.c_size_t, _V]),
     "mipnerf_b200_philox_uniform": (C.c_int, [C.POINTER(Rng), C.c_int, C.c_int64, C.c_int, _V, _V]),
+    "mipnerf_b200_philox_normal": (C.c_int, [C.POINTER(Rng), C.c_int, C.c_int64, C.c_int, _V, _V]),
     "mipnerf_b200_distloss": (C.c_int, [_V, _V, C.c_int64, C.c_int, _V, _V]),
     "mipnerf_b200_train_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int64]),
     "mipnerf_b200_forward_backward": (C.c_int, [C.POINTER(Config), C.POINTER(Weights), C.POINTER(RaysStruct), C.c_int,

@@ -63,6 +63,8 @@ int check_config(const mipnerf_b200_config* c, Dims* d) {
   if (!c->use_viewdirs && c->net_width != c->net_width_condition)
     return fail(MIPNERF_B200_EUNSUPPORTED,
                 "use_viewdirs=False needs net_width == net_width_condition (reference color_layer shape)");
+  if (!(c->density_noise >= 0.f) || c->density_noise > 3.0e38f)
+    return fail(MIPNERF_B200_EINVAL, "density_noise=%g: need a finite standard deviation >= 0", (double)c->density_noise);
   d->xyz_dim = (c->max_deg_point - c->min_deg_point) * 6;
   d->view_dim = c->deg_view * 6 + 3;
   d->n_lin = c->net_depth + 2 + c->net_depth_condition + 1;
@@ -243,6 +245,18 @@ int mipnerf_b200_pack_weights(const mipnerf_b200_config* cfg, const mipnerf_b200
   return MIPNERF_B200_OK;
 }
 
+// randomized with density_noise > 0 (models/mip_nerf.py:232-233): the injected-noise entry points need the normals too
+static int check_density_normals(const mipnerf_b200_config* cfg, int randomized, const mipnerf_b200_rng* rng,
+                                 const mipnerf_b200_level_out* outs, int64_t num_rays) {
+  if (!randomized || !(cfg->density_noise > 0.f) || rng || num_rays == 0) return MIPNERF_B200_OK;
+  for (int l = 0; l < cfg->num_levels; ++l)
+    if (!outs[l].density_normal)
+      return fail(MIPNERF_B200_EINVAL,
+                  "randomized=1 with density_noise > 0 needs outs[%d].density_normal (injected noise) or the _rng "
+                  "entry point (in-kernel Philox)", l);
+  return MIPNERF_B200_OK;
+}
+
 static int forward_impl(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w,
                         const mipnerf_b200_rays* rays, int randomized, const float* t_rand,
                         const float* u_jitter, const mipnerf_b200_rng* rng, int white_bkgd, int precision,
@@ -261,6 +275,7 @@ static int forward_impl(const mipnerf_b200_config* cfg, const mipnerf_b200_weigh
   for (int l = 0; l < cfg->num_levels; ++l)
     if (rays->num_rays > 0 && (!outs[l].comp_rgb || !outs[l].distance || !outs[l].acc))
       return fail(MIPNERF_B200_EINVAL, "outs[%d] misses comp_rgb/distance/acc", l);
+  if ((rc = check_density_normals(cfg, randomized, rng, outs, rays->num_rays))) return rc;
   const size_t need = mipnerf_b200_workspace_bytes(cfg, rays->num_rays, precision);
   if (rays->num_rays > 0 && (!workspace || workspace_bytes < need))
     return fail(MIPNERF_B200_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
@@ -306,6 +321,8 @@ static int forward_impl(const mipnerf_b200_config* cfg, const mipnerf_b200_weigh
       if ((rc = mlp_forward_fp32(cfg, d, w, s.enc, cfg->use_viewdirs ? s.venc : nullptr, cnt, n, s, s.raw_rgb,
                                  s.raw_density, st)))
         return rc;
+      CUDA_TRY(mipnerf::launch_add_density_noise(                                   // models/mip_nerf.py:232-233
+          s.raw_density, mipnerf::density_noise_draws(cfg, randomized, outs[l].density_normal, rng, off, l, n), cnt, n, st));
       CUDA_TRY(mipnerf::launch_composite(s.raw_rgb, s.raw_density, t_cur, rc_.directions,
                                          outs[l].comp_rgb + off * 3, outs[l].distance + off, outs[l].acc + off,
                                          w_cur, cnt, n, white_bkgd, 1, cfg->density_bias, rgb_scale,
@@ -332,6 +349,15 @@ int mipnerf_b200_forward_rng(const mipnerf_b200_config* cfg, const mipnerf_b200_
   if (!rng) return fail(MIPNERF_B200_EINVAL, "rng is NULL");
   return forward_impl(cfg, w, rays, 1, nullptr, nullptr, rng, white_bkgd, precision, outs, workspace,
                       workspace_bytes, stream);
+}
+
+int mipnerf_b200_philox_normal(const mipnerf_b200_rng* rng, int level, int64_t num_rays, int num_samples, float* out,
+                               void* stream) {
+  if (!rng || level < 0 || level >= 64 || num_rays < 0 || num_samples < 1 || (num_rays > 0 && !out))
+    return fail(MIPNERF_B200_EINVAL, "bad argument");
+  const mipnerf::Draws d = mipnerf::draws_philox(rng->seed, rng->offset, 0, mipnerf::kDensityNoiseStream + level, 1.f);
+  CUDA_TRY(mipnerf::launch_philox_normal(d, out, num_rays, num_samples, (cudaStream_t)stream));
+  return MIPNERF_B200_OK;
 }
 
 int mipnerf_b200_philox_uniform(const mipnerf_b200_rng* rng, int stream_id, int64_t num_rays, int ncols, float* out,
@@ -535,6 +561,7 @@ static int forward_backward_fused(const mipnerf_b200_config* cfg, const Dims& d,
       lo[l].t_samples = outs[l].t_samples ? outs[l].t_samples + off * (n + 1) : s.t[l];
       lo[l].weights = outs[l].weights ? outs[l].weights + off * n : s.w[l];
       lo[l].inds = outs[l].inds ? outs[l].inds + off * (n + 1) : nullptr;
+      lo[l].density_normal = outs[l].density_normal ? outs[l].density_normal + off * n : nullptr;
       dump.act[l] = s.act[l], dump.v[l] = s.v[l], dump.raw_rgb[l] = s.raw_rgb[l], dump.raw_density[l] = s.raw_density[l];
     }
     CUDA_TRY(mipnerf::tc_forward(cfg, &wl, &rc_, randomized, t_rand ? t_rand + off * (n + 1) : nullptr,
@@ -643,6 +670,10 @@ static int forward_backward_impl(const mipnerf_b200_config* cfg, const mipnerf_b
   for (int l = 0; l < cfg->num_levels; ++l)
     if (rays->num_rays > 0 && (!outs[l].comp_rgb || !outs[l].distance || !outs[l].acc))
       return fail(MIPNERF_B200_EINVAL, "outs[%d] misses comp_rgb/distance/acc", l);
+  {
+    const int rcn = check_density_normals(cfg, randomized, rng, outs, rays->num_rays);
+    if (rcn) return rcn;
+  }
   const size_t need = mipnerf_b200_train_workspace_bytes(cfg, rays->num_rays);
   if (rays->num_rays > 0 && (!workspace || workspace_bytes < need))
     return fail(MIPNERF_B200_EWORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, need);
@@ -762,6 +793,9 @@ static int forward_backward_impl(const mipnerf_b200_config* cfg, const mipnerf_b
       const mipnerf_b200_linear& cl = w->linears[d.n_lin - 1];
       CUDA_TRY(mipnerf::launch_linear_f32(h_last, W, W, nullptr, 0, 0, 1, dl.weight, dl.bias, s.raw_density, 1, m, 1,
                                           0, st));
+      // density noise (models/mip_nerf.py:232-233), in place: render_backward then takes softplus' at the noisy point
+      CUDA_TRY(mipnerf::launch_add_density_noise(
+          s.raw_density, mipnerf::density_noise_draws(cfg, randomized, outs[l].density_normal, rng, off, l, n), cnt, n, st));
       if (!tc) {
         CUDA_TRY(mipnerf::launch_linear_f32(h_last, W, W, nullptr, 0, 0, 1, el.weight, el.bias, s.bott, W, m, W, 0, st));
         CUDA_TRY(mipnerf::launch_linear_f32(s.bott, W, W, s.venc, d.view_dim, d.view_dim, n, vl.weight, vl.bias, s.v,

@@ -22,6 +22,9 @@ cudaError_t launch_rays_from_pixels(const float* cam_table, const int64_t* offse
 cudaError_t launch_coarse_t(const float* near, const float* far, const Draws& t_rand, float* t_out,
                             int64_t num_rays, int n, int randomized, int disparity, cudaStream_t st);
 cudaError_t launch_philox_uniform(const Draws& d, float* out, int64_t num_rays, int ncols, cudaStream_t st);
+cudaError_t launch_philox_normal(const Draws& d, float* out, int64_t num_rays, int ncols, cudaStream_t st);
+// raw_density [num_rays, ncols] += d.scale * normal (models/mip_nerf.py:232-233); no-op when `d` is inactive
+cudaError_t launch_add_density_noise(float* raw_density, const Draws& d, int64_t num_rays, int ncols, cudaStream_t st);
 cudaError_t launch_cast_rays(const float* origins, const float* directions, const float* radii,
                              const float* t, float* means, float* covs, int64_t num_rays, int n,
                              cudaStream_t st);

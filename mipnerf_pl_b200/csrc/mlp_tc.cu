@@ -201,7 +201,14 @@ struct LevelParams {
   int white_bkgd;
   int disable_integration;
   float density_bias, rgb_scale, rgb_padding;
+  Draws dnoise;  // density noise of randomized mode (models/mip_nerf.py:232-233): normals [B,128] or in-kernel; scale = std
 };
+
+// raw density of (ray, row) with the density noise added; kept out of line so that the (default) noise-free
+// instantiations of the level kernel carry none of the generator's registers or code
+__device__ __noinline__ float noisy_raw_density(float raw, const Draws d, int64_t ray, int row) {
+  return add_density_noise(raw, d, ray, row, kN);
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -568,8 +575,9 @@ __device__ __forceinline__ void ts_issue_half(uint32_t d_tmem, uint32_t a_tmem, 
   }
 }
 
-template <int kFmt, bool kPair, bool kX3, bool kTrain = false, bool kTS = false>
+template <int kFmt, bool kPair, bool kX3, bool kTrain = false, bool kTS = false, bool kNoise = false>
 __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParams p) {
+  static_assert(!kNoise || (kPair && !kTS && !kTrain), "density noise: the v1 CTA-pair kernels (kTrain checks p.dnoise itself)");
   static_assert(!kX3 || kPair, "split-operand modes exist for the CTA-pair kernel only");
   static_assert(!kTS || (kPair && !kX3 && !kTrain), "the TS variant is the plain CTA-pair inference kernel");
   static_assert(!kTrain || (kPair && !kX3), "the training forward (activation dump) is the plain CTA-pair kernel");
@@ -1168,15 +1176,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_level_kernel(const LevelParam
         named_bar_sync(1 + slot, 128);  // vb_s is rewritten before the next ray's view epilogue
         continue;
       }
-      if (kTrain && valid) {  // training: the raw heads as well (render_backward recomputes the rest)
-        const int64_t sidx = ray * kN + row;
+      float raw_dens = dens + c_small.b_density;
+      if (kNoise || kTrain) {  // models/mip_nerf.py:232-233 (randomized and density_noise > 0)
+        if (draws_active(p.dnoise) && valid) raw_dens = noisy_raw_density(raw_dens, p.dnoise, ray, row);
+      }
+      if (kTrain && valid) {  // training: the raw heads as well (render_backward recomputes the rest; the density
+        const int64_t sidx = ray * kN + row;  // head WITH its noise, so that softplus' is taken at the same point)
         p.raw_rgb_keep[sidx * 3 + 0] = rgb0 + c_small.b_color[0];
         p.raw_rgb_keep[sidx * 3 + 1] = rgb1 + c_small.b_color[1];
         p.raw_rgb_keep[sidx * 3 + 2] = rgb2 + c_small.b_color[2];
-        p.raw_density_keep[sidx] = dens + c_small.b_density;
+        p.raw_density_keep[sidx] = raw_dens;
       }
       // ---- activations + compositing over the ray's 128 samples (4 warps of this slot)
-      const float density = density_activation(dens + c_small.b_density, p.density_bias);
+      const float density = density_activation(raw_dens, p.density_bias);
       const float cr = rgb_activation(rgb0 + c_small.b_color[0], p.rgb_scale, p.rgb_padding);
       const float cg = rgb_activation(rgb1 + c_small.b_color[1], p.rgb_scale, p.rgb_padding);
       const float cb = rgb_activation(rgb2 + c_small.b_color[2], p.rgb_scale, p.rgb_padding);
@@ -1848,9 +1860,9 @@ bool g_attr_set[2][2][2] = {};
 inline int fmt_of(int precision) { return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_BF16X3) ? 1 : 0; }
 inline bool is_x3(int precision) { return precision == MIPNERF_B200_FP16X3 || precision == MIPNERF_B200_BF16X3; }
 
-template <int kFmt, bool kPair, bool kX3 = false, bool kTrain = false, bool kTS = false>
+template <int kFmt, bool kPair, bool kX3 = false, bool kTrain = false, bool kTS = false, bool kNoise = false>
 cudaError_t launch_level_t(const LevelParams& p, cudaStream_t st) {
-  auto kern = mlp_level_kernel<kFmt, kPair, kX3, kTrain, kTS>;
+  auto kern = mlp_level_kernel<kFmt, kPair, kX3, kTrain, kTS, kNoise>;
   static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
@@ -1985,6 +1997,13 @@ cudaError_t launch_level(const LevelParams& p, int precision, cudaStream_t st) {
   if (p.act_dump)  // training forward: the CTA-pair kernel with the activation dump
     return precision == MIPNERF_B200_BF16 ? launch_level_t<1, true, false, true>(p, st)
                                           : launch_level_t<0, true, false, true>(p, st);
+  if (draws_active(p.dnoise)) {  // density noise (randomized, density_noise > 0): the v1 CTA-pair kernels' kNoise build
+    if (is_x3(precision))
+      return fmt_of(precision) ? launch_level_t<1, true, true, false, false, true>(p, st)
+                               : launch_level_t<0, true, true, false, false, true>(p, st);
+    return precision == MIPNERF_B200_BF16 ? launch_level_t<1, true, false, false, false, true>(p, st)
+                                          : launch_level_t<0, true, false, false, false, true>(p, st);
+  }
   if (is_x3(precision))  // split-operand parity modes: the CTA-pair kernel, whatever variant is selected
     return fmt_of(precision) ? launch_level_t<1, true, true>(p, st) : launch_level_t<0, true, true>(p, st);
   if (tc_variant() == 4)  // "v4": the CTA-pair kernel with the activations in tensor memory (TS-form MMAs)
@@ -2105,6 +2124,18 @@ Draws level_draws(int randomized, const float* array, const mipnerf_b200_rng* rn
   return draws_philox(rng->seed, rng->offset, off, stream, scale);
 }
 
+// The density-noise normals of one launch of level `level` (models/mip_nerf.py:232-233): rows `off..` of the caller's
+// [B,n] array, or the in-kernel generator (stream 32 + level); inactive unless randomized and density_noise > 0.
+Draws density_noise_draws(const mipnerf_b200_config* c, int randomized, const float* normal, const mipnerf_b200_rng* rng,
+                          int64_t off, int level, int n) {
+  if (!randomized || !(c->density_noise > 0.f)) return draws_from_array(nullptr);
+  Draws d = normal ? draws_from_array(normal + off * n)
+                   : (rng ? draws_philox(rng->seed, rng->offset, off, kDensityNoiseStream + level, 1.f)
+                          : draws_from_array(nullptr));
+  d.scale = c->density_noise;
+  return d;
+}
+
 cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights* w, const mipnerf_b200_rays* rays,
                        int randomized, const float* t_rand, const float* u_jitter, const mipnerf_b200_rng* rng,
                        int white_bkgd, int precision, mipnerf_b200_level_out* outs, void* workspace,
@@ -2183,6 +2214,8 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
       p.white_bkgd = white_bkgd;
       p.disable_integration = c->disable_integration;
       p.density_bias = c->density_bias, p.rgb_scale = rgb_scale, p.rgb_padding = c->rgb_padding;
+      p.dnoise = density_noise_draws(c, randomized, outs[l].density_normal, rng, off, l, kN);
+      if (!outs[l].density_normal) p.dnoise.ray_base += ray_base;
       e = launch_level(p, precision, st);
       if (e != cudaSuccess) return e;
       t_prev = t_cur;

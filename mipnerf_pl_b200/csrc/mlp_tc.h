@@ -32,6 +32,9 @@ cudaError_t tc_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weight
                        const TcTrainDump* dump = nullptr, int64_t ray_base = 0);
 // the uniforms of one launch (see mlp_tc.cu)
 Draws level_draws(int randomized, const float* array, const mipnerf_b200_rng* rng, int64_t off, int stream, int ncols);
+// the density-noise normals of one launch of `level` (inactive unless randomized and cfg->density_noise > 0)
+Draws density_noise_draws(const mipnerf_b200_config* cfg, int randomized, const float* normal,
+                          const mipnerf_b200_rng* rng, int64_t off, int level, int n);
 cudaError_t tc_mlp_forward(const mipnerf_b200_config* cfg, const mipnerf_b200_weights* w, const float* x,
                            const float* view_enc, int64_t num_rays, int precision, float* raw_rgb,
                            float* raw_density, void* workspace, cudaStream_t st);

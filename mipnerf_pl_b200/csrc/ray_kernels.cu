@@ -39,6 +39,21 @@ __global__ void philox_uniform_kernel(const Draws d, float* __restrict__ out, in
   out[idx] = draw_uniform(d, idx / ncols, (int)(idx % ncols), ncols);
 }
 
+// the standard normals of the density noise for (seed, offset, level): test / reproduction helper
+__global__ void philox_normal_kernel(const Draws d, float* __restrict__ out, int64_t num_rays, int ncols) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * ncols) return;
+  out[idx] = draw_normal(d, idx / ncols, (int)(idx % ncols), ncols);
+}
+// raw_density[ray, j] += density_noise * normal[ray, j]   (models/mip_nerf.py:232-233; the fp32 path keeps the raw
+// heads in HBM between the MLP and the compositing, so the noise is one in-place pass; the tensor-core level kernels
+// add it in their compositing epilogue instead)
+__global__ void add_density_noise_kernel(float* __restrict__ raw_density, const Draws d, int64_t num_rays, int ncols) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= num_rays * ncols) return;
+  raw_density[idx] = add_density_noise(raw_density[idx], d, idx / ncols, (int)(idx % ncols), ncols);
+}
+
 // ---------------------------------------------------------------------------------------------
 // cast_rays: one thread per (ray, sample) -> means, covs [B,N,3]
 // ---------------------------------------------------------------------------------------------
@@ -405,6 +420,18 @@ cudaError_t launch_distloss(const float* weights, const float* t, float* out, in
 cudaError_t launch_philox_uniform(const Draws& d, float* out, int64_t num_rays, int ncols, cudaStream_t st) {
   if (num_rays == 0) return cudaSuccess;
   philox_uniform_kernel<<<blocks_for(num_rays * ncols, 256), 256, 0, st>>>(d, out, num_rays, ncols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_philox_normal(const Draws& d, float* out, int64_t num_rays, int ncols, cudaStream_t st) {
+  if (num_rays == 0) return cudaSuccess;
+  philox_normal_kernel<<<blocks_for(num_rays * ncols, 256), 256, 0, st>>>(d, out, num_rays, ncols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_density_noise(float* raw_density, const Draws& d, int64_t num_rays, int ncols, cudaStream_t st) {
+  if (num_rays == 0 || !draws_active(d)) return cudaSuccess;
+  add_density_noise_kernel<<<blocks_for(num_rays * ncols, 256), 256, 0, st>>>(raw_density, d, num_rays, ncols);
   return cudaGetLastError();
 }
 

@@ -66,6 +66,25 @@ __device__ __forceinline__ float draw_uniform(const Draws& d, int64_t ray, int j
   return __fmul_rn((float)(x >> 8) * 5.9604644775390625e-08f, d.scale);  // 2^-24
 }
 
+// ---- density noise of randomized=True (models/mip_nerf.py:232-233: raw_density += density_noise * randn) ----------
+// Standard normal j of `ray`: explicit array element (caller-injected draws, what the parity tests feed from the
+// reference's own torch.randn), or Box-Muller on two 24-bit Philox uniforms of counter (ray, j, stream 32 + level).
+__device__ __forceinline__ float draw_normal(const Draws& d, int64_t ray, int j, int ncols) {
+  if (d.ptr) return __ldg(d.ptr + ray * ncols + j);
+  const uint64_t g = (uint64_t)(d.ray_base + ray);
+  const uint32_t k0 = (uint32_t)d.seed, k1 = (uint32_t)(d.seed >> 32) ^ (uint32_t)(d.offset >> 32);
+  const uint32_t c2 = (uint32_t)j | ((uint32_t)d.stream << 24);
+  const uint32_t x0 = philox4x32_10_first((uint32_t)g, (uint32_t)(g >> 32), c2, (uint32_t)d.offset, k0, k1);
+  const uint32_t x1 = philox4x32_10_first((uint32_t)g, (uint32_t)(g >> 32), c2 | 0x800000u, (uint32_t)d.offset, k0, k1);
+  const float u1 = (float)((x0 >> 8) + 1u) * 5.9604644775390625e-08f;  // (0, 1]
+  const float u2 = (float)(x1 >> 8) * 5.9604644775390625e-08f;         // [0, 1)
+  return __fmul_rn(sqrtf(__fmul_rn(-2.0f, logf(u1))), cospif(__fmul_rn(2.0f, u2)));
+}
+// raw density + scale * normal, mul and add rounded separately like the reference's two torch ops
+__device__ __forceinline__ float add_density_noise(float raw_density, const Draws& d, int64_t ray, int j, int ncols) {
+  return __fadd_rn(raw_density, __fmul_rn(d.scale, draw_normal(d, ray, j, ncols)));
+}
+
 // fencepost j of n+1; `jit` = t_rand[ray][j] for the stratified draw when has_jitter, ignored otherwise
 __device__ __forceinline__ float coarse_fencepost(float nr, float fr, int j, int n, int disparity, bool has_jitter,
                                                   float jit) {

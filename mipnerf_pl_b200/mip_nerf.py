@@ -17,7 +17,7 @@ from typing import List, Optional
 import torch
 
 from . import _cabi
-from .ops import _dev, _f32, _ptr, _stream, draw_t_rand, draw_u_jitter
+from .ops import _dev, _f32, _ptr, _stream, draw_density_normal, draw_t_rand, draw_u_jitter
 from .rays import Rays
 
 
@@ -248,22 +248,20 @@ class MipNerf(torch.nn.Module):
             max_deg_point=self.max_deg_point, deg_view=self.deg_view, use_viewdirs=int(bool(self.use_viewdirs)),
             disparity=int(bool(self.disparity)), disable_integration=int(bool(self.disable_integration)),
             resample_padding=float(self.resample_padding), density_bias=float(self.density_bias),
-            rgb_padding=float(self.rgb_padding))
+            rgb_padding=float(self.rgb_padding), density_noise=float(self.density_noise))
 
     def forward(self, rays: Rays, randomized: bool, white_bkgd: bool, *, t_rand: Optional[torch.Tensor] = None,
-                u_jitter: Optional[torch.Tensor] = None, return_inds: bool = False):
+                u_jitter: Optional[torch.Tensor] = None, density_normal=None, return_inds: bool = False):
         """rays -> [(comp_rgb [B,3], distance [B], acc [B], weights [B,N], t_samples [B,N+1])] * levels
-        (models/mip_nerf.py:172-248).  `t_rand` / `u_jitter` inject the noise of randomized mode;
-        with `return_inds` a sixth element (searchsorted indices, None for level 0) is appended."""
+        (models/mip_nerf.py:172-248).  `t_rand` / `u_jitter` / `density_normal` (one [B,N] tensor of standard normals
+        per level, models/mip_nerf.py:233) inject the noise of randomized mode; without any of them the kernels draw
+        in-kernel.  With `return_inds` a sixth element (searchsorted indices, None for level 0) is appended."""
         if self.ray_shape == 'cylinder':
             raise NotImplementedError  # models/mip.py:97-98
         assert self.ray_shape == 'cone'
         if self.use_viewdirs and not self._append_identity:
             raise RuntimeError("append_identity=False: view encoding width does not match view_layers "
                                "(same failure as the reference)")
-        if randomized and self.density_noise > 0:
-            raise NotImplementedError("density_noise > 0: the reference adds CPU noise (models/mip_nerf.py:233) "
-                                      "and fails on GPU tensors; not carried over")
         dev = _dev(rays.origins)
         b = rays.origins.shape[0]
         n = self.num_samples
@@ -274,13 +272,21 @@ class MipNerf(torch.nn.Module):
         rs = _cabi.RaysStruct(keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(),
                               keep[4].data_ptr(), keep[5].data_ptr(), b)
         rng = None
-        if randomized and t_rand is None and u_jitter is None:
+        noisy = bool(randomized) and self.density_noise > 0     # models/mip_nerf.py:232
+        if randomized and t_rand is None and u_jitter is None and density_normal is None:
             rng = self.next_rng()                       # in-kernel Philox: no torch.rand launch, no [B,N+1] arrays
+            normals = [None] * self.num_levels
         elif randomized:
             t_rand = _f32(t_rand) if t_rand is not None else draw_t_rand(b, n, dev)
             u_jitter = _f32(u_jitter) if u_jitter is not None else draw_u_jitter(b, n + 1, dev)
+            normals = list(density_normal) if density_normal is not None else [None] * self.num_levels
+            if len(normals) != self.num_levels:
+                raise ValueError(f"density_normal: expected {self.num_levels} tensors (one per level)")
+            normals = [(_f32(x).reshape(b, n) if x is not None else draw_density_normal(b, n, dev)) if noisy else None
+                       for x in normals]
         else:
             t_rand = u_jitter = None
+            normals = [None] * self.num_levels
         ws, wkeep = self.mlp._weights_struct(cfg, prec, dev)
         outs = (_cabi.LevelOut * self.num_levels)()
         # One allocation for everything: the per-level pixel outputs (comp_rgb | distance | acc = 5 floats/ray) of
@@ -301,7 +307,7 @@ class MipNerf(torch.nn.Module):
             t = flat[q + n * b:q + (2 * n + 1) * b].view(b, n + 1)
             inds = torch.empty(b, n + 1, device=dev, dtype=torch.int64) if (return_inds and lvl > 0) else None
             outs[lvl] = _cabi.LevelOut(comp.data_ptr(), dist.data_ptr(), acc.data_ptr(), w.data_ptr(),
-                                       t.data_ptr(), _ptr(inds))
+                                       t.data_ptr(), _ptr(inds), _ptr(normals[lvl]))
             ret.append((comp, dist, acc, w, t, inds) if return_inds else (comp, dist, acc, w, t))
         lib = _cabi.lib()
         nbytes = lib.mipnerf_b200_workspace_bytes(C.byref(cfg), b, prec)

@@ -5,7 +5,7 @@ marshals CUDA tensors into the matching C-ABI entry point of
 libmipnerf_b200.so.  CPU tensors are rejected: there is no fallback path.
 
 Differences that the C ABI forces and that are visible here:
-  * random draws are explicit optional arguments (`t_rand`, `u_jitter`) so a
+  * random draws are explicit optional arguments (`t_rand`, `u_jitter`, `density_normal`) so a
     caller (or a parity test) can inject the noise; when omitted they are
     drawn with torch's CUDA generator;
   * everything is fp32; other dtypes are cast at the boundary.
@@ -74,6 +74,24 @@ def philox_uniform(seed: int, offset: int, stream_id: int, batch: int, num_draws
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().mipnerf_b200_philox_uniform(C.byref(rng), stream_id, batch, num_draws, out.data_ptr(),
                                                             _stream(dev)), "philox_uniform")
+    return out
+
+
+def draw_density_normal(batch: int, num_samples: int, device) -> torch.Tensor:
+    """torch.randn(raw_density.shape) of models/mip_nerf.py:233 (one [B,N] draw per level)."""
+    return torch.randn(batch, num_samples, device=device, dtype=torch.float32)
+
+
+def philox_normal(seed: int, offset: int, level: int, batch: int, num_samples: int, device) -> torch.Tensor:
+    """The standard normals the kernels draw in-kernel for (seed, offset) as the density noise of `level`
+    (models/mip_nerf.py:232-233).  Passed as `density_normal[level]` they reproduce the in-kernel randomized
+    forward bit for bit."""
+    dev = torch.device(device)
+    out = torch.empty(batch, num_samples, device=dev)
+    rng = _cabi.Rng(seed & 0xFFFFFFFFFFFFFFFF, offset)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().mipnerf_b200_philox_normal(C.byref(rng), level, batch, num_samples, out.data_ptr(),
+                                                           _stream(dev)), "philox_normal")
     return out
 
 

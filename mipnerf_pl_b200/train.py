@@ -24,7 +24,7 @@ import torch
 
 from . import _cabi
 from .mip_nerf import MipNerf, _Workspace
-from .ops import _dev, _f32, _ptr, _stream, draw_t_rand, draw_u_jitter
+from .ops import _dev, _f32, _ptr, _stream, draw_density_normal, draw_t_rand, draw_u_jitter
 from .rays import Rays
 
 
@@ -185,14 +185,12 @@ def _level_multipliers(num_levels: int, coarse_loss_mult: float, dist_mult: floa
 
 def _run(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white_bkgd: bool,
          coarse_loss_mult: float, dist_mult: float, disable_multiscale_loss: bool, t_rand, u_jitter,
-         grad_tensors: Sequence[torch.Tensor], accumulate: bool, mask_sum, global_rays):
+         grad_tensors: Sequence[torch.Tensor], accumulate: bool, mask_sum, global_rays, density_normal=None):
     if not model.stop_resample_grad:
         raise NotImplementedError("training kernels implement stop_resample_grad=True (the reference default)")
     prec = _cabi.PRECISIONS[model.precision]   # fp32: the parity mode; bf16 / fp16: forward + dgrad GEMMs on tcgen05
     if model.ray_shape != "cone":
         raise NotImplementedError
-    if randomized and model.density_noise > 0:
-        raise NotImplementedError("density_noise > 0 is not carried over (models/mip_nerf.py:233)")
     dev = _dev(rays.origins)
     b, n, levels = rays.origins.shape[0], model.num_samples, model.num_levels
     cfg = model._config()
@@ -200,11 +198,18 @@ def _run(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white
             _f32(rays.near).reshape(-1), _f32(rays.far).reshape(-1)]
     rs = _cabi.RaysStruct(*[k.data_ptr() for k in keep], b)
     rng = None
-    if randomized and t_rand is None and u_jitter is None:
-        rng = model.next_rng()          # uniforms drawn inside the kernels (Philox), as every training step does
+    noisy = bool(randomized) and model.density_noise > 0    # models/mip_nerf.py:232-233
+    normals = [None] * levels
+    if randomized and t_rand is None and u_jitter is None and density_normal is None:
+        rng = model.next_rng()          # uniforms / normals drawn inside the kernels (Philox), as every training step does
     elif randomized:
         t_rand = _f32(t_rand) if t_rand is not None else draw_t_rand(b, n, dev)
         u_jitter = _f32(u_jitter) if u_jitter is not None else draw_u_jitter(b, n + 1, dev)
+        if noisy:
+            given = list(density_normal) if density_normal is not None else [None] * levels
+            if len(given) != levels:
+                raise ValueError(f"density_normal: expected {levels} tensors (one per level)")
+            normals = [_f32(x).reshape(b, n) if x is not None else draw_density_normal(b, n, dev) for x in given]
     else:
         t_rand = u_jitter = None
     target = _f32(rgbs[..., :3]).reshape(b, 3)
@@ -230,7 +235,8 @@ def _run(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white
     for lvl in range(levels):
         comp, dist, acc = torch.empty(b, 3, device=dev), torch.empty(b, device=dev), torch.empty(b, device=dev)
         w, t = torch.empty(b, n, device=dev), torch.empty(b, n + 1, device=dev)
-        outs[lvl] = _cabi.LevelOut(comp.data_ptr(), dist.data_ptr(), acc.data_ptr(), w.data_ptr(), t.data_ptr(), None)
+        outs[lvl] = _cabi.LevelOut(comp.data_ptr(), dist.data_ptr(), acc.data_ptr(), w.data_ptr(), t.data_ptr(), None,
+                                   _ptr(normals[lvl]))
         ret.append((comp, dist, acc, w, t))
     lib = _cabi.lib()
     nbytes = lib.mipnerf_b200_train_workspace_bytes(C.byref(cfg), b)
@@ -256,7 +262,7 @@ def _param_list(model: MipNerf) -> List[torch.nn.Parameter]:
 
 def forward_backward(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized: bool, white_bkgd: bool, *,
                      coarse_loss_mult: float = 0.1, dist_mult: float = 0.01, disable_multiscale_loss: bool = False,
-                     t_rand=None, u_jitter=None, accumulate: bool = False, mask_sum=None,
+                     t_rand=None, u_jitter=None, density_normal=None, accumulate: bool = False, mask_sum=None,
                      global_rays: Optional[int] = None) -> Dict[str, object]:
     """Forward + backward of the training loss; gradients are written (or added, with `accumulate`)
     into `param.grad`.  For a ray shard of a larger batch pass the GLOBAL `mask_sum` / `global_rays`;
@@ -276,7 +282,7 @@ def forward_backward(model: MipNerf, rays: Rays, rgbs: torch.Tensor, randomized:
         elif not p.grad.is_contiguous():
             p.grad = p.grad.contiguous()
     return _run(model, rays, rgbs, randomized, white_bkgd, coarse_loss_mult, dist_mult, disable_multiscale_loss,
-                t_rand, u_jitter, [p.grad for p in params], accumulate, mask_sum, global_rays)
+                t_rand, u_jitter, [p.grad for p in params], accumulate, mask_sum, global_rays, density_normal)
 
 
 class _FusedLoss(torch.autograd.Function):
@@ -285,7 +291,7 @@ class _FusedLoss(torch.autograd.Function):
         grads = [torch.empty_like(p) for p in params]
         out = _run(model, rays, rgbs, randomized, white_bkgd, kwargs["coarse_loss_mult"], kwargs["dist_mult"],
                    kwargs["disable_multiscale_loss"], kwargs.get("t_rand"), kwargs.get("u_jitter"), grads, False,
-                   kwargs.get("mask_sum"), kwargs.get("global_rays"))
+                   kwargs.get("mask_sum"), kwargs.get("global_rays"), kwargs.get("density_normal"))
         holder.update(out)
         ctx.grads = grads
         return out["loss"].clone()

@@ -331,9 +331,12 @@ def mlp_forward(params: Dict[str, torch.Tensor], x, view_enc, net_depth=8, skip_
 
 def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white_bkgd: bool,
             config: Optional[dict] = None, t_rand=None, u_jitter=None,
-            return_debug=False, operand_dtype=None, grad=False, operand_split=False) -> List[Tuple[torch.Tensor, ...]]:
+            return_debug=False, operand_dtype=None, grad=False, operand_split=False,
+            density_normal=None) -> List[Tuple[torch.Tensor, ...]]:
     """MipNerf.forward (models/mip_nerf.py:172-248): list over levels of
     (comp_rgb [B,3], distance [B], acc [B], weights [B,N], t_samples [B,N+1]).
+    `density_normal`: per level, the [B,N] standard normals standing in for torch.randn of models/mip_nerf.py:233
+    (used when randomized and config['density_noise'] > 0; drawn with torch.randn when omitted, like the reference).
     `grad=True` keeps the autograd graph (training); the resampler then runs under no_grad on detached
     weights, which is what stop_resample_grad=True does (models/mip.py:250-264)."""
     cfg = dict(DEFAULT_CONFIG)
@@ -362,6 +365,10 @@ def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white
             raw_rgb, raw_density = mlp_forward(params, enc, view_enc, cfg["mlp_net_depth"],
                                                cfg["mlp_skip_index"], cfg["mlp_net_depth_condition"],
                                                operand_dtype=operand_dtype, operand_split=operand_split)
+            if randomized and cfg["density_noise"] > 0:  # models/mip_nerf.py:232-233
+                z = (density_normal[level].reshape(raw_density.shape) if density_normal is not None
+                     else torch.randn(raw_density.shape, dtype=raw_density.dtype))
+                raw_density = raw_density + cfg["density_noise"] * z
             rgb = torch.sigmoid(raw_rgb) * (1 + 2 * cfg["rgb_padding"]) - cfg["rgb_padding"]
             density = F.softplus(raw_density + cfg["density_bias"])
             comp_rgb, distance, acc, weights = volumetric_rendering(rgb, density, t, rays.directions, white_bkgd)
@@ -372,10 +379,12 @@ def forward(params: Dict[str, torch.Tensor], rays: Rays, randomized: bool, white
 
 
 def training_loss(params: Dict[str, torch.Tensor], rays: Rays, rgbs, randomized: bool, white_bkgd: bool,
-                  coarse_loss_mult=0.1, disable_multiscale_loss=False, config=None, t_rand=None, u_jitter=None):
+                  coarse_loss_mult=0.1, disable_multiscale_loss=False, config=None, t_rand=None, u_jitter=None,
+                  density_normal=None):
     """MipNeRFSystem.training_step's loss (models/nerf_system.py:95-111) with the autograd graph over
     `params` kept: (loss, [mse per level], [distloss per level], ret)."""
-    ret = forward(params, rays, randomized, white_bkgd, config, t_rand=t_rand, u_jitter=u_jitter, grad=True)
+    ret = forward(params, rays, randomized, white_bkgd, config, t_rand=t_rand, u_jitter=u_jitter, grad=True,
+                  density_normal=density_normal)
     mask = torch.ones_like(rays.lossmult) if disable_multiscale_loss else rays.lossmult
     losses, dls = [], []
     for (rgb, _, _, weights, t_samples) in ret:

@@ -81,11 +81,18 @@ def forward_case(name, num_rays, seed, weights_kind, randomized, white_bkgd, mul
     if randomized:
         # replay the reference's draws: torch.rand(B,N+1) at level 0 (mip.py:159), then
         # empty(B,N+1).uniform_(to=s-eps) at level 1 (mip.py:201-202), from a seeded CPU generator.
+        # With density_noise > 0 each level also draws randn(B,N,1) right after its MLP (mip_nerf.py:233), i.e. the
+        # generator is consumed in the order rand, randn, uniform_, randn.
+        noisy = model.density_noise > 0
         torch.manual_seed(1234 + seed)
         extra["t_rand"] = torch.rand(num_rays, n + 1).numpy()
+        if noisy:
+            extra["density_normal_l0"] = torch.randn(num_rays, n, 1).numpy()[..., 0]
         if model.num_levels > 1:
             s = 1 / (n + 1)
             extra["u_jitter"] = torch.empty(num_rays, n + 1).uniform_(to=(s - F32_EPS)).numpy()
+            if noisy:
+                extra["density_normal_l1"] = torch.randn(num_rays, n, 1).numpy()[..., 0]
         torch.manual_seed(1234 + seed)
     with torch.no_grad(), CaptureSearchsorted() as cap:
         ret = model(to_ref_rays(rays), randomized, white_bkgd)
@@ -337,12 +344,22 @@ def metrics_case():
     save("metrics.npz", **out)
 
 
+def density_noise_case():
+    # randomized forward with the density-noise regulariser on (models/mip_nerf.py:232-233; std 1.0 is the value the
+    # NeRF papers use on real scenes), CPU reference, the generator's draws replayed into the fixture
+    forward_case("forward_density_noise.npz", 24, seed=5, weights_kind="trained_like", randomized=True,
+                 white_bkgd=True, density_noise=1.0)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":    # regenerate only metrics.npz
         metrics_case()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "training":   # regenerate only training.npz
         training_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "density_noise":   # regenerate only forward_density_noise.npz
+        density_noise_case()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "datasets":   # regenerate only datasets.npz
         datasets_case()
@@ -354,6 +371,7 @@ if __name__ == "__main__":
                  white_bkgd=True)
     forward_case("forward_config0.npz", 256, seed=3, weights_kind="xavier", randomized=False, white_bkgd=True,
                  num_samples=64, num_levels=1)
+    density_noise_case()
     resampler_case()
     stages_case()
     training_case()

@@ -28,14 +28,14 @@ def test_header_symbols_all_exported(lib):
     assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mipnerf_b200_abi_version() == _cabi.ABI_VERSION == 3
+    assert lib.mipnerf_b200_abi_version() == _cabi.ABI_VERSION == 4
 
 
 def test_ctypes_structs_match_header_layout():
     assert C.sizeof(_cabi.Linear) == 24
-    assert C.sizeof(_cabi.Config) == 18 * 4
+    assert C.sizeof(_cabi.Config) == 19 * 4
     assert C.sizeof(_cabi.RaysStruct) == 7 * 8
-    assert C.sizeof(_cabi.LevelOut) == 6 * 8
+    assert C.sizeof(_cabi.LevelOut) == 7 * 8
     assert C.sizeof(_cabi.Weights) == 8 + 4 + 4 + 8 + 8
     assert C.sizeof(_cabi.LinearGrad) == 16
     assert C.sizeof(_cabi.Loss) == 8 * 8
@@ -211,4 +211,4 @@ def test_public_header_is_plain_c_and_links(tmp_path):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                     str(src), "-o", str(exe), "-L", libdir, "-l:libmipnerf_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.split() == ["3", "3"], out
+    assert out.returncode == 0 and out.stdout.split() == ["4", "4"], out

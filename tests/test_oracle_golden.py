@@ -25,6 +25,7 @@ def bit_equal(a, b, what):
     ("forward_trained_like.npz", "trained_like", {}),
     ("forward_randomized.npz", "trained_like", {}),
     ("forward_config0.npz", "xavier", dict(num_samples=64, num_levels=1)),
+    ("forward_density_noise.npz", "trained_like", dict(density_noise=1.0)),   # models/mip_nerf.py:232-233
 ])
 def test_forward_matches_reference(name, kind, cfg):
     g = golden(name)
@@ -33,8 +34,10 @@ def test_forward_matches_reference(name, kind, cfg):
     rays = oracle_rays(golden_rays(g))
     t_rand = torch.from_numpy(g["t_rand"]) if "t_rand" in g else None
     u_jit = torch.from_numpy(g["u_jitter"]) if "u_jitter" in g else None
+    normals = ([torch.from_numpy(g[f"density_normal_l{lvl}"]) for lvl in range(2)]
+               if "density_normal_l0" in g else None)
     ret, dbg = oracle.forward(params, rays, bool(randomized), bool(white), cfg, t_rand=t_rand, u_jitter=u_jit,
-                              return_debug=True)
+                              return_debug=True, density_normal=normals)
     want = golden_levels(g)
     assert len(ret) == len(want)
     for lvl, (got, ref) in enumerate(zip(ret, want)):
