@@ -52,6 +52,15 @@ def test_argument_validation_without_gpu(lib):
     assert rc == _cabi.EUNSUPPORTED and b"num_samples" in lib.mipnerf_b200_last_error()
     rc = lib.mipnerf_b200_forward(C.byref(cfg), None, None, 0, None, None, 1, 0, None, None, 0, None)
     assert rc == _cabi.EINVAL
+    # density_noise (models/mip_nerf.py:232-233) travels in the config: a negative / non-finite std is a bad argument
+    assert abs(mp.MipNerf(density_noise=0.25)._config().density_noise - 0.25) < 1e-7
+    for std in (-1.0, float("nan"), float("inf")):
+        neg = mp.MipNerf(density_noise=std)._config()
+        assert lib.mipnerf_b200_workspace_bytes(C.byref(neg), 16, _cabi.FP32) == 0
+        rc = lib.mipnerf_b200_forward(C.byref(neg), None, None, 0, None, None, 1, 0, None, None, 0, None)
+        assert rc == _cabi.EINVAL and b"density_noise" in lib.mipnerf_b200_last_error(), std
+    rc = lib.mipnerf_b200_philox_normal(None, 0, 4, 128, None, None)
+    assert rc == _cabi.EINVAL
     with pytest.raises(NotImplementedError):
         _cabi.check(_cabi.EUNSUPPORTED, "x")
     with pytest.raises(ValueError):
