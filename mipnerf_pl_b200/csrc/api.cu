@@ -286,8 +286,8 @@ static int forward_impl(const mipnerf_b200_config* cfg, const mipnerf_b200_weigh
   if (precision != MIPNERF_B200_FP32) {
     if (!mipnerf::tc_supported(cfg, precision))
       return fail(MIPNERF_B200_EUNSUPPORTED,
-                  "tensor-core path supports only the default 8x256 / N=128 / deg 0..16 / deg_view 4 model "
-                  "with precision bf16|fp16|fp16x3|bf16x3; use MIPNERF_B200_FP32 for other shapes");
+                  "tensor-core path supports the 8x256 / 1x128 / N=128 model with min_deg_point 0, max_deg_point 1..16, "
+                  "deg_view 1..4 and precision bf16|fp16|fp16x3|bf16x3; use MIPNERF_B200_FP32 for other shapes");
     if (!w->packed || w->packed_precision != precision ||
         w->packed_bytes < mipnerf::tc_packed_bytes(cfg, precision))
       return fail(MIPNERF_B200_EINVAL, "weights->packed missing or packed for another precision");
@@ -471,12 +471,14 @@ FusedScratch carve_fused(const mipnerf_b200_config* c, const Dims& d, int64_t ra
 // MIPNERF_B200_TRAIN_FUSED=0 keeps the per-layer tensor-core path (A/B runs).
 bool train_fused_supported(const mipnerf_b200_config* c, int precision) {
   return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16) && mipnerf::tc_supported(c, precision) &&
+         mipnerf::tc_default_degrees(c) &&  // the backward's tile images carry the full 96 / 27 encodings
          c->num_levels <= 2 && c->net_depth == 8;
 }
 
 // Tensor-core GEMMs of the training step exist for the default widths only (linear_tc.cu).
 bool train_tc_supported(const mipnerf_b200_config* c, const Dims& d) {
-  if (!(c->net_width == 256 && c->net_width_condition == 128 && d.xyz_dim == 96 && c->net_depth <= kMaxTrainDepth))
+  if (!(c->net_width == 256 && c->net_width_condition == 128 && d.xyz_dim == 96 && d.view_dim == 27 &&
+        c->net_depth <= kMaxTrainDepth))
     return false;
   // packed-operand slots the step needs (forward + skip + transposed dgrad images + bottleneck / view layer x 2):
   // must fit the kTrainImages slots carved from the workspace

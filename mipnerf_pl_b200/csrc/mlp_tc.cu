@@ -1752,6 +1752,23 @@ __global__ void __launch_bounds__(256) pack_v1_image_kernel(const PackV1Src src,
   }
 }
 
+// dst [rows, in_dst] <- src [rows, in_src]: the first `prefix` columns copied; the rest is two halves (sin | shifted sin)
+// of half_dst columns each, of which the model has the first half_src (lower encoding degrees); the others are zero
+__global__ void expand_encoding_columns_kernel(const float* __restrict__ src, int in_src, float* __restrict__ dst,
+                                               int in_dst, int rows, int prefix, int half_src, int half_dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * in_dst) return;
+  const int r = idx / in_dst, c = idx % in_dst;
+  float v = 0.f;
+  if (c < prefix) {
+    v = src[(size_t)r * in_src + c];
+  } else {
+    const int j = c - prefix, h = j / half_dst, i = j % half_dst;
+    if (h < 2 && i < half_src) v = src[(size_t)r * in_src + prefix + h * half_src + i];
+  }
+  dst[idx] = v;
+}
+
 struct SmallSrc {
   const float* bias[9];
   const float* w_density;
@@ -2034,22 +2051,38 @@ int set_trace_ptr(unsigned long long* ptr) {
 }
 #endif
 
+// Encoding degrees below the kernels' own (max_deg_point < 16, deg_view < 4; min_deg_point = 0): the level kernels always
+// compute the 96 IPE features of degrees 0..15 and the 27 view features of degrees 0..3, and the MODEL's narrower
+// layers.0 / layers.5 / view_layers.0 weights are zero-padded to those widths when the operand image is packed (feature
+// column 3 l + c of the sin half and 48 + 3 l + c of the shifted-sin half <- the model's columns 3 l + c and
+// 3 L + 3 l + c; models/mip.py:322-341, :353-363).  The extra features meet exact zeros in the GEMM, so the result is the
+// narrower model's, at the default model's speed.
+bool tc_default_degrees(const mipnerf_b200_config* c) { return c->max_deg_point == 16 && c->deg_view == 4; }
 bool tc_supported(const mipnerf_b200_config* c, int precision) {
   return (precision == MIPNERF_B200_BF16 || precision == MIPNERF_B200_FP16 || is_x3(precision)) &&
          c->num_samples == kN &&
-         c->min_deg_point == 0 && c->max_deg_point == 16 && c->deg_view == 4 && c->use_viewdirs &&
+         c->min_deg_point == 0 && c->max_deg_point >= 1 && c->max_deg_point <= 16 && c->deg_view >= 1 &&
+         c->deg_view <= 4 && c->use_viewdirs &&
          c->net_depth == 8 && c->net_width == kWidth && c->net_depth_condition == 1 &&
          c->net_width_condition == kCond && c->skip_index == 4 && c->num_rgb_channels == 3 &&
          c->num_density_channels == 1;
 }
 bool tc_mlp_supported(const mipnerf_b200_config* c, int samples_per_ray, int precision) {
   mipnerf_b200_config c2 = *c;
-  c2.num_samples = kN;
-  return samples_per_ray == kN && tc_supported(&c2, precision);
+  c2.num_samples = kN;  // MLP-only mode takes the caller's [B,128,96] / [B,27] encodings as they are: default degrees only
+  return samples_per_ray == kN && tc_default_degrees(c) && tc_supported(&c2, precision);
 }
 
+// zero-padded fp32 copies of layers.0 [256,96], layers.5 [256,352], view_layers.0 [128,283] behind the operand image
+constexpr size_t kPad0Bytes = (size_t)kWidth * kFeat * sizeof(float);
+constexpr size_t kPad5Bytes = (size_t)kWidth * (kWidth + kFeat) * sizeof(float);
+constexpr size_t kPadViewBytes = (size_t)kCond * (kWidth + kViewDim) * sizeof(float);
+constexpr size_t kPadOffset = (kV3Offset + kV3Bytes + 255) / 256 * 256;
+constexpr size_t kPadBytes = kPad0Bytes + kPad5Bytes + kPadViewBytes;
+
 size_t tc_packed_bytes(const mipnerf_b200_config* c, int precision) {
-  return tc_supported(c, precision) ? kV3Offset + kV3Bytes : 0;
+  if (!tc_supported(c, precision)) return 0;
+  return tc_default_degrees(c) ? kV3Offset + kV3Bytes : kPadOffset + kPadBytes;
 }
 
 size_t tc_workspace_bytes(const mipnerf_b200_config* c, int64_t num_rays, int precision) {
@@ -2067,10 +2100,27 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
   cudaError_t e = cudaMemsetAsync(img, 0, with_v3 ? kV3Offset + kV3Bytes : kV3Offset, st);
   if (e != cudaSuccess) return e;
   LaunchScope scope(kKernPackWeights, st);
+  mipnerf_b200_linear lin[12];
+  for (int i = 0; i < 12; ++i) lin[i] = w->linears[i];
+  if (!tc_default_degrees(c)) {  // lower encoding degrees: pack from zero-padded copies of the three encoding-fed layers
+    float* pad0 = reinterpret_cast<float*>(img + kPadOffset);
+    float* pad5 = reinterpret_cast<float*>(img + kPadOffset + kPad0Bytes);
+    float* padv = reinterpret_cast<float*>(img + kPadOffset + kPad0Bytes + kPad5Bytes);
+    const int hx = 3 * c->max_deg_point, hv = 3 * c->deg_view;
+    auto expand = [&](int li, float* dst, int in_dst, int rows, int prefix, int half_src, int half_dst) {
+      expand_encoding_columns_kernel<<<(rows * in_dst + 255) / 256, 256, 0, st>>>(lin[li].weight, lin[li].in_features, dst,
+                                                                                  in_dst, rows, prefix, half_src, half_dst);
+      lin[li].weight = dst, lin[li].in_features = in_dst;
+    };
+    expand(0, pad0, kFeat, kWidth, 0, hx, kFeat / 2);
+    expand(5, pad5, kWidth + kFeat, kWidth, kWidth, hx, kFeat / 2);
+    expand(10, padv, kWidth + kViewDim, kCond, kWidth + 3, hv, (kViewDim - 3) / 2);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
   PackV1Src v1{};
   for (int l = 0; l < kNumLayers; ++l) {
     const int li = l < 8 ? l : (l == 8 ? 9 : 10);  // layers.l | extra_layer | view_layers.0
-    v1.weight[l] = w->linears[li].weight, v1.in_features[l] = w->linears[li].in_features;
+    v1.weight[l] = lin[li].weight, v1.in_features[l] = lin[li].in_features;
   }
   for (int part = 0; part < parts; ++part) {
     uint8_t* base = img + (part ? kLoOffset : 0);
@@ -2081,7 +2131,7 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
   // repacks every optimiser step and runs the v1 pair kernel only, so it skips them
   for (int l = 0; with_v3 && l < kNumLayers; ++l) {
     const int li = l < 8 ? l : (l == 8 ? 9 : 10);
-    const mipnerf_b200_linear& lin = w->linears[li];
+    const mipnerf_b200_linear& lin3 = lin[li];
     const int type = layer_type3(l), nb = sched_count3(type);
     const int fbase = l == 5 ? kWidth : 0;  // K offset of the feature columns: layer 5 is [h (256) | x (96)]
     for (int r = 0; r < 2; ++r) {
@@ -2092,25 +2142,25 @@ cudaError_t tc_pack_weights(const mipnerf_b200_config* c, const mipnerf_b200_wei
         const int kbase = blk.kind < 4 ? 64 * blk.kind : (blk.kind == 4 ? fbase : fbase + 64);
         const int kcount = blk.kind == 5 ? 32 : 64;
         if (bf)
-          pack_stage_kernel<1><<<(32 * kcount + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, row0, kbase, kcount,
+          pack_stage_kernel<1><<<(32 * kcount + 255) / 256, 256, 0, st>>>(lin3.weight, lin3.in_features, row0, kbase, kcount,
                                                                          dst, 32, 0);
         else
-          pack_stage_kernel<0><<<(32 * kcount + 255) / 256, 256, 0, st>>>(lin.weight, lin.in_features, row0, kbase, kcount,
+          pack_stage_kernel<0><<<(32 * kcount + 255) / 256, 256, 0, st>>>(lin3.weight, lin3.in_features, row0, kbase, kcount,
                                                                          dst, 32, 0);
       }
     }
   }
   SmallSrc src;
-  for (int l = 0; l < 8; ++l) src.bias[l] = w->linears[l].bias;
-  src.bias[8] = w->linears[9].bias;  // extra_layer
-  src.w_density = w->linears[8].weight;
-  src.b_density = w->linears[8].bias;
-  src.w_color = w->linears[11].weight;
-  src.b_color = w->linears[11].bias;
+  for (int l = 0; l < 8; ++l) src.bias[l] = lin[l].bias;
+  src.bias[8] = lin[9].bias;  // extra_layer
+  src.w_density = lin[8].weight;
+  src.b_density = lin[8].bias;
+  src.w_color = lin[11].weight;
+  src.b_color = lin[11].bias;
   pack_small_params_kernel<<<(9 * kWidth + 255) / 256, 256, 0, st>>>(src,
                                                                       reinterpret_cast<SmallParams*>(img + kSmallOffset));
   pack_view_dir_kernel<<<((kViewDim + 1) * kCond + 255) / 256, 256, 0, st>>>(
-      w->linears[10].weight, w->linears[10].bias, reinterpret_cast<float*>(img + kViewDirOffset));
+      lin[10].weight, lin[10].bias, reinterpret_cast<float*>(img + kViewDirOffset));
   return cudaGetLastError();
 }
 
@@ -2156,6 +2206,8 @@ cudaError_t tc_forward(const mipnerf_b200_config* c, const mipnerf_b200_weights*
     // v1 kernels produce fenceposts and the view bias inside the level kernels (IPE warps); the shared-stream
     // variant keeps the separate prologue / resample launches.
     const bool fused_prologue = dump != nullptr || fused_prologue_enabled(precision);  // training: always the v1 pair kernel
+    if (!fused_prologue && !tc_default_degrees(c)) return cudaErrorNotSupported;  // the stand-alone prologue reads the
+                                                                                  // model's own (narrower) view layer
     // in-kernel Philox: the counter is the ray index of the caller's whole batch (ray_base = offset of `rays` in it)
     auto draws = [&](const float* array, int stream) {
       Draws d = level_draws(randomized, array, rng, off, stream, kN + 1);

@@ -11,6 +11,7 @@ namespace mipnerf {
 
 // true iff (cfg, precision) is the shape the fused tensor-core kernels are specialised for.
 bool tc_supported(const mipnerf_b200_config* cfg, int precision);
+bool tc_default_degrees(const mipnerf_b200_config* cfg);  // max_deg_point == 16 && deg_view == 4 (no weight padding)
 bool tc_mlp_supported(const mipnerf_b200_config* cfg, int samples_per_ray, int precision);
 size_t tc_packed_bytes(const mipnerf_b200_config* cfg, int precision);
 size_t tc_workspace_bytes(const mipnerf_b200_config* cfg, int64_t num_rays, int precision);

@@ -72,6 +72,8 @@ def forward_case(name, num_rays, seed, weights_kind, randomized, white_bkgd, mul
     shape_kw = {}
     if "max_deg_point" in model_kw or "min_deg_point" in model_kw:
         shape_kw["xyz_dim"] = 6 * (model_kw.get("max_deg_point", 16) - model_kw.get("min_deg_point", 0))
+    if "deg_view" in model_kw:
+        shape_kw["view_dim"] = 6 * model_kw["deg_view"] + 3
     sd = make_state_dict(seed=seed, kind=weights_kind, **shape_kw)
     model = RefMipNerf(**model_kw)
     model.load_state_dict(sd)
@@ -344,6 +346,13 @@ def metrics_case():
     save("metrics.npz", **out)
 
 
+def degrees_case():
+    # lower encoding degrees than the default 16 / 4 (NeRF's own 10 for points; 2 for view directions): layers.0 is
+    # [256,60], layers.5 [256,316], view_layers.0 [128,271]
+    forward_case("forward_deg10_view2.npz", 32, seed=6, weights_kind="trained_like", randomized=False,
+                 white_bkgd=True, max_deg_point=10, deg_view=2)
+
+
 def density_noise_case():
     # randomized forward with the density-noise regulariser on (models/mip_nerf.py:232-233; std 1.0 is the value the
     # NeRF papers use on real scenes), CPU reference, the generator's draws replayed into the fixture
@@ -357,6 +366,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "training":   # regenerate only training.npz
         training_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "degrees":   # regenerate only forward_deg10_view2.npz
+        degrees_case()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "density_noise":   # regenerate only forward_density_noise.npz
         density_noise_case()
@@ -372,6 +384,7 @@ if __name__ == "__main__":
     forward_case("forward_config0.npz", 256, seed=3, weights_kind="xavier", randomized=False, white_bkgd=True,
                  num_samples=64, num_levels=1)
     density_noise_case()
+    degrees_case()
     resampler_case()
     stages_case()
     training_case()

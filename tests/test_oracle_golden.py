@@ -26,11 +26,17 @@ def bit_equal(a, b, what):
     ("forward_randomized.npz", "trained_like", {}),
     ("forward_config0.npz", "xavier", dict(num_samples=64, num_levels=1)),
     ("forward_density_noise.npz", "trained_like", dict(density_noise=1.0)),   # models/mip_nerf.py:232-233
+    ("forward_deg10_view2.npz", "trained_like", dict(max_deg_point=10, deg_view=2)),
 ])
 def test_forward_matches_reference(name, kind, cfg):
     g = golden(name)
     seed, randomized, white = (int(v) for v in g["meta"])
-    params = make_state_dict(seed=seed, kind=kind)
+    shape = {}
+    if "max_deg_point" in cfg:
+        shape["xyz_dim"] = 6 * cfg["max_deg_point"]
+    if "deg_view" in cfg:
+        shape["view_dim"] = 6 * cfg["deg_view"] + 3
+    params = make_state_dict(seed=seed, kind=kind, **shape)
     rays = oracle_rays(golden_rays(g))
     t_rand = torch.from_numpy(g["t_rand"]) if "t_rand" in g else None
     u_jit = torch.from_numpy(g["u_jitter"]) if "u_jitter" in g else None
