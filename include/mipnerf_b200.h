@@ -31,7 +31,12 @@ extern "C" {
 #define MIPNERF_B200_ECUDA (-3)        /* a CUDA runtime call or launch failed                       */
 #define MIPNERF_B200_EWORKSPACE (-4)   /* workspace smaller than mipnerf_b200_workspace_bytes()      */
 
-/* Arithmetic the MLP contraction runs in (everything else on the path is always fp32). */
+/* Arithmetic the MLP contraction runs in (everything else on the path is always fp32).
+ * FP32 takes any config check_config accepts.  The tensor-core precisions take the reference's shipped architecture:
+ * 8x256 trunk with the skip after layer 4, one 128-wide view layer, num_samples = 128, use_viewdirs, min_deg_point = 0,
+ * max_deg_point 1..16 and deg_view 1..4 (narrower encodings are zero-padded into the operand image by
+ * mipnerf_b200_pack_weights); the tensor-core TRAINING step and mipnerf_b200_mlp_forward need max_deg_point = 16 and
+ * deg_view = 4.  Anything else answers MIPNERF_B200_EUNSUPPORTED (mipnerf_b200_packed_weights_bytes() == 0). */
 #define MIPNERF_B200_FP32 0 /* CUDA-core FFMA, fp32 operands: the 1e-4 parity mode                   */
 #define MIPNERF_B200_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM             */
 #define MIPNERF_B200_FP16 2 /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM             */
