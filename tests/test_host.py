@@ -61,6 +61,21 @@ def test_argument_validation_without_gpu(lib):
         assert rc == _cabi.EINVAL and b"density_noise" in lib.mipnerf_b200_last_error(), std
     rc = lib.mipnerf_b200_philox_normal(None, 0, 4, 128, None, None)
     assert rc == _cabi.EINVAL
+    # tensor-core shape contract (include/mipnerf_b200.h): the operand image exists for the shipped architecture with
+    # max_deg_point 1..16 / deg_view 1..4 (narrower encodings add the zero-padded fp32 copies: 603 KB), not otherwise
+    base = lib.mipnerf_b200_packed_weights_bytes(C.byref(cfg), _cabi.BF16)
+    assert base > 0 and lib.mipnerf_b200_packed_weights_bytes(C.byref(cfg), _cabi.FP32) == 0
+    for kw in (dict(max_deg_point=10), dict(deg_view=2), dict(max_deg_point=1, deg_view=1)):
+        narrow = mp.MipNerf(**kw)._config()
+        nb = lib.mipnerf_b200_packed_weights_bytes(C.byref(narrow), _cabi.BF16)
+        assert base < nb <= base + 604 * 1024 + 256, (kw, nb - base)
+        assert lib.mipnerf_b200_workspace_bytes(C.byref(narrow), 4096, _cabi.BF16) == \
+            lib.mipnerf_b200_workspace_bytes(C.byref(cfg), 4096, _cabi.BF16)
+    for kw in (dict(min_deg_point=1), dict(max_deg_point=17), dict(num_samples=64), dict(mlp_net_width=128),
+               dict(mlp_net_depth=6), dict(use_viewdirs=False, mlp_net_width_condition=256)):
+        other = mp.MipNerf(**kw)._config()
+        assert lib.mipnerf_b200_packed_weights_bytes(C.byref(other), _cabi.BF16) == 0, kw
+        assert lib.mipnerf_b200_workspace_bytes(C.byref(other), 16, _cabi.FP32) > 0, kw      # the fp32 path takes it
     with pytest.raises(NotImplementedError):
         _cabi.check(_cabi.EUNSUPPORTED, "x")
     with pytest.raises(ValueError):
