@@ -55,3 +55,26 @@ def test_bench_cpu_arm_prefers_the_reference():
     assert kind == "reference"
     out = forward(make_state_dict(seed=0), mp.random_ray_batch(8, seed=0))
     assert len(out) == 2 and out[1][0].shape == (8, 3)
+
+
+@pytest.mark.parametrize("name,kind,kw,shape", [
+    ("forward_density_noise.npz", "trained_like", dict(density_noise=1.0), {}),
+    ("forward_deg10_view2.npz", "trained_like", dict(max_deg_point=10, deg_view=2), dict(xyz_dim=60, view_dim=15)),
+])
+def test_round2_goldens_are_the_installed_references_outputs(name, kind, kw, shape):
+    """The fixtures added in round 2 (density noise, lower encoding degrees) re-derived from the unmodified reference in
+    baseline/_ref, bit for bit — including the order in which the reference consumes its generator when density_noise >
+    0 (rand, randn, uniform_, randn; tests/golden/make_golden.py seeds it with 1234 + seed)."""
+    from helpers import golden, golden_levels, golden_rays
+    RefMipNerf, RefRays, _ = ref_loader.load()
+    g = golden(name)
+    seed, randomized, white = (int(v) for v in g["meta"])
+    model = RefMipNerf(**kw)
+    model.load_state_dict(make_state_dict(seed=seed, kind=kind, **shape))
+    rays = golden_rays(g)
+    torch.manual_seed(1234 + seed)
+    with torch.no_grad():
+        ret = model.eval()(RefRays(*rays), bool(randomized), bool(white))
+    for lvl, want in enumerate(golden_levels(g)):
+        for k, field in enumerate(("comp_rgb", "distance", "acc", "weights", "t_samples")):
+            assert torch.equal(ret[lvl][k], torch.from_numpy(want[k])), (name, lvl, field)
