@@ -63,7 +63,7 @@ def test_bench_cpu_arm_prefers_the_reference():
 ])
 def test_round2_goldens_are_the_installed_references_outputs(name, kind, kw, shape):
     """The fixtures added in round 2 (density noise, lower encoding degrees) re-derived from the unmodified reference in
-    baseline/_ref, bit for bit — including the order in which the reference consumes its generator when density_noise >
+    baseline/_ref (bit for bit on the host that wrote them; the contract's 1e-4 elsewhere) — including the order in which the reference consumes its generator when density_noise >
     0 (rand, randn, uniform_, randn; tests/golden/make_golden.py seeds it with 1234 + seed)."""
     from helpers import golden, golden_levels, golden_rays
     RefMipNerf, RefRays, _ = ref_loader.load()
@@ -75,6 +75,13 @@ def test_round2_goldens_are_the_installed_references_outputs(name, kind, kw, sha
     torch.manual_seed(1234 + seed)
     with torch.no_grad():
         ret = model.eval()(RefRays(*rays), bool(randomized), bool(white))
+    from helpers import assert_level_close
+    exact = True
     for lvl, want in enumerate(golden_levels(g)):
-        for k, field in enumerate(("comp_rgb", "distance", "acc", "weights", "t_samples")):
-            assert torch.equal(ret[lvl][k], torch.from_numpy(want[k])), (name, lvl, field)
+        # the contract's tolerance everywhere (torch's sgemm may block differently on a host with another core count /
+        # ISA than the one that wrote the fixture) ...
+        assert_level_close(ret[lvl], want, what=f"{name} level {lvl} ", level=lvl)
+        exact = exact and all(torch.equal(ret[lvl][k], torch.from_numpy(want[k])) for k in range(5))
+    # ... the coarse fenceposts have no MLP upstream: bit-exact on any host
+    assert torch.equal(ret[0][4], torch.from_numpy(golden_levels(g)[0][4]))
+    print(f"{name}: {'bit-identical to' if exact else 'within 1e-4 of'} the committed fixture on this host")
